@@ -1,0 +1,164 @@
+"""Pin the NumPy oracle (oracle/acro_oracle.py) against the reference's own outputs.
+
+The fixtures were produced by tests/golden/make_golden.py from the unmodified reference
+(or are the arrays of the trajectory files it ships).  CPU only.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err
+from oracle import acro_oracle as O
+
+TOL = 1e-9  # contract of BASELINE.json north_star; observed errors are ~1e-13
+
+
+def test_dynamics_kat():
+    g = golden("dyn_kat")
+    assert rel_err(O.continuous_dynamics(g["x"], g["u"]), g["f"]) < 1e-12
+    assert rel_err(O.dynamics(g["x"], g["u"]), g["step"]) < 1e-12
+    A, B = O.Calculate_A_B_matrixes(g["x"], g["u"])
+    assert rel_err(A, g["A_c"]) < 1e-12
+    assert rel_err(B, g["B_c"]) < 1e-12
+    assert np.all(B[:, :, 0] == 0.0) and np.all(B[:, :2, :] == 0.0)
+
+
+def test_survey_known_answers():
+    x = np.array([0.3, -0.2, 0.5, -0.7])
+    u = np.array([1.0, 2.0])
+    np.testing.assert_allclose(O.continuous_dynamics(x, u), [0.5, -0.7, -8.097062412610704, 18.791857037341483], rtol=1e-13)
+    np.testing.assert_allclose(O.dynamics(x, u), [0.30842243714633577, -0.21036198377515106, 0.34430441728616834,
+                                                  -0.34211929152559867], rtol=1e-13)
+
+
+def test_shipped_optimal_trajectory_satisfies_rk4_step():
+    """500 known-answer vectors: x[k+1] == dynamics(x[k], u[k]) on the shipped file."""
+    d = golden("acrobot_optimal_trajectory")
+    nxt = O.dynamics(d["x"][:-1], d["u"])
+    assert np.max(np.abs(nxt - d["x"][1:])) < 5e-15
+
+
+def test_fully_actuated_file_satisfies_actuated_step():
+    d = golden("fully_actuated_trajectory")
+    m = O.Model(actuated_tau1=True)
+    nxt = O.dynamics(d["x"][:-1], d["u"], m)
+    assert np.max(np.abs(nxt - d["x"][1:])) < 1e-9
+
+
+def test_first_iteration_blocks(fa_ref):
+    g = golden("newton_task2_blocks")
+    x_ref, u_ref, _ = fa_ref
+    assert u_ref.shape[0] == x_ref.shape[0] - 1
+    u0 = np.zeros_like(u_ref)
+    xo = O.simulate_open_loop(g["x0"], u0)
+    assert rel_err(xo, g["x_open"]) < 1e-12
+    Ad, Bd, q, r, QT2, qT = O.build_stage_lists(xo, u0, x_ref, u_ref)
+    assert rel_err(Ad, g["A_list"]) < 1e-12 and rel_err(Bd, g["B_list"]) < 1e-12
+    assert rel_err(q, g["q_list"]) < 1e-12 and rel_err(r, g["r_list"]) < 1e-12
+    assert rel_err(qT, g["q_T"]) < 1e-12 and rel_err(QT2, g["Q_T_block"]) == 0
+    K, s, dJ = O.calculate_K_and_sigma(Ad, Bd, q, r, 2 * O.Q_NEWTON, 2 * O.R_NEWTON, QT2, qT)
+    assert rel_err(K, g["K0"]) < 1e-11 and rel_err(s, g["sigma0"]) < 1e-11
+    assert abs(dJ - g["delta_J0"]) < 1e-11 * abs(g["delta_J0"])
+    lam = O.compute_costate_trajectory(xo, u0, x_ref, u_ref)
+    assert rel_err(lam, g["lam"]) < 1e-11
+    np.testing.assert_allclose(g["delta_J0"], -169165.70417990963, rtol=1e-12)
+
+
+def test_newton_task2_first_iterations_and_costs(fa_ref):
+    g = golden("newton_task2")
+    x_ref, u_ref, _ = fa_ref
+    x, u, K, s, h = O.newton_Algorithm(g["x0"], x_ref, u_ref, max_iters=4, tol=1e-4, gamma_0=0.1, keep_trajs=True)
+    assert rel_err(h["cost"], g["cost"][:5]) < 1e-12
+    assert rel_err(h["sigma_norm"], g["sigma_norm"][:4]) < 1e-12
+    assert rel_err(np.array(h["x_trajs"]), g["x_trajs"][:5]) < 1e-11
+    assert h["n_try"] == list(g["n_try"][:4])
+    np.testing.assert_allclose(g["cost"][:3], [407310.76108107425, 391453.8670466373, 378640.1632285486], rtol=1e-13)
+    assert len(g["sigma_norm"]) == 393 and abs(g["cost"][-1] - 28063.21834988143) < 1e-6
+
+
+def test_newton_task2_golden_matches_shipped_file():
+    """The reference re-run here reproduces the file it ships (2.3e-13 / 6.0e-13)."""
+    g = golden("newton_task2")
+    d = golden("acrobot_optimal_trajectory")
+    assert np.max(np.abs(g["x"] - d["x"])) < 1e-11 and np.max(np.abs(g["u"] - d["u"])) < 1e-11
+
+
+def test_newton_backtracking_gamma1(fa_ref):
+    """gamma_0 = 1 exercises the Armijo back-tracking: same tries, same accepted step sizes."""
+    g = golden("newton_gamma1")
+    x_ref, u_ref, _ = fa_ref
+    x, u, K, s, h = O.newton_Algorithm(g["x0"], x_ref, u_ref, max_iters=8, tol=1e-4, gamma_0=1.0, keep_trajs=True)
+    assert h["n_try"] == list(g["n_try"][:8])
+    assert h["gamma"] == list(g["gamma_acc"][:8])  # bit-identical step sizes (sequential gamma *= beta)
+    assert rel_err(h["cost"], g["cost"][:9]) < 1e-10
+    assert rel_err(np.array(h["x_trajs"]), g["x_trajs"][:9]) < 1e-9
+    assert max(g["n_try"]) > 1
+
+
+def test_newton_task1_recipe():
+    g = golden("newton_task1")
+    x, u, K, s, h = O.newton_Algorithm(g["x0"], g["x_ref"], g["u_ref"], max_iters=5, tol=1e-4, gamma_0=0.05, keep_trajs=True)
+    assert rel_err(h["cost"], g["cost"][:6]) < 1e-12
+    assert rel_err(np.array(h["x_trajs"])[:5], g["x_trajs"][:5]) < 1e-11
+    assert len(g["sigma_norm"]) == 173 and abs(g["cost"][-1] - 27.48962661922637) < 1e-9
+
+
+def test_newton_c2_rows(fa_ref):
+    g = golden("newton_c2_rows")
+    x_ref, u_ref, _ = fa_ref
+    for i in range(2):
+        x, u, K, s, h = O.newton_Algorithm(g["x0"][i], x_ref, u_ref, max_iters=6, tol=1e-4, gamma_0=0.1)
+        assert rel_err(x, g["x"][i]) < 1e-11 and rel_err(u, g["u"][i]) < 1e-11
+        assert rel_err(K, g["K"][i]) < 1e-10 and rel_err(s, g["sigma"][i]) < 1e-10
+        assert rel_err(h["cost"], g["cost"][i]) < 1e-12
+
+
+def test_sweep(fa_ref):
+    g = golden("sweep_iter0")
+    t2 = golden("newton_task2_blocks")
+    x_ref, u_ref, _ = fa_ref
+    idx = np.arange(0, 200, 9)
+    c = O.stepsize_sweep(t2["x_open"], np.zeros_like(u_ref), t2["K0"], t2["sigma0"], x_ref, u_ref, g["steps"][idx])
+    assert rel_err(c, g["costs"][idx]) < 1e-11
+
+
+def test_lqr_gains_and_tracking():
+    g = golden("lqr_tracking")
+    d = golden("acrobot_optimal_trajectory")
+    K = O.solve_LQR_tracking(d["x"], d["u"])
+    assert rel_err(K, g["K_reg"]) < 1e-11
+    np.testing.assert_allclose(K[0][1], [1.6085004079175165, -5.314848245482309, -4.725771848391788, -4.1000147935985405], rtol=1e-10)
+    xt, ut = O.simulate_tracking(d["x"], d["u"], g["K_reg"], g["x0"])
+    ok = np.isfinite(g["x_track"]).all(axis=(1, 2)) & (np.abs(g["x_track"]).max(axis=(1, 2)) < 50)
+    assert ok[:20].all()
+    assert rel_err(xt[ok], g["x_track"][ok]) < TOL and rel_err(ut[ok], g["u_track"][ok]) < TOL
+    np.testing.assert_allclose(xt[0, -1], [3.141507366148879, 3.088315439801646e-05, -2.0527577096561255e-04,
+                                           6.888578496876233e-04], atol=1e-10)
+
+
+def test_p_inf():
+    g = golden("p_inf")
+    P, it = O.compute_P_inf(g["A_f"], g["B_f"], g["Q"], g["R"], return_iters=True)
+    assert it == 434
+    assert rel_err(P, g["P_inf"]) < 1e-12
+    A_f, B_f = O.linearize_discrete(O.X_F, O.U_F)
+    assert rel_err(A_f, g["A_f"]) < 1e-13 and rel_err(B_f, g["B_f"]) < 1e-13
+    P0 = O.compute_P_inf(g["A0"], g["B0"], O.Q_LQR, O.R_LQR)
+    assert rel_err(P0, g["P0"]) < 1e-9
+
+
+def test_mpc_riccati_equals_kkt():
+    """The QP of solver_mpc (trajectory_tracking.py:80-117): Riccati form == dense KKT solve (unpinned vs IPOPT)."""
+    d = golden("acrobot_optimal_trajectory")
+    g = golden("p_inf")
+    Ad, Bd = O.linearize_discrete(d["x"][:-1], d["u"])
+    for H, t0 in ((75, 0), (50, 100), (20, 490)):
+        A_f, B_f = g["A_f"], g["B_f"]
+        Aw = [Ad[t0 + j] if t0 + j < 500 else A_f for j in range(H - 1)]
+        Bw = [Bd[t0 + j] if t0 + j < 500 else B_f for j in range(H - 1)]
+        x0 = 0.1 * np.ones(4)
+        U0, X, U = O.solver_mpc(x0, Aw, Bw, O.Q_MPC, O.R_MPC, g["P_inf"], H)
+        U0k, Xk, Uk = O.solver_mpc_kkt(x0, Aw, Bw, O.Q_MPC, O.R_MPC, g["P_inf"], H)
+        assert rel_err(U0, U0k) < 1e-8 and rel_err(X, Xk) < 1e-8 and rel_err(U, Uk) < 1e-8
+        if t0 == 0:
+            # figures/mpc/tracking_dx_0.1_err.png: initial control error ~0.81 (-0.80644713)
+            assert abs(U0[1] + 0.80644713) < 1e-6
