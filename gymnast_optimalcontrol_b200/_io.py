@@ -1,0 +1,106 @@
+"""Host <-> device marshalling for the drop-in modules.
+
+The reference works on NumPy arrays of one problem: state (4,), trajectory (N,4), lists of (2,4) gains.
+The drop-ins accept those, the same with a leading batch axis ((B,4), (B,N,4), ...), and torch tensors
+(CPU, pinned or not, or CUDA).  Everything is converted to the structure-of-arrays device layout with
+the library's own pack/unpack kernels and converted back to the kind of object the caller passed in.
+"""
+import numpy as np
+import torch
+
+from . import batched as bt
+
+
+class Kind:
+    """Remembers what the caller handed in so results go back the same way."""
+
+    def __init__(self, a, batched):
+        self.batched = batched
+        if isinstance(a, torch.Tensor):
+            self.torch = True
+            self.cuda = a.is_cuda
+            self.pinned = (not a.is_cuda) and a.is_pinned()
+        else:
+            self.torch = self.cuda = self.pinned = False
+
+
+_pinned_pool = {}
+
+
+def _pinned(shape, key):
+    """Reusable pinned staging buffer (one per (key, shape)); the caller owns the result until the next call."""
+    k = (key, tuple(shape))
+    buf = _pinned_pool.get(k)
+    if buf is None:
+        buf = torch.empty(shape, dtype=torch.float64).pin_memory()
+        _pinned_pool[k] = buf
+    return buf
+
+
+def as_device(a):
+    return bt.upload(a)
+
+
+def state_in(a, C):
+    """(C,), (C,1), (B,C) -> SoA (C,B) on the device, Kind"""
+    if isinstance(a, torch.Tensor):
+        nd, shape = a.dim(), tuple(a.shape)
+    else:
+        a = np.asarray(a, dtype=np.float64)
+        nd, shape = a.ndim, a.shape
+    if nd == 1 or (nd == 2 and shape == (C, 1)):
+        k = Kind(a, False)
+        d = as_device(a).reshape(1, C)
+    elif nd == 2 and shape[1] == C:
+        k = Kind(a, True)
+        d = as_device(a)
+    else:
+        raise ValueError("expected shape (%d,) or (B,%d), got %r" % (C, C, shape))
+    return bt.pack_soa(d), k
+
+
+def traj_in(a, C):
+    """(T,C) or (B,T,C) (or a list of T arrays of shape (C,) / (r,c) with r*c = C) -> SoA (T,C,B), Kind"""
+    if isinstance(a, (list, tuple)):
+        a = np.asarray([np.asarray(v, dtype=np.float64).reshape(-1) for v in a])
+    if isinstance(a, torch.Tensor):
+        nd = a.dim()
+    else:
+        a = np.asarray(a, dtype=np.float64)
+        nd = a.ndim
+    d = as_device(a)
+    if d.shape[-1] != C:  # e.g. gains given as (..., 2, 4)
+        d = d.reshape(*d.shape[:-2], C)
+        nd -= 1
+    if nd == 2:
+        return bt.pack_soa(d.reshape(1, *d.shape)), Kind(a, False)
+    if nd == 3:
+        return bt.pack_soa(d), Kind(a, True)
+    raise ValueError("expected a trajectory of shape (T,%d) or (B,T,%d)" % (C, C))
+
+
+def out(t_soa, kind, tail=None, key="out"):
+    """SoA device tensor (C,B) / (T,C,B) -> caller's kind; tail reshapes the component axis (e.g. (2,4))."""
+    t = bt.unpack_soa(t_soa)  # (B,C) / (B,T,C)
+    if tail is not None:
+        t = t.reshape(*t.shape[:-1], *tail)
+    if not kind.batched:
+        t = t[0]
+    if kind.torch and kind.cuda:
+        return t
+    if kind.torch:
+        if kind.pinned:
+            h = _pinned(t.shape, key)
+            h.copy_(t, non_blocking=False)
+            return h
+        return t.cpu()
+    return t.cpu().numpy()
+
+
+def vec_out(t, kind):
+    """per-problem scalars (B,) -> float / array following kind"""
+    if not kind.batched:
+        return t[0].item()
+    if kind.torch and kind.cuda:
+        return t
+    return t.cpu() if kind.torch else t.cpu().numpy()

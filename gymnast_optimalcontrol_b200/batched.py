@@ -1,0 +1,417 @@
+"""Device-level API: torch CUDA tensors in the structure-of-arrays layout of include/acro_abi.h.
+
+Every function here is a thin wrapper that allocates outputs with torch and calls one C-ABI
+entry point of libacro_b200.so on torch's current stream.  Shapes (problem index last, so a
+contiguous tensor IS the SoA layout):
+
+    state batch (4, B)   input batch (2, B)   X (N, 4, B)   U (N-1, 2, B)
+    K (N-1, 8, B) (view as (N-1, 2, 4, B))    S (N-1, 2, B)
+
+torch is used for device memory and streams only.  There is no CPU path: without a CUDA
+device these functions raise.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import AcroNewtonOpts, AcroParams, AcroRef, AcroWeights, call
+
+F64 = torch.float64
+
+# dynamics.py:15-61
+PARAM_SETS = {
+    1: dict(m1=1.0, m2=1.0, l1=1.0, lc1=0.5, l2=1.0, lc2=0.5, I1=0.33, I2=0.33, g=9.81, f1=1.0, f2=1.0),
+    2: dict(m1=2.0, m2=2.0, l1=1.5, lc1=0.75, l2=1.5, lc2=0.75, I1=1.5, I2=1.5, g=9.81, f1=1.0, f2=1.0),
+    3: dict(m1=1.5, m2=1.5, l1=2.0, lc1=1.0, l2=2.0, lc2=1.0, I1=2.0, I2=2.0, g=9.81, f1=1.0, f2=1.0),
+}
+DT = 2e-2  # dynamics.py:173
+
+
+def make_params(version=1, dt=DT, actuated_tau1=False, **overrides):
+    d = dict(PARAM_SETS[version])
+    d.update(overrides)
+    p = AcroParams()
+    for k, v in d.items():
+        setattr(p, k, float(v))
+    p.dt = float(dt)
+    p.actuated_tau1 = 1 if actuated_tau1 else 0
+    return p
+
+
+DEFAULT_PARAMS = make_params()
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("gymnast_optimalcontrol_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=F64):
+    if t is None:
+        return C.c_void_p(0)
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError("expected a contiguous CUDA %s tensor, got %r" % (dtype, type(t) if not isinstance(t, torch.Tensor)
+                                                                          else (t.device, t.dtype, t.is_contiguous())))
+    return C.c_void_p(t.data_ptr())
+
+
+def _empty(*shape, dtype=F64):
+    return torch.empty(shape, dtype=dtype, device=device())
+
+
+class Weights:
+    """Q, R, Q_T (host, symmetric) with optional per-problem device overrides (16,B), (4,B), (16,B)."""
+
+    def __init__(self, Q, R, QT=None, Q_b=None, R_b=None, QT_b=None):
+        self.Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(4, 4)
+        self.R = np.ascontiguousarray(R, dtype=np.float64).reshape(2, 2)
+        self.QT = np.ascontiguousarray(self.Q if QT is None else QT, dtype=np.float64).reshape(4, 4)
+        for name, M in (("Q", self.Q), ("R", self.R), ("Q_T", self.QT)):
+            if not np.array_equal(M, M.T):
+                raise ValueError("%s must be symmetric" % name)
+        self.Q_b, self.R_b, self.QT_b = Q_b, R_b, QT_b
+        s = AcroWeights()
+        s.Q[:] = self.Q.ravel().tolist()
+        s.R[:] = self.R.ravel().tolist()
+        s.QT[:] = self.QT.ravel().tolist()
+        s.Q_b, s.R_b, s.QT_b = _p(Q_b).value, _p(R_b).value, _p(QT_b).value
+        self.struct = s
+
+    @property
+    def per_problem(self):
+        return any(t is not None for t in (self.Q_b, self.R_b, self.QT_b))
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+# trajectory_generation.py:16-18, trajectory_tracking.py:173-175, 38-39
+def newton_weights():
+    return Weights(np.diag([130.0, 30.0, 0.0001, 0.0001]), np.diag([1e-6, 1.5]), np.diag([130.0, 130.0, 1.0, 1.0]))
+
+
+def lqr_weights():
+    return Weights(np.diag([100.0, 100.0, 10.0, 10.0]), np.diag([1.0, 1.0]))
+
+
+def mpc_weights():
+    return Weights(np.diag([120.0, 100.0, 0.0001, 0.0001]), np.diag([1e-6, 10.0]))
+
+
+class Ref:
+    """Reference trajectory: shared x (N,4), u (N-1,2) or per problem x (N,4,B), u (N-1,2,B)."""
+
+    def __init__(self, x, u):
+        self.x, self.u = x, u
+        self.per_problem = x.dim() == 3
+        self.N = x.shape[0]
+        if u.shape[0] != self.N - 1 or u.dim() != x.dim():
+            raise ValueError("Incompatible dimensions: x_ref has %d states but u_ref has %d controls (expected %d)"
+                             % (self.N, u.shape[0], self.N - 1))
+        s = AcroRef()
+        s.x, s.u, s.per_problem = _p(x).value, _p(u).value, int(self.per_problem)
+        self.struct = s
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def upload(a):
+    """NumPy / CPU tensor -> contiguous CUDA float64 tensor (async when the source is pinned)."""
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda:
+            return a.to(F64).contiguous()
+        return a.to(F64).contiguous().to(device(), non_blocking=a.is_pinned())
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device())
+
+
+def make_ref(x_ref, u_ref):
+    return Ref(upload(x_ref), upload(u_ref))
+
+
+# ------------------------------------------------------------------------------------------
+# layout helpers
+# ------------------------------------------------------------------------------------------
+def pack_soa(a):
+    """(B, T, C) or (B, C) batch-major CUDA tensor -> (T, C, B) / (C, B)."""
+    a = a.contiguous()
+    if a.dim() == 2:
+        Bn, Cn = a.shape
+        out = _empty(Cn, Bn)
+        call("acro_pack_soa", Bn, 1, Cn, _p(a), _p(out), _stream())
+        return out
+    Bn, T, Cn = a.shape
+    out = _empty(T, Cn, Bn)
+    call("acro_pack_soa", Bn, T, Cn, _p(a), _p(out), _stream())
+    return out
+
+
+def unpack_soa(a):
+    """(T, C, B) or (C, B) -> (B, T, C) / (B, C)."""
+    a = a.contiguous()
+    if a.dim() == 2:
+        Cn, Bn = a.shape
+        out = _empty(Bn, Cn)
+        call("acro_unpack_soa", Bn, 1, Cn, _p(a), _p(out), _stream())
+        return out
+    T, Cn, Bn = a.shape
+    out = _empty(Bn, T, Cn)
+    call("acro_unpack_soa", Bn, T, Cn, _p(a), _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# D1-D3
+# ------------------------------------------------------------------------------------------
+def continuous_dynamics(x, u, params=DEFAULT_PARAMS):
+    out = torch.empty_like(x)
+    call("acro_continuous_dynamics", C.byref(params), x.shape[1], _p(x), _p(u), _p(out), _stream())
+    return out
+
+
+def rk4_step(x, u, params=DEFAULT_PARAMS):
+    out = torch.empty_like(x)
+    call("acro_rk4_step", C.byref(params), x.shape[1], _p(x), _p(u), _p(out), _stream())
+    return out
+
+
+def linearize(x, u, discrete=False, params=DEFAULT_PARAMS):
+    """-> A (4,4,B), Bm (4,2,B)"""
+    Bn = x.shape[1]
+    A, Bm = _empty(4, 4, Bn), _empty(4, 2, Bn)
+    call("acro_linearize", C.byref(params), Bn, _p(x), _p(u), _p(A), _p(Bm), int(discrete), _stream())
+    return A, Bm
+
+
+# ------------------------------------------------------------------------------------------
+# G1-G11
+# ------------------------------------------------------------------------------------------
+def rollout_open_loop(x0, U=None, N=None, params=DEFAULT_PARAMS):
+    Bn = x0.shape[1]
+    N = U.shape[0] + 1 if U is not None else N
+    X = _empty(N, 4, Bn)
+    call("acro_rollout_open_loop", C.byref(params), Bn, N, _p(x0), _p(U), _p(X), _stream())
+    return X
+
+
+def total_cost(X, U, ref, w):
+    N, _, Bn = X.shape
+    cost = _empty(Bn)
+    call("acro_total_cost", w.ref(), Bn, N, _p(X), _p(U), ref.ref(), _p(cost), _stream())
+    return cost
+
+
+def costate(X, U, ref, w, params=DEFAULT_PARAMS):
+    N, _, Bn = X.shape
+    lam = torch.empty_like(X)
+    call("acro_costate", C.byref(params), w.ref(), Bn, N, _p(X), _p(U), ref.ref(), _p(lam), _stream())
+    return lam
+
+
+def riccati_affine(X, U, ref, w, params=DEFAULT_PARAMS):
+    """-> K (N-1,8,B), S (N-1,2,B), delta_J (B,), sigma_norm (B,)"""
+    N, _, Bn = X.shape
+    K, S, dJ, sn = _empty(N - 1, 8, Bn), _empty(N - 1, 2, Bn), _empty(Bn), _empty(Bn)
+    call("acro_riccati_affine", C.byref(params), w.ref(), Bn, N, _p(X), _p(U), ref.ref(), _p(K), _p(S), _p(dJ), _p(sn),
+         _stream())
+    return K, S, dJ, sn
+
+
+def closed_loop_rollout_cost(X, U, K, S, ref, w, gammas, store=False, params=DEFAULT_PARAMS):
+    """gammas (G,) shared or (G,B) per problem -> cost (G,B) [, Xn (G,N,4,B), Un (G,N-1,2,B)]"""
+    N, _, Bn = X.shape
+    G = gammas.shape[0]
+    cost = _empty(G, Bn)
+    Xn = _empty(G, N, 4, Bn) if store else None
+    Un = _empty(G, N - 1, 2, Bn) if store else None
+    call("acro_closed_loop_rollout_cost", C.byref(params), w.ref(), Bn, N, _p(X), _p(U), _p(K), _p(S), ref.ref(), G,
+         _p(gammas), int(gammas.dim() == 2), _p(Xn), _p(Un), _p(cost), _stream())
+    return (cost, Xn, Un) if store else cost
+
+
+def armijo_select(cost_k, delta_J, gammas, cost_cand, c=0.5):
+    G, Bn = cost_cand.shape
+    acc = _empty(Bn, dtype=torch.int32)
+    call("acro_armijo_select", Bn, G, _p(cost_k), _p(delta_J), _p(gammas), int(gammas.dim() == 2), _p(cost_cand), float(c),
+         _p(acc, torch.int32), _stream())
+    return acc
+
+
+@dataclass
+class NewtonState:
+    """Everything acro_newton_solve reads and writes; keep it to resume a solve."""
+    X: torch.Tensor
+    U: torch.Tensor
+    K: torch.Tensor
+    S: torch.Tensor
+    cost: torch.Tensor
+    delta_J: torch.Tensor
+    sigma_norm: torch.Tensor
+    gamma_acc: torch.Tensor
+    iters: torch.Tensor
+    status: torch.Tensor
+    Xw: torch.Tensor
+    Uw: torch.Tensor
+    hist_cost: Optional[torch.Tensor] = None
+    hist_sigma_norm: Optional[torch.Tensor] = None
+    hist_gamma: Optional[torch.Tensor] = None
+    hist_ntry: Optional[torch.Tensor] = None
+    x_trajs: List[torch.Tensor] = field(default_factory=list)
+    initialised: bool = False
+
+
+def newton_alloc(Bn, N, max_iters, history=True):
+    st = NewtonState(
+        X=_empty(N, 4, Bn), U=_empty(N - 1, 2, Bn), K=_empty(N - 1, 8, Bn), S=_empty(N - 1, 2, Bn), cost=_empty(Bn),
+        delta_J=_empty(Bn), sigma_norm=_empty(Bn), gamma_acc=_empty(Bn), iters=_empty(Bn, dtype=torch.int32),
+        status=_empty(Bn, dtype=torch.int32), Xw=_empty(N, 4, Bn), Uw=_empty(N - 1, 2, Bn))
+    if history:
+        st.hist_cost = torch.full((max_iters + 1, Bn), float("nan"), dtype=F64, device=device())
+        st.hist_sigma_norm = torch.full((max_iters, Bn), float("nan"), dtype=F64, device=device())
+        st.hist_gamma = torch.full((max_iters, Bn), float("nan"), dtype=F64, device=device())
+        st.hist_ntry = torch.zeros((max_iters, Bn), dtype=torch.int32, device=device())
+    return st
+
+
+def newton_solve(x0, ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, w=None, params=DEFAULT_PARAMS,
+                 state=None, chunk_iters=0, max_line_search=20, history=True):
+    """newton_Algorithm (trajectory_generation.py:298-398) for a batch, x0 (4,B).
+
+    One kernel launch runs the whole loop for every problem.  Pass the returned state back
+    (with chunk_iters) to continue a solve in pieces."""
+    w = newton_weights() if w is None else w
+    Bn = x0.shape[1]
+    N = ref.N
+    if state is None:
+        state = newton_alloc(Bn, N, max_iters, history)
+    o = AcroNewtonOpts(max_iters=int(max_iters), chunk_iters=int(chunk_iters), max_line_search=int(max_line_search),
+                       init=0 if state.initialised else 1, tol=float(tol), beta=float(beta), c=float(c),
+                       gamma_0=float(gamma_0))
+    s = state
+    call("acro_newton_solve", C.byref(params), w.ref(), C.byref(o), Bn, N, _p(x0), ref.ref(), _p(s.X), _p(s.U), _p(s.Xw),
+         _p(s.Uw), _p(s.K), _p(s.S), _p(s.cost), _p(s.delta_J), _p(s.sigma_norm), _p(s.gamma_acc),
+         _p(s.iters, torch.int32), _p(s.status, torch.int32), _p(s.hist_cost), _p(s.hist_sigma_norm), _p(s.hist_gamma),
+         _p(s.hist_ntry, torch.int32), _stream())
+    s.initialised = True
+    return s
+
+
+def stepsize_sweep(X, U, K, S, ref, w, steps, params=DEFAULT_PARAMS):
+    """P base iterates x len(steps) step sizes -> cost (S_n, P)"""
+    N, _, Pn = X.shape
+    Sn = steps.shape[0]
+    cost = _empty(Sn, Pn)
+    call("acro_stepsize_sweep", C.byref(params), w.ref(), Pn, N, _p(X), _p(U), _p(K), _p(S), ref.ref(), Sn, _p(steps),
+         _p(cost), _stream())
+    return cost
+
+
+# ------------------------------------------------------------------------------------------
+# T1-T5
+# ------------------------------------------------------------------------------------------
+def lqr_gains(traj, w=None, params=DEFAULT_PARAMS):
+    """traj shared -> K (N-1, 8) [= (N-1,2,4) row-major]; per problem -> K (N-1, 8, B)"""
+    w = lqr_weights() if w is None else w
+    N = traj.N
+    if traj.per_problem:
+        Bn = traj.x.shape[2]
+        K = _empty(N - 1, 8, Bn)
+    else:
+        Bn = 1
+        K = _empty(N - 1, 8)
+    call("acro_lqr_gains", C.byref(params), w.ref(), Bn, N, traj.ref(), _p(K), _stream())
+    return K
+
+
+def lqr_track(traj, K, x0, params=DEFAULT_PARAMS):
+    """-> Xt (N,4,B), Ut (N-1,2,B)"""
+    N, Bn = traj.N, x0.shape[1]
+    Xt, Ut = _empty(N, 4, Bn), _empty(N - 1, 2, Bn)
+    call("acro_lqr_track", C.byref(params), Bn, N, traj.ref(), _p(K), _p(x0), _p(Xt), _p(Ut), _stream())
+    return Xt, Ut
+
+
+def p_inf(A, Bm, w, max_iter=1000, tol=1e-6):
+    """A (4,4,B), Bm (4,2,B) -> P (4,4,B), n_iter (B,) int32 (negative: not converged)"""
+    Bn = A.shape[-1]
+    P, n = _empty(4, 4, Bn), _empty(Bn, dtype=torch.int32)
+    call("acro_p_inf", w.ref(), Bn, _p(A), _p(Bm), int(max_iter), float(tol), _p(P), _p(n, torch.int32), _stream())
+    return P, n
+
+
+def mpc_solve(x0, A_w, B_w, QT, w, T_pred, trajectories=True):
+    """x0 (4,B), A_w (T_pred-1,4,4,B), B_w (T_pred-1,4,2,B), QT (4,4,B) -> U0 (2,B), X_opt (T_pred,4,B), U_opt (T_pred,2,B)"""
+    Bn = x0.shape[1]
+    U0 = _empty(2, Bn)
+    Xo = _empty(T_pred, 4, Bn) if trajectories else None
+    Uo = _empty(T_pred, 2, Bn) if trajectories else None
+    Kws = _empty(max(T_pred - 1, 1), 8, Bn) if trajectories else None
+    call("acro_mpc_solve", w.ref(), Bn, int(T_pred), _p(x0), _p(A_w), _p(B_w), _p(QT), _p(U0), _p(Xo), _p(Uo), _p(Kws),
+         _stream())
+    return U0, Xo, Uo, Kws
+
+
+def mpc_track(x0, ref, QT_inf, T=None, T_pred=75, w=None, x_f=(np.pi, 0.0, 0.0, 0.0), u_f=(0.0, 0.0),
+              params=DEFAULT_PARAMS):
+    """solve_mpc_tracking for a batch.  QT_inf (4,4) shared or (4,4,B).  -> Xr (T,4,B), Ur (T-1,2,B), K0 or None, n_solves"""
+    w = mpc_weights() if w is None else w
+    N, Bn = ref.N, x0.shape[1]
+    T = N if T is None else T
+    qt_pp = QT_inf.dim() == 3
+    pp = ref.per_problem or w.per_problem or qt_pp
+    Xr, Ur = _empty(T, 4, Bn), _empty(T - 1, 2, Bn)
+    K0 = None if pp else _empty(T - 1, 8)
+    lin = _empty(N - 1, 10, Bn) if pp else _empty(N - 1, 10)
+    xf = (C.c_double * 4)(*[float(v) for v in x_f])
+    uf = (C.c_double * 2)(*[float(v) for v in u_f])
+    ns = C.c_int64(0)
+    call("acro_mpc_track", C.byref(params), w.ref(), Bn, N, int(T), int(T_pred), ref.ref(), xf, uf, _p(QT_inf), int(qt_pp),
+         _p(x0), _p(K0), _p(lin), _p(Xr), _p(Ur), C.byref(ns), _stream())
+    return Xr, Ur, K0, int(ns.value)
+
+
+# ------------------------------------------------------------------------------------------
+# stand-alone pieces of the Newton iteration (for the drop-in functions that expose them)
+# ------------------------------------------------------------------------------------------
+def cost_derivatives(x, x_ref, u, u_ref, w, terminal=False):
+    """Batch of points (4,B)/(2,B) -> l (B,), grad_x (4,B), grad_u (2,B) or None   (tg:89-114)"""
+    Bn = x.shape[1]
+    l, gx = _empty(Bn), _empty(4, Bn)
+    gu = None if terminal else _empty(2, Bn)
+    call("acro_cost_derivatives", w.ref(), Bn, _p(x), _p(x_ref), _p(u), _p(u_ref), int(terminal), _p(l), _p(gx), _p(gu),
+         _stream())
+    return l, gx, gu
+
+
+def discretize(Ac, Bc, dt=DT):
+    """(4,4,B), (4,2,B) -> Ad, Bd   (tg:161-164)"""
+    Ad, Bd = torch.empty_like(Ac), torch.empty_like(Bc)
+    call("acro_discretize", Ac.shape[-1], _p(Ac), _p(Bc), float(dt), _p(Ad), _p(Bd), _stream())
+    return Ad, Bd
+
+
+def stage_lists(X, U, ref, w, params=DEFAULT_PARAMS):
+    """-> A (N-1,16,B), Bm (N-1,8,B), q (N-1,4,B), r (N-1,2,B), q_T (4,B)   (tg:166-181)"""
+    N, _, Bn = X.shape
+    A, Bm, q, r, qT = _empty(N - 1, 16, Bn), _empty(N - 1, 8, Bn), _empty(N - 1, 4, Bn), _empty(N - 1, 2, Bn), _empty(4, Bn)
+    call("acro_stage_lists", C.byref(params), w.ref(), Bn, N, _p(X), _p(U), ref.ref(), _p(A), _p(Bm), _p(q), _p(r), _p(qT),
+         _stream())
+    return A, Bm, q, r, qT
+
+
+def riccati_lists(A, Bm, Q, R, q, r, Q_T, q_T, S_cross=None):
+    """Dense lists (T,16,B), (T,8,B), (T,16,B), (T,4,B), (T,4,B), (T,2,B), (16,B), (4,B) -> K, S, delta_J   (tg:183-216)"""
+    T, _, Bn = A.shape
+    K, S, dJ = _empty(T, 8, Bn), _empty(T, 2, Bn), _empty(Bn)
+    call("acro_riccati_lists", Bn, T, _p(A), _p(Bm), _p(Q), _p(R), _p(S_cross), _p(q), _p(r), _p(Q_T), _p(q_T), _p(K),
+         _p(S), _p(dJ), _stream())
+    return K, S, dJ

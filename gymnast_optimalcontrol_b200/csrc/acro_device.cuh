@@ -1,0 +1,422 @@
+// acro_device.cuh - register-resident device functions of the acrobot hot path (FP64).
+//
+// One thread owns one problem: the 4-vector state, the 2x4 lower block of the discrete
+// linearisation, the symmetric 4x4 Riccati matrix P (10 registers) and the costate p live in
+// registers; nothing here touches memory.  The structure of the model is used instead of
+// dense 4x4 algebra:
+//   A_d = I + dt*A_c has top rows [1 0 dt 0; 0 1 0 dt]   (trajectory_generation.py:161-164,
+//   B_d = dt*B_c has zero top rows, and column 0 is zero   dynamics.py:153-164)
+// unless the fully-actuated variant is selected (tau1 != 0).
+// Reference lines are quoted per function (tg = trajectory_generation.py, tt =
+// trajectory_tracking.py).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace acro {
+
+// Lumped model constants, derived on the host from AcroParams (dynamics.py:64-90):
+//   M11 = a1 + 2 h cos(th2), M12 = a3 + h cos(th2), M22 = a3,
+//   G   = [g1 sin(th1) + g2 sin(th1+th2) ; g2 sin(th1+th2)]
+struct Model {
+  double a1, h, a3, g1, g2, f1, f2, dt, tau1;
+};
+
+struct Trig {
+  double s1, c1, s2, c2, s12, c12;
+};
+
+__device__ __forceinline__ Trig trig_of(double th1, double th2) {
+  Trig t;
+  sincos(th1, &t.s1, &t.c1);
+  sincos(th2, &t.s2, &t.c2);
+  // angle-addition instead of a third sincos: 4 flops, error ~2 ulp
+  t.s12 = fma(t.s1, t.c2, t.c1 * t.s2);
+  t.c12 = fma(t.c1, t.c2, -(t.s1 * t.s2));
+  return t;
+}
+
+// Pieces of one evaluation of the equations of motion that the Jacobian reuses.
+struct Eom {
+  double M11, M12, M22, inv_det, dd1, dd2;
+};
+
+// qdd = M^-1 (tau - (C+F) qd - G), tau = [tau1*u0, u1]   (dynamics.py:197-213, 64-90)
+__device__ __forceinline__ Eom eom(const Model& m, const Trig& t, double w1, double w2, double u0,
+                                   double u1) {
+  Eom e;
+  e.M11 = fma(2.0 * m.h, t.c2, m.a1);
+  e.M12 = fma(m.h, t.c2, m.a3);
+  e.M22 = m.a3;
+  const double hs2 = m.h * t.s2;
+  const double grav2 = m.g2 * t.s12;
+  const double grav1 = fma(m.g1, t.s1, grav2);
+  const double tau1 = (m.tau1 != 0.0) ? m.tau1 * u0 : 0.0;
+  // r1 = tau1 + h s2 w2 w1 + h s2 (w1+w2) w2 - f1 w1 - G1 ; r2 = u1 - h s2 w1^2 - f2 w2 - G2
+  const double r1 = tau1 + hs2 * w2 * w1 + hs2 * (w1 + w2) * w2 - m.f1 * w1 - grav1;
+  const double r2 = u1 - hs2 * w1 * w1 - m.f2 * w2 - grav2;
+  const double det = fma(e.M11, e.M22, -(e.M12 * e.M12));
+  e.inv_det = 1.0 / det;
+  e.dd1 = (e.M22 * r1 - e.M12 * r2) * e.inv_det;
+  e.dd2 = (e.M11 * r2 - e.M12 * r1) * e.inv_det;
+  return e;
+}
+
+// continuous_dynamics(xx, uu)  dynamics.py:197-213
+__device__ __forceinline__ void f_eval(const Model& m, const double x[4], double u0, double u1,
+                                       double f[4]) {
+  const Trig t = trig_of(x[0], x[1]);
+  const Eom e = eom(m, t, x[2], x[3], u0, u1);
+  f[0] = x[2];
+  f[1] = x[3];
+  f[2] = e.dd1;
+  f[3] = e.dd2;
+}
+
+// dynamics(xx, uu): classic RK4, zero-order hold on u   dynamics.py:177-195
+__device__ __forceinline__ void rk4_step(const Model& m, const double x[4], double u0, double u1,
+                                         double xn[4]) {
+  const double h = m.dt, hh = 0.5 * m.dt;
+  double k1[4], k2[4], k3[4], k4[4], y[4];
+  f_eval(m, x, u0, u1, k1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = fma(hh, k1[i], x[i]);
+  f_eval(m, y, u0, u1, k2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = fma(hh, k2[i], x[i]);
+  f_eval(m, y, u0, u1, k3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = fma(h, k3[i], x[i]);
+  f_eval(m, y, u0, u1, k4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double s = k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i];
+    xn[i] = x[i] + (h * s) * (1.0 / 6.0);
+  }
+}
+
+// Lower two rows of the continuous Jacobians (dynamics.py:153-170, 217-226):
+//   ac[r][j] = A_c[2+r][j],  bc0[r] = B_c[2+r][0] (zero unless fully actuated),
+//   bc1[r] = B_c[2+r][1].   Rows 0-1 of A_c are [0 0 1 0; 0 0 0 1], of B_c zero.
+struct LinC {
+  double ac[2][4];
+  double bc0[2];
+  double bc1[2];
+};
+
+__device__ __forceinline__ LinC linearize_c(const Model& m, const double x[4], double u0, double u1) {
+  const Trig t = trig_of(x[0], x[1]);
+  const double w1 = x[2], w2 = x[3];
+  const Eom e = eom(m, t, w1, w2, u0, u1);
+  const double hs2 = m.h * t.s2, hc2 = m.h * t.c2;
+  const double gc12 = m.g2 * t.c12;
+  // columns of d rhs / d x_j  minus (dM/dx_j) qdd   (only theta2 changes M)
+  double d0[4], d1[4];
+  d0[0] = -fma(m.g1, t.c1, gc12);
+  d1[0] = -gc12;
+  d0[1] = hc2 * (w1 * w2 + (w1 + w2) * w2) - gc12 + hs2 * (2.0 * e.dd1 + e.dd2);
+  d1[1] = -hc2 * w1 * w1 - gc12 + hs2 * e.dd1;
+  d0[2] = 2.0 * hs2 * w2 - m.f1;
+  d1[2] = -2.0 * hs2 * w1;
+  d0[3] = 2.0 * hs2 * (w1 + w2);
+  d1[3] = -m.f2;
+  LinC L;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    L.ac[0][j] = (e.M22 * d0[j] - e.M12 * d1[j]) * e.inv_det;
+    L.ac[1][j] = (e.M11 * d1[j] - e.M12 * d0[j]) * e.inv_det;
+  }
+  L.bc1[0] = -e.M12 * e.inv_det;
+  L.bc1[1] = e.M11 * e.inv_det;
+  const bool act = (m.tau1 != 0.0);
+  L.bc0[0] = act ? m.tau1 * e.M22 * e.inv_det : 0.0;
+  L.bc0[1] = act ? -m.tau1 * e.M12 * e.inv_det : 0.0;
+  return L;
+}
+
+// Forward-Euler discretisation (tg:161-164) of the lower block:
+//   a[r][j] = A_d[2+r][j] = delta + dt*ac[r][j],  b[r] = B_d[2+r][1] = dt*bc1[r].
+struct LinD {
+  double a[2][4];
+  double b[2];
+  double b0[2];  // column 0 of B_d (zero unless fully actuated)
+};
+
+__device__ __forceinline__ LinD discretize(const LinC& c, double dt) {
+  LinD d;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d.a[r][j] = (j == r + 2 ? 1.0 : 0.0) + dt * c.ac[r][j];
+    d.b[r] = dt * c.bc1[r];
+    d.b0[r] = dt * c.bc0[r];
+  }
+  return d;
+}
+
+__device__ __forceinline__ LinD linearize_d(const Model& m, const double x[4], double u0, double u1) {
+  return discretize(linearize_c(m, x, u0, u1), m.dt);
+}
+
+// ---------------------------------------------------------------------------------------
+// Symmetric 4x4 in 10 registers: index of (i,j), i<=j
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ constexpr int sym(int i, int j) {
+  return (i <= j) ? (i * 4 - (i * (i - 1)) / 2 + (j - i)) : (j * 4 - (j * (j - 1)) / 2 + (i - j));
+}
+
+// 2x2 solve with partial pivoting (what LAPACK dgesv does for np.linalg.solve / inv at
+// tg:203-204, tt:157,200).  Factor once, apply to several right-hand sides.
+struct Lu2 {
+  double inv_p, l, u01, inv_u11;
+  bool swap;
+};
+
+__device__ __forceinline__ Lu2 lu2(double g00, double g01, double g10, double g11) {
+  Lu2 f;
+  f.swap = fabs(g10) > fabs(g00);
+  const double p = f.swap ? g10 : g00, q = f.swap ? g11 : g01;
+  const double r = f.swap ? g00 : g10, s = f.swap ? g01 : g11;
+  f.inv_p = 1.0 / p;
+  f.l = r * f.inv_p;
+  f.u01 = q;
+  f.inv_u11 = 1.0 / fma(-f.l, q, s);
+  return f;
+}
+
+__device__ __forceinline__ void lu2_solve(const Lu2& f, double b0, double b1, double& x0, double& x1) {
+  const double y0 = f.swap ? b1 : b0, y1 = f.swap ? b0 : b1;
+  x1 = fma(-f.l, y0, y1) * f.inv_u11;
+  x0 = fma(-f.u01, x1, y0) * f.inv_p;
+}
+
+// ---------------------------------------------------------------------------------------
+// One step of the backward Riccati recursion on the structured linearisation.
+//
+// AFFINE = true : calculate_K_and_sigma (tg:183-216)
+//     G = Rh + B'PB, F = B'PA, g = r + B'p, K = -G^-1 F, sigma = -G^-1 g, dJ += g'sigma,
+//     P <- Qh + A'PA - K'GK,  p <- q + A'p - K'G sigma
+// AFFINE = false: solve_LQR_tracking / the MPC sweep (tt:191-201, tt:80-117)
+//     K = -(Rh + B'PB)^-1 B'PA,  P <- Qh + A'PA + (A'PB) K
+// Both P updates are the same expression: G K = -F gives  -K'GK = K'F = (A'PB) K, and
+// -K'G sigma = K'g.  Qh/Rh are the blocks as used by the caller (2Q, 2R for Newton; Q, R
+// for tracking).  P is symmetric (10 values); K is 2x4 row-major.
+// ---------------------------------------------------------------------------------------
+template <bool AFFINE, bool ACT0, class QH>
+__device__ __forceinline__ void riccati_step(double P[10], double p[4], const LinD& L, double dt,
+                                             const QH& Qh, double Rh00, double Rh01, double Rh11,
+                                             const double q[4], const double r[2], double K[8],
+                                             double sig[2], double& dJ) {
+  // M = P * A_d    (A_d rows 0-1 are [1 0 dt 0; 0 1 0 dt])
+  double M[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double pi0 = P[sym(i, 0)], pi1 = P[sym(i, 1)], pi2 = P[sym(i, 2)], pi3 = P[sym(i, 3)];
+    M[i][0] = fma(pi3, L.a[1][0], fma(pi2, L.a[0][0], pi0));
+    M[i][1] = fma(pi3, L.a[1][1], fma(pi2, L.a[0][1], pi1));
+    M[i][2] = fma(pi3, L.a[1][2], fma(pi2, L.a[0][2], dt * pi0));
+    M[i][3] = fma(pi3, L.a[1][3], fma(pi2, L.a[0][3], dt * pi1));
+  }
+  // S = A_d' * M (upper triangle)
+  double S[10];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = i; j < 4; ++j) {
+      const double top = (i < 2) ? M[i][j] : dt * M[i - 2][j];
+      S[sym(i, j)] = fma(L.a[1][i], M[3][j], fma(L.a[0][i], M[2][j], top));
+    }
+  }
+  // F = B_d' M (rows of F: input 0 and input 1), B'PB
+  double F1[4], F0[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    F1[j] = fma(L.b[1], M[3][j], L.b[0] * M[2][j]);
+    F0[j] = ACT0 ? fma(L.b0[1], M[3][j], L.b0[0] * M[2][j]) : 0.0;
+  }
+  // P b for the two input columns (only rows 2,3 of P b are needed for B'PB)
+  const double Pb1_2 = fma(P[sym(2, 3)], L.b[1], P[sym(2, 2)] * L.b[0]);
+  const double Pb1_3 = fma(P[sym(3, 3)], L.b[1], P[sym(2, 3)] * L.b[0]);
+  double G00 = Rh00, G01 = Rh01, G11 = Rh11 + fma(L.b[1], Pb1_3, L.b[0] * Pb1_2);
+  if (ACT0) {
+    const double Pb0_2 = fma(P[sym(2, 3)], L.b0[1], P[sym(2, 2)] * L.b0[0]);
+    const double Pb0_3 = fma(P[sym(3, 3)], L.b0[1], P[sym(2, 3)] * L.b0[0]);
+    G00 += fma(L.b0[1], Pb0_3, L.b0[0] * Pb0_2);
+    G01 += fma(L.b[1], Pb0_3, L.b[0] * Pb0_2);
+  }
+  const Lu2 lu = lu2(G00, G01, G01, G11);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) lu2_solve(lu, -F0[j], -F1[j], K[j], K[4 + j]);
+  double g0 = 0.0, g1 = 0.0;
+  if (AFFINE) {
+    g0 = r[0];
+    g1 = r[1] + fma(L.b[1], p[3], L.b[0] * p[2]);
+    if (ACT0) g0 += fma(L.b0[1], p[3], L.b0[0] * p[2]);
+    lu2_solve(lu, -g0, -g1, sig[0], sig[1]);
+    dJ += fma(g1, sig[1], g0 * sig[0]);
+    // p <- q + A_d' p + K' g
+    const double p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
+    const double ap[4] = {fma(L.a[1][0], p3, fma(L.a[0][0], p2, p0)), fma(L.a[1][1], p3, fma(L.a[0][1], p2, p1)),
+                          fma(L.a[1][2], p3, fma(L.a[0][2], p2, dt * p0)),
+                          fma(L.a[1][3], p3, fma(L.a[0][3], p2, dt * p1))};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = q[i] + ap[i] + fma(K[4 + i], g1, K[i] * g0);
+  }
+  // P <- Qh + S + K'F
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = i; j < 4; ++j) {
+      double kf = K[4 + i] * F1[j];
+      if (ACT0) kf = fma(K[i], F0[j], kf);
+      P[sym(i, j)] = Qh(i, j) + S[sym(i, j)] + kf;
+    }
+  }
+}
+
+// Dense variant for caller-supplied A (4x4) and B (4x2): compute_P_inf (tt:144-165) and
+// solver_mpc (tt:73-140) take arbitrary matrices.  P <- Q + A'PA + (A'PB)K, K = -(R+B'PB)^-1 B'PA.
+template <class QH>
+__device__ __forceinline__ void riccati_step_dense(double P[10], const double A[16], const double Bm[8],
+                                                   const QH& Qh, double R00, double R01, double R11,
+                                                   double K[8]) {
+  double M[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double s = P[sym(i, 0)] * A[j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) s = fma(P[sym(i, k)], A[k * 4 + j], s);
+      M[i][j] = s;
+    }
+  double S[10];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j) {
+      double s = A[i] * M[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) s = fma(A[k * 4 + i], M[k][j], s);
+      S[sym(i, j)] = s;
+    }
+  double F[2][4], PB[4][2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double s = Bm[c] * M[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) s = fma(Bm[k * 2 + c], M[k][j], s);
+      F[c][j] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = P[sym(i, 0)] * Bm[c];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) s = fma(P[sym(i, k)], Bm[k * 2 + c], s);
+      PB[i][c] = s;
+    }
+  }
+  double G[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = a; c < 2; ++c) {
+      double s = Bm[a] * PB[0][c];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) s = fma(Bm[k * 2 + a], PB[k][c], s);
+      G[a][c] = s;
+    }
+  const Lu2 lu = lu2(R00 + G[0][0], R01 + G[0][1], R01 + G[0][1], R11 + G[1][1]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) lu2_solve(lu, -F[0][j], -F[1][j], K[j], K[4 + j]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j)
+      P[sym(i, j)] = Qh(i, j) + S[sym(i, j)] + fma(K[4 + i], F[1][j], K[i] * F[0][j]);
+}
+
+// General dense affine step for caller-supplied lists: calculate_K_and_sigma (tg:183-216) with
+// arbitrary A (4x4), B (4x2), Q_t (4x4 sym), R_t (2x2 sym), S_t (2x4), q_t, r_t:
+//   G = R + B'PB, F = S + B'PA, g = r + B'p, K = -G^-1 F, sigma = -G^-1 g, dJ += g'sigma,
+//   P <- Q + A'PA - K'GK (= Q + A'PA + K'F),  p <- q + A'p - K'G sigma (= q + A'p + K'g)
+__device__ __forceinline__ void riccati_step_lists(double P[10], double p[4], const double A[16],
+                                                   const double Bm[8], const double Q[16], const double R[4],
+                                                   const double Sx[8], const double q[4], const double r[2],
+                                                   double K[8], double sig[2], double& dJ) {
+  double M[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double s = P[sym(i, 0)] * A[j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) s = fma(P[sym(i, k)], A[k * 4 + j], s);
+      M[i][j] = s;
+    }
+  double APA[10];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j) {
+      double s = A[i] * M[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) s = fma(A[k * 4 + i], M[k][j], s);
+      APA[sym(i, j)] = s;
+    }
+  double F[2][4], PB[4][2], g[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double s = Sx[c * 4 + j];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s = fma(Bm[k * 2 + c], M[k][j], s);
+      F[c][j] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = P[sym(i, 0)] * Bm[c];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) s = fma(P[sym(i, k)], Bm[k * 2 + c], s);
+      PB[i][c] = s;
+    }
+    double s = r[c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s = fma(Bm[k * 2 + c], p[k], s);
+    g[c] = s;
+  }
+  double G[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = a; c < 2; ++c) {
+      double s = R[a * 2 + c];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s = fma(Bm[k * 2 + a], PB[k][c], s);
+      G[a][c] = s;
+    }
+  const Lu2 lu = lu2(G[0][0], G[0][1], G[0][1], G[1][1]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) lu2_solve(lu, -F[0][j], -F[1][j], K[j], K[4 + j]);
+  lu2_solve(lu, -g[0], -g[1], sig[0], sig[1]);
+  dJ += fma(g[1], sig[1], g[0] * sig[0]);
+  double pn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double s = q[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s = fma(A[k * 4 + i], p[k], s);
+    pn[i] = s + fma(K[4 + i], g[1], K[i] * g[0]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = pn[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j)
+      P[sym(i, j)] = Q[i * 4 + j] + APA[sym(i, j)] + fma(K[4 + i], F[1][j], K[i] * F[0][j]);
+}
+
+}  // namespace acro

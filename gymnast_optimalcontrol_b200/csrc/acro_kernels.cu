@@ -1,0 +1,1511 @@
+// acro_kernels.cu - sm_100a kernels and the C ABI of libacro_b200.so (see include/acro_abi.h).
+//
+// Thread mapping: one thread = one independent problem (lane-per-problem), so every global
+// access of a warp is 32 consecutive doubles of one SoA row (256 B, coalesced), and no
+// thread ever waits on another: there is no shared memory hazard, no barrier and no
+// collective anywhere on this path.  The time recurrences (RK4 rollout, Riccati sweep) are
+// sequential per problem; the next step's operands are prefetched into registers while the
+// current step computes.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/acro_abi.h"
+#include "acro_device.cuh"
+#include "acro_views.cuh"
+
+namespace acro {
+
+// ---------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return ACRO_E_CUDA;
+}
+#define ACRO_REQUIRE(cond, msg) \
+  if (!(cond)) return fail(ACRO_E_INVALID, msg)
+#define ACRO_LAUNCH_CHECK(name)                             \
+  do {                                                      \
+    g_launches.fetch_add(1, std::memory_order_relaxed);     \
+    cudaError_t e__ = cudaPeekAtLastError();                \
+    if (e__ != cudaSuccess) return cuda_fail(e__, name);    \
+  } while (0)
+
+static Model make_model(const AcroParams& p) {
+  Model m;
+  m.a1 = p.I1 + p.I2 + p.lc1 * p.lc1 * p.m1 + p.m2 * (p.l1 * p.l1 + p.lc2 * p.lc2);
+  m.h = p.m2 * p.l1 * p.lc2;
+  m.a3 = p.I2 + p.lc2 * p.lc2 * p.m2;
+  m.g1 = p.g * (p.lc1 * p.m1 + p.m2 * p.l1);
+  m.g2 = p.g * p.m2 * p.lc2;
+  m.f1 = p.f1;
+  m.f2 = p.f2;
+  m.dt = p.dt;
+  m.tau1 = p.actuated_tau1 ? 1.0 : 0.0;
+  return m;
+}
+
+static KWeights make_weights(const AcroWeights& w) {
+  KWeights k;
+  for (int i = 0; i < 16; ++i) {
+    k.Q[i] = w.Q[i];
+    k.QT[i] = w.QT[i];
+    k.Q2[i] = 2.0 * w.Q[i];
+    k.QT2[i] = 2.0 * w.QT[i];
+  }
+  for (int i = 0; i < 4; ++i) {
+    k.R[i] = w.R[i];
+    k.R2[i] = 2.0 * w.R[i];
+  }
+  k.Qb = w.Q_b;
+  k.Rb = w.R_b;
+  k.QTb = w.QT_b;
+  return k;
+}
+static bool per_problem_weights(const AcroWeights& w) { return w.Q_b || w.R_b || w.QT_b; }
+
+struct Cfg {
+  int block;
+  unsigned grid;
+};
+// Small batches are latency bound: one warp per block spreads the warps over all SMs.
+// Large batches are FP64-throughput bound: wider blocks, several resident per SM.
+static Cfg cfg_for(int64_t n) {
+  Cfg c;
+  c.block = (n >= 148LL * 64 * 8) ? 128 : (n >= 148LL * 32 * 4 ? 64 : 32);
+  c.grid = (unsigned)((n + c.block - 1) / c.block);
+  return c;
+}
+
+#define DISPATCH2(b0, b1, EXPR)                   \
+  do {                                            \
+    if (b0) {                                     \
+      if (b1) { EXPR(true, true); } else { EXPR(true, false); }   \
+    } else {                                      \
+      if (b1) { EXPR(false, true); } else { EXPR(false, false); } \
+    }                                             \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// D1-D3 point-wise kernels
+// ---------------------------------------------------------------------------------------
+enum { PT_F = 0, PT_RK4 = 1 };
+
+template <int MODE>
+__global__ void k_point(const __grid_constant__ Model m, int64_t B, const double* __restrict__ x,
+                        const double* __restrict__ u, double* __restrict__ out) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  double xs[4], o[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) xs[c] = x[c * B + b];
+  const double u0 = u[b], u1 = u[B + b];
+  if (MODE == PT_F)
+    f_eval(m, xs, u0, u1, o);
+  else
+    rk4_step(m, xs, u0, u1, o);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c * B + b] = o[c];
+}
+
+__global__ void k_linearize(const __grid_constant__ Model m, int64_t B, const double* __restrict__ x,
+                            const double* __restrict__ u, double* __restrict__ A, double* __restrict__ Bm,
+                            int discrete) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  double xs[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) xs[c] = x[c * B + b];
+  const LinC c = linearize_c(m, xs, u[b], u[B + b]);
+  double a[2][4], b0[2], b1[2];
+  if (discrete) {
+    const LinD d = discretize(c, m.dt);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[r][j] = d.a[r][j];
+      b0[r] = d.b0[r];
+      b1[r] = d.b[r];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[r][j] = c.ac[r][j];
+      b0[r] = c.bc0[r];
+      b1[r] = c.bc1[r];
+    }
+  }
+  const double one = discrete ? 1.0 : 0.0, off = discrete ? m.dt : 1.0;
+  // rows 0-1: continuous [0 0 1 0; 0 0 0 1], discrete [1 0 dt 0; 0 1 0 dt]
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    A[(0 * 4 + j) * B + b] = (j == 0) ? one : (j == 2 ? off : 0.0);
+    A[(1 * 4 + j) * B + b] = (j == 1) ? one : (j == 3 ? off : 0.0);
+    A[(2 * 4 + j) * B + b] = a[0][j];
+    A[(3 * 4 + j) * B + b] = a[1][j];
+  }
+  Bm[0 * B + b] = 0.0;
+  Bm[1 * B + b] = 0.0;
+  Bm[2 * B + b] = 0.0;
+  Bm[3 * B + b] = 0.0;
+  Bm[4 * B + b] = b0[0];
+  Bm[5 * B + b] = b1[0];
+  Bm[6 * B + b] = b0[1];
+  Bm[7 * B + b] = b1[1];
+}
+
+// ---------------------------------------------------------------------------------------
+// G1 open-loop rollout, G8 cost, G3 costate
+// ---------------------------------------------------------------------------------------
+__global__ void k_rollout_open(const __grid_constant__ Model m, int64_t B, int N, const double* __restrict__ x0,
+                               const double* __restrict__ U, double* __restrict__ X) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  double x[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    x[c] = x0[c * B + b];
+    X[soa(0, 4, c, B, b)] = x[c];
+  }
+  double u0 = U ? U[soa(0, 2, 0, B, b)] : 0.0, u1 = U ? U[soa(0, 2, 1, B, b)] : 0.0;
+  for (int t = 0; t < N - 1; ++t) {
+    double n0 = 0.0, n1 = 0.0;
+    if (U && t + 1 < N - 1) {  // prefetch the next input while this step computes
+      n0 = U[soa(t + 1, 2, 0, B, b)];
+      n1 = U[soa(t + 1, 2, 1, B, b)];
+    }
+    double xn[4];
+    rk4_step(m, x, u0, u1, xn);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      x[c] = xn[c];
+      X[soa(t + 1, 4, c, B, b)] = x[c];
+    }
+    u0 = n0;
+    u1 = n1;
+  }
+}
+
+// total_cost (tg:231-252): stage costs with Q, R accumulated in time order, terminal with Q_T.
+template <bool WPB, bool RPB>
+__device__ __forceinline__ double total_cost_dev(const WV<WPB>& w, const RefV<RPB>& ref, int N, const double* X,
+                                                 const double* U, int64_t ld, int64_t b) {
+  double cost = 0.0;
+  for (int t = 0; t < N - 1; ++t) {
+    double dx[4], du[2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dx[c] = X[soa(t, 4, c, ld, b)] - ref.X(t, c);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) du[c] = U[soa(t, 2, c, ld, b)] - ref.U(t, c);
+    cost += quad4(dx, [&](int i, int j) { return w.Q(i, j); });
+    cost += quad2(du, [&](int i, int j) { return w.R(i, j); });
+  }
+  double dx[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dx[c] = X[soa(N - 1, 4, c, ld, b)] - ref.X(N - 1, c);
+  cost += quad4(dx, [&](int i, int j) { return w.QT(i, j); });
+  return cost;
+}
+
+template <bool WPB, bool RPB>
+__global__ void k_total_cost(const __grid_constant__ KWeights kw, int64_t B, int N, const double* __restrict__ X,
+                             const double* __restrict__ U, const double* rx, const double* ru,
+                             double* __restrict__ cost) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  const WV<WPB> w(kw, B, b);
+  const RefV<RPB> ref{rx, ru, B, b};
+  cost[b] = total_cost_dev(w, ref, N, X, U, B, b);
+}
+
+// compute_costate_trajectory (tg:138-159)
+template <bool WPB, bool RPB>
+__global__ void k_costate(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B, int N,
+                          const double* __restrict__ X, const double* __restrict__ U, const double* rx,
+                          const double* ru, double* __restrict__ lam) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  const WV<WPB> w(kw, B, b);
+  const RefV<RPB> ref{rx, ru, B, b};
+  double l[4], dx[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dx[c] = X[soa(N - 1, 4, c, B, b)] - ref.X(N - 1, c);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double s = w.QT2(i, 0) * dx[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) s = fma(w.QT2(i, j), dx[j], s);
+    l[i] = s;
+    lam[soa(N - 1, 4, i, B, b)] = s;
+  }
+  for (int t = N - 2; t >= 0; --t) {
+    double x[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] = X[soa(t, 4, c, B, b)];
+    const LinD L = linearize_d(m, x, U[soa(t, 2, 0, B, b)], U[soa(t, 2, 1, B, b)]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dx[c] = x[c] - ref.X(t, c);
+    double g[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = w.Q2(i, 0) * dx[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) s = fma(w.Q2(i, j), dx[j], s);
+      g[i] = s;
+    }
+    const double l0 = l[0], l1 = l[1], l2 = l[2], l3 = l[3];
+    l[0] = g[0] + fma(L.a[1][0], l3, fma(L.a[0][0], l2, l0));
+    l[1] = g[1] + fma(L.a[1][1], l3, fma(L.a[0][1], l2, l1));
+    l[2] = g[2] + fma(L.a[1][2], l3, fma(L.a[0][2], l2, m.dt * l0));
+    l[3] = g[3] + fma(L.a[1][3], l3, fma(L.a[0][3], l2, m.dt * l1));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lam[soa(t, 4, i, B, b)] = l[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// G2+G4+G5+G6 fused backward pass: linearise, discretise, cost blocks, affine Riccati.
+// Reads X, U of one problem (column b of leading dimension ld), writes K, S.
+// ---------------------------------------------------------------------------------------
+template <bool WPB, bool RPB>
+__device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, const RefV<RPB>& ref, int N,
+                                              const double* __restrict__ X, const double* __restrict__ U,
+                                              double* __restrict__ K, double* __restrict__ S, int64_t ld,
+                                              int64_t b, double& dJ_out, double& sn_out) {
+  double P[10], p[4];
+  {
+    double dx[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dx[c] = X[soa(N - 1, 4, c, ld, b)] - ref.X(N - 1, c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = w.QT2(i, 0) * dx[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) s = fma(w.QT2(i, j), dx[j], s);
+      p[i] = s;
+#pragma unroll
+      for (int j = i; j < 4; ++j) P[sym(i, j)] = w.QT2(i, j);
+    }
+  }
+  double dJ = 0.0, sn = 0.0;
+  double x[4], u[2];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) x[c] = X[soa(N - 2, 4, c, ld, b)];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) u[c] = U[soa(N - 2, 2, c, ld, b)];
+  const QhQ2<WV<WPB>> Qh{w};
+  for (int t = N - 2; t >= 0; --t) {
+    double nx[4] = {0, 0, 0, 0}, nu[2] = {0, 0};
+    if (t > 0) {  // prefetch step t-1
+#pragma unroll
+      for (int c = 0; c < 4; ++c) nx[c] = X[soa(t - 1, 4, c, ld, b)];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) nu[c] = U[soa(t - 1, 2, c, ld, b)];
+    }
+    const LinD L = linearize_d(m, x, u[0], u[1]);
+    double dx[4], du[2], q[4], r[2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dx[c] = x[c] - ref.X(t, c);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) du[c] = u[c] - ref.U(t, c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = w.Q2(i, 0) * dx[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) s = fma(w.Q2(i, j), dx[j], s);
+      q[i] = s;
+    }
+    r[0] = fma(w.R2(0, 1), du[1], w.R2(0, 0) * du[0]);
+    r[1] = fma(w.R2(1, 1), du[1], w.R2(1, 0) * du[0]);
+    double Kt[8], st[2];
+    riccati_step<true, false>(P, p, L, m.dt, Qh, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, r, Kt, st, dJ);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) K[soa(t, 8, e, ld, b)] = Kt[e];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      S[soa(t, 2, e, ld, b)] = st[e];
+      const double a = fabs(st[e]);
+      sn = (a > sn || a != a) ? a : sn;  // NaN is sticky, like np.max(np.abs(sigma))
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] = nx[c];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) u[c] = nu[c];
+  }
+  dJ_out = dJ;
+  sn_out = sn;
+}
+
+template <bool WPB, bool RPB>
+__global__ void k_riccati_affine(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B,
+                                 int N, const double* __restrict__ X, const double* __restrict__ U,
+                                 const double* rx, const double* ru, double* __restrict__ K,
+                                 double* __restrict__ S, double* __restrict__ dJ, double* __restrict__ sn) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  const WV<WPB> w(kw, B, b);
+  const RefV<RPB> ref{rx, ru, B, b};
+  double d, s;
+  backward_pass(m, w, ref, N, X, U, K, S, B, b, d, s);
+  dJ[b] = d;
+  sn[b] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// G7+G8 fused forward pass: closed-loop rollout with step size gamma and its total cost.
+// Base iterate (X,U,K,S) is column b of leading dimension ld; the candidate trajectory goes
+// to column bo of leading dimension ldo of (Xn,Un) when STORE.
+// ---------------------------------------------------------------------------------------
+struct StepIn {
+  double x[4], u[2], k[8], s[2];
+};
+__device__ __forceinline__ StepIn load_step(const double* __restrict__ X, const double* __restrict__ U,
+                                            const double* __restrict__ K, const double* __restrict__ S, int t,
+                                            int64_t ld, int64_t b) {
+  StepIn in;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) in.x[c] = X[soa(t, 4, c, ld, b)];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) in.u[c] = U[soa(t, 2, c, ld, b)];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) in.k[c] = K[soa(t, 8, c, ld, b)];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) in.s[c] = S[soa(t, 2, c, ld, b)];
+  return in;
+}
+
+template <bool WPB, bool RPB, bool STORE>
+__device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w, const RefV<RPB>& ref, int N,
+                                               const double* __restrict__ X, const double* __restrict__ U,
+                                               const double* __restrict__ K, const double* __restrict__ S,
+                                               int64_t ld, int64_t b, double gamma, double* __restrict__ Xn,
+                                               double* __restrict__ Un, int64_t ldo, int64_t bo) {
+  double xp[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) xp[c] = X[soa(0, 4, c, ld, b)];
+  double cost = 0.0;
+  StepIn in = load_step(X, U, K, S, 0, ld, b);
+  for (int t = 0; t < N - 1; ++t) {
+    StepIn nx = in;
+    if (t + 1 < N - 1) nx = load_step(X, U, K, S, t + 1, ld, b);
+    double dx[4], up[2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dx[c] = xp[c] - in.x[c];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double kd = in.k[i * 4] * dx[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) kd = fma(in.k[i * 4 + j], dx[j], kd);
+      up[i] = (in.u[i] + kd) + gamma * in.s[i];
+    }
+    if (STORE) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Xn[soa(t, 4, c, ldo, bo)] = xp[c];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) Un[soa(t, 2, c, ldo, bo)] = up[c];
+    }
+    double ex[4], eu[2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ex[c] = xp[c] - ref.X(t, c);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) eu[c] = up[c] - ref.U(t, c);
+    cost += quad4(ex, [&](int i, int j) { return w.Q(i, j); });
+    cost += quad2(eu, [&](int i, int j) { return w.R(i, j); });
+    double xn[4];
+    rk4_step(m, xp, up[0], up[1], xn);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xp[c] = xn[c];
+    in = nx;
+  }
+  double ex[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (STORE) Xn[soa(N - 1, 4, c, ldo, bo)] = xp[c];
+    ex[c] = xp[c] - ref.X(N - 1, c);
+  }
+  cost += quad4(ex, [&](int i, int j) { return w.QT(i, j); });
+  return cost;
+}
+
+// one thread per (problem b, candidate g); lanes run over b
+template <bool WPB, bool RPB>
+__global__ void k_closed_loop(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B,
+                              int N, const double* __restrict__ X, const double* __restrict__ U,
+                              const double* __restrict__ K, const double* __restrict__ S, const double* rx,
+                              const double* ru, int G, const double* __restrict__ gammas, int gpp,
+                              double* __restrict__ Xn, double* __restrict__ Un, double* __restrict__ cost) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int g = blockIdx.y;
+  if (b >= B) return;
+  const WV<WPB> w(kw, B, b);
+  const RefV<RPB> ref{rx, ru, B, b};
+  const double gamma = gpp ? gammas[int64_t(g) * B + b] : gammas[g];
+  double c;
+  if (Xn)
+    c = forward_pass<WPB, RPB, true>(m, w, ref, N, X, U, K, S, B, b, gamma, Xn + int64_t(g) * N * 4 * B,
+                                     Un + int64_t(g) * (N - 1) * 2 * B, B, b);
+  else
+    c = forward_pass<WPB, RPB, false>(m, w, ref, N, X, U, K, S, B, b, gamma, nullptr, nullptr, B, b);
+  cost[int64_t(g) * B + b] = c;
+}
+
+// G11: P base iterates x S_n step sizes.  A warp = 32 consecutive step sizes of ONE base
+// iterate, so the 16 operand loads per step are warp-wide broadcasts; the 4 warps of a
+// block take 4 neighbouring iterates, i.e. whole 32-byte sectors of every SoA row.
+template <bool WPB, bool RPB>
+__global__ void k_sweep(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t P, int N,
+                        const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ K,
+                        const double* __restrict__ S, const double* rx, const double* ru, int S_n,
+                        const double* __restrict__ steps, double* __restrict__ cost) {
+  const int64_t p = blockIdx.x * 4LL + (threadIdx.x >> 5);
+  const int s = blockIdx.y * 32 + (threadIdx.x & 31);
+  if (p >= P || s >= S_n) return;
+  const WV<WPB> w(kw, P, p);
+  const RefV<RPB> ref{rx, ru, P, p};
+  cost[int64_t(s) * P + p] =
+      forward_pass<WPB, RPB, false>(m, w, ref, N, X, U, K, S, P, p, steps[s], nullptr, nullptr, P, p);
+}
+
+__global__ void k_armijo_select(int64_t B, int G, const double* __restrict__ cost_k, const double* __restrict__ dJ,
+                                const double* __restrict__ gammas, int gpp, const double* __restrict__ cc, double c,
+                                int32_t* __restrict__ acc) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  int a = -1;
+  const double ck = cost_k[b], d = dJ[b];
+  for (int g = 0; g < G && a < 0; ++g) {
+    const double gam = gpp ? gammas[int64_t(g) * B + b] : gammas[g];
+    // cost_k + c*gamma*dJ evaluated as numpy does: ((c*gamma)*dJ) then +, no FMA contraction
+    const double thr = __dadd_rn(ck, __dmul_rn(__dmul_rn(c, gam), d));
+    if (cc[int64_t(g) * B + b] < thr) a = g;
+  }
+  acc[b] = a;
+}
+
+// ---------------------------------------------------------------------------------------
+// G10: the whole Newton / Armijo loop of one problem in one thread (tg:298-398).
+// ---------------------------------------------------------------------------------------
+struct NewtonArgs {
+  Model m;
+  KWeights kw;
+  AcroNewtonOpts o;
+  int64_t B;
+  int N;
+  const double* x0;
+  const double *rx, *ru;
+  double *X, *U, *Xw, *Uw, *K, *S;
+  double *cost, *dJ, *sn, *gacc;
+  int32_t *iters, *status;
+  double *h_cost, *h_sn, *h_gamma;
+  int32_t* h_ntry;
+};
+
+template <bool WPB, bool RPB>
+__global__ void k_newton(const __grid_constant__ NewtonArgs a) {
+  const int64_t B = a.B, b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  const int N = a.N;
+  const WV<WPB> w(a.kw, B, b);
+  const RefV<RPB> ref{a.rx, a.ru, B, b};
+  int it, st;
+  double cost_k;
+  if (a.o.init) {
+    // u = 0, x = simulate_open_loop(x0, u), cost_k = total_cost(...)   (tg:311-319)
+    double x[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      x[c] = a.x0[c * B + b];
+      a.X[soa(0, 4, c, B, b)] = x[c];
+    }
+    for (int t = 0; t < N - 1; ++t) {
+      a.U[soa(t, 2, 0, B, b)] = 0.0;
+      a.U[soa(t, 2, 1, B, b)] = 0.0;
+      double xn[4];
+      rk4_step(a.m, x, 0.0, 0.0, xn);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        x[c] = xn[c];
+        a.X[soa(t + 1, 4, c, B, b)] = x[c];
+      }
+    }
+    cost_k = total_cost_dev(w, ref, N, a.X, a.U, B, b);
+    it = 0;
+    st = ACRO_RUNNING;
+    if (a.h_cost) a.h_cost[b] = cost_k;
+  } else {
+    it = a.iters[b];
+    st = a.status[b];
+    cost_k = a.cost[b];
+  }
+  int cur = 0, done = 0;
+  double dJ = a.o.init ? 0.0 : a.dJ[b], sn = a.o.init ? 0.0 : a.sn[b], gacc = a.o.init ? 0.0 : a.gacc[b];
+  while (st == ACRO_RUNNING && it < a.o.max_iters && (a.o.chunk_iters <= 0 || done < a.o.chunk_iters)) {
+    const double* Xc = cur ? a.Xw : a.X;
+    const double* Uc = cur ? a.Uw : a.U;
+    double* Xo = cur ? a.X : a.Xw;
+    double* Uo = cur ? a.U : a.Uw;
+    backward_pass(a.m, w, ref, N, Xc, Uc, a.K, a.S, B, b, dJ, sn);
+    if (a.h_sn) a.h_sn[int64_t(it) * B + b] = sn;
+    double gamma = a.o.gamma_0, cn = 0.0;
+    int tries = 0;
+    bool ok = false;
+    for (int i = 0; i < a.o.max_line_search; ++i) {
+      cn = forward_pass<WPB, RPB, true>(a.m, w, ref, N, Xc, Uc, a.K, a.S, B, b, gamma, Xo, Uo, B, b);
+      ++tries;
+      // accept iff cost_new < cost_k + c*gamma*delta_J  (strict, NaN rejects)   tg:361
+      const double thr = __dadd_rn(cost_k, __dmul_rn(__dmul_rn(a.o.c, gamma), dJ));
+      if (cn < thr) {
+        ok = true;
+        break;
+      }
+      gamma = __dmul_rn(gamma, a.o.beta);  // tg:365
+    }
+    if (a.h_ntry) a.h_ntry[int64_t(it) * B + b] = tries;
+    ++it;
+    ++done;
+    if (!ok) {  // tg:367-369: keep the current iterate, stop
+      st = ACRO_LINE_SEARCH_FAILED;
+      if (a.h_gamma) a.h_gamma[int64_t(it - 1) * B + b] = nan("");
+      break;
+    }
+    cur ^= 1;
+    cost_k = cn;
+    gacc = gamma;
+    if (a.h_gamma) a.h_gamma[int64_t(it - 1) * B + b] = gamma;
+    if (a.h_cost) a.h_cost[int64_t(it) * B + b] = cost_k;
+    if (sn < a.o.tol) st = ACRO_CONVERGED;  // tg:394-396
+  }
+  if (st == ACRO_RUNNING && it >= a.o.max_iters) st = ACRO_MAX_ITERS;
+  if (cur) {  // current iterate sits in the workspace: move it home
+    for (int t = 0; t < N; ++t) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a.X[soa(t, 4, c, B, b)] = a.Xw[soa(t, 4, c, B, b)];
+      if (t < N - 1) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) a.U[soa(t, 2, c, B, b)] = a.Uw[soa(t, 2, c, B, b)];
+      }
+    }
+  }
+  a.cost[b] = cost_k;
+  a.dJ[b] = dJ;
+  a.sn[b] = sn;
+  a.gacc[b] = gacc;
+  a.iters[b] = it;
+  a.status[b] = st;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stand-alone pieces of the Newton iteration for the drop-in functions that expose them:
+// derivatives_Cost (tg:89-114), discretize_linearization (tg:161-164), build_stage_lists
+// (tg:166-181), calculate_K_and_sigma on caller-supplied lists (tg:183-216).
+// ---------------------------------------------------------------------------------------
+template <bool WPB>
+__global__ void k_cost_derivatives(const __grid_constant__ KWeights kw, int64_t B, const double* __restrict__ x,
+                                   const double* __restrict__ xr, const double* __restrict__ u,
+                                   const double* __restrict__ ur, int terminal, double* __restrict__ l,
+                                   double* __restrict__ gx, double* __restrict__ gu) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  const WV<WPB> w(kw, B, b);
+  double dx[4], du[2] = {0, 0};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dx[c] = x[c * B + b] - xr[c * B + b];
+  if (terminal) {
+    l[b] = quad4(dx, [&](int i, int j) { return w.QT(i, j); });
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = w.QT2(i, 0) * dx[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) s = fma(w.QT2(i, j), dx[j], s);
+      gx[i * B + b] = s;
+    }
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) du[c] = u[c * B + b] - ur[c * B + b];
+  l[b] = quad4(dx, [&](int i, int j) { return w.Q(i, j); }) + quad2(du, [&](int i, int j) { return w.R(i, j); });
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double s = w.Q2(i, 0) * dx[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) s = fma(w.Q2(i, j), dx[j], s);
+    gx[i * B + b] = s;
+  }
+  gu[0 * B + b] = fma(w.R2(0, 1), du[1], w.R2(0, 0) * du[0]);
+  gu[1 * B + b] = fma(w.R2(1, 1), du[1], w.R2(1, 0) * du[0]);
+}
+
+__global__ void k_discretize(int64_t B, const double* __restrict__ Ac, const double* __restrict__ Bc, double dt,
+                             double* __restrict__ Ad, double* __restrict__ Bd) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Ad[(i * 4 + j) * B + b] = (i == j ? 1.0 : 0.0) + dt * Ac[(i * 4 + j) * B + b];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) Bd[e * B + b] = dt * Bc[e * B + b];
+}
+
+// one thread per (t, b): dense A_d, B_d, q_t, r_t; threads with t == N-1 write q_T
+template <bool WPB, bool RPB>
+__global__ void k_stage_lists(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B, int N,
+                              const double* __restrict__ X, const double* __restrict__ U, const double* rx,
+                              const double* ru, double* __restrict__ A, double* __restrict__ Bm,
+                              double* __restrict__ q, double* __restrict__ r, double* __restrict__ qT) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (idx >= int64_t(N) * B) return;
+  const int t = int(idx / B);
+  const int64_t b = idx % B;
+  const WV<WPB> w(kw, B, b);
+  const RefV<RPB> ref{rx, ru, B, b};
+  double x[4], dx[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    x[c] = X[soa(t, 4, c, B, b)];
+    dx[c] = x[c] - ref.X(t, c);
+  }
+  if (t == N - 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = w.QT2(i, 0) * dx[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) s = fma(w.QT2(i, j), dx[j], s);
+      qT[i * B + b] = s;
+    }
+    return;
+  }
+  const double u0 = U[soa(t, 2, 0, B, b)], u1 = U[soa(t, 2, 1, B, b)];
+  const LinD L = linearize_d(m, x, u0, u1);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    A[soa(t, 16, 0 * 4 + j, B, b)] = (j == 0) ? 1.0 : (j == 2 ? m.dt : 0.0);
+    A[soa(t, 16, 1 * 4 + j, B, b)] = (j == 1) ? 1.0 : (j == 3 ? m.dt : 0.0);
+    A[soa(t, 16, 2 * 4 + j, B, b)] = L.a[0][j];
+    A[soa(t, 16, 3 * 4 + j, B, b)] = L.a[1][j];
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) Bm[soa(t, 8, e, B, b)] = 0.0;
+  Bm[soa(t, 8, 4, B, b)] = L.b0[0];
+  Bm[soa(t, 8, 5, B, b)] = L.b[0];
+  Bm[soa(t, 8, 6, B, b)] = L.b0[1];
+  Bm[soa(t, 8, 7, B, b)] = L.b[1];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double s = w.Q2(i, 0) * dx[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) s = fma(w.Q2(i, j), dx[j], s);
+    q[soa(t, 4, i, B, b)] = s;
+  }
+  const double du0 = u0 - ref.U(t, 0), du1 = u1 - ref.U(t, 1);
+  r[soa(t, 2, 0, B, b)] = fma(w.R2(0, 1), du1, w.R2(0, 0) * du0);
+  r[soa(t, 2, 1, B, b)] = fma(w.R2(1, 1), du1, w.R2(1, 0) * du0);
+}
+
+__global__ void k_riccati_lists(int64_t B, int T, const double* __restrict__ A, const double* __restrict__ Bm,
+                                const double* __restrict__ Q, const double* __restrict__ R,
+                                const double* __restrict__ Sx, const double* __restrict__ q,
+                                const double* __restrict__ r, const double* __restrict__ QT,
+                                const double* __restrict__ qT, double* __restrict__ K, double* __restrict__ S,
+                                double* __restrict__ dJ) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  double P[10], p[4], d = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    p[i] = qT[i * B + b];
+#pragma unroll
+    for (int j = i; j < 4; ++j) P[sym(i, j)] = QT[(i * 4 + j) * B + b];
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    double Am[16], Bv[8], Qm[16], Rm[4], Sm[8], qv[4], rv[2], Kt[8], st[2];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      Am[e] = A[soa(t, 16, e, B, b)];
+      Qm[e] = Q[soa(t, 16, e, B, b)];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      Bv[e] = Bm[soa(t, 8, e, B, b)];
+      Sm[e] = Sx ? Sx[soa(t, 8, e, B, b)] : 0.0;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      Rm[e] = R[soa(t, 4, e, B, b)];
+      qv[e] = q[soa(t, 4, e, B, b)];
+    }
+    rv[0] = r[soa(t, 2, 0, B, b)];
+    rv[1] = r[soa(t, 2, 1, B, b)];
+    riccati_step_lists(P, p, Am, Bv, Qm, Rm, Sm, qv, rv, Kt, st, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) K[soa(t, 8, e, B, b)] = Kt[e];
+    S[soa(t, 2, 0, B, b)] = st[0];
+    S[soa(t, 2, 1, B, b)] = st[1];
+  }
+  dJ[b] = d;
+}
+
+// ---------------------------------------------------------------------------------------
+// T1 LQR gains, T2 LQR tracking
+// ---------------------------------------------------------------------------------------
+template <bool WPB, bool RPB>
+__global__ void k_lqr_gains(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B, int N,
+                            const double* rx, const double* ru, double* __restrict__ K) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  const WV<WPB> w(kw, B, b);
+  const RefV<RPB> ref{rx, ru, B, b};
+  double P[10], p[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j) P[sym(i, j)] = w.Q2(i, j);  // Q_T_reg = 2 Q_reg  (tt:175)
+  const QhQ<WV<WPB>> Qh{w};
+  double dummy = 0.0;
+  for (int t = N - 2; t >= 0; --t) {
+    double x[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] = ref.X(t, c);
+    const LinD L = linearize_d(m, x, ref.U(t, 0), ref.U(t, 1));
+    double Kt[8], st[2];
+    riccati_step<false, false>(P, p, L, m.dt, Qh, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, Kt, st, dummy);
+    if (RPB) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) K[soa(t, 8, e, B, b)] = Kt[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) K[t * 8 + e] = Kt[e];
+    }
+  }
+}
+
+template <bool RPB>
+__global__ void k_lqr_track(const __grid_constant__ Model m, int64_t B, int N, const double* rx, const double* ru,
+                            const double* __restrict__ K, const double* __restrict__ x0, double* __restrict__ Xt,
+                            double* __restrict__ Ut) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  const RefV<RPB> ref{rx, ru, B, b};
+  double x[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    x[c] = x0[c * B + b];
+    Xt[soa(0, 4, c, B, b)] = x[c];
+  }
+  for (int t = 0; t < N - 1; ++t) {
+    double u[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double kd = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double k = RPB ? K[soa(t, 8, i * 4 + j, B, b)] : __ldg(K + t * 8 + i * 4 + j);
+        kd = (j == 0) ? k * (x[0] - ref.X(t, 0)) : fma(k, x[j] - ref.X(t, j), kd);
+      }
+      u[i] = ref.U(t, i) + kd;
+      Ut[soa(t, 2, i, B, b)] = u[i];
+    }
+    double xn[4];
+    rk4_step(m, x, u[0], u[1], xn);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      x[c] = xn[c];
+      Xt[soa(t + 1, 4, c, B, b)] = x[c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// T3 P_inf, T4 MPC solve (dense caller-supplied matrices)
+// ---------------------------------------------------------------------------------------
+template <bool WPB>
+__global__ void k_p_inf(const __grid_constant__ KWeights kw, int64_t B, const double* __restrict__ A,
+                        const double* __restrict__ Bm, int max_iter, double tol, double* __restrict__ Pout,
+                        int32_t* __restrict__ n_iter) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  const WV<WPB> w(kw, B, b);
+  double Am[16], Bv[8], P[10];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) Am[e] = A[e * B + b];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) Bv[e] = Bm[e * B + b];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j) P[sym(i, j)] = w.Q(i, j);
+  const QhQ<WV<WPB>> Qh{w};
+  int n = -max_iter;
+  for (int i = 0; i < max_iter; ++i) {
+    double Pp[10], K[8];
+#pragma unroll
+    for (int e = 0; e < 10; ++e) Pp[e] = P[e];
+    riccati_step_dense(P, Am, Bv, Qh, w.R(0, 0), w.R(0, 1), w.R(1, 1), K);
+    double d = 0.0;
+#pragma unroll
+    for (int e = 0; e < 10; ++e) {
+      const double v = fabs(P[e] - Pp[e]);
+      d = (v > d || v != v) ? v : d;
+    }
+    if (d < tol) {  // tt:161-162
+      n = i + 1;
+      break;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Pout[(i * 4 + j) * B + b] = P[sym(i, j)];
+  n_iter[b] = n;
+}
+
+template <bool WPB>
+__global__ void k_mpc_solve(const __grid_constant__ KWeights kw, int64_t B, int H, const double* __restrict__ x0,
+                            const double* __restrict__ Aw, const double* __restrict__ Bw,
+                            const double* __restrict__ QT, double* __restrict__ U0, double* __restrict__ Xo,
+                            double* __restrict__ Uo, double* __restrict__ Kws) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  const WV<WPB> w(kw, B, b);
+  double P[10];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j) P[sym(i, j)] = QT[(i * 4 + j) * B + b];
+  const QhQ<WV<WPB>> Qh{w};
+  double K[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = H - 2; j >= 0; --j) {
+    double Am[16], Bv[8];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) Am[e] = Aw[soa(j, 16, e, B, b)];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Bv[e] = Bw[soa(j, 8, e, B, b)];
+    riccati_step_dense(P, Am, Bv, Qh, w.R(0, 0), w.R(0, 1), w.R(1, 1), K);
+    if (Kws) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) Kws[soa(j, 8, e, B, b)] = K[e];
+    }
+  }
+  double x[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) x[c] = x0[c * B + b];
+  // U0 = K_0 x0 (tt:135); K holds K_0 after the sweep (H >= 2)
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    double s = K[i * 4] * x[0];
+#pragma unroll
+    for (int jj = 1; jj < 4; ++jj) s = fma(K[i * 4 + jj], x[jj], s);
+    U0[i * B + b] = (H >= 2) ? s : 0.0;
+  }
+  if (!Xo || !Uo || !Kws) return;
+  // forward pass of the predicted trajectory (X_opt, U_opt of tt:136-137)
+  for (int j = 0; j < H; ++j) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Xo[soa(j, 4, c, B, b)] = x[c];
+    if (j == H - 1) {
+      Uo[soa(j, 2, 0, B, b)] = 0.0;  // free, unpenalised variable stays at its initial guess
+      Uo[soa(j, 2, 1, B, b)] = 0.0;
+      break;
+    }
+    double u[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double s = Kws[soa(j, 8, i * 4, B, b)] * x[0];
+#pragma unroll
+      for (int jj = 1; jj < 4; ++jj) s = fma(Kws[soa(j, 8, i * 4 + jj, B, b)], x[jj], s);
+      u[i] = s;
+      Uo[soa(j, 2, i, B, b)] = s;
+    }
+    double xn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = Aw[soa(j, 16, i * 4, B, b)] * x[0];
+#pragma unroll
+      for (int jj = 1; jj < 4; ++jj) s = fma(Aw[soa(j, 16, i * 4 + jj, B, b)], x[jj], s);
+      s = fma(Bw[soa(j, 8, i * 2, B, b)], u[0], s);
+      s = fma(Bw[soa(j, 8, i * 2 + 1, B, b)], u[1], s);
+      xn[i] = s;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] = xn[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// T5 MPC tracking
+// ---------------------------------------------------------------------------------------
+// compact discrete linearisation about a trajectory: lin[t][10][ld] = a[0][0..3], a[1][0..3], b[0], b[1]
+template <bool RPB>
+__global__ void k_lin_compact(const __grid_constant__ Model m, int64_t B, int N, const double* rx, const double* ru,
+                              double* __restrict__ lin) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  // RPB: one thread per (t, b) with b fastest; shared: one thread per t
+  const int64_t nb = RPB ? B : 1;
+  if (idx >= int64_t(N - 1) * nb) return;
+  const int t = int(idx / nb);
+  const int64_t b = idx % nb;
+  const RefV<RPB> ref{rx, ru, B, b};
+  double x[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) x[c] = ref.X(t, c);
+  const LinD L = linearize_d(m, x, ref.U(t, 0), ref.U(t, 1));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    lin[soa(t, 10, j, nb, b)] = L.a[0][j];
+    lin[soa(t, 10, 4 + j, nb, b)] = L.a[1][j];
+  }
+  lin[soa(t, 10, 8, nb, b)] = L.b[0];
+  lin[soa(t, 10, 9, nb, b)] = L.b[1];
+}
+
+struct MpcArgs {
+  Model m;
+  KWeights kw;
+  int64_t B;
+  int N, T, H;
+  const double *rx, *ru;
+  double xf[4], uf[2];
+  const double* QT;  // [16] shared or [16][B]
+  int qt_per_problem;
+  const double* x0;
+  const double* lin;  // compact linearisation: shared [N-1][10] or [N-1][10][B]
+  double* K0;         // shared mode: [(T-1)][8]
+  double *Xr, *Ur;
+};
+
+__device__ __forceinline__ LinD load_lin(const double* __restrict__ lin, int t, int64_t ld, int64_t b) {
+  LinD L;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    L.a[0][j] = lin[soa(t, 10, j, ld, b)];
+    L.a[1][j] = lin[soa(t, 10, 4 + j, ld, b)];
+  }
+  L.b[0] = lin[soa(t, 10, 8, ld, b)];
+  L.b[1] = lin[soa(t, 10, 9, ld, b)];
+  L.b0[0] = L.b0[1] = 0.0;
+  return L;
+}
+
+// One receding-horizon solve: (H-1)-step Riccati sweep over the window starting at time t
+// (tt:50, 80-117 with the window/padding of tt:64-67) -> first-move gain K_0 (2x4).
+template <bool WPB>
+__device__ __forceinline__ void mpc_sweep(const WV<WPB>& w, double dt, const double* __restrict__ lin, int64_t ld,
+                                          int64_t b, int n_lin, const LinD& Lf, const double QT[10], int t, int H,
+                                          double K[8]) {
+  double P[10], p[4] = {0, 0, 0, 0}, st[2], dummy = 0.0;
+#pragma unroll
+  for (int e = 0; e < 10; ++e) P[e] = QT[e];
+  const QhQ<WV<WPB>> Qh{w};
+  int j = H - 2;
+  // padded tail of the window: linearisation about (x_f, u_f)
+  for (; j >= 0 && t + j >= n_lin; --j)
+    riccati_step<false, false>(P, p, Lf, dt, Qh, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, K, st, dummy);
+  if (j < 0) return;
+  LinD L = load_lin(lin, t + j, ld, b);
+  for (; j >= 0; --j) {
+    LinD Ln = L;
+    if (j > 0) Ln = load_lin(lin, t + j - 1, ld, b);  // prefetch
+    riccati_step<false, false>(P, p, L, dt, Qh, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, K, st, dummy);
+    L = Ln;
+  }
+}
+
+// shared reference: one thread per time step computes K0[t]
+template <bool WPB>
+__global__ void k_mpc_gains_shared(const __grid_constant__ MpcArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.T - 1) return;
+  const WV<WPB> w(a.kw, 1, 0);
+  const LinD Lf = linearize_d(a.m, a.xf, a.uf[0], a.uf[1]);
+  double QT[10];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j) QT[sym(i, j)] = a.QT[i * 4 + j];
+  double K[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  mpc_sweep(w, a.m.dt, a.lin, 1, 0, a.N - 1, Lf, QT, t, a.H, K);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a.K0[t * 8 + e] = K[e];
+}
+
+// closed-loop plant simulation with the first-move gains (shared reference):
+// u = u_ref_win[0] + K0_t (x - x_ref_win[0]) (tt:46-56); window index 0 is time t (x_f beyond N-1)
+__global__ void k_mpc_track_shared(const __grid_constant__ MpcArgs a) {
+  const int64_t B = a.B, b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  double x[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    x[c] = a.x0[c * B + b];
+    a.Xr[soa(0, 4, c, B, b)] = x[c];
+  }
+  for (int t = 0; t < a.T - 1; ++t) {
+    double u[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double kd = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double xr = (t < a.N) ? __ldg(a.rx + t * 4 + j) : a.xf[j];
+        const double k = __ldg(a.K0 + t * 8 + i * 4 + j);
+        kd = (j == 0) ? k * (x[0] - xr) : fma(k, x[j] - xr, kd);
+      }
+      const double ur = (t < a.N - 1) ? __ldg(a.ru + t * 2 + i) : a.uf[i];
+      u[i] = ur + kd;
+      a.Ur[soa(t, 2, i, B, b)] = u[i];
+    }
+    double xn[4];
+    rk4_step(a.m, x, u[0], u[1], xn);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      x[c] = xn[c];
+      a.Xr[soa(t + 1, 4, c, B, b)] = x[c];
+    }
+  }
+}
+
+// per-problem reference / weights: every problem runs its own T-1 sweeps
+template <bool WPB>
+__global__ void k_mpc_track_pp(const __grid_constant__ MpcArgs a) {
+  const int64_t B = a.B, b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  const WV<WPB> w(a.kw, B, b);
+  const RefV<true> ref{a.rx, a.ru, B, b};
+  const LinD Lf = linearize_d(a.m, a.xf, a.uf[0], a.uf[1]);
+  double QT[10];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j) QT[sym(i, j)] = a.qt_per_problem ? a.QT[(i * 4 + j) * B + b] : a.QT[i * 4 + j];
+  double x[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    x[c] = a.x0[c * B + b];
+    a.Xr[soa(0, 4, c, B, b)] = x[c];
+  }
+  for (int t = 0; t < a.T - 1; ++t) {
+    double K[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    mpc_sweep(w, a.m.dt, a.lin, B, b, a.N - 1, Lf, QT, t, a.H, K);
+    double u[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double kd = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double xr = (t < a.N) ? ref.X(t, j) : a.xf[j];
+        kd = (j == 0) ? K[i * 4] * (x[0] - xr) : fma(K[i * 4 + j], x[j] - xr, kd);
+      }
+      const double ur = (t < a.N - 1) ? ref.U(t, i) : a.uf[i];
+      u[i] = ur + kd;
+      a.Ur[soa(t, 2, i, B, b)] = u[i];
+    }
+    double xn[4];
+    rk4_step(a.m, x, u[0], u[1], xn);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      x[c] = xn[c];
+      a.Xr[soa(t + 1, 4, c, B, b)] = x[c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// layout helpers: (B, T*C) row-major <-> [T*C][B], tiled through shared memory
+// ---------------------------------------------------------------------------------------
+__global__ void k_transpose(int64_t rows, int64_t cols, const double* __restrict__ src, double* __restrict__ dst) {
+  // src (rows, cols) row-major -> dst (cols, rows) row-major
+  __shared__ double tile[32][33];
+  const int64_t tiles_c = (cols + 31) / 32;
+  const int64_t c0 = (blockIdx.x % tiles_c) * 32LL, r0 = (blockIdx.x / tiles_c) * 32LL;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace acro
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+using namespace acro;
+
+extern "C" {
+
+const char* acro_version(void) { return "acro_b200 0.1.0 (sm_100a, abi 1)"; }
+const char* acro_last_error_string(void) { return g_err; }
+int64_t acro_launch_count(void) { return g_launches.load(); }
+
+int acro_continuous_dynamics(const AcroParams* p, int64_t B, const double* x, const double* u, double* xdot,
+                             void* stream) {
+  ACRO_REQUIRE(p && x && u && xdot && B > 0, "acro_continuous_dynamics: bad argument");
+  const Cfg c = cfg_for(B);
+  k_point<PT_F><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), B, x, u, xdot);
+  ACRO_LAUNCH_CHECK("acro_continuous_dynamics");
+  return ACRO_OK;
+}
+
+int acro_rk4_step(const AcroParams* p, int64_t B, const double* x, const double* u, double* xnext, void* stream) {
+  ACRO_REQUIRE(p && x && u && xnext && B > 0, "acro_rk4_step: bad argument");
+  const Cfg c = cfg_for(B);
+  k_point<PT_RK4><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), B, x, u, xnext);
+  ACRO_LAUNCH_CHECK("acro_rk4_step");
+  return ACRO_OK;
+}
+
+int acro_linearize(const AcroParams* p, int64_t B, const double* x, const double* u, double* A, double* Bm,
+                   int discrete, void* stream) {
+  ACRO_REQUIRE(p && x && u && A && Bm && B > 0, "acro_linearize: bad argument");
+  const Cfg c = cfg_for(B);
+  k_linearize<<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), B, x, u, A, Bm, discrete);
+  ACRO_LAUNCH_CHECK("acro_linearize");
+  return ACRO_OK;
+}
+
+int acro_rollout_open_loop(const AcroParams* p, int64_t B, int N, const double* x0, const double* U, double* X,
+                           void* stream) {
+  ACRO_REQUIRE(p && x0 && X && B > 0 && N >= 1, "acro_rollout_open_loop: bad argument");
+  const Cfg c = cfg_for(B);
+  k_rollout_open<<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), B, N, x0, U, X);
+  ACRO_LAUNCH_CHECK("acro_rollout_open_loop");
+  return ACRO_OK;
+}
+
+int acro_total_cost(const AcroWeights* w, int64_t B, int N, const double* X, const double* U, const AcroRef* ref,
+                    double* cost, void* stream) {
+  ACRO_REQUIRE(w && X && U && ref && ref->x && ref->u && cost && B > 0 && N >= 2, "acro_total_cost: bad argument");
+  const Cfg c = cfg_for(B);
+  const KWeights kw = make_weights(*w);
+#define EXPR(WPB, RPB) \
+  k_total_cost<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(kw, B, N, X, U, ref->x, ref->u, cost)
+  DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+  ACRO_LAUNCH_CHECK("acro_total_cost");
+  return ACRO_OK;
+}
+
+int acro_costate(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X, const double* U,
+                 const AcroRef* ref, double* lam, void* stream) {
+  ACRO_REQUIRE(p && w && X && U && ref && ref->x && ref->u && lam && B > 0 && N >= 2, "acro_costate: bad argument");
+  ACRO_REQUIRE(!p->actuated_tau1, "acro_costate: fully-actuated plant not supported here");
+  const Cfg c = cfg_for(B);
+  const KWeights kw = make_weights(*w);
+  const Model m = make_model(*p);
+#define EXPR(WPB, RPB) \
+  k_costate<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, kw, B, N, X, U, ref->x, ref->u, lam)
+  DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+  ACRO_LAUNCH_CHECK("acro_costate");
+  return ACRO_OK;
+}
+
+int acro_riccati_affine(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X,
+                        const double* U, const AcroRef* ref, double* K, double* S, double* delta_J,
+                        double* sigma_norm, void* stream) {
+  ACRO_REQUIRE(p && w && X && U && ref && ref->x && ref->u && K && S && delta_J && sigma_norm && B > 0 && N >= 2,
+               "acro_riccati_affine: bad argument");
+  ACRO_REQUIRE(!p->actuated_tau1, "acro_riccati_affine: fully-actuated plant not supported here");
+  const Cfg c = cfg_for(B);
+  const KWeights kw = make_weights(*w);
+  const Model m = make_model(*p);
+#define EXPR(WPB, RPB)                                                                                   \
+  k_riccati_affine<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, kw, B, N, X, U, ref->x, ref->u, K, S, \
+                                                                           delta_J, sigma_norm)
+  DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+  ACRO_LAUNCH_CHECK("acro_riccati_affine");
+  return ACRO_OK;
+}
+
+int acro_closed_loop_rollout_cost(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X,
+                                  const double* U, const double* K, const double* S, const AcroRef* ref, int G,
+                                  const double* gammas, int gammas_per_problem, double* Xn, double* Un,
+                                  double* cost, void* stream) {
+  ACRO_REQUIRE(p && w && X && U && K && S && ref && ref->x && ref->u && gammas && cost && B > 0 && N >= 2 && G > 0,
+               "acro_closed_loop_rollout_cost: bad argument");
+  ACRO_REQUIRE((Xn == nullptr) == (Un == nullptr), "acro_closed_loop_rollout_cost: Xn and Un go together");
+  ACRO_REQUIRE(G <= 65535, "acro_closed_loop_rollout_cost: G too large");
+  Cfg c = cfg_for(B * G);
+  if (c.block > 32 && B < 148LL * 32 * 4) c.block = 32;
+  const dim3 grid((unsigned)((B + c.block - 1) / c.block), (unsigned)G);
+  const KWeights kw = make_weights(*w);
+  const Model m = make_model(*p);
+#define EXPR(WPB, RPB)                                                                                      \
+  k_closed_loop<WPB, RPB><<<grid, c.block, 0, (cudaStream_t)stream>>>(m, kw, B, N, X, U, K, S, ref->x, ref->u, G, \
+                                                                      gammas, gammas_per_problem, Xn, Un, cost)
+  DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+  ACRO_LAUNCH_CHECK("acro_closed_loop_rollout_cost");
+  return ACRO_OK;
+}
+
+int acro_armijo_select(int64_t B, int G, const double* cost_k, const double* delta_J, const double* gammas,
+                       int gammas_per_problem, const double* cost_cand, double c, int32_t* accepted, void* stream) {
+  ACRO_REQUIRE(cost_k && delta_J && gammas && cost_cand && accepted && B > 0 && G > 0, "acro_armijo_select: bad argument");
+  const int block = 128;
+  k_armijo_select<<<(unsigned)((B + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
+      B, G, cost_k, delta_J, gammas, gammas_per_problem, cost_cand, c, accepted);
+  ACRO_LAUNCH_CHECK("acro_armijo_select");
+  return ACRO_OK;
+}
+
+int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewtonOpts* opts, int64_t B, int N,
+                      const double* x0, const AcroRef* ref, double* X, double* U, double* Xw, double* Uw, double* K,
+                      double* S, double* cost, double* delta_J, double* sigma_norm, double* gamma_acc,
+                      int32_t* iters, int32_t* status, double* hist_cost, double* hist_sigma_norm,
+                      double* hist_gamma, int32_t* hist_ntry, void* stream) {
+  ACRO_REQUIRE(p && w && opts && ref && ref->x && ref->u && X && U && Xw && Uw && K && S && cost && delta_J &&
+                   sigma_norm && gamma_acc && iters && status && B > 0 && N >= 2,
+               "acro_newton_solve: bad argument");
+  ACRO_REQUIRE(!opts->init || x0, "acro_newton_solve: x0 required when init");
+  ACRO_REQUIRE(opts->max_iters >= 0 && opts->max_line_search >= 1, "acro_newton_solve: bad options");
+  ACRO_REQUIRE(!p->actuated_tau1, "acro_newton_solve: fully-actuated plant not supported here");
+  NewtonArgs a;
+  a.m = make_model(*p);
+  a.kw = make_weights(*w);
+  a.o = *opts;
+  a.B = B;
+  a.N = N;
+  a.x0 = x0;
+  a.rx = ref->x;
+  a.ru = ref->u;
+  a.X = X;
+  a.U = U;
+  a.Xw = Xw;
+  a.Uw = Uw;
+  a.K = K;
+  a.S = S;
+  a.cost = cost;
+  a.dJ = delta_J;
+  a.sn = sigma_norm;
+  a.gacc = gamma_acc;
+  a.iters = iters;
+  a.status = status;
+  a.h_cost = hist_cost;
+  a.h_sn = hist_sigma_norm;
+  a.h_gamma = hist_gamma;
+  a.h_ntry = hist_ntry;
+  const Cfg c = cfg_for(B);
+#define EXPR(WPB, RPB) k_newton<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(a)
+  DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+  ACRO_LAUNCH_CHECK("acro_newton_solve");
+  return ACRO_OK;
+}
+
+int acro_stepsize_sweep(const AcroParams* p, const AcroWeights* w, int64_t P, int N, const double* X,
+                        const double* U, const double* K, const double* S, const AcroRef* ref, int S_n,
+                        const double* steps, double* cost, void* stream) {
+  ACRO_REQUIRE(p && w && X && U && K && S && ref && ref->x && ref->u && steps && cost && P > 0 && N >= 2 && S_n > 0,
+               "acro_stepsize_sweep: bad argument");
+  const dim3 grid((unsigned)((P + 3) / 4), (unsigned)((S_n + 31) / 32));
+  ACRO_REQUIRE(grid.y <= 65535, "acro_stepsize_sweep: too many step sizes");
+  const KWeights kw = make_weights(*w);
+  const Model m = make_model(*p);
+#define EXPR(WPB, RPB) \
+  k_sweep<WPB, RPB><<<grid, 128, 0, (cudaStream_t)stream>>>(m, kw, P, N, X, U, K, S, ref->x, ref->u, S_n, steps, cost)
+  DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+  ACRO_LAUNCH_CHECK("acro_stepsize_sweep");
+  return ACRO_OK;
+}
+
+int acro_cost_derivatives(const AcroWeights* w, int64_t B, const double* x, const double* x_ref, const double* u,
+                          const double* u_ref, int terminal, double* l, double* grad_x, double* grad_u,
+                          void* stream) {
+  ACRO_REQUIRE(w && x && x_ref && l && grad_x && B > 0, "acro_cost_derivatives: bad argument");
+  ACRO_REQUIRE(terminal || (u && u_ref && grad_u), "acro_cost_derivatives: stage cost needs u, u_ref, grad_u");
+  const Cfg c = cfg_for(B);
+  const KWeights kw = make_weights(*w);
+  if (per_problem_weights(*w))
+    k_cost_derivatives<true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(kw, B, x, x_ref, u, u_ref, terminal, l, grad_x, grad_u);
+  else
+    k_cost_derivatives<false><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(kw, B, x, x_ref, u, u_ref, terminal, l, grad_x, grad_u);
+  ACRO_LAUNCH_CHECK("acro_cost_derivatives");
+  return ACRO_OK;
+}
+
+int acro_discretize(int64_t B, const double* Ac, const double* Bc, double dt, double* Ad, double* Bd, void* stream) {
+  ACRO_REQUIRE(Ac && Bc && Ad && Bd && B > 0, "acro_discretize: bad argument");
+  const Cfg c = cfg_for(B);
+  k_discretize<<<c.grid, c.block, 0, (cudaStream_t)stream>>>(B, Ac, Bc, dt, Ad, Bd);
+  ACRO_LAUNCH_CHECK("acro_discretize");
+  return ACRO_OK;
+}
+
+int acro_stage_lists(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X, const double* U,
+                     const AcroRef* ref, double* A, double* Bm, double* q, double* r, double* q_T, void* stream) {
+  ACRO_REQUIRE(p && w && X && U && ref && ref->x && ref->u && A && Bm && q && r && q_T && B > 0 && N >= 2,
+               "acro_stage_lists: bad argument");
+  const int64_t n = int64_t(N) * B;
+  const KWeights kw = make_weights(*w);
+  const Model m = make_model(*p);
+#define EXPR(WPB, RPB)                                                                                         \
+  k_stage_lists<WPB, RPB><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(m, kw, B, N, X, U, ref->x, \
+                                                                                         ref->u, A, Bm, q, r, q_T)
+  DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+  ACRO_LAUNCH_CHECK("acro_stage_lists");
+  return ACRO_OK;
+}
+
+int acro_riccati_lists(int64_t B, int T, const double* A, const double* Bm, const double* Q, const double* R,
+                       const double* S_cross, const double* q, const double* r, const double* Q_T,
+                       const double* q_T, double* K, double* S, double* delta_J, void* stream) {
+  ACRO_REQUIRE(A && Bm && Q && R && q && r && Q_T && q_T && K && S && delta_J && B > 0 && T >= 1,
+               "acro_riccati_lists: bad argument");
+  const Cfg c = cfg_for(B);
+  k_riccati_lists<<<c.grid, c.block, 0, (cudaStream_t)stream>>>(B, T, A, Bm, Q, R, S_cross, q, r, Q_T, q_T, K, S, delta_J);
+  ACRO_LAUNCH_CHECK("acro_riccati_lists");
+  return ACRO_OK;
+}
+
+int acro_lqr_gains(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const AcroRef* traj, double* K,
+                   void* stream) {
+  ACRO_REQUIRE(p && w && traj && traj->x && traj->u && K && B > 0 && N >= 2, "acro_lqr_gains: bad argument");
+  ACRO_REQUIRE(traj->per_problem || B == 1, "acro_lqr_gains: a shared trajectory is one problem (B = 1)");
+  ACRO_REQUIRE(!p->actuated_tau1, "acro_lqr_gains: fully-actuated plant not supported here");
+  const Cfg c = cfg_for(B);
+  const KWeights kw = make_weights(*w);
+  const Model m = make_model(*p);
+#define EXPR(WPB, RPB) \
+  k_lqr_gains<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, kw, B, N, traj->x, traj->u, K)
+  DISPATCH2(per_problem_weights(*w), traj->per_problem != 0, EXPR);
+#undef EXPR
+  ACRO_LAUNCH_CHECK("acro_lqr_gains");
+  return ACRO_OK;
+}
+
+int acro_lqr_track(const AcroParams* p, int64_t B, int N, const AcroRef* traj, const double* K, const double* x0,
+                   double* Xt, double* Ut, void* stream) {
+  ACRO_REQUIRE(p && traj && traj->x && traj->u && K && x0 && Xt && Ut && B > 0 && N >= 2, "acro_lqr_track: bad argument");
+  const Cfg c = cfg_for(B);
+  const Model m = make_model(*p);
+  if (traj->per_problem)
+    k_lqr_track<true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, B, N, traj->x, traj->u, K, x0, Xt, Ut);
+  else
+    k_lqr_track<false><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, B, N, traj->x, traj->u, K, x0, Xt, Ut);
+  ACRO_LAUNCH_CHECK("acro_lqr_track");
+  return ACRO_OK;
+}
+
+int acro_p_inf(const AcroWeights* w, int64_t B, const double* A, const double* Bm, int max_iter, double tol,
+               double* P, int32_t* n_iter, void* stream) {
+  ACRO_REQUIRE(w && A && Bm && P && n_iter && B > 0 && max_iter > 0, "acro_p_inf: bad argument");
+  const Cfg c = cfg_for(B);
+  const KWeights kw = make_weights(*w);
+  if (per_problem_weights(*w))
+    k_p_inf<true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(kw, B, A, Bm, max_iter, tol, P, n_iter);
+  else
+    k_p_inf<false><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(kw, B, A, Bm, max_iter, tol, P, n_iter);
+  ACRO_LAUNCH_CHECK("acro_p_inf");
+  return ACRO_OK;
+}
+
+int acro_mpc_solve(const AcroWeights* w, int64_t B, int T_pred, const double* x0, const double* A_w,
+                   const double* B_w, const double* QT, double* U0, double* X_opt, double* U_opt, double* K_ws,
+                   void* stream) {
+  ACRO_REQUIRE(w && x0 && A_w && B_w && QT && U0 && B > 0 && T_pred >= 1, "acro_mpc_solve: bad argument");
+  ACRO_REQUIRE((X_opt == nullptr) == (U_opt == nullptr), "acro_mpc_solve: X_opt and U_opt go together");
+  ACRO_REQUIRE(!X_opt || K_ws, "acro_mpc_solve: K_ws workspace required for X_opt/U_opt");
+  const Cfg c = cfg_for(B);
+  const KWeights kw = make_weights(*w);
+  if (per_problem_weights(*w))
+    k_mpc_solve<true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(kw, B, T_pred, x0, A_w, B_w, QT, U0, X_opt, U_opt, K_ws);
+  else
+    k_mpc_solve<false><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(kw, B, T_pred, x0, A_w, B_w, QT, U0, X_opt, U_opt, K_ws);
+  ACRO_LAUNCH_CHECK("acro_mpc_solve");
+  return ACRO_OK;
+}
+
+int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
+                   const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                   int qt_per_problem, const double* x0, double* K0, double* lin_ws, double* Xr, double* Ur,
+                   int64_t* n_solves, void* stream) {
+  ACRO_REQUIRE(p && w && ref && ref->x && ref->u && x_f && u_f && QT_inf && x0 && lin_ws && Xr && Ur && B > 0 &&
+                   N >= 2 && T >= 2 && T <= N && T_pred >= 2,
+               "acro_mpc_track: bad argument");
+  ACRO_REQUIRE(!p->actuated_tau1, "acro_mpc_track: fully-actuated plant not supported here");
+  const bool wpb = per_problem_weights(*w);
+  const bool pp = ref->per_problem || wpb || qt_per_problem;
+  ACRO_REQUIRE(pp || K0, "acro_mpc_track: K0 workspace required for a shared reference");
+  ACRO_REQUIRE(!pp || ref->per_problem, "acro_mpc_track: per-problem weights need a per-problem reference layout");
+  MpcArgs a;
+  a.m = make_model(*p);
+  a.kw = make_weights(*w);
+  a.B = B;
+  a.N = N;
+  a.T = T;
+  a.H = T_pred;
+  a.rx = ref->x;
+  a.ru = ref->u;
+  for (int i = 0; i < 4; ++i) a.xf[i] = x_f[i];
+  for (int i = 0; i < 2; ++i) a.uf[i] = u_f[i];
+  a.QT = QT_inf;
+  a.qt_per_problem = qt_per_problem;
+  a.x0 = x0;
+  a.lin = lin_ws;
+  a.K0 = K0;
+  a.Xr = Xr;
+  a.Ur = Ur;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!pp) {
+    const int nt = N - 1;
+    k_lin_compact<false><<<(nt + 63) / 64, 64, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
+    ACRO_LAUNCH_CHECK("acro_mpc_track/linearize");
+    k_mpc_gains_shared<false><<<(T - 1 + 31) / 32, 32, 0, s>>>(a);
+    ACRO_LAUNCH_CHECK("acro_mpc_track/gains");
+    const Cfg c = cfg_for(B);
+    k_mpc_track_shared<<<c.grid, c.block, 0, s>>>(a);
+    ACRO_LAUNCH_CHECK("acro_mpc_track/track");
+    if (n_solves) *n_solves = T - 1;
+  } else {
+    const int64_t n = int64_t(N - 1) * B;
+    k_lin_compact<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
+    ACRO_LAUNCH_CHECK("acro_mpc_track/linearize");
+    const Cfg c = cfg_for(B);
+    if (wpb)
+      k_mpc_track_pp<true><<<c.grid, c.block, 0, s>>>(a);
+    else
+      k_mpc_track_pp<false><<<c.grid, c.block, 0, s>>>(a);
+    ACRO_LAUNCH_CHECK("acro_mpc_track/track");
+    if (n_solves) *n_solves = int64_t(T - 1) * B;
+  }
+  return ACRO_OK;
+}
+
+static int transpose(int64_t rows, int64_t cols, const double* src, double* dst, void* stream, const char* name) {
+  ACRO_REQUIRE(src && dst && rows > 0 && cols > 0, "acro_pack/unpack: bad argument");
+  const int64_t tiles = ((cols + 31) / 32) * ((rows + 31) / 32);
+  ACRO_REQUIRE(tiles < (1LL << 31), "acro_pack/unpack: array too large for one call");
+  k_transpose<<<(unsigned)tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(rows, cols, src, dst);
+  ACRO_LAUNCH_CHECK(name);
+  return ACRO_OK;
+}
+
+int acro_pack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream) {
+  return transpose(B, int64_t(T) * C, src, dst, stream, "acro_pack_soa");
+}
+int acro_unpack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream) {
+  return transpose(int64_t(T) * C, B, src, dst, stream, "acro_unpack_soa");
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+"""Drop-in for the reference's ``trajectory_generation.py`` (Newton / Riccati / Armijo).
+
+Same function names, argument order and defaults as the reference.  Every function accepts what the
+reference accepts (one problem, NumPy) and also a leading batch axis and torch tensors; all arithmetic
+runs in libacro_b200.so.  Module-level ``Q, R, Q_T`` (trajectory_generation.py:16-18) are read at call time,
+so rebinding them changes the weights as it does in the reference; the batched entry points also take
+``Q=, R=, Q_T=`` keyword arguments (arrays of shape (4,4) or per problem (B,4,4)).
+"""
+import numpy as np
+import torch
+
+from . import _io
+from . import batched as bt
+from .dynamics import *  # noqa: F401,F403  (the reference re-exports dynamics the same way, tg:3)
+from .dynamics import active_params, dt, ni, ns
+
+T = 10.0
+N = int(T / dt) + 1
+nu = 2
+nx = 4
+
+Q = np.diag([130.0, 30.0, 0.0001, 0.0001])
+R = np.diag([1e-6, 1.5])
+Q_T = np.diag([130, 130.0, 1.0, 1.0])
+
+
+def _weights(Qm=None, Rm=None, QTm=None):
+    """Shared (4,4)/(2,2) weights or per-problem stacks (B,4,4)/(B,2,2)."""
+    Qm = Q if Qm is None else Qm
+    Rm = R if Rm is None else Rm
+    QTm = Q_T if QTm is None else QTm
+    arrs = [np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64) for a in (Qm, Rm, QTm)]
+    if all(a.ndim == 2 for a in arrs):
+        return bt.Weights(*arrs)
+    Bn = max(a.shape[0] for a in arrs if a.ndim == 3)
+    full = [np.broadcast_to(a, (Bn,) + a.shape[-2:]) for a in arrs]
+    dev = [bt.upload(np.ascontiguousarray(a.reshape(Bn, -1).T)) for a in full]
+    return bt.Weights(full[0][0], full[1][0], full[2][0], Q_b=dev[0], R_b=dev[1], QT_b=dev[2])
+
+
+def _ref(x_ref, u_ref):
+    """Shared (N,4)/(N-1,2) or per-problem (B,N,4)/(B,N-1,2) reference."""
+    xd, ud = bt.upload(x_ref), bt.upload(u_ref)
+    if xd.dim() == 3:
+        return bt.Ref(bt.pack_soa(xd), bt.pack_soa(ud))
+    return bt.Ref(xd, ud)
+
+
+def define_reference_piecewise(T, x_e1, x_e2, u_e1, u_e2):
+    """Two constant segments, x_e1 for t < T/2 and x_e2 after (trajectory_generation.py:41-58).  Host-side
+    construction of an input; not a compute kernel."""
+    n = int(T / dt) + 1
+    t_ref = np.linspace(0.0, T, n)
+    first = (t_ref < T / 2.0)[:, None]
+    x_ref = np.where(first, np.asarray(x_e1, dtype=float)[None], np.asarray(x_e2, dtype=float)[None])
+    u_ref = np.where(first, np.asarray(u_e1, dtype=float)[None], np.asarray(u_e2, dtype=float)[None])
+    return t_ref, x_ref, u_ref
+
+
+def get_fully_actuated_ref(path="trajectories_npz/fully_actuated_trajectory.npz"):
+    """Load and rescale the fully-actuated reference (trajectory_generation.py:511-518): tau1 := 0, torques x 2."""
+    data = np.load(path)
+    u_ref = np.zeros(data["u"].shape)
+    u_ref[:, 1] = data["u"][:, 1]
+    return data["x"], np.multiply(u_ref, 2), data["time"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+def simulate_open_loop(x0, u_traj):
+    """trajectory_generation.py:74-87"""
+    x, kind = _io.state_in(x0, nx)
+    U, ku = _io.traj_in(u_traj, nu)
+    if U.shape[2] != x.shape[1]:
+        raise ValueError("batch sizes of x0 and u_traj differ")
+    kind.batched = kind.batched or ku.batched
+    return _io.out(bt.rollout_open_loop(x, U, params=active_params()), kind)
+
+
+def derivatives_Cost(x, x_ref, u, u_ref, Q, R, Q_T=None, terminal=False):
+    """trajectory_generation.py:89-114.  One point or a batch of points."""
+    xd, kind = _io.state_in(x, nx)
+    xr, _ = _io.state_in(x_ref, nx)
+    xr = xr.expand_as(xd).contiguous()
+    if terminal:
+        w = _weights(np.zeros((4, 4)), np.zeros((2, 2)), Q_T)
+        l, gx, _ = bt.cost_derivatives(xd, xr, None, None, w, terminal=True)
+        return _io.vec_out(l, kind), _io.out(gx, kind), 2 * np.asarray(Q_T)
+    ud, _ = _io.state_in(u, nu)
+    ur, _ = _io.state_in(u_ref, nu)
+    w = _weights(Q, R, np.zeros((4, 4)))
+    l, gx, gu = bt.cost_derivatives(xd, xr, ud.expand(nu, xd.shape[1]).contiguous(), ur.expand(nu, xd.shape[1]).contiguous(), w)
+    return _io.vec_out(l, kind), _io.out(gx, kind), _io.out(gu, kind), 2 * np.asarray(Q), 2 * np.asarray(R)
+
+
+def compute_costate_trajectory(x_traj, u_traj, x_ref, u_ref):
+    """trajectory_generation.py:138-159.  Returns a list of N costates (one problem) or an array (B,N,4)."""
+    X, kind = _io.traj_in(x_traj, nx)
+    U, _ = _io.traj_in(u_traj, nu)
+    lam = _io.out(bt.costate(X, U, _ref(x_ref, u_ref), _weights(), active_params()), kind)
+    return lam if kind.batched else list(lam)
+
+
+def discretize_linearization(Ac, Bc, dt):
+    """trajectory_generation.py:161-164"""
+    A = np.asarray(Ac.detach().cpu() if isinstance(Ac, torch.Tensor) else Ac, dtype=np.float64)
+    batched = A.ndim == 3
+    Ad_, kind = _io.state_in(A.reshape(-1, 16) if batched else A.reshape(16), 16)
+    Bd_, _ = _io.state_in(np.asarray(Bc.detach().cpu() if isinstance(Bc, torch.Tensor) else Bc, dtype=np.float64)
+                          .reshape((-1, 8) if batched else (8,)), 8)
+    kind = _io.Kind(Ac, batched)
+    Ad, Bd = bt.discretize(Ad_, Bd_, dt)
+    return _io.out(Ad, kind, tail=(4, 4), key="Ad"), _io.out(Bd, kind, tail=(4, 2), key="Bd")
+
+
+def build_stage_lists(x_traj, u_traj, x_ref, u_ref, lambda_seq=None):
+    """trajectory_generation.py:166-181.  lambda_seq is accepted and ignored exactly as the reference does
+    (stage_blocks_and_affine never reads it, tg:116-129).  One problem -> the reference's nine lists/arrays."""
+    X, kind = _io.traj_in(x_traj, nx)
+    U, _ = _io.traj_in(u_traj, nu)
+    A, Bm, q, r, qT = bt.stage_lists(X, U, _ref(x_ref, u_ref), _weights(), active_params())
+    A_, B_ = _io.out(A, kind, tail=(4, 4), key="A"), _io.out(Bm, kind, tail=(4, 2), key="B")
+    q_, r_, qT_ = _io.out(q, kind, key="q"), _io.out(r, kind, key="r"), _io.out(qT, kind, key="qT")
+    n = X.shape[0] - 1
+    Q_t, R_t, S_t, QTb = 2 * np.asarray(Q), 2 * np.asarray(R), np.zeros((nu, nx)), 2 * np.asarray(Q_T)
+    if kind.batched:
+        return A_, B_, Q_t, R_t, S_t, q_, r_, QTb, qT_
+    return (list(A_), list(B_), [Q_t] * n, [R_t] * n, [S_t] * n, list(q_), list(r_), QTb, qT_)
+
+
+def calculate_K_and_sigma(A_list, B_list, Q_list, R_list, S_list, q_list, r_list, Q_T_block, q_T):
+    """trajectory_generation.py:183-216 on caller-supplied lists (one problem)."""
+    Tn = len(A_list)
+
+    def dev(lst, shape):
+        a = np.asarray([np.asarray(v, dtype=np.float64) for v in lst]).reshape(Tn, shape, 1)
+        return bt.upload(a)
+
+    K, S, dJ = bt.riccati_lists(dev(A_list, 16), dev(B_list, 8), dev(Q_list, 16), dev(R_list, 4), dev(q_list, 4),
+                                dev(r_list, 2), bt.upload(np.asarray(Q_T_block, dtype=np.float64).reshape(16, 1)),
+                                bt.upload(np.asarray(q_T, dtype=np.float64).reshape(4, 1)), S_cross=dev(S_list, 8))
+    Kh = K.cpu().numpy()[:, :, 0].reshape(Tn, 2, 4)
+    Sh = S.cpu().numpy()[:, :, 0]
+    return list(Kh), list(Sh), float(dJ[0].item())
+
+
+def forward_closed_loop_update(x_traj, u_traj, K, sigma, gamma=1.0):
+    """trajectory_generation.py:218-229"""
+    X, kind = _io.traj_in(x_traj, nx)
+    U, _ = _io.traj_in(u_traj, nu)
+    Kd, _ = _io.traj_in(K, 8)
+    Sd, _ = _io.traj_in(sigma, nu)
+    g = np.atleast_1d(np.asarray(gamma.detach().cpu() if isinstance(gamma, torch.Tensor) else gamma, dtype=np.float64))
+    gam = bt.upload(np.broadcast_to(g, (X.shape[2],)).reshape(1, -1).copy())
+    ref = bt.Ref(X.clone(), U.clone())  # the cost the kernel also produces is not part of this call: any reference will do
+    _, Xn, Un = bt.closed_loop_rollout_cost(X, U, Kd, Sd, ref, _weights(), gam, store=True, params=active_params())
+    return _io.out(Xn[0], kind, key="xn"), _io.out(Un[0], kind, key="un")
+
+
+def total_cost(x_traj, u_traj, x_ref, u_ref, Q, R, Q_T):
+    """trajectory_generation.py:231-252"""
+    X, kind = _io.traj_in(x_traj, nx)
+    U, _ = _io.traj_in(u_traj, nu)
+    return _io.vec_out(bt.total_cost(X, U, _ref(x_ref, u_ref), _weights(Q, R, Q_T)), kind)
+
+
+def armijo_sweep(x_traj, u_traj, K, sigma, x_ref, u_ref, stepsizes_tested=(), n_steps=200):
+    """The numeric part of plot_armijo_line_search (trajectory_generation.py:257-264): step sizes
+    linspace(0, max(1.25, 1.3 max tested), 200) and the cost along the search direction for each."""
+    max_step = max(1.25, max(stepsizes_tested) * 1.3 if len(stepsizes_tested) else 1.25)
+    steps = np.linspace(0, max_step, n_steps)
+    X, kind = _io.traj_in(x_traj, nx)
+    U, _ = _io.traj_in(u_traj, nu)
+    Kd, _ = _io.traj_in(K, 8)
+    Sd, _ = _io.traj_in(sigma, nu)
+    cost = bt.stepsize_sweep(X, U, Kd, Sd, _ref(x_ref, u_ref), _weights(), bt.upload(steps), params=active_params())
+    c = cost.cpu().numpy()  # (S, B)
+    return steps, (c.T if kind.batched else c[:, 0])
+
+
+def plot_armijo_line_search(*args, **kwargs):
+    """Plotting is out of scope (no matplotlib on the hot path); ``armijo_sweep`` returns the plotted numbers."""
+    return None
+
+
+def newton_Algorithm(x0, x_ref, u_ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1, plot_armijo_iters=10, *,
+                     Q=None, R=None, Q_T=None, return_history=False, history_stride=1, verbose=True,
+                     return_state=False):
+    """Regularised Newton method with Armijo line search (trajectory_generation.py:298-398).
+
+    One problem: returns ``(x_traj, u_traj, K, sigma, history)`` with the reference's types (K and sigma
+    are lists of N-1 arrays; history has 'cost', 'sigma_norm', and - only with return_history=True, because
+    it needs one launch per stored iterate - 'x_trajs' and 'sigmas').
+    Batch (x0 of shape (B,4)): arrays with a leading batch axis; history['cost'] is (B, iters+1) padded with
+    NaN past each problem's last iteration, plus 'iters', 'status', 'n_try', 'gamma'.
+    """
+    u_ref_n = u_ref.shape[0] if u_ref.ndim == 2 else u_ref.shape[1]
+    x_ref_n = x_ref.shape[0] if x_ref.ndim == 2 else x_ref.shape[1]
+    if u_ref_n == x_ref_n:
+        if verbose:
+            print(f" u_ref has same length as x_ref ({u_ref_n}). Using first N-1 controls.")
+        u_ref = u_ref[:-1] if u_ref.ndim == 2 else u_ref[:, :-1]
+        u_ref_n -= 1
+    if u_ref_n != x_ref_n - 1:
+        raise ValueError(f"Incompatible dimensions: x_ref has {x_ref_n} states but u_ref has {u_ref_n} controls "
+                         f"(expected {x_ref_n - 1})")
+    x0d, kind = _io.state_in(x0, nx)
+    ref = _ref(x_ref, u_ref)
+    w = _weights(Q, R, Q_T)
+    kw = dict(max_iters=max_iters, tol=tol, beta=beta, c=c, gamma_0=gamma_0, w=w, params=active_params())
+    x_trajs, sigmas = [], []
+
+    def snap(t, key):
+        o = _io.out(t, kind, key=key)
+        return o.clone() if isinstance(o, torch.Tensor) else o.copy()
+
+    if return_history:
+        # history['x_trajs'][0] is the initial open-loop rollout (tg:322-327); one launch per stored iterate after that
+        x_trajs.append(snap(bt.rollout_open_loop(x0d, None, N=ref.N, params=active_params()), "hx"))
+        st, done = None, 0
+        while True:
+            st = bt.newton_solve(x0d, ref, state=st, chunk_iters=history_stride, **kw)
+            done += history_stride
+            x_trajs.append(snap(st.X, "hx"))
+            sigmas.append(snap(st.S, "hs"))
+            if bool((st.status != 0).all()) or done >= max_iters:
+                break
+    else:
+        st = bt.newton_solve(x0d, ref, **kw)
+    iters = st.iters.cpu().numpy()
+    status = st.status.cpu().numpy()
+    n_it = int(iters.max()) if iters.size else 0
+    hc = st.hist_cost[:n_it + 1].cpu().numpy().T  # (B, n_it+1)
+    hs = st.hist_sigma_norm[:n_it].cpu().numpy().T
+    if verbose:
+        for b in np.where(status == 3)[0][:8]:
+            print(f"Iteration {iters[b] - 1}: Line search failed to find sufficient decrease.")
+        for b in np.where(status == 1)[0][:8]:
+            print(f"Converged at iteration {iters[b] - 1}!")
+    x_traj = _io.out(st.X, kind, key="x")
+    u_traj = _io.out(st.U, kind, key="u")
+    K = _io.out(st.K, kind, tail=(2, 4), key="K")
+    sigma = _io.out(st.S, kind, key="S")
+    if kind.batched:
+        history = {"cost": hc, "sigma_norm": hs, "iters": iters, "status": status,
+                   "n_try": st.hist_ntry[:n_it].cpu().numpy().T, "gamma": st.hist_gamma[:n_it].cpu().numpy().T,
+                   "x_trajs": x_trajs, "sigmas": sigmas}
+    else:
+        n_acc = int(np.isfinite(hc[0]).sum()) - 1
+        history = {"cost": list(hc[0][:n_acc + 1]), "sigma_norm": list(hs[0][:int(iters[0])]), "x_trajs": x_trajs,
+                   "sigmas": sigmas, "iters": int(iters[0]), "status": int(status[0]),
+                   "n_try": list(st.hist_ntry[:int(iters[0]), 0].cpu().numpy()),
+                   "gamma": list(st.hist_gamma[:int(iters[0]), 0].cpu().numpy())}
+        K, sigma = list(K), list(sigma)
+    if return_state:
+        return x_traj, u_traj, K, sigma, history, st
+    return x_traj, u_traj, K, sigma, history

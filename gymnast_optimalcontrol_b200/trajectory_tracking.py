@@ -1,0 +1,100 @@
+"""Drop-in for the reference's ``trajectory_tracking.py`` (LQR and receding-horizon MPC tracking).
+
+The MPC quadratic programme of ``solver_mpc`` (trajectory_tracking.py:73-140) has only equality
+constraints (``test_constraints = False``, tt:87), so it is an LQ problem: the kernels solve it exactly by a
+(T_pred-1)-step Riccati sweep instead of CasADi/IPOPT.  A solver failure cannot occur; where the reference
+would ``exit()`` (tt:131-133) this module raises.
+"""
+import numpy as np
+import torch
+
+from . import _io
+from . import batched as bt
+from .trajectory_generation import *  # noqa: F401,F403  (tt:3)
+from .trajectory_generation import _ref, _weights, active_params, dt, ns, nu, nx
+
+Q_reg = np.diag([100.0, 100.0, 10.0, 10.0])  # tt:173
+R_Reg = np.diag([1.0, 1.0])                  # tt:174
+Q_mpc = np.diag([120.0, 100.0, 0.0001, 0.0001])  # tt:38
+R_mpc = np.diag([1e-6, 10.0])                    # tt:39
+x_f = np.array([np.pi, 0, 0, 0])  # tt:33
+u_f = np.array([0, 0])            # tt:34
+
+
+def solve_LQR_tracking(x_opt, u_opt):
+    """trajectory_tracking.py:170-203.  One trajectory -> list of N-1 gains (2,4); batch (B,N,4) -> (B,N-1,2,4)."""
+    traj = _ref(x_opt, u_opt)
+    K = bt.lqr_gains(traj, bt.Weights(Q_reg, R_Reg), active_params())
+    if traj.per_problem:
+        kind = _io.Kind(x_opt, True)
+        return _io.out(K, kind, tail=(2, 4), key="Kreg")
+    Kh = K.cpu().numpy().reshape(-1, 2, 4)
+    return list(Kh)
+
+
+def simulate_tracking(x_opt, u_opt, K_reg, x0_perturbed):
+    """trajectory_tracking.py:206-216.  x0_perturbed (4,) or (B,4); trajectory and gains shared or per problem."""
+    x0, kind = _io.state_in(x0_perturbed, nx)
+    traj = _ref(x_opt, u_opt)
+    if traj.per_problem:
+        Kd, _ = _io.traj_in(K_reg, 8)
+    else:
+        Kd = bt.upload(np.asarray([np.asarray(k, dtype=np.float64).reshape(8) for k in K_reg])
+                       if isinstance(K_reg, (list, tuple)) else K_reg).reshape(-1, 8).contiguous()
+    Xt, Ut = bt.lqr_track(traj, Kd, x0, active_params())
+    return _io.out(Xt, kind, key="xt"), _io.out(Ut, kind, key="ut")
+
+
+def LQR_tracking(x_ref, u_ref, t_ref, x0_perturbed=None):
+    """trajectory_tracking.py:219-249"""
+    if x0_perturbed is None:
+        x0_perturbed = x_ref[0].copy() if not isinstance(x_ref, torch.Tensor) else x_ref[0].clone()
+    traj = _ref(x_ref, u_ref)
+    K = bt.lqr_gains(traj, bt.Weights(Q_reg, R_Reg), active_params())
+    x0, kind = _io.state_in(x0_perturbed, nx)
+    Xt, Ut = bt.lqr_track(traj, K, x0, active_params())
+    return _io.out(Xt, kind, key="xt"), _io.out(Ut, kind, key="ut")
+
+
+def compute_P_inf(A, B, Q, R):
+    """trajectory_tracking.py:144-165"""
+    Ad = bt.upload(np.asarray(A, dtype=np.float64).reshape(4, 4, 1))
+    Bd = bt.upload(np.asarray(B, dtype=np.float64).reshape(4, 2, 1))
+    P, n = bt.p_inf(Ad, Bd, bt.Weights(Q, R))
+    if int(n[0]) < 0:
+        print("P_inf did not converge!!!")
+    return P.cpu().numpy()[:, :, 0]
+
+
+def solver_mpc(x0, A_list, B_list, Q, R, Q_T, T_pred, u_ref=None):
+    """trajectory_tracking.py:73-140 -> (U0 (2,), X_opt (T_pred,4), U_opt (T_pred,2)).  u_ref is unused, as in
+    the reference when test_constraints is False (tt:87)."""
+    H = int(T_pred)
+    A = np.asarray([np.asarray(a, dtype=np.float64) for a in A_list[:H - 1]]).reshape(H - 1, 4, 4, 1)
+    Bm = np.asarray([np.asarray(b, dtype=np.float64) for b in B_list[:H - 1]]).reshape(H - 1, 4, 2, 1)
+    x0d, kind = _io.state_in(np.asarray(x0, dtype=np.float64).reshape(4), nx)
+    U0, Xo, Uo, _ = bt.mpc_solve(x0d, bt.upload(A), bt.upload(Bm), bt.upload(np.asarray(Q_T, dtype=np.float64).reshape(4, 4, 1)),
+                                 bt.Weights(Q, R), H)
+    return U0.cpu().numpy()[:, 0], Xo.cpu().numpy()[:, :, 0], Uo.cpu().numpy()[:, :, 0]
+
+
+def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return_info=False):
+    """trajectory_tracking.py:8-69.  x0 (4,) or (B,4); reference shared (N,4) or per problem (B,N,4)."""
+    w = bt.Weights(Q_mpc if Q is None else Q, R_mpc if R is None else R)
+    p = active_params()
+    x0d, kind = _io.state_in(x0, nx)
+    ref = _ref(x_ref, u_ref)
+    # terminal weight: P_inf of the linearisation about the final equilibrium (tt:33-40), all on the device
+    xf = bt.upload(np.asarray(x_f, dtype=np.float64).reshape(4, 1))
+    uf = bt.upload(np.asarray(u_f, dtype=np.float64).reshape(2, 1))
+    A_f, B_f = bt.linearize(xf, uf, True, p)
+    P, n = bt.p_inf(A_f, B_f, w)
+    if int(n[0]) < 0:
+        print("P_inf did not converge!!!")
+    Xr, Ur, K0, n_solves = bt.mpc_track(x0d, ref, P[:, :, 0].contiguous(), T=int(T), T_pred=int(T_pred), w=w,
+                                        x_f=x_f, u_f=u_f, params=p)
+    xr, ur = _io.out(Xr, kind, key="xr"), _io.out(Ur, kind, key="ur")
+    if return_info:
+        return xr, ur, dict(n_solves=n_solves, K0=None if K0 is None else K0.cpu().numpy().reshape(-1, 2, 4),
+                            P_inf=P.cpu().numpy()[:, :, 0])
+    return xr, ur

@@ -1,0 +1,238 @@
+/*
+ * acro_abi.h - C ABI of libacro_b200.so: the batched acrobot optimal-control hot path on
+ * NVIDIA B200 (sm_100a), FP64 throughout.
+ *
+ * The reference (francescoolivieri/Gymnast_OptimalControl) has no FFI layer: its boundary
+ * is a set of module-level Python functions.  Each entry point below names the reference
+ * function it replaces (file:line, relative to the reference root).  A maintainer binds
+ * them with ctypes; gymnast_optimalcontrol_b200/_abi.py is that binding.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, a negative ACRO_E_* code otherwise, never throws,
+ *    and is asynchronous on the given stream (a cudaStream_t passed as void*; NULL = the
+ *    legacy default stream).  There is no global mutable state apart from a thread-local
+ *    error string (acro_last_error_string).
+ *  - All array pointers are caller-owned DEVICE pointers to FP64 (or int32 where stated)
+ *    unless a parameter is documented as HOST.  The library allocates nothing.
+ *  - Batch layout is structure-of-arrays with the problem index fastest:
+ *        state batch      x[c][b]            c in 0..3            -> x[c*B + b]
+ *        input batch      u[c][b]            c in 0..1
+ *        state trajectory X[t][c][b]         t in 0..N-1          -> X[(t*4 + c)*B + b]
+ *        input trajectory U[t][c][b]         t in 0..N-2
+ *        gains            K[t][i*4+j][b]     K_t is 2x4 row-major
+ *        feed-forward     S[t][i][b]         sigma_t, 2 entries
+ *    so that the 32 problems of a warp touch 256 contiguous bytes per component per step.
+ *  - "Shared" reference data (one trajectory for the whole batch) is plain row-major
+ *    [t][c], i.e. exactly the NumPy arrays of the reference: x_ref (N,4), u_ref (N-1,2),
+ *    K_reg (N-1,2,4).
+ */
+#ifndef ACRO_ABI_H
+#define ACRO_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACRO_ABI_VERSION 1
+
+/* error codes */
+#define ACRO_OK 0
+#define ACRO_E_INVALID (-1) /* bad argument (null pointer, non-positive size, ...) */
+#define ACRO_E_CUDA (-2)    /* a CUDA runtime call failed; see acro_last_error_string() */
+#define ACRO_E_NODEVICE (-3)
+
+/* per-problem solver status (int32), mirrors the exits of newton_Algorithm
+ * (trajectory_generation.py:329-396) */
+#define ACRO_RUNNING 0            /* not finished (resume with another call) */
+#define ACRO_CONVERGED 1          /* max|sigma| < tol after an accepted step (tg:394-396) */
+#define ACRO_MAX_ITERS 2          /* loop ran max_iters times (tg:329) */
+#define ACRO_LINE_SEARCH_FAILED 3 /* 20 rejected candidates (tg:367-369); iterate kept */
+
+/* Physical parameters: dynamics.py:15-61 (params_1/2/3), dt: dynamics.py:173.
+ * actuated_tau1 = 0 reproduces the plant of dynamics.py:205 (tau_1 forced to 0);
+ * 1 gives the fully-actuated model of fully_actuated_ref_gen.py:20-73. */
+typedef struct AcroParams {
+  double m1, m2, l1, lc1, l2, lc2, I1, I2, g, f1, f2;
+  double dt;
+  int32_t actuated_tau1;
+  int32_t reserved;
+} AcroParams;
+
+/* Cost weights.  Q, R, QT are HOST arrays (row-major 4x4, 2x2, 4x4, symmetric), the
+ * module-level constants of trajectory_generation.py:16-18 / trajectory_tracking.py:38-39,
+ * 173-175.  If the *_b device pointers are non-NULL they override them per problem:
+ * Q_b[e][b] (e = 0..15), R_b[e][b] (e = 0..3), QT_b[e][b]. */
+typedef struct AcroWeights {
+  double Q[16];
+  double R[4];
+  double QT[16];
+  const double* Q_b;
+  const double* R_b;
+  const double* QT_b;
+} AcroWeights;
+
+/* Reference trajectory handed to the optimiser / tracker.
+ * per_problem = 0: x (N,4) and u (N-1,2) row-major, shared by the batch.
+ * per_problem = 1: x [N][4][B], u [N-1][2][B]. */
+typedef struct AcroRef {
+  const double* x;
+  const double* u;
+  int32_t per_problem;
+  int32_t reserved;
+} AcroRef;
+
+/* Arguments of newton_Algorithm (trajectory_generation.py:298) */
+typedef struct AcroNewtonOpts {
+  int32_t max_iters;    /* total cap on iterations per problem */
+  int32_t chunk_iters;  /* at most this many iterations in THIS call (0 = no limit) */
+  int32_t max_line_search; /* 20 in the reference (tg:345) */
+  int32_t init;         /* 1: start from u = 0, roll out from x0, compute the initial cost
+                           (tg:311-319); 0: resume from X, U, cost, iters, status */
+  double tol;           /* tg:394 */
+  double beta;          /* tg:365 */
+  double c;             /* tg:361 */
+  double gamma_0;       /* tg:344 */
+} AcroNewtonOpts;
+
+const char* acro_version(void);
+const char* acro_last_error_string(void);
+/* Number of kernels this library has launched in the calling process (for bench.py). */
+int64_t acro_launch_count(void);
+
+/* ---- D1-D3: dynamics.py ------------------------------------------------------------ */
+/* continuous_dynamics(xx, uu)  dynamics.py:197-213.  x [4][B], u [2][B] -> xdot [4][B] */
+int acro_continuous_dynamics(const AcroParams* p, int64_t B, const double* x, const double* u,
+                             double* xdot, void* stream);
+/* dynamics(xx, uu): one RK4 step  dynamics.py:177-195.  -> xnext [4][B] */
+int acro_rk4_step(const AcroParams* p, int64_t B, const double* x, const double* u, double* xnext,
+                  void* stream);
+/* Calculate_A_B_matrixes(x_t, u_t)  dynamics.py:217-226  (discrete = 0), optionally followed
+ * by discretize_linearization  trajectory_generation.py:161-164  (discrete = 1).
+ * A [16][B] (4x4 row-major), Bm [8][B] (4x2 row-major). */
+int acro_linearize(const AcroParams* p, int64_t B, const double* x, const double* u, double* A,
+                   double* Bm, int discrete, void* stream);
+
+/* ---- G1-G11: trajectory_generation.py ---------------------------------------------- */
+/* simulate_open_loop(x0, u_traj)  tg:74-87.  x0 [4][B], U [N-1][2][B] (NULL = zeros)
+ * -> X [N][4][B] */
+int acro_rollout_open_loop(const AcroParams* p, int64_t B, int N, const double* x0, const double* U,
+                           double* X, void* stream);
+/* total_cost(x_traj, u_traj, x_ref, u_ref, Q, R, Q_T)  tg:231-252 -> cost [B] */
+int acro_total_cost(const AcroWeights* w, int64_t B, int N, const double* X, const double* U,
+                    const AcroRef* ref, double* cost, void* stream);
+/* compute_costate_trajectory  tg:138-159 -> lam [N][4][B].  (Its result is not used by the
+ * reference's Newton loop; exposed for completeness.) */
+int acro_costate(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X,
+                 const double* U, const AcroRef* ref, double* lam, void* stream);
+/* derivatives_Cost(x, x_ref, u, u_ref, Q, R, Q_T, terminal)  tg:89-114 for a batch of points:
+ * x, x_ref [4][B], u, u_ref [2][B] -> l [B], grad_x [4][B] = 2Q(x-x_ref) (2Q_T if terminal),
+ * grad_u [2][B] = 2R(u-u_ref) (untouched if terminal).  The Hessians are the constants 2Q, 2R, 2Q_T. */
+int acro_cost_derivatives(const AcroWeights* w, int64_t B, const double* x, const double* x_ref,
+                          const double* u, const double* u_ref, int terminal, double* l, double* grad_x,
+                          double* grad_u, void* stream);
+/* discretize_linearization(Ac, Bc, dt)  tg:161-164: Ad = I + dt Ac, Bd = dt Bc on [16][B], [8][B]. */
+int acro_discretize(int64_t B, const double* Ac, const double* Bc, double dt, double* Ad, double* Bd,
+                    void* stream);
+/* build_stage_lists(x_traj, u_traj, x_ref, u_ref, lambda_seq)  tg:166-181 (lambda_seq is ignored by the
+ * reference, tg:116-129): -> A [N-1][16][B], Bm [N-1][8][B], q [N-1][4][B], r [N-1][2][B], q_T [4][B].
+ * The quadratic blocks are the constants 2Q, 2R, S = 0 and 2Q_T. */
+int acro_stage_lists(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X,
+                     const double* U, const AcroRef* ref, double* A, double* Bm, double* q, double* r,
+                     double* q_T, void* stream);
+/* calculate_K_and_sigma(A_list, B_list, Q_list, R_list, S_list, q_list, r_list, Q_T_block, q_T)
+ * tg:183-216 on caller-supplied dense lists: A [T][16][B], Bm [T][8][B], Q [T][16][B], R [T][4][B],
+ * S_cross [T][8][B] (NULL = 0), q [T][4][B], r [T][2][B], Q_T [16][B], q_T [4][B]
+ * -> K [T][8][B], S [T][2][B], delta_J [B]. */
+int acro_riccati_lists(int64_t B, int T, const double* A, const double* Bm, const double* Q, const double* R,
+                       const double* S_cross, const double* q, const double* r, const double* Q_T,
+                       const double* q_T, double* K, double* S, double* delta_J, void* stream);
+/* build_stage_lists + calculate_K_and_sigma fused  tg:166-216:
+ * -> K [N-1][8][B], S [N-1][2][B], delta_J [B] (expected_reduction), sigma_norm [B] = max|sigma| */
+int acro_riccati_affine(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X,
+                        const double* U, const AcroRef* ref, double* K, double* S, double* delta_J,
+                        double* sigma_norm, void* stream);
+/* forward_closed_loop_update + total_cost for a set of G step sizes  tg:218-252.
+ * One rollout per (problem b, candidate g).  gammas: [G][B] if gammas_per_problem else [G].
+ * cost out [G][B].  Xn [G][N][4][B] and Un [G][N-1][2][B] may be NULL (cost only). */
+int acro_closed_loop_rollout_cost(const AcroParams* p, const AcroWeights* w, int64_t B, int N,
+                                  const double* X, const double* U, const double* K, const double* S,
+                                  const AcroRef* ref, int G, const double* gammas,
+                                  int gammas_per_problem, double* Xn, double* Un, double* cost,
+                                  void* stream);
+/* The Armijo test of tg:352-365 on precomputed candidate costs: first g (in order) with
+ * cost_cand[g][b] < cost_k[b] + c*gamma[g]*delta_J[b] (strict; NaN rejects) -> accepted [B]
+ * (int32, -1 = none). */
+int acro_armijo_select(int64_t B, int G, const double* cost_k, const double* delta_J,
+                       const double* gammas, int gammas_per_problem, const double* cost_cand,
+                       double c, int32_t* accepted, void* stream);
+/* newton_Algorithm  tg:298-398, one problem per thread, whole loop on the device.
+ * In/out: X [N][4][B], U [N-1][2][B] (current iterate; written by init), cost [B],
+ * iters [B] int32, status [B] int32.  x0 [4][B] is read when opts->init.
+ * Workspace: Xw, Uw same sizes as X, U.  Out: K, S of the last computed iteration
+ * (evaluated on the pre-update trajectory, as the reference returns them), delta_J [B],
+ * sigma_norm [B], gamma_acc [B] (last accepted step).
+ * Optional history (NULL to skip): hist_cost [(max_iters+1)][B], hist_sigma_norm
+ * [max_iters][B], hist_gamma [max_iters][B], hist_ntry [max_iters][B] int32. */
+int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewtonOpts* opts, int64_t B,
+                      int N, const double* x0, const AcroRef* ref, double* X, double* U, double* Xw,
+                      double* Uw, double* K, double* S, double* cost, double* delta_J,
+                      double* sigma_norm, double* gamma_acc, int32_t* iters, int32_t* status,
+                      double* hist_cost, double* hist_sigma_norm, double* hist_gamma,
+                      int32_t* hist_ntry, void* stream);
+/* The step-size sweep of plot_armijo_line_search  tg:257-264: P base iterates (X,U,K,S with
+ * batch size P) x S_n shared step sizes steps[S_n] -> cost [S_n][P]. */
+int acro_stepsize_sweep(const AcroParams* p, const AcroWeights* w, int64_t P, int N, const double* X,
+                        const double* U, const double* K, const double* S, const AcroRef* ref, int S_n,
+                        const double* steps, double* cost, void* stream);
+
+/* ---- T1-T5: trajectory_tracking.py ------------------------------------------------- */
+/* solve_LQR_tracking(x_opt, u_opt)  tt:170-203 with weights w->Q (Q_reg), w->R (R_reg) and
+ * P_T = 2 Q_reg.  traj = the trajectory linearised about (AcroRef layout; shared => B = 1
+ * problem and K is (N-1,2,4) row-major, per-problem => K [N-1][8][B]). */
+int acro_lqr_gains(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const AcroRef* traj,
+                   double* K, void* stream);
+/* simulate_tracking(x_opt, u_opt, K_reg, x0_perturbed)  tt:206-216.
+ * traj/K shared (K (N-1,2,4)) or per-problem (K [N-1][8][B]) following traj->per_problem.
+ * x0 [4][B] -> Xt [N][4][B], Ut [N-1][2][B]. */
+int acro_lqr_track(const AcroParams* p, int64_t B, int N, const AcroRef* traj, const double* K,
+                   const double* x0, double* Xt, double* Ut, void* stream);
+/* compute_P_inf(A, B, Q, R)  tt:144-165.  A [16][B], Bm [8][B], weights from w->Q, w->R
+ * (or per problem) -> P [16][B], n_iter [B] int32 (max_iter reached => n_iter = -max_iter). */
+int acro_p_inf(const AcroWeights* w, int64_t B, const double* A, const double* Bm, int max_iter,
+               double tol, double* P, int32_t* n_iter, void* stream);
+/* solver_mpc(x0, A_list, B_list, Q, R, Q_T, T_pred)  tt:73-140 restated as the
+ * equality-constrained LQ problem it is.  x0 [4][B]; window A_w [(T_pred-1)][16][B],
+ * B_w [(T_pred-1)][8][B]; terminal weight QT [16][B]; w->Q, w->R stage weights.
+ * -> U0 [2][B], X_opt [T_pred][4][B], U_opt [T_pred][2][B] (X_opt/U_opt may be NULL),
+ * K_ws [(T_pred-1)][8][B]: the gains of the sweep (out; required when X_opt/U_opt are asked for,
+ * else may be NULL). */
+int acro_mpc_solve(const AcroWeights* w, int64_t B, int T_pred, const double* x0, const double* A_w,
+                   const double* B_w, const double* QT, double* U0, double* X_opt, double* U_opt,
+                   double* K_ws, void* stream);
+/* solve_mpc_tracking(x0, x_ref, u_ref, T)  tt:8-69: T-1 receding-horizon solves per problem,
+ * each a (T_pred-1)-step Riccati sweep over the sliding window of the linearisation about
+ * the reference (padded with the linearisation about x_f, u_f), then one plant step.
+ * ref shared: the first-move gains are computed once per time step by one sweep each
+ * (K0 [(T-1)][8] workspace/out, row-major) and applied to every problem;
+ * ref per problem: every problem runs its own sweeps.  lin_ws is a workspace for the compact
+ * linearisation: [N-1][10] (shared) or [N-1][10][B] (per problem).
+ * x_f HOST [4], u_f HOST [2]  (tt:33-34).
+ * QT_inf: DEVICE terminal weight (from acro_p_inf), [16] or, if qt_per_problem, [16][B].
+ * -> Xr [T][4][B], Ur [T-1][2][B]; n_solves (HOST int64*, may be NULL) = Riccati sweeps run. */
+int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
+                   const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                   int qt_per_problem, const double* x0, double* K0, double* lin_ws, double* Xr,
+                   double* Ur, int64_t* n_solves, void* stream);
+
+/* ---- layout helpers (batch-major <-> structure-of-arrays) -------------------------- */
+/* src (B, T, C) row-major  ->  dst [T][C][B] */
+int acro_pack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream);
+/* src [T][C][B]  ->  dst (B, T, C) row-major */
+int acro_unpack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACRO_ABI_H */

@@ -35,13 +35,15 @@ class CallLog:
     """Records gamma of every forward_closed_loop_update call and every total_cost value."""
 
     def __init__(self):
-        self.gammas, self.costs = [], []
+        self.gammas, self.costs, self.u_new = [], [], []
         self._f, self._c = rtg.forward_closed_loop_update, rtg.total_cost
 
     def __enter__(self):
         def f(x, u, K, s, gamma=1.0):
             self.gammas.append(float(gamma))
-            return self._f(x, u, K, s, gamma=gamma)
+            out = self._f(x, u, K, s, gamma=gamma)
+            self.u_new.append(out[1].copy())
+            return out
 
         def c(*a, **k):
             v = self._c(*a, **k)
@@ -100,7 +102,13 @@ def run_newton(x0, x_ref, u_ref, max_iters, tol, gamma_0, keep=4):
         n_try.append(j - i)
         gam_acc.append(g[j - 1])
         i = j
-    return dict(x=x, u=u, K=np.array(K), sigma=np.array(sig), cost=np.array(h["cost"]),
+    acc_calls = np.cumsum(n_try) - 1
+    u_trajs = [np.zeros_like(u)] + [log.u_new[c] for c in acc_calls[:keep]]
+    # the iterate the returned K / sigma were computed on (tg:338 runs before the update at tg:384)
+    n_acc = len(h["cost"]) - 1
+    x_prev = h["x_trajs"][n_acc - 1]
+    u_prev = log.u_new[acc_calls[n_acc - 2]] if n_acc >= 2 else np.zeros_like(u)
+    return dict(u_trajs=np.array(u_trajs), x_prev=x_prev, u_prev=u_prev, x=x, u=u, K=np.array(K), sigma=np.array(sig), cost=np.array(h["cost"]),
                 sigma_norm=np.array(h["sigma_norm"]), x_trajs=np.array(h["x_trajs"][:keep + 1]),
                 sigmas=np.array([np.array(s) for s in h["sigmas"][:keep]]),
                 cand_gammas=np.array(log.gammas), cand_costs=np.array(log.costs[1:]),

@@ -1,0 +1,102 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/acro_abi.h declares, the ctypes
+binding covers them, and the host-side logic of the drop-in modules (argument checks, error behaviour)
+mirrors the reference.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "acro_abi.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(acro_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from gymnast_optimalcontrol_b200 import _abi
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libacro_b200.so does not export %s" % n
+    bound = set(_abi.SIGNATURES) | set(_abi.QUERIES)
+    assert set(names) == bound, (set(names) ^ bound)
+    assert b"sm_100a" in lib.acro_version.__call__.__self__.acro_version() if False else True
+    assert "sm_100a" in _abi.version()
+    assert _abi.launch_count() == 0
+
+
+def test_struct_layouts_match_header():
+    from gymnast_optimalcontrol_b200 import _abi
+    assert ctypes.sizeof(_abi.AcroParams) == 12 * 8 + 8
+    assert ctypes.sizeof(_abi.AcroWeights) == 36 * 8 + 3 * 8
+    assert ctypes.sizeof(_abi.AcroRef) == 24
+    assert ctypes.sizeof(_abi.AcroNewtonOpts) == 16 + 32
+
+
+def test_invalid_arguments_return_error_codes_without_a_gpu():
+    from gymnast_optimalcontrol_b200 import _abi
+    p = _abi.AcroParams()
+    rc = _abi.lib.acro_rk4_step(ctypes.byref(p), 0, None, None, None, None)
+    assert rc == _abi.E_INVALID
+    assert b"acro_rk4_step" in _abi.lib.acro_last_error_string()
+    with pytest.raises(_abi.AcroError):
+        _abi.call("acro_pack_soa", 0, 1, 4, None, None, None)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gymnast_optimalcontrol_b200 import dynamics
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dynamics.dynamics(np.zeros(4), np.zeros(2))
+
+
+def test_newton_argument_checks_mirror_reference():
+    """ValueError on incompatible u_ref length before anything else happens (trajectory_generation.py:305-306)."""
+    from gymnast_optimalcontrol_b200 import trajectory_generation as tg
+    with pytest.raises(ValueError, match="Incompatible dimensions"):
+        tg.newton_Algorithm(np.zeros(4), np.zeros((501, 4)), np.zeros((400, 2)), 3)
+    assert tg.N == 501 and tg.nx == 4 and tg.nu == 2 and tg.dt == 2e-2
+    assert np.array_equal(tg.Q, np.diag([130.0, 30.0, 0.0001, 0.0001]))
+    assert np.array_equal(tg.R, np.diag([1e-6, 1.5])) and np.array_equal(tg.Q_T, np.diag([130, 130.0, 1.0, 1.0]))
+
+
+def test_weights_must_be_symmetric():
+    from gymnast_optimalcontrol_b200 import batched as bt
+    Q = np.eye(4)
+    Q[0, 1] = 1.0
+    with pytest.raises(ValueError, match="symmetric"):
+        bt.Weights(Q, np.eye(2))
+
+
+def test_reference_builders_match_reference_shapes():
+    from gymnast_optimalcontrol_b200 import trajectory_generation as tg
+    t, x, u = tg.define_reference_piecewise(10.0, [0, 0, 0, 0], [0.1, -0.1, 0, 0], [0, 0], [0.5, 0.5])
+    assert x.shape == (501, 4) and u.shape == (501, 2) and t.shape == (501,)
+    assert np.all(x[:250] == 0) and np.all(x[250:, 0] == 0.1) and np.all(u[250:] == 0.5)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "newton_task1.npz"))
+    t2, x2, u2 = tg.define_reference_piecewise(10.0, g["x_e1"], g["x_e2"], g["u_e1"], g["u_e2"])
+    assert np.array_equal(x2, g["x_ref"]) and np.array_equal(u2, g["u_ref"]) and np.array_equal(t2, g["t_ref"])
+    xr, ur, tr = tg.get_fully_actuated_ref(os.path.join(ROOT, "tests", "golden", "fully_actuated_trajectory.npz"))
+    g2 = np.load(os.path.join(ROOT, "tests", "golden", "newton_task2.npz"))
+    assert np.array_equal(xr, g2["x_ref"]) and np.array_equal(ur, g2["u_ref"])
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gymnast_optimalcontrol_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), "%s mentions the oracle" % f

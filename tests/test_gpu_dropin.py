@@ -1,0 +1,152 @@
+"""The drop-in modules used the way main.py uses the reference (task_1..task_4 recipes), on the GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden, rel_err
+from oracle import acro_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from gymnast_optimalcontrol_b200 import dynamics as dyn
+    from gymnast_optimalcontrol_b200 import trajectory_generation as tg
+    from gymnast_optimalcontrol_b200 import trajectory_tracking as tt
+    return dyn, tg, tt
+
+
+def test_dynamics_single_and_batched(mods):
+    dyn, tg, tt = mods
+    g = golden("dyn_kat")
+    x, u = g["x"][0], g["u"][0]
+    out = dyn.dynamics(x, u)
+    assert isinstance(out, np.ndarray) and out.shape == (4,)
+    np.testing.assert_allclose(out, [0.30842243714633577, -0.21036198377515106, 0.34430441728616834, -0.34211929152559867],
+                               rtol=1e-12)
+    np.testing.assert_allclose(dyn.continuous_dynamics(x, u), [0.5, -0.7, -8.097062412610704, 18.791857037341483], rtol=1e-12)
+    A, B = dyn.Calculate_A_B_matrixes(x, u)
+    assert A.shape == (4, 4) and B.shape == (4, 2)
+    assert rel_err(A, g["A_c"][0]) < TOL and rel_err(B, g["B_c"][0]) < TOL
+    assert rel_err(dyn.dynamics(g["x"], g["u"]), g["step"]) < TOL
+    Ab, Bb = dyn.Calculate_A_B_matrixes(g["x"], g["u"])
+    assert rel_err(Ab, g["A_c"]) < TOL and rel_err(Bb, g["B_c"]) < TOL
+    xt = torch.from_numpy(g["x"]).cuda()
+    ut = torch.from_numpy(g["u"]).cuda()
+    o = dyn.dynamics(xt, ut)
+    assert o.is_cuda and rel_err(o.cpu().numpy(), g["step"]) < TOL
+    Ad, Bd = tg.discretize_linearization(A, B, dyn.dt)
+    assert rel_err(Ad, np.eye(4) + dyn.dt * g["A_c"][0]) < 1e-15 and rel_err(Bd, dyn.dt * g["B_c"][0]) < 1e-15
+    assert dyn.set_params(2).m1 == 2.0 and dyn.active_params().m1 == 1.0  # set_params does not rebind (dynamics.py:147)
+
+
+def test_task2_recipe(mods):
+    """main.py:55-71 with a short iteration cap; the pieces are exposed one by one like the reference's functions."""
+    dyn, tg, tt = mods
+    g = golden("newton_task2")
+    b = golden("newton_task2_blocks")
+    x_ref, u_ref, t_ref = tg.get_fully_actuated_ref(os.path.join(GOLDEN, "fully_actuated_trajectory.npz"))
+    x0 = np.array([0, 0, 0, 0])
+    x, u, K, sigma, hist = tg.newton_Algorithm(x0, x_ref, u_ref, max_iters=4, tol=1e-4, gamma_0=0.1, plot_armijo_iters=7,
+                                               return_history=True, verbose=False)
+    assert x.shape == (501, 4) and u.shape == (500, 2) and len(K) == 500 and K[0].shape == (2, 4) and sigma[0].shape == (2,)
+    assert rel_err(hist["cost"], g["cost"][:5]) < TOL and rel_err(hist["sigma_norm"], g["sigma_norm"][:4]) < TOL
+    assert rel_err(np.array(hist["x_trajs"]), g["x_trajs"][:5]) < TOL
+    assert rel_err(np.array(hist["sigmas"]), g["sigmas"][:4]) < TOL
+    # the stand-alone steps
+    u0 = np.zeros_like(u_ref)
+    xo = tg.simulate_open_loop(x0, u0)
+    assert rel_err(xo, b["x_open"]) < TOL
+    lam = tg.compute_costate_trajectory(xo, u0, x_ref, u_ref)
+    assert len(lam) == 501 and rel_err(np.array(lam), b["lam"]) < TOL
+    lists = tg.build_stage_lists(xo, u0, x_ref, u_ref, lam)
+    assert rel_err(np.array(lists[0]), b["A_list"]) < TOL and rel_err(np.array(lists[1]), b["B_list"]) < TOL
+    assert rel_err(np.array(lists[5]), b["q_list"]) < TOL and rel_err(np.array(lists[6]), b["r_list"]) < TOL
+    assert rel_err(lists[7], b["Q_T_block"]) == 0 and rel_err(lists[8], b["q_T"]) < TOL
+    K0, s0, dJ = tg.calculate_K_and_sigma(*lists)
+    assert rel_err(np.array(K0), b["K0"]) < TOL and rel_err(np.array(s0), b["sigma0"]) < TOL
+    assert abs(dJ - b["delta_J0"]) < TOL * abs(b["delta_J0"])
+    xn, un = tg.forward_closed_loop_update(xo, u0, K0, s0, gamma=0.1)
+    assert rel_err(xn, g["x_trajs"][1]) < TOL
+    c = tg.total_cost(xn, un, x_ref, u_ref, tg.Q, tg.R, tg.Q_T)
+    assert abs(c - g["cost"][1]) < TOL * g["cost"][1]
+    l, gx, gu, hx, hu = tg.derivatives_Cost(xo[3], x_ref[3], u0[3], u_ref[3], tg.Q, tg.R)
+    lo, gxo, guo, hxo, huo = O.derivatives_Cost(xo[3], x_ref[3], u0[3], u_ref[3], tg.Q, tg.R)
+    assert abs(l - lo) < TOL * max(1, abs(lo)) and rel_err(gx, gxo) < TOL and rel_err(gu, guo) < TOL
+    assert np.array_equal(hx, hxo) and np.array_equal(hu, huo)
+    lT, gT, hT = tg.derivatives_Cost(xo[-1], x_ref[-1], np.zeros(2), np.zeros(2), Q=None, R=None, Q_T=tg.Q_T, terminal=True)
+    lTo, gTo, hTo = O.derivatives_Cost(xo[-1], x_ref[-1], None, None, None, None, Q_T=tg.Q_T, terminal=True)
+    assert abs(lT - lTo) < TOL * max(1, abs(lTo)) and rel_err(gT, gTo) < TOL and np.array_equal(hT, hTo)
+    s = golden("sweep_iter0")
+    steps, costs = tg.armijo_sweep(xo, u0, K0, s0, x_ref, u_ref)
+    assert np.array_equal(steps, s["steps"]) and rel_err(costs, s["costs"]) < TOL
+
+
+def test_task1_recipe_length_mismatch_message(mods, capsys):
+    dyn, tg, tt = mods
+    g = golden("newton_task1")
+    x, u, K, s, h = tg.newton_Algorithm(g["x0"], g["x_ref"], g["u_ref"], max_iters=3, tol=1e-4, gamma_0=0.05)
+    assert "u_ref has same length as x_ref (501)" in capsys.readouterr().out  # tg:302
+    assert rel_err(h["cost"], g["cost"][:4]) < TOL and u.shape == (500, 2)
+
+
+def test_batched_newton_through_the_dropin(mods, fa_ref):
+    dyn, tg, tt = mods
+    x_ref, u_ref, _ = fa_ref
+    x0 = np.random.default_rng(1).uniform(-0.2, 0.2, (4096, 4))[:48]
+    x, u, K, s, h = tg.newton_Algorithm(x0, x_ref, u_ref, max_iters=6, tol=1e-4, gamma_0=0.1, verbose=False)
+    g = golden("newton_c2_rows")
+    assert x.shape == (48, 501, 4) and K.shape == (48, 500, 2, 4) and h["cost"].shape == (48, 7)
+    assert rel_err(x[1:4], g["x"]) < TOL and rel_err(K[1:4], g["K"]) < TOL and rel_err(h["cost"][1:4], g["cost"]) < TOL
+    # per-problem weights through keyword arguments
+    Qs = np.repeat(tg.Q[None], 48, 0)
+    Qs[5] = np.diag([50.0, 60.0, 0.1, 0.1])
+    x2, u2, K2, s2, h2 = tg.newton_Algorithm(x0, x_ref, u_ref, max_iters=3, tol=1e-4, gamma_0=0.1, verbose=False, Q=Qs)
+    xo, uo, Ko, so, ho = O.newton_Algorithm(x0[5], x_ref, u_ref, max_iters=3, tol=1e-4, gamma_0=0.1, Q=Qs[5])
+    assert rel_err(x2[5], xo) < TOL and rel_err(K2[5], Ko) < TOL
+    xo, uo, Ko, so, ho = O.newton_Algorithm(x0[6], x_ref, u_ref, max_iters=3, tol=1e-4, gamma_0=0.1)
+    assert rel_err(x2[6], xo) < TOL
+
+
+def test_task3_recipe(mods):
+    """main.py:99-119: LQR tracking with +0.2 / +0.3 on all states."""
+    dyn, tg, tt = mods
+    g = golden("lqr_tracking")
+    d = golden("acrobot_optimal_trajectory")
+    x_ref, u_ref, t_ref = d["x"], d["u"], d["t"]
+    for i, dist in enumerate((0.2, 0.3)):
+        xt, ut = tt.LQR_tracking(x_ref, u_ref, t_ref, x0_perturbed=x_ref[0].copy() + dist)
+        assert xt.shape == (501, 4) and ut.shape == (500, 2)
+        assert rel_err(xt, g["x_track"][i]) < TOL and rel_err(ut, g["u_track"][i]) < TOL
+    K = tt.solve_LQR_tracking(x_ref, u_ref)
+    assert len(K) == 500 and rel_err(np.array(K), g["K_reg"]) < TOL
+    xt, ut = tt.simulate_tracking(x_ref, u_ref, K, g["x0"][:20])
+    assert rel_err(xt, g["x_track"][:20]) < TOL
+    xt0, _ = tt.LQR_tracking(x_ref, u_ref, t_ref)
+    assert np.max(np.abs(xt0 - x_ref)) < 1e-9
+
+
+def test_task4_recipe(mods):
+    """main.py:122-145: MPC tracking with +0.1; compute_P_inf and solver_mpc stand-alone."""
+    dyn, tg, tt = mods
+    d = golden("acrobot_optimal_trajectory")
+    g = golden("p_inf")
+    x_ref, u_ref, t_ref = d["x"], d["u"], d["t"]
+    P = tt.compute_P_inf(g["A_f"], g["B_f"], g["Q"], g["R"])
+    assert rel_err(P, g["P_inf"]) < TOL
+    x0 = x_ref[0].copy() + 0.1
+    xr, ur = tt.solve_mpc_tracking(x0, x_ref, u_ref, len(t_ref))
+    xo, uo = O.solve_mpc_tracking(x0, x_ref, u_ref, 501)
+    assert xr.shape == (501, 4) and ur.shape == (500, 2)
+    assert rel_err(xr, xo) < TOL and rel_err(ur, uo) < TOL
+    assert abs(abs(ur[0, 1] - u_ref[0, 1]) - 0.80644713) < 1e-6  # figures/mpc/tracking_dx_0.1_err.png (~0.81)
+    Ad, Bd = O.linearize_discrete(x_ref[:-1], u_ref)
+    U0, X, U = tt.solver_mpc(x0 - x_ref[0], list(Ad[:75]), list(Bd[:75]), tt.Q_mpc, tt.R_mpc, P, 75, u_ref[:75])
+    U0o, Xo, Uo = O.solver_mpc_kkt(x0 - x_ref[0], list(Ad[:74]), list(Bd[:74]), O.Q_MPC, O.R_MPC, g["P_inf"], 75)
+    assert X.shape == (75, 4) and U.shape == (75, 2)
+    assert rel_err(U0, U0o) < 1e-7 and rel_err(X, Xo) < 1e-7 and rel_err(U, Uo) < 1e-7
+    assert rel_err(ur[0] - u_ref[0], U0) < TOL

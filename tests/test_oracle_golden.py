@@ -162,3 +162,25 @@ def test_mpc_riccati_equals_kkt():
         if t0 == 0:
             # figures/mpc/tracking_dx_0.1_err.png: initial control error ~0.81 (-0.80644713)
             assert abs(U0[1] + 0.80644713) < 1e-6
+
+
+def test_gain_conditioning(fa_ref):
+    """Evidence for the tolerance used on FREE-RUNNING gains: near convergence the Riccati sweep is ill-conditioned.
+    The same oracle code on iterates that differ by 1e-13 gives gains that differ by far more than 1e-9 |K|_inf,
+    while sigma stays within 1e-9 (hard parts)."""
+    g = golden("newton_task2")
+    x_ref, u_ref, _ = fa_ref
+
+    def ks(x, u):
+        Ad, Bd, q, r, QT2, qT = O.build_stage_lists(x, u, x_ref, u_ref)
+        return O.calculate_K_and_sigma(Ad, Bd, q, r, 2 * O.Q_NEWTON, 2 * O.R_NEWTON, QT2, qT)[:2]
+
+    rng = np.random.default_rng(0)
+    K0, S0 = ks(g["x"], g["u"])
+    worst = 0.0
+    for _ in range(3):
+        K1, S1 = ks(g["x"] + 1e-13 * rng.normal(size=g["x"].shape), g["u"] + 1e-13 * rng.normal(size=g["u"].shape))
+        worst = max(worst, rel_err(K1, K0))
+        assert rel_err(S1, S0) < 1e-9
+    assert np.abs(K0).max() > 400
+    assert 1e-10 < worst < 1e-6
