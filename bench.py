@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py - Newton iterations/s of the batched acrobot hot path (BASELINE.json metric) on N B200s.
+
+A "step" is one pass of the hot path over one batch: `--iters` regularised-Newton iterations (backward
+affine Riccati sweep + Armijo closed-loop rollouts, trajectory_generation.py:329-396) for each of the
+`--batch` independent swing-up problems of config 2 (B = 4096 randomised initial states, N = 501 time
+steps as shipped, gamma_0 = 0.1, weights of trajectory_generation.py:16-18), starting from the open-loop
+rollout (tol = 0: no early exit, every problem runs every iteration).
+
+    value   device-resident throughput: inputs already in HBM, CUDA events around K steps
+    e2e     the same through the drop-in trajectory_generation.newton_Algorithm with HOST (pinned) buffers:
+            per step H2D of x0 / x_ref / u_ref and D2H of x_traj, u_traj, K, sigma and the history
+    roofline / cpu_baseline / clocks: see DESIGN.md section "Measurement"
+
+Multi-GPU (torchrun): every rank solves its own 4096 problems (weak scaling, no collective on the hot
+path); one NCCL gather of the per-problem summary (cost, status, iterations) per step is inside the timed
+region.  `--impl reference` times the CPU oracle port (the reference is pure Python / NumPy and cannot
+travel to the GPU box) on rank 0's host cores.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_STEPS = 501
+FLOPS_FIXED, FLOPS_PER_TRY = 1114.0, 940.0  # per problem-step-iteration, FMA = 2, sin/cos = 40
+BYTES_STEP_ITER = 304.0                      # read x,u; write K,sigma; read x,u,K,sigma; write x+,u+
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2
+
+
+def load_reference_trajectory():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "fully_actuated_trajectory.npz"))
+    u_ref = np.zeros(d["u"].shape)
+    u_ref[:, 1] = 2.0 * d["u"][:, 1]  # trajectory_generation.py:511-518
+    return np.ascontiguousarray(d["x"]), u_ref
+
+
+def make_x0(batch, rank):
+    x0 = np.random.default_rng(1 + rank).uniform(-0.2, 0.2, (batch, 4))
+    if rank == 0:
+        x0[0] = 0.0  # problem 0 = task_2 of main.py, whose result the reference ships
+    return x0
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    x0, iters = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import acro_oracle as O
+    x_ref, u_ref = load_reference_trajectory()
+    t = time.perf_counter()
+    x, u, K, s, h = O.newton_Algorithm(x0, x_ref, u_ref, max_iters=iters, tol=0.0, gamma_0=0.1)
+    return time.perf_counter() - t, h["iters"], float(h["cost"][-1])
+
+
+def cpu_newton_rate(pool, cores, iters_per_problem, seed=0):
+    """`cores` problems of the workload, one per worker, `iters_per_problem` Newton iterations each."""
+    x0 = make_x0(4096, 0)[seed * cores:(seed + 1) * cores]
+    t = time.perf_counter()
+    res = pool.map(_cpu_worker, [(x0[i], iters_per_problem) for i in range(cores)])
+    wall = time.perf_counter() - t
+    done = sum(r[1] for r in res)
+    return done / wall, wall, done
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ipp = a.cpu_iters
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(min(a.warmup, 1)):
+            cpu_newton_rate(pool, cores, 1)
+        t0 = time.perf_counter()
+        done = 0
+        for s in range(a.steps):
+            r, wall, d = cpu_newton_rate(pool, cores, ipp, seed=s % 8)
+            done += d
+        total = time.perf_counter() - t0
+    value = done / total
+    sample = "%d problems of the 4096 (one per core) x %d Newton iterations per step" % (cores, ipp)
+    print(json.dumps({
+        "impl": "reference", "metric": "newton_iterations_per_sec", "value": value,
+        "unit": "Newton iterations/s (N=501 time steps each)", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, sample_note=sample),
+        "cpu_baseline": {"value": value, "unit": "Newton iterations/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "NumPy oracle port (oracle/acro_oracle.py), one problem per process like the reference's "
+                                 "per-problem Python loop; the reference itself is Python+SymPy and is not on this box"},
+        "e2e": {"value": value, "unit": "Newton iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(a, sample_note=None):
+    c = {"workload": "config 2: batched Newton+Armijo swing-up solves, B=%d problems per GPU from randomised initial states, "
+                     "N=501 (T=10 s, dt=0.02 as shipped), %d Newton iterations per step, gamma_0=0.1, tol=0 (no early exit)"
+                     % (a.batch, a.iters),
+         "batch_per_gpu": a.batch, "horizon_steps": N_STEPS - 1, "newton_iters_per_step": a.iters,
+         "l2": "working set 361 MB per GPU (X,U,Xw,Uw,K,S) > 126 MB L2, no flush needed"}
+    if sample_note:
+        c["cpu_sample"] = sample_note
+    return c
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def fp64_peak_tflops(bt, torch):
+    """DFMA-chain microbenchmark (acro_bench_fp64_peak): achievable FP64 pipe rate of this GPU."""
+    import ctypes as C
+    blocks, threads, iters = 148 * 8, 256, 20000
+    out = torch.empty(blocks * threads, dtype=torch.float64, device="cuda")
+    best = 0.0
+    for i in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        bt.call("acro_bench_fp64_peak", blocks, threads, iters, C.c_void_p(out.data_ptr()),
+                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        e1.record()
+        torch.cuda.synchronize()
+        if i:
+            best = max(best, blocks * threads * iters * 16.0 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def run_native(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from gymnast_optimalcontrol_b200 import _abi
+    from gymnast_optimalcontrol_b200 import batched as bt
+    from gymnast_optimalcontrol_b200 import trajectory_generation as tg
+
+    B, iters = a.batch, a.iters
+    x_ref, u_ref = load_reference_trajectory()
+    x0 = make_x0(B, rank)
+    ref = bt.make_ref(x_ref, u_ref)
+    w = bt.newton_weights()
+    x0d = bt.upload(np.ascontiguousarray(x0.T))
+    state = bt.newton_alloc(B, N_STEPS, iters, history=True)
+    summary_all = torch.empty(world, 3, B, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        state.initialised = False
+        bt.newton_solve(x0d, ref, max_iters=iters, tol=0.0, gamma_0=0.1, w=w, state=state)
+        if world > 1:  # the only collective: per-problem summary to every rank over NVLink
+            summ = torch.stack([state.cost, state.status.to(torch.float64), state.iters.to(torch.float64)])
+            dist.all_gather_into_tensor(summary_all.view(world * 3, B), summ)
+
+    # ---- device-resident throughput
+    for _ in range(a.warmup):
+        step_device()
+    barrier()
+    l0 = _abi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(a.steps):
+            step_device()
+        e1.record()
+        barrier()
+    launches = _abi.launch_count() - l0
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    done_iters = int(state.iters.sum().item())
+    ntry_mean = float(state.hist_ntry[:iters].double().mean().item())
+    cost_mean = float(state.cost.mean().item())
+
+    # ---- end to end through the drop-in with host buffers
+    x0_host = torch.from_numpy(x0).pin_memory()
+    xr_host = torch.from_numpy(x_ref).pin_memory()
+    ur_host = torch.from_numpy(u_ref).pin_memory()
+
+    def step_e2e():
+        out = tg.newton_Algorithm(x0_host, xr_host, ur_host, max_iters=iters, tol=0.0, gamma_0=0.1, verbose=False)
+        return out
+
+    for _ in range(max(1, min(a.warmup, 2))):
+        out = step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        out = step_e2e()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    h2d = x0_host.numel() * 8 + xr_host.numel() * 8 + ur_host.numel() * 8
+    d2h = sum(o.numel() * 8 for o in out[:4]) + sum(np.asarray(v).nbytes for k, v in out[4].items()
+                                                    if k in ("cost", "sigma_norm", "iters", "status", "n_try", "gamma"))
+    e2e_cost_mean = float(out[4]["cost"][:, -1].mean())
+
+    times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = float(times[0]), float(times[1])
+    total_iters = B * iters * a.steps * world
+    value = total_iters / t_dev
+    e2e_value = total_iters / t_e2e
+
+    if rank == 0:
+        peaks = measured_peaks()
+        fp64_meas = fp64_peak_tflops(_abi, torch)
+        flops_iter = (FLOPS_FIXED + FLOPS_PER_TRY * ntry_mean) * (N_STEPS - 1)
+        per_gpu_rate = value / world
+        ach_tflops = per_gpu_rate * flops_iter / 1e12
+        ach_gbs = per_gpu_rate * BYTES_STEP_ITER * (N_STEPS - 1) / 1e9
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roof = {"bound": "fp64", "achieved": ach_tflops, "peak": fp64_meas, "unit": "TFLOP/s", "frac": ach_tflops / fp64_meas,
+                "traffic": a.traffic_bytes,
+                "peak_source": "DFMA-chain microbenchmark (acro_bench_fp64_peak) run in this process; nominal %.1f" % FP64_NOMINAL_TFLOPS,
+                "frac_of_nominal": ach_tflops / FP64_NOMINAL_TFLOPS,
+                "kernel": "acro::k_newton<false,false>", "launch_ms": 1e3 * t_dev / max(launches, 1),
+                "algorithmic_flops_per_launch": flops_iter * B * iters, "algorithmic_bytes_per_launch": BYTES_STEP_ITER * (N_STEPS - 1) * B * iters,
+                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650"},
+                "note": "latency bound at B=4096: 128 warps on 592 SM sub-partitions; see DESIGN.md"}
+        cpu = None
+        if world == 1 and not a.no_cpu:
+            cores = os.cpu_count() or 1
+            with mp.get_context("fork").Pool(cores) as pool:
+                r, wall, d = cpu_newton_rate(pool, cores, a.cpu_iters)
+            cpu = {"value": r, "unit": "Newton iterations/s", "cores": cores, "kind": "port",
+                   "sample": "%d problems of the 4096 (one per core) x %d Newton iterations, %.1f s of wall time" % (cores, a.cpu_iters, wall)}
+        line = {
+            "metric": "newton_iterations_per_sec", "value": value, "unit": "Newton iterations/s (N=501 time steps each)",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(a),
+            "step_iters_per_sec": value * (N_STEPS - 1), "newton_iters_per_sec_10k_step_equivalent": value * (N_STEPS - 1) / 1e4,
+            "e2e": {"value": e2e_value, "unit": "Newton iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * t_e2e / a.steps, "api": "trajectory_generation.newton_Algorithm(x0[B,4] pinned host, x_ref, u_ref)"},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
+            "check": {"iterations_done_last_step_rank0": done_iters, "armijo_tries_mean": ntry_mean, "mean_final_cost": cost_mean,
+                      "e2e_mean_final_cost": e2e_cost_mean},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--iters", type=int, default=50, help="Newton iterations per problem per step")
+    ap.add_argument("--cpu-iters", type=int, default=40, help="Newton iterations per problem in the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes per launch from the ncu capture (profiles/)")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_native(a)
+
+
+if __name__ == "__main__":
+    main()

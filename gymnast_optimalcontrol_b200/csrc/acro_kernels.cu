@@ -1141,6 +1141,24 @@ __global__ void k_transpose(int64_t rows, int64_t cols, const double* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// FP64 pipe peak: 8 independent DFMA chains per thread (the roofline denominator bench.py
+// measures in the same run, since MEASURED_PEAKS.json has no FP64 entry).
+// ---------------------------------------------------------------------------------------
+__global__ void k_fp64_peak(double* __restrict__ out, int iters, double b, double c) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 1e-3 * (threadIdx.x + k);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  out[blockIdx.x * int64_t(blockDim.x) + threadIdx.x] = s;
+}
+
 }  // namespace acro
 
 // =========================================================================================
@@ -1489,6 +1507,13 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
     ACRO_LAUNCH_CHECK("acro_mpc_track/track");
     if (n_solves) *n_solves = int64_t(T - 1) * B;
   }
+  return ACRO_OK;
+}
+
+int acro_bench_fp64_peak(int blocks, int threads, int iters, double* out, void* stream) {
+  ACRO_REQUIRE(out && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0, "acro_bench_fp64_peak: bad argument");
+  k_fp64_peak<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters, 0.999999, 1e-7);
+  ACRO_LAUNCH_CHECK("acro_bench_fp64_peak");
   return ACRO_OK;
 }
 

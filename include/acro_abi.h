@@ -226,6 +226,12 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
                    int qt_per_problem, const double* x0, double* K0, double* lin_ws, double* Xr,
                    double* Ur, int64_t* n_solves, void* stream);
 
+/* ---- measurement helper ------------------------------------------------------------- */
+/* Runs blocks x threads threads, each doing iters x 8 independent dependent-chain DFMAs
+ * (16 flops per thread per iteration); out [blocks*threads].  Timed by bench.py to get the
+ * achievable FP64 pipe peak of the device it runs on. */
+int acro_bench_fp64_peak(int blocks, int threads, int iters, double* out, void* stream);
+
 /* ---- layout helpers (batch-major <-> structure-of-arrays) -------------------------- */
 /* src (B, T, C) row-major  ->  dst [T][C][B] */
 int acro_pack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream);
