@@ -301,26 +301,40 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
     }
   }
   double dJ = 0.0, sn = 0.0;
-  double x[4], u[2];
+  // operands of step t (state, input, reference) are loaded one iteration ahead, so no load result is
+  // consumed in the iteration that issued it (all loads of an iteration share scoreboard slots)
+  double x[4], u[2], xr[4], ur[2];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) x[c] = X[soa(N - 2, 4, c, ld, b)];
+  for (int c = 0; c < 4; ++c) {
+    x[c] = X[soa(N - 2, 4, c, ld, b)];
+    xr[c] = ref.X(N - 2, c);
+  }
 #pragma unroll
-  for (int c = 0; c < 2; ++c) u[c] = U[soa(N - 2, 2, c, ld, b)];
+  for (int c = 0; c < 2; ++c) {
+    u[c] = U[soa(N - 2, 2, c, ld, b)];
+    ur[c] = ref.U(N - 2, c);
+  }
   const QhQ2<WV<WPB>> Qh{w};
   for (int t = N - 2; t >= 0; --t) {
-    double nx[4] = {0, 0, 0, 0}, nu[2] = {0, 0};
-    if (t > 0) {  // prefetch step t-1
+    double nx[4] = {0, 0, 0, 0}, nu[2] = {0, 0}, nxr[4] = {0, 0, 0, 0}, nur[2] = {0, 0};
+    if (t > 0) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) nx[c] = X[soa(t - 1, 4, c, ld, b)];
+      for (int c = 0; c < 4; ++c) {
+        nx[c] = X[soa(t - 1, 4, c, ld, b)];
+        nxr[c] = ref.X(t - 1, c);
+      }
 #pragma unroll
-      for (int c = 0; c < 2; ++c) nu[c] = U[soa(t - 1, 2, c, ld, b)];
+      for (int c = 0; c < 2; ++c) {
+        nu[c] = U[soa(t - 1, 2, c, ld, b)];
+        nur[c] = ref.U(t - 1, c);
+      }
     }
     const LinD L = linearize_d(m, x, u[0], u[1]);
     double dx[4], du[2], q[4], r[2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) dx[c] = x[c] - ref.X(t, c);
+    for (int c = 0; c < 4; ++c) dx[c] = x[c] - xr[c];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) du[c] = u[c] - ref.U(t, c);
+    for (int c = 0; c < 2; ++c) du[c] = u[c] - ur[c];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       double s = w.Q2(i, 0) * dx[0];
@@ -341,9 +355,15 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
       sn = (a > sn || a != a) ? a : sn;  // NaN is sticky, like np.max(np.abs(sigma))
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) x[c] = nx[c];
+    for (int c = 0; c < 4; ++c) {
+      x[c] = nx[c];
+      xr[c] = nxr[c];
+    }
 #pragma unroll
-    for (int c = 0; c < 2; ++c) u[c] = nu[c];
+    for (int c = 0; c < 2; ++c) {
+      u[c] = nu[c];
+      ur[c] = nur[c];
+    }
   }
   dJ_out = dJ;
   sn_out = sn;
@@ -370,12 +390,17 @@ __global__ void k_riccati_affine(const __grid_constant__ Model m, const __grid_c
 // to column bo of leading dimension ldo of (Xn,Un) when STORE.
 // ---------------------------------------------------------------------------------------
 struct StepIn {
-  double x[4], u[2], k[8], s[2];
+  double x[4], u[2], k[8], s[2], xr[4], ur[2];
 };
+template <class REF>
 __device__ __forceinline__ StepIn load_step(const double* __restrict__ X, const double* __restrict__ U,
-                                            const double* __restrict__ K, const double* __restrict__ S, int t,
-                                            int64_t ld, int64_t b) {
+                                            const double* __restrict__ K, const double* __restrict__ S,
+                                            const REF& ref, int t, int64_t ld, int64_t b) {
   StepIn in;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) in.xr[c] = ref.X(t, c);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) in.ur[c] = ref.U(t, c);
 #pragma unroll
   for (int c = 0; c < 4; ++c) in.x[c] = X[soa(t, 4, c, ld, b)];
 #pragma unroll
@@ -397,10 +422,13 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
 #pragma unroll
   for (int c = 0; c < 4; ++c) xp[c] = X[soa(0, 4, c, ld, b)];
   double cost = 0.0;
-  StepIn in = load_step(X, U, K, S, 0, ld, b);
+  StepIn in = load_step(X, U, K, S, ref, 0, ld, b);
+  double xrT[4];  // terminal reference, loaded early
+#pragma unroll
+  for (int c = 0; c < 4; ++c) xrT[c] = ref.X(N - 1, c);
   for (int t = 0; t < N - 1; ++t) {
     StepIn nx = in;
-    if (t + 1 < N - 1) nx = load_step(X, U, K, S, t + 1, ld, b);
+    if (t + 1 < N - 1) nx = load_step(X, U, K, S, ref, t + 1, ld, b);
     double dx[4], up[2];
 #pragma unroll
     for (int c = 0; c < 4; ++c) dx[c] = xp[c] - in.x[c];
@@ -419,9 +447,9 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
     }
     double ex[4], eu[2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) ex[c] = xp[c] - ref.X(t, c);
+    for (int c = 0; c < 4; ++c) ex[c] = xp[c] - in.xr[c];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) eu[c] = up[c] - ref.U(t, c);
+    for (int c = 0; c < 2; ++c) eu[c] = up[c] - in.ur[c];
     cost += quad4(ex, [&](int i, int j) { return w.Q(i, j); });
     cost += quad2(eu, [&](int i, int j) { return w.R(i, j); });
     double xn[4];
@@ -434,7 +462,7 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     if (STORE) Xn[soa(N - 1, 4, c, ldo, bo)] = xp[c];
-    ex[c] = xp[c] - ref.X(N - 1, c);
+    ex[c] = xp[c] - xrT[c];
   }
   cost += quad4(ex, [&](int i, int j) { return w.QT(i, j); });
   return cost;
@@ -1145,6 +1173,19 @@ __global__ void k_transpose(int64_t rows, int64_t cols, const double* __restrict
 // FP64 pipe peak: 8 independent DFMA chains per thread (the roofline denominator bench.py
 // measures in the same run, since MEASURED_PEAKS.json has no FP64 entry).
 // ---------------------------------------------------------------------------------------
+// one dependent DFMA chain per thread: with one warp per block this measures the DFMA latency
+__global__ void k_fp64_chain(double* __restrict__ out, int iters, double b, double c, long long* __restrict__ cycles) {
+  double a = 1e-3 * threadIdx.x;
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a = fma(a, b, c);
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * int64_t(blockDim.x) + threadIdx.x] = a;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 __global__ void k_fp64_peak(double* __restrict__ out, int iters, double b, double c) {
   double a[8];
 #pragma unroll
@@ -1514,6 +1555,13 @@ int acro_bench_fp64_peak(int blocks, int threads, int iters, double* out, void* 
   ACRO_REQUIRE(out && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0, "acro_bench_fp64_peak: bad argument");
   k_fp64_peak<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters, 0.999999, 1e-7);
   ACRO_LAUNCH_CHECK("acro_bench_fp64_peak");
+  return ACRO_OK;
+}
+
+int acro_bench_fp64_chain(int blocks, int threads, int iters, double* out, long long* cycles, void* stream) {
+  ACRO_REQUIRE(out && cycles && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0, "acro_bench_fp64_chain: bad argument");
+  k_fp64_chain<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters, 0.999999, 1e-7, cycles);
+  ACRO_LAUNCH_CHECK("acro_bench_fp64_chain");
   return ACRO_OK;
 }
 
