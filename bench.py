@@ -197,6 +197,7 @@ def run_native(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gymnast_optimalcontrol_b200 import _abi
     from gymnast_optimalcontrol_b200 import batched as bt
+    from gymnast_optimalcontrol_b200 import sharding
     from gymnast_optimalcontrol_b200 import trajectory_generation as tg
 
     B, iters = a.batch, a.iters
@@ -206,7 +207,7 @@ def run_native(a):
     w = bt.newton_weights()
     x0d = bt.upload(np.ascontiguousarray(x0.T))
     state = bt.newton_alloc(B, N_STEPS, iters, history=True)
-    summary_all = torch.empty(world, 3, B, dtype=torch.float64, device="cuda") if world > 1 else None
+    gathered = {}
 
     def barrier():
         if world > 1:
@@ -216,9 +217,9 @@ def run_native(a):
     def step_device():
         state.initialised = False
         bt.newton_solve(x0d, ref, max_iters=iters, tol=0.0, gamma_0=0.1, w=w, state=state)
-        if world > 1:  # the only collective: per-problem summary to every rank over NVLink
-            summ = torch.stack([state.cost, state.status.to(torch.float64), state.iters.to(torch.float64)])
-            dist.all_gather_into_tensor(summary_all.view(world * 3, B), summ)
+        if world > 1:  # the only collective: the per-problem summary of every shard, over NCCL/NVLink
+            summ = sharding.pack_summary(state.cost, state.status, state.iters, state.gamma_acc, state.sigma_norm)
+            gathered["summary"] = sharding.gather_summary(summ, B * world)
 
     # ---- device-resident throughput
     for _ in range(a.warmup):
