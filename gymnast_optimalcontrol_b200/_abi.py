@@ -61,7 +61,7 @@ SIGNATURES = {
     "acro_mpc_track": [PP, PW, I64, I32, I32, I32, PR, C.POINTER(C.c_double), C.POINTER(C.c_double), P, I32, P, P, P,
                        P, P, C.POINTER(C.c_int64), P],
     "acro_bench_fp64_peak": [I32, I32, I32, P, P],
-    "acro_bench_fp64_chain": [I32, I32, I32, P, P, P],
+    "acro_bench_fp64_chain": [I32, I32, I32, I32, I32, P, P, P],
     "acro_pack_soa": [I64, I32, I32, P, P, P],
     "acro_unpack_soa": [I64, I32, I32, P, P, P],
 }

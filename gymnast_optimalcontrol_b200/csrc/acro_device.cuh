@@ -19,20 +19,89 @@ namespace acro {
 //   G   = [g1 sin(th1) + g2 sin(th1+th2) ; g2 sin(th1+th2)]
 struct Model {
   double a1, h, a3, g1, g2, f1, f2, dt, tau1;
+  double h2;    // 2 h
+  double det0;  // a1 a3 - a3^2 : det M = det0 - h^2 cos^2(th2)
+  double hsq;   // h^2
+  // sin/cos constants (see sincos2): they travel in the kernel-parameter constant bank so that they reach
+  // the DFMAs through uniform registers (LDCU.128, two constants per instruction) instead of being rebuilt
+  // from 32-bit immediates before every use.
+  double tc[16];
 };
+
+// 2/pi, -pi/2 split in two, 1.5*2^52, then the minimax coefficients of fdlibm's __kernel_sin / __kernel_cos
+// on [-pi/4, pi/4]:  sin r = r + r^3 (S1 + z (S2 + ... z S6)),  cos r = 1 - z/2 + z^2 (C1 + z (C2 + ... z C6)),  z = r^2
+#define ACRO_TRIG_CONSTANTS                                                                                  \
+  {6.36619772367581382433e-01, -1.57079632679489655800e+00, -6.12323399573676603587e-17, 6755399441055744.0, \
+   -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,                     \
+   2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,                      \
+   4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,                      \
+   -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11}
 
 struct Trig {
   double s1, c1, s2, c2, s12, c12;
 };
 
-__device__ __forceinline__ Trig trig_of(double th1, double th2) {
+// Largest |angle| the polynomial path handles: up to here round(x 2/pi) fits the low word of the 1.5*2^52
+// trick and the two-FMA Cody-Waite reduction (first FMA exact) leaves an error below 1e-24.
+#define ACRO_TRIG_FAST_MAX 1.0e9
+
+// sin and cos of two angles in lockstep (~1 ulp).  No branch: for |x| > ACRO_TRIG_FAST_MAX the result is
+// meaningless but finite, and callers that may see such angles check and redo with the library routine;
+// inf / nan propagate to nan like the library.
+__device__ __forceinline__ void sincos2(const Model& m, double xa, double xb, double& sa, double& ca, double& sb,
+                                        double& cb) {
+  const double qma = fma(xa, m.tc[0], m.tc[3]), qmb = fma(xb, m.tc[0], m.tc[3]);
+  const int ja = __double2loint(qma), jb = __double2loint(qmb);
+  const double qa = qma - m.tc[3], qb = qmb - m.tc[3];
+  double ra = fma(qa, m.tc[1], xa), rb = fma(qb, m.tc[1], xb);
+  ra = fma(qa, m.tc[2], ra);
+  rb = fma(qb, m.tc[2], rb);
+  const double za = ra * ra, zb = rb * rb;
+  double psa = fma(za, m.tc[9], m.tc[8]), psb = fma(zb, m.tc[9], m.tc[8]);
+  double pca = fma(za, m.tc[15], m.tc[14]), pcb = fma(zb, m.tc[15], m.tc[14]);
+#pragma unroll
+  for (int k = 3; k >= 0; --k) {
+    psa = fma(za, psa, m.tc[4 + k]);
+    psb = fma(zb, psb, m.tc[4 + k]);
+    pca = fma(za, pca, m.tc[10 + k]);
+    pcb = fma(zb, pcb, m.tc[10 + k]);
+  }
+  const double sra = fma(ra * za, psa, ra), srb = fma(rb * zb, psb, rb);
+  const double cra = fma(za * za, pca, fma(za, -0.5, 1.0)), crb = fma(zb * zb, pcb, fma(zb, -0.5, 1.0));
+  const double s0a = (ja & 1) ? cra : sra, c0a = (ja & 1) ? sra : cra;
+  const double s0b = (jb & 1) ? crb : srb, c0b = (jb & 1) ? srb : crb;
+  sa = (ja & 2) ? -s0a : s0a;
+  ca = ((ja + 1) & 2) ? -c0a : c0a;
+  sb = (jb & 2) ? -s0b : s0b;
+  cb = ((jb + 1) & 2) ? -c0b : c0b;
+}
+
+// FAST = true: polynomial path (caller guarantees or checks |angles| <= ACRO_TRIG_FAST_MAX);
+// FAST = false: CUDA library sincos (Payne-Hanek reduction for huge arguments).
+template <bool FAST>
+__device__ __forceinline__ Trig trig_of(const Model& m, double th1, double th2) {
   Trig t;
-  sincos(th1, &t.s1, &t.c1);
-  sincos(th2, &t.s2, &t.c2);
+  if (FAST) {
+    sincos2(m, th1, th2, t.s1, t.c1, t.s2, t.c2);
+  } else {
+    sincos(th1, &t.s1, &t.c1);
+    sincos(th2, &t.s2, &t.c2);
+  }
   // angle-addition instead of a third sincos: 4 flops, error ~2 ulp
   t.s12 = fma(t.s1, t.c2, t.c1 * t.s2);
   t.c12 = fma(t.c1, t.c2, -(t.s1 * t.s2));
   return t;
+}
+
+// 1/d for a normal, finite d: hardware approximation (about 20 bits) + two Newton steps, no special-case
+// branch.  Used for det M, which is bounded away from 0 and infinity by the physical parameters.
+__device__ __forceinline__ double rcp_nr(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
 }
 
 // Pieces of one evaluation of the equations of motion that the Jacobian reuses.
@@ -44,7 +113,7 @@ struct Eom {
 __device__ __forceinline__ Eom eom(const Model& m, const Trig& t, double w1, double w2, double u0,
                                    double u1) {
   Eom e;
-  e.M11 = fma(2.0 * m.h, t.c2, m.a1);
+  e.M11 = fma(m.h2, t.c2, m.a1);
   e.M12 = fma(m.h, t.c2, m.a3);
   e.M22 = m.a3;
   const double hs2 = m.h * t.s2;
@@ -54,17 +123,18 @@ __device__ __forceinline__ Eom eom(const Model& m, const Trig& t, double w1, dou
   // r1 = tau1 + h s2 w2 w1 + h s2 (w1+w2) w2 - f1 w1 - G1 ; r2 = u1 - h s2 w1^2 - f2 w2 - G2
   const double r1 = tau1 + hs2 * w2 * w1 + hs2 * (w1 + w2) * w2 - m.f1 * w1 - grav1;
   const double r2 = u1 - hs2 * w1 * w1 - m.f2 * w2 - grav2;
-  const double det = fma(e.M11, e.M22, -(e.M12 * e.M12));
-  e.inv_det = 1.0 / det;
+  // det M = M11 M22 - M12^2 = (a1 a3 - a3^2) - h^2 cos^2(th2): two dependent operations after cos(th2)
+  const double det = fma(-m.hsq, t.c2 * t.c2, m.det0);
+  e.inv_det = rcp_nr(det);
   e.dd1 = (e.M22 * r1 - e.M12 * r2) * e.inv_det;
   e.dd2 = (e.M11 * r2 - e.M12 * r1) * e.inv_det;
   return e;
 }
 
 // continuous_dynamics(xx, uu)  dynamics.py:197-213
-__device__ __forceinline__ void f_eval(const Model& m, const double x[4], double u0, double u1,
-                                       double f[4]) {
-  const Trig t = trig_of(x[0], x[1]);
+template <bool FAST>
+__device__ __forceinline__ void f_eval_t(const Model& m, const double x[4], double u0, double u1, double f[4]) {
+  const Trig t = trig_of<FAST>(m, x[0], x[1]);
   const Eom e = eom(m, t, x[2], x[3], u0, u1);
   f[0] = x[2];
   f[1] = x[3];
@@ -72,26 +142,50 @@ __device__ __forceinline__ void f_eval(const Model& m, const double x[4], double
   f[3] = e.dd2;
 }
 
-// dynamics(xx, uu): classic RK4, zero-order hold on u   dynamics.py:177-195
-__device__ __forceinline__ void rk4_step(const Model& m, const double x[4], double u0, double u1,
-                                         double xn[4]) {
+__device__ __forceinline__ bool angles_ok(double a, double b) {
+  return !(fmax(fabs(a), fabs(b)) > ACRO_TRIG_FAST_MAX);  // nan counts as ok: it propagates either way
+}
+
+__device__ __forceinline__ void f_eval(const Model& m, const double x[4], double u0, double u1, double f[4]) {
+  if (angles_ok(x[0], x[1]))
+    f_eval_t<true>(m, x, u0, u1, f);
+  else
+    f_eval_t<false>(m, x, u0, u1, f);
+}
+
+// dynamics(xx, uu): classic RK4, zero-order hold on u   dynamics.py:177-195.
+// Returns the largest |angle| any of the four stages saw.
+template <bool FAST>
+__device__ __forceinline__ double rk4_step_t(const Model& m, const double x[4], double u0, double u1, double xn[4]) {
   const double h = m.dt, hh = 0.5 * m.dt;
   double k1[4], k2[4], k3[4], k4[4], y[4];
-  f_eval(m, x, u0, u1, k1);
+  double amax = fmax(fabs(x[0]), fabs(x[1]));
+  f_eval_t<FAST>(m, x, u0, u1, k1);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = fma(hh, k1[i], x[i]);
-  f_eval(m, y, u0, u1, k2);
+  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  f_eval_t<FAST>(m, y, u0, u1, k2);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = fma(hh, k2[i], x[i]);
-  f_eval(m, y, u0, u1, k3);
+  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  f_eval_t<FAST>(m, y, u0, u1, k3);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = fma(h, k3[i], x[i]);
-  f_eval(m, y, u0, u1, k4);
+  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  f_eval_t<FAST>(m, y, u0, u1, k4);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const double s = k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i];
     xn[i] = x[i] + (h * s) * (1.0 / 6.0);
   }
+  return amax;
+}
+
+// One branch per step instead of one per sin/cos: run the polynomial path, and only if some stage angle
+// was beyond its range (a diverging rollout on its way to overflow) redo the step with the library routine.
+__device__ __forceinline__ void rk4_step(const Model& m, const double x[4], double u0, double u1, double xn[4]) {
+  const double amax = rk4_step_t<true>(m, x, u0, u1, xn);
+  if (amax > ACRO_TRIG_FAST_MAX) rk4_step_t<false>(m, x, u0, u1, xn);
 }
 
 // Lower two rows of the continuous Jacobians (dynamics.py:153-170, 217-226):
@@ -103,8 +197,9 @@ struct LinC {
   double bc1[2];
 };
 
-__device__ __forceinline__ LinC linearize_c(const Model& m, const double x[4], double u0, double u1) {
-  const Trig t = trig_of(x[0], x[1]);
+template <bool FAST>
+__device__ __forceinline__ LinC linearize_c_t(const Model& m, const double x[4], double u0, double u1) {
+  const Trig t = trig_of<FAST>(m, x[0], x[1]);
   const double w1 = x[2], w2 = x[3];
   const Eom e = eom(m, t, w1, w2, u0, u1);
   const double hs2 = m.h * t.s2, hc2 = m.h * t.c2;
@@ -131,6 +226,11 @@ __device__ __forceinline__ LinC linearize_c(const Model& m, const double x[4], d
   L.bc0[0] = act ? m.tau1 * e.M22 * e.inv_det : 0.0;
   L.bc0[1] = act ? -m.tau1 * e.M12 * e.inv_det : 0.0;
   return L;
+}
+
+__device__ __forceinline__ LinC linearize_c(const Model& m, const double x[4], double u0, double u1) {
+  if (angles_ok(x[0], x[1])) return linearize_c_t<true>(m, x, u0, u1);
+  return linearize_c_t<false>(m, x, u0, u1);
 }
 
 // Forward-Euler discretisation (tg:161-164) of the lower block:

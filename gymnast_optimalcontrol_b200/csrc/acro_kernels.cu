@@ -54,6 +54,11 @@ static Model make_model(const AcroParams& p) {
   m.f2 = p.f2;
   m.dt = p.dt;
   m.tau1 = p.actuated_tau1 ? 1.0 : 0.0;
+  m.h2 = 2.0 * m.h;
+  m.det0 = m.a1 * m.a3 - m.a3 * m.a3;
+  m.hsq = m.h * m.h;
+  const double tc[16] = ACRO_TRIG_CONSTANTS;
+  for (int i = 0; i < 16; ++i) m.tc[i] = tc[i];
   return m;
 }
 
@@ -1174,12 +1179,32 @@ __global__ void k_transpose(int64_t rows, int64_t cols, const double* __restrict
 // measures in the same run, since MEASURED_PEAKS.json has no FP64 entry).
 // ---------------------------------------------------------------------------------------
 // one dependent DFMA chain per thread: with one warp per block this measures the DFMA latency
-__global__ void k_fp64_chain(double* __restrict__ out, int iters, double b, double c, long long* __restrict__ cycles) {
-  double a = 1e-3 * threadIdx.x;
-  const long long t0 = clock64();
-  for (int i = 0; i < iters; i += 8) {
+// `chains` (1..8) independent chains per thread; only lanes < active_lanes of each warp work
+template <int CH>
+__device__ __forceinline__ double chain_body(int iters, double b, double c) {
+  double a[CH];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a = fma(a, b, c);
+  for (int k = 0; k < CH; ++k) a[k] = 1e-3 * (threadIdx.x + k);
+  for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int k = 0; k < CH; ++k) a[k] = fma(a[k], b, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) s += a[k];
+  return s;
+}
+__global__ void k_fp64_chain(double* __restrict__ out, int iters, double b, double c, long long* __restrict__ cycles,
+                             int chains, int active_lanes) {
+  double a = 0.0;
+  const long long t0 = clock64();
+  if ((threadIdx.x & 31) < active_lanes) {
+    if (chains == 1) a = chain_body<1>(iters, b, c);
+    else if (chains == 2) a = chain_body<2>(iters, b, c);
+    else if (chains == 4) a = chain_body<4>(iters, b, c);
+    else a = chain_body<8>(iters, b, c);
   }
   const long long t1 = clock64();
   out[blockIdx.x * int64_t(blockDim.x) + threadIdx.x] = a;
@@ -1558,9 +1583,10 @@ int acro_bench_fp64_peak(int blocks, int threads, int iters, double* out, void* 
   return ACRO_OK;
 }
 
-int acro_bench_fp64_chain(int blocks, int threads, int iters, double* out, long long* cycles, void* stream) {
+int acro_bench_fp64_chain(int blocks, int threads, int iters, int chains, int active_lanes, double* out,
+                          long long* cycles, void* stream) {
   ACRO_REQUIRE(out && cycles && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0, "acro_bench_fp64_chain: bad argument");
-  k_fp64_chain<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters, 0.999999, 1e-7, cycles);
+  k_fp64_chain<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters, 0.999999, 1e-7, cycles, chains, active_lanes);
   ACRO_LAUNCH_CHECK("acro_bench_fp64_chain");
   return ACRO_OK;
 }

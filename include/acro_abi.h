@@ -231,9 +231,11 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
  * (16 flops per thread per iteration); out [blocks*threads].  Timed by bench.py to get the
  * achievable FP64 pipe peak of the device it runs on. */
 int acro_bench_fp64_peak(int blocks, int threads, int iters, double* out, void* stream);
-/* One dependent DFMA chain of `iters` links per thread; cycles[blocks] (int64) = clock64 ticks of
- * thread 0 of each block.  cycles/iters with one warp per SM sub-partition = DFMA latency. */
-int acro_bench_fp64_chain(int blocks, int threads, int iters, double* out, long long* cycles, void* stream);
+/* `chains` (1, 2, 4 or 8) independent dependent-DFMA chains of `iters` links per thread, executed only by
+ * lanes < active_lanes of every warp; cycles[blocks] (int64) = clock64 ticks of thread 0 of each block.
+ * cycles/iters with one chain and one warp per SM sub-partition = DFMA latency. */
+int acro_bench_fp64_chain(int blocks, int threads, int iters, int chains, int active_lanes, double* out,
+                          long long* cycles, void* stream);
 
 /* ---- layout helpers (batch-major <-> structure-of-arrays) -------------------------- */
 /* src (B, T, C) row-major  ->  dst [T][C][B] */
