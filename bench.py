@@ -160,7 +160,7 @@ def workload_config(a, sample_note=None):
                      "N=501 (T=10 s, dt=0.02 as shipped), %d Newton iterations per step, gamma_0=0.1, tol=0 (no early exit)"
                      % (a.batch, a.iters),
          "batch_per_gpu": a.batch, "horizon_steps": N_STEPS - 1, "newton_iters_per_step": a.iters,
-         "l2": "working set 361 MB per GPU (X,U,Xw,Uw,K,S) > 126 MB L2, no flush needed"}
+         "l2": "working set 525 MB per GPU (X,U,Xw,Uw,lin,K,S) > 126 MB L2, no flush needed"}
     if sample_note:
         c["cpu_sample"] = sample_note
     return c

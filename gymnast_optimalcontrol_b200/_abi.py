@@ -52,7 +52,7 @@ SIGNATURES = {
     "acro_riccati_affine": [PP, PW, I64, I32, P, P, PR, P, P, P, P, P],
     "acro_closed_loop_rollout_cost": [PP, PW, I64, I32, P, P, P, P, PR, I32, P, I32, P, P, P, P],
     "acro_armijo_select": [I64, I32, P, P, P, I32, P, F64, P, P],
-    "acro_newton_solve": [PP, PW, PO, I64, I32, P, PR] + [P] * 16 + [P],
+    "acro_newton_solve": [PP, PW, PO, I64, I32, P, PR] + [P] * 17 + [P],
     "acro_stepsize_sweep": [PP, PW, I64, I32, P, P, P, P, PR, I32, P, P, P],
     "acro_lqr_gains": [PP, PW, I64, I32, PR, P, P],
     "acro_lqr_track": [PP, I64, I32, PR, P, P, P, P, P],
@@ -62,6 +62,7 @@ SIGNATURES = {
                        P, P, C.POINTER(C.c_int64), P],
     "acro_bench_fp64_peak": [I32, I32, I32, P, P],
     "acro_bench_fp64_chain": [I32, I32, I32, I32, I32, P, P, P],
+    "acro_transpose": [I64, I64, P, P, P],
     "acro_pack_soa": [I64, I32, I32, P, P, P],
     "acro_unpack_soa": [I64, I32, I32, P, P, P],
 }

@@ -60,7 +60,7 @@ def state_in(a, C):
 
 
 def traj_in(a, C):
-    """(T,C) or (B,T,C) (or a list of T arrays of shape (C,) / (r,c) with r*c = C) -> SoA (T,C,B), Kind"""
+    """(T,C) or (B,T,C) (or a list of T arrays of shape (C,) / (r,c) with r*c = C) -> Traj (tiled device layout), Kind"""
     if isinstance(a, (list, tuple)):
         a = np.asarray([np.asarray(v, dtype=np.float64).reshape(-1) for v in a])
     if isinstance(a, torch.Tensor):
@@ -73,14 +73,14 @@ def traj_in(a, C):
         d = d.reshape(*d.shape[:-2], C)
         nd -= 1
     if nd == 2:
-        return bt.pack_soa(d.reshape(1, *d.shape)), Kind(a, False)
+        return bt.Traj.from_batch_major(d.reshape(1, *d.shape)), Kind(a, False)
     if nd == 3:
-        return bt.pack_soa(d), Kind(a, True)
+        return bt.Traj.from_batch_major(d), Kind(a, True)
     raise ValueError("expected a trajectory of shape (T,%d) or (B,T,%d)" % (C, C))
 
 
 def out(t_soa, kind, tail=None, key="out"):
-    """SoA device tensor (C,B) / (T,C,B) -> caller's kind; tail reshapes the component axis (e.g. (2,4))."""
+    """Device point batch (C,B) or Traj -> caller's kind; tail reshapes the component axis (e.g. (2,4))."""
     t = bt.unpack_soa(t_soa)  # (B,C) / (B,T,C)
     if tail is not None:
         t = t.reshape(*t.shape[:-1], *tail)

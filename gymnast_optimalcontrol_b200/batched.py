@@ -1,11 +1,12 @@
 """Device-level API: torch CUDA tensors in the structure-of-arrays layout of include/acro_abi.h.
 
 Every function here is a thin wrapper that allocates outputs with torch and calls one C-ABI
-entry point of libacro_b200.so on torch's current stream.  Shapes (problem index last, so a
-contiguous tensor IS the SoA layout):
+entry point of libacro_b200.so on torch's current stream.
 
-    state batch (4, B)   input batch (2, B)   X (N, 4, B)   U (N-1, 2, B)
-    K (N-1, 8, B) (view as (N-1, 2, 4, B))    S (N-1, 2, B)
+    point batches   plain tensors, problem index last:  state (4, B), input (2, B), scalars (B,)
+    time-indexed    ``Traj`` objects: a tensor of shape (T, ntiles, C, 32) in the tiled layout
+                    A[t][tile][c][lane] of include/acro_abi.h plus the true batch size B
+                    (X: C=4, U: C=2, K: C=8 = 2x4 row-major, S: C=2)
 
 torch is used for device memory and streams only.  There is no CPU path: without a CUDA
 device these functions raise.
@@ -55,9 +56,54 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class Traj:
+    """A time-indexed batch array in the device layout A[t][tile][c][lane] (tile = b // 32, lane = b % 32)."""
+    __slots__ = ("data", "B")
+
+    def __init__(self, data, B):
+        if data.dim() != 4 or data.shape[3] != 32 or data.shape[1] != ntiles(B):
+            raise ValueError("expected shape (T, %d, C, 32) for B = %d, got %r" % (ntiles(B), B, tuple(data.shape)))
+        self.data, self.B = data, int(B)
+
+    T = property(lambda self: self.data.shape[0])
+    C = property(lambda self: self.data.shape[2])
+
+    @staticmethod
+    def empty(T, C, B):
+        return Traj(_empty(T, ntiles(B), C, 32), B)
+
+    @staticmethod
+    def zeros(T, C, B):
+        return Traj(torch.zeros(T, ntiles(B), C, 32, dtype=F64, device=device()), B)
+
+    @staticmethod
+    def from_batch_major(a):
+        """(B, T, C) CUDA tensor -> Traj (acro_pack_soa)."""
+        a = a.contiguous()
+        Bn, T, Cn = a.shape
+        out = Traj.empty(T, Cn, Bn)
+        call("acro_pack_soa", Bn, T, Cn, _p(a), _p(out), _stream())
+        return out
+
+    def batch_major(self):
+        """-> (B, T, C) CUDA tensor (acro_unpack_soa)."""
+        out = _empty(self.B, self.T, self.C)
+        call("acro_unpack_soa", self.B, self.T, self.C, _p(self), _p(out), _stream())
+        return out
+
+    def clone(self):
+        return Traj(self.data.clone(), self.B)
+
+
+def ntiles(B):
+    return (int(B) + 31) // 32
+
+
 def _p(t, dtype=F64):
     if t is None:
         return C.c_void_p(0)
+    if isinstance(t, Traj):
+        t = t.data
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
         raise TypeError("expected a contiguous CUDA %s tensor, got %r" % (dtype, type(t) if not isinstance(t, torch.Tensor)
                                                                           else (t.device, t.dtype, t.is_contiguous())))
@@ -108,15 +154,19 @@ def mpc_weights():
 
 
 class Ref:
-    """Reference trajectory: shared x (N,4), u (N-1,2) or per problem x (N,4,B), u (N-1,2,B)."""
+    """Reference trajectory: shared tensors x (N,4), u (N-1,2), or per problem Traj x (C=4), u (C=2)."""
 
     def __init__(self, x, u):
         self.x, self.u = x, u
-        self.per_problem = x.dim() == 3
-        self.N = x.shape[0]
-        if u.shape[0] != self.N - 1 or u.dim() != x.dim():
+        self.per_problem = isinstance(x, Traj)
+        if self.per_problem != isinstance(u, Traj):
+            raise ValueError("x_ref and u_ref must both be shared or both per problem")
+        self.N = x.T if self.per_problem else x.shape[0]
+        nu_ = u.T if self.per_problem else u.shape[0]
+        if nu_ != self.N - 1:
             raise ValueError("Incompatible dimensions: x_ref has %d states but u_ref has %d controls (expected %d)"
-                             % (self.N, u.shape[0], self.N - 1))
+                             % (self.N, nu_, self.N - 1))
+        self.B = x.B if self.per_problem else None
         s = AcroRef()
         s.x, s.u, s.per_problem = _p(x).value, _p(u).value, int(self.per_problem)
         self.struct = s
@@ -135,37 +185,35 @@ def upload(a):
 
 
 def make_ref(x_ref, u_ref):
-    return Ref(upload(x_ref), upload(u_ref))
+    """Shared (N,4)/(N-1,2) or batch-major per-problem (B,N,4)/(B,N-1,2) host or device arrays -> Ref."""
+    xd, ud = upload(x_ref), upload(u_ref)
+    if xd.dim() == 3:
+        return Ref(Traj.from_batch_major(xd), Traj.from_batch_major(ud))
+    return Ref(xd, ud)
 
 
 # ------------------------------------------------------------------------------------------
 # layout helpers
 # ------------------------------------------------------------------------------------------
 def pack_soa(a):
-    """(B, T, C) or (B, C) batch-major CUDA tensor -> (T, C, B) / (C, B)."""
+    """batch-major CUDA tensor (B, T, C) -> Traj;  (B, C) -> plain (C, B)."""
     a = a.contiguous()
-    if a.dim() == 2:
-        Bn, Cn = a.shape
-        out = _empty(Cn, Bn)
-        call("acro_pack_soa", Bn, 1, Cn, _p(a), _p(out), _stream())
-        return out
-    Bn, T, Cn = a.shape
-    out = _empty(T, Cn, Bn)
-    call("acro_pack_soa", Bn, T, Cn, _p(a), _p(out), _stream())
+    if a.dim() == 3:
+        return Traj.from_batch_major(a)
+    Bn, Cn = a.shape
+    out = _empty(Cn, Bn)
+    call("acro_transpose", Bn, Cn, _p(a), _p(out), _stream())
     return out
 
 
 def unpack_soa(a):
-    """(T, C, B) or (C, B) -> (B, T, C) / (B, C)."""
+    """Traj -> (B, T, C);  plain (C, B) -> (B, C)."""
+    if isinstance(a, Traj):
+        return a.batch_major()
     a = a.contiguous()
-    if a.dim() == 2:
-        Cn, Bn = a.shape
-        out = _empty(Bn, Cn)
-        call("acro_unpack_soa", Bn, 1, Cn, _p(a), _p(out), _stream())
-        return out
-    T, Cn, Bn = a.shape
-    out = _empty(Bn, T, Cn)
-    call("acro_unpack_soa", Bn, T, Cn, _p(a), _p(out), _stream())
+    Cn, Bn = a.shape
+    out = _empty(Bn, Cn)
+    call("acro_transpose", Cn, Bn, _p(a), _p(out), _stream())
     return out
 
 
@@ -196,46 +244,47 @@ def linearize(x, u, discrete=False, params=DEFAULT_PARAMS):
 # G1-G11
 # ------------------------------------------------------------------------------------------
 def rollout_open_loop(x0, U=None, N=None, params=DEFAULT_PARAMS):
+    """x0 (4,B), U Traj (C=2) or None (zeros, N given) -> X Traj"""
     Bn = x0.shape[1]
-    N = U.shape[0] + 1 if U is not None else N
-    X = _empty(N, 4, Bn)
+    N = U.T + 1 if U is not None else N
+    X = Traj.empty(N, 4, Bn)
     call("acro_rollout_open_loop", C.byref(params), Bn, N, _p(x0), _p(U), _p(X), _stream())
     return X
 
 
 def total_cost(X, U, ref, w):
-    N, _, Bn = X.shape
-    cost = _empty(Bn)
-    call("acro_total_cost", w.ref(), Bn, N, _p(X), _p(U), ref.ref(), _p(cost), _stream())
+    cost = _empty(X.B)
+    call("acro_total_cost", w.ref(), X.B, X.T, _p(X), _p(U), ref.ref(), _p(cost), _stream())
     return cost
 
 
 def costate(X, U, ref, w, params=DEFAULT_PARAMS):
-    N, _, Bn = X.shape
-    lam = torch.empty_like(X)
-    call("acro_costate", C.byref(params), w.ref(), Bn, N, _p(X), _p(U), ref.ref(), _p(lam), _stream())
+    lam = Traj.empty(X.T, 4, X.B)
+    call("acro_costate", C.byref(params), w.ref(), X.B, X.T, _p(X), _p(U), ref.ref(), _p(lam), _stream())
     return lam
 
 
 def riccati_affine(X, U, ref, w, params=DEFAULT_PARAMS):
-    """-> K (N-1,8,B), S (N-1,2,B), delta_J (B,), sigma_norm (B,)"""
-    N, _, Bn = X.shape
-    K, S, dJ, sn = _empty(N - 1, 8, Bn), _empty(N - 1, 2, Bn), _empty(Bn), _empty(Bn)
+    """-> K Traj (C=8), S Traj (C=2), delta_J (B,), sigma_norm (B,)"""
+    N, Bn = X.T, X.B
+    K, S, dJ, sn = Traj.empty(N - 1, 8, Bn), Traj.empty(N - 1, 2, Bn), _empty(Bn), _empty(Bn)
     call("acro_riccati_affine", C.byref(params), w.ref(), Bn, N, _p(X), _p(U), ref.ref(), _p(K), _p(S), _p(dJ), _p(sn),
          _stream())
     return K, S, dJ, sn
 
 
 def closed_loop_rollout_cost(X, U, K, S, ref, w, gammas, store=False, params=DEFAULT_PARAMS):
-    """gammas (G,) shared or (G,B) per problem -> cost (G,B) [, Xn (G,N,4,B), Un (G,N-1,2,B)]"""
-    N, _, Bn = X.shape
+    """gammas (G,) shared or (G,B) per problem -> cost (G,B) [, list of G Traj Xn, list of G Traj Un]"""
+    N, Bn = X.T, X.B
     G = gammas.shape[0]
     cost = _empty(G, Bn)
-    Xn = _empty(G, N, 4, Bn) if store else None
-    Un = _empty(G, N - 1, 2, Bn) if store else None
+    Xn = _empty(G, N, ntiles(Bn), 4, 32) if store else None
+    Un = _empty(G, N - 1, ntiles(Bn), 2, 32) if store else None
     call("acro_closed_loop_rollout_cost", C.byref(params), w.ref(), Bn, N, _p(X), _p(U), _p(K), _p(S), ref.ref(), G,
          _p(gammas), int(gammas.dim() == 2), _p(Xn), _p(Un), _p(cost), _stream())
-    return (cost, Xn, Un) if store else cost
+    if store:
+        return cost, [Traj(Xn[g], Bn) for g in range(G)], [Traj(Un[g], Bn) for g in range(G)]
+    return cost
 
 
 def armijo_select(cost_k, delta_J, gammas, cost_cand, c=0.5):
@@ -249,31 +298,32 @@ def armijo_select(cost_k, delta_J, gammas, cost_cand, c=0.5):
 @dataclass
 class NewtonState:
     """Everything acro_newton_solve reads and writes; keep it to resume a solve."""
-    X: torch.Tensor
-    U: torch.Tensor
-    K: torch.Tensor
-    S: torch.Tensor
+    X: Traj
+    U: Traj
+    K: Traj
+    S: Traj
     cost: torch.Tensor
     delta_J: torch.Tensor
     sigma_norm: torch.Tensor
     gamma_acc: torch.Tensor
     iters: torch.Tensor
     status: torch.Tensor
-    Xw: torch.Tensor
-    Uw: torch.Tensor
+    Xw: Traj
+    Uw: Traj
+    lin: Traj
     hist_cost: Optional[torch.Tensor] = None
     hist_sigma_norm: Optional[torch.Tensor] = None
     hist_gamma: Optional[torch.Tensor] = None
     hist_ntry: Optional[torch.Tensor] = None
-    x_trajs: List[torch.Tensor] = field(default_factory=list)
     initialised: bool = False
 
 
 def newton_alloc(Bn, N, max_iters, history=True):
     st = NewtonState(
-        X=_empty(N, 4, Bn), U=_empty(N - 1, 2, Bn), K=_empty(N - 1, 8, Bn), S=_empty(N - 1, 2, Bn), cost=_empty(Bn),
-        delta_J=_empty(Bn), sigma_norm=_empty(Bn), gamma_acc=_empty(Bn), iters=_empty(Bn, dtype=torch.int32),
-        status=_empty(Bn, dtype=torch.int32), Xw=_empty(N, 4, Bn), Uw=_empty(N - 1, 2, Bn))
+        X=Traj.empty(N, 4, Bn), U=Traj.empty(N - 1, 2, Bn), K=Traj.empty(N - 1, 8, Bn), S=Traj.empty(N - 1, 2, Bn),
+        cost=_empty(Bn), delta_J=_empty(Bn), sigma_norm=_empty(Bn), gamma_acc=_empty(Bn),
+        iters=_empty(Bn, dtype=torch.int32), status=_empty(Bn, dtype=torch.int32), Xw=Traj.empty(N, 4, Bn),
+        Uw=Traj.empty(N - 1, 2, Bn), lin=Traj.empty(N - 1, 10, Bn))
     if history:
         st.hist_cost = torch.full((max_iters + 1, Bn), float("nan"), dtype=F64, device=device())
         st.hist_sigma_norm = torch.full((max_iters, Bn), float("nan"), dtype=F64, device=device())
@@ -283,22 +333,26 @@ def newton_alloc(Bn, N, max_iters, history=True):
 
 
 def newton_solve(x0, ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, w=None, params=DEFAULT_PARAMS,
-                 state=None, chunk_iters=0, max_line_search=20, history=True):
+                 state=None, chunk_iters=0, max_line_search=20, history=True, warm_start_U=None):
     """newton_Algorithm (trajectory_generation.py:298-398) for a batch, x0 (4,B).
 
     One kernel launch runs the whole loop for every problem.  Pass the returned state back
-    (with chunk_iters) to continue a solve in pieces."""
+    (with chunk_iters) to continue a solve in pieces.  warm_start_U (Traj, C=2) replaces the reference's
+    u = 0 initial guess (tg:311)."""
     w = newton_weights() if w is None else w
     Bn = x0.shape[1]
     N = ref.N
     if state is None:
         state = newton_alloc(Bn, N, max_iters, history)
+    init = 0 if state.initialised else 1
+    if init and warm_start_U is not None:
+        state.U.data.copy_(warm_start_U.data)
+        init = 2
     o = AcroNewtonOpts(max_iters=int(max_iters), chunk_iters=int(chunk_iters), max_line_search=int(max_line_search),
-                       init=0 if state.initialised else 1, tol=float(tol), beta=float(beta), c=float(c),
-                       gamma_0=float(gamma_0))
+                       init=init, tol=float(tol), beta=float(beta), c=float(c), gamma_0=float(gamma_0))
     s = state
     call("acro_newton_solve", C.byref(params), w.ref(), C.byref(o), Bn, N, _p(x0), ref.ref(), _p(s.X), _p(s.U), _p(s.Xw),
-         _p(s.Uw), _p(s.K), _p(s.S), _p(s.cost), _p(s.delta_J), _p(s.sigma_norm), _p(s.gamma_acc),
+         _p(s.Uw), _p(s.lin), _p(s.K), _p(s.S), _p(s.cost), _p(s.delta_J), _p(s.sigma_norm), _p(s.gamma_acc),
          _p(s.iters, torch.int32), _p(s.status, torch.int32), _p(s.hist_cost), _p(s.hist_sigma_norm), _p(s.hist_gamma),
          _p(s.hist_ntry, torch.int32), _stream())
     s.initialised = True
@@ -307,10 +361,9 @@ def newton_solve(x0, ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, w=N
 
 def stepsize_sweep(X, U, K, S, ref, w, steps, params=DEFAULT_PARAMS):
     """P base iterates x len(steps) step sizes -> cost (S_n, P)"""
-    N, _, Pn = X.shape
     Sn = steps.shape[0]
-    cost = _empty(Sn, Pn)
-    call("acro_stepsize_sweep", C.byref(params), w.ref(), Pn, N, _p(X), _p(U), _p(K), _p(S), ref.ref(), Sn, _p(steps),
+    cost = _empty(Sn, X.B)
+    call("acro_stepsize_sweep", C.byref(params), w.ref(), X.B, X.T, _p(X), _p(U), _p(K), _p(S), ref.ref(), Sn, _p(steps),
          _p(cost), _stream())
     return cost
 
@@ -319,12 +372,12 @@ def stepsize_sweep(X, U, K, S, ref, w, steps, params=DEFAULT_PARAMS):
 # T1-T5
 # ------------------------------------------------------------------------------------------
 def lqr_gains(traj, w=None, params=DEFAULT_PARAMS):
-    """traj shared -> K (N-1, 8) [= (N-1,2,4) row-major]; per problem -> K (N-1, 8, B)"""
+    """traj shared -> K tensor (N-1, 8) [= (N-1,2,4) row-major]; per problem -> K Traj (C=8)"""
     w = lqr_weights() if w is None else w
     N = traj.N
     if traj.per_problem:
-        Bn = traj.x.shape[2]
-        K = _empty(N - 1, 8, Bn)
+        Bn = traj.B
+        K = Traj.empty(N - 1, 8, Bn)
     else:
         Bn = 1
         K = _empty(N - 1, 8)
@@ -333,9 +386,9 @@ def lqr_gains(traj, w=None, params=DEFAULT_PARAMS):
 
 
 def lqr_track(traj, K, x0, params=DEFAULT_PARAMS):
-    """-> Xt (N,4,B), Ut (N-1,2,B)"""
+    """-> Xt Traj (C=4), Ut Traj (C=2)"""
     N, Bn = traj.N, x0.shape[1]
-    Xt, Ut = _empty(N, 4, Bn), _empty(N - 1, 2, Bn)
+    Xt, Ut = Traj.empty(N, 4, Bn), Traj.empty(N - 1, 2, Bn)
     call("acro_lqr_track", C.byref(params), Bn, N, traj.ref(), _p(K), _p(x0), _p(Xt), _p(Ut), _stream())
     return Xt, Ut
 
@@ -349,12 +402,13 @@ def p_inf(A, Bm, w, max_iter=1000, tol=1e-6):
 
 
 def mpc_solve(x0, A_w, B_w, QT, w, T_pred, trajectories=True):
-    """x0 (4,B), A_w (T_pred-1,4,4,B), B_w (T_pred-1,4,2,B), QT (4,4,B) -> U0 (2,B), X_opt (T_pred,4,B), U_opt (T_pred,2,B)"""
+    """x0 (4,B), A_w Traj (T_pred-1, C=16), B_w Traj (T_pred-1, C=8), QT (4,4,B)
+    -> U0 (2,B), X_opt Traj (T_pred, 4), U_opt Traj (T_pred, 2), gains Traj (T_pred-1, 8)"""
     Bn = x0.shape[1]
     U0 = _empty(2, Bn)
-    Xo = _empty(T_pred, 4, Bn) if trajectories else None
-    Uo = _empty(T_pred, 2, Bn) if trajectories else None
-    Kws = _empty(max(T_pred - 1, 1), 8, Bn) if trajectories else None
+    Xo = Traj.empty(T_pred, 4, Bn) if trajectories else None
+    Uo = Traj.empty(T_pred, 2, Bn) if trajectories else None
+    Kws = Traj.empty(max(T_pred - 1, 1), 8, Bn) if trajectories else None
     call("acro_mpc_solve", w.ref(), Bn, int(T_pred), _p(x0), _p(A_w), _p(B_w), _p(QT), _p(U0), _p(Xo), _p(Uo), _p(Kws),
          _stream())
     return U0, Xo, Uo, Kws
@@ -362,15 +416,15 @@ def mpc_solve(x0, A_w, B_w, QT, w, T_pred, trajectories=True):
 
 def mpc_track(x0, ref, QT_inf, T=None, T_pred=75, w=None, x_f=(np.pi, 0.0, 0.0, 0.0), u_f=(0.0, 0.0),
               params=DEFAULT_PARAMS):
-    """solve_mpc_tracking for a batch.  QT_inf (4,4) shared or (4,4,B).  -> Xr (T,4,B), Ur (T-1,2,B), K0 or None, n_solves"""
+    """solve_mpc_tracking for a batch.  QT_inf (4,4) shared or (4,4,B).  -> Xr Traj, Ur Traj, K0 or None, n_solves"""
     w = mpc_weights() if w is None else w
     N, Bn = ref.N, x0.shape[1]
     T = N if T is None else T
     qt_pp = QT_inf.dim() == 3
     pp = ref.per_problem or w.per_problem or qt_pp
-    Xr, Ur = _empty(T, 4, Bn), _empty(T - 1, 2, Bn)
+    Xr, Ur = Traj.empty(T, 4, Bn), Traj.empty(T - 1, 2, Bn)
     K0 = None if pp else _empty(T - 1, 8)
-    lin = _empty(N - 1, 10, Bn) if pp else _empty(N - 1, 10)
+    lin = Traj.empty(N - 1, 10, Bn) if pp else _empty(N - 1, 10)
     xf = (C.c_double * 4)(*[float(v) for v in x_f])
     uf = (C.c_double * 2)(*[float(v) for v in u_f])
     ns = C.c_int64(0)
@@ -400,18 +454,19 @@ def discretize(Ac, Bc, dt=DT):
 
 
 def stage_lists(X, U, ref, w, params=DEFAULT_PARAMS):
-    """-> A (N-1,16,B), Bm (N-1,8,B), q (N-1,4,B), r (N-1,2,B), q_T (4,B)   (tg:166-181)"""
-    N, _, Bn = X.shape
-    A, Bm, q, r, qT = _empty(N - 1, 16, Bn), _empty(N - 1, 8, Bn), _empty(N - 1, 4, Bn), _empty(N - 1, 2, Bn), _empty(4, Bn)
+    """-> A Traj (C=16), Bm Traj (C=8), q Traj (C=4), r Traj (C=2), q_T (4,B)   (tg:166-181)"""
+    N, Bn = X.T, X.B
+    A, Bm, q, r = Traj.empty(N - 1, 16, Bn), Traj.empty(N - 1, 8, Bn), Traj.empty(N - 1, 4, Bn), Traj.empty(N - 1, 2, Bn)
+    qT = _empty(4, Bn)
     call("acro_stage_lists", C.byref(params), w.ref(), Bn, N, _p(X), _p(U), ref.ref(), _p(A), _p(Bm), _p(q), _p(r), _p(qT),
          _stream())
     return A, Bm, q, r, qT
 
 
 def riccati_lists(A, Bm, Q, R, q, r, Q_T, q_T, S_cross=None):
-    """Dense lists (T,16,B), (T,8,B), (T,16,B), (T,4,B), (T,4,B), (T,2,B), (16,B), (4,B) -> K, S, delta_J   (tg:183-216)"""
-    T, _, Bn = A.shape
-    K, S, dJ = _empty(T, 8, Bn), _empty(T, 2, Bn), _empty(Bn)
+    """Dense lists as Traj (C = 16, 8, 16, 4, 4, 2), Q_T (16,B), q_T (4,B) -> K Traj, S Traj, delta_J   (tg:183-216)"""
+    T, Bn = A.T, A.B
+    K, S, dJ = Traj.empty(T, 8, Bn), Traj.empty(T, 2, Bn), _empty(Bn)
     call("acro_riccati_lists", Bn, T, _p(A), _p(Bm), _p(Q), _p(R), _p(S_cross), _p(q), _p(r), _p(Q_T), _p(q_T), _p(K),
          _p(S), _p(dJ), _stream())
     return K, S, dJ

@@ -197,11 +197,8 @@ struct LinC {
   double bc1[2];
 };
 
-template <bool FAST>
-__device__ __forceinline__ LinC linearize_c_t(const Model& m, const double x[4], double u0, double u1) {
-  const Trig t = trig_of<FAST>(m, x[0], x[1]);
-  const double w1 = x[2], w2 = x[3];
-  const Eom e = eom(m, t, w1, w2, u0, u1);
+// Jacobian from the pieces of an evaluation of the equations of motion at the same (x, u)
+__device__ __forceinline__ LinC jacobian_from(const Model& m, const Trig& t, const Eom& e, double w1, double w2) {
   const double hs2 = m.h * t.s2, hc2 = m.h * t.c2;
   const double gc12 = m.g2 * t.c12;
   // columns of d rhs / d x_j  minus (dM/dx_j) qdd   (only theta2 changes M)
@@ -226,6 +223,13 @@ __device__ __forceinline__ LinC linearize_c_t(const Model& m, const double x[4],
   L.bc0[0] = act ? m.tau1 * e.M22 * e.inv_det : 0.0;
   L.bc0[1] = act ? -m.tau1 * e.M12 * e.inv_det : 0.0;
   return L;
+}
+
+template <bool FAST>
+__device__ __forceinline__ LinC linearize_c_t(const Model& m, const double x[4], double u0, double u1) {
+  const Trig t = trig_of<FAST>(m, x[0], x[1]);
+  const Eom e = eom(m, t, x[2], x[3], u0, u1);
+  return jacobian_from(m, t, e, x[2], x[3]);
 }
 
 __device__ __forceinline__ LinC linearize_c(const Model& m, const double x[4], double u0, double u1) {
@@ -255,6 +259,50 @@ __device__ __forceinline__ LinD discretize(const LinC& c, double dt) {
 
 __device__ __forceinline__ LinD linearize_d(const Model& m, const double x[4], double u0, double u1) {
   return discretize(linearize_c(m, x, u0, u1), m.dt);
+}
+
+// RK4 step that also returns the discrete linearisation about (x, u): the first stage already evaluates the
+// sines, cosines and accelerations the Jacobian needs, so the backward pass of the next Newton iteration can
+// read A_d, B_d instead of redoing two sincos and one evaluation of the equations of motion per step.
+template <bool FAST>
+__device__ __forceinline__ double rk4_step_lin_t(const Model& m, const double x[4], double u0, double u1,
+                                                 double xn[4], LinD& L) {
+  const double h = m.dt, hh = 0.5 * m.dt;
+  double k1[4], k2[4], k3[4], k4[4], y[4];
+  double amax = fmax(fabs(x[0]), fabs(x[1]));
+  {
+    const Trig t = trig_of<FAST>(m, x[0], x[1]);
+    const Eom e = eom(m, t, x[2], x[3], u0, u1);
+    k1[0] = x[2];
+    k1[1] = x[3];
+    k1[2] = e.dd1;
+    k1[3] = e.dd2;
+    L = discretize(jacobian_from(m, t, e, x[2], x[3]), m.dt);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = fma(hh, k1[i], x[i]);
+  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  f_eval_t<FAST>(m, y, u0, u1, k2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = fma(hh, k2[i], x[i]);
+  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  f_eval_t<FAST>(m, y, u0, u1, k3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = fma(h, k3[i], x[i]);
+  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  f_eval_t<FAST>(m, y, u0, u1, k4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double s = k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i];
+    xn[i] = x[i] + (h * s) * (1.0 / 6.0);
+  }
+  return amax;
+}
+
+__device__ __forceinline__ void rk4_step_lin(const Model& m, const double x[4], double u0, double u1, double xn[4],
+                                             LinD& L) {
+  const double amax = rk4_step_lin_t<true>(m, x, u0, u1, xn, L);
+  if (amax > ACRO_TRIG_FAST_MAX) rk4_step_lin_t<false>(m, x, u0, u1, xn, L);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/acro_abi.h"
@@ -281,15 +282,62 @@ __global__ void k_costate(const __grid_constant__ Model m, const __grid_constant
   }
 }
 
+// Pull the rows of step t of an SoA array towards L2 ahead of the register prefetch: every lane names its
+// own element, so one instruction covers the 256 B row of the warp; no register, no scoreboard.
+#define ACRO_PF_DIST 4
+template <int C>
+__device__ __forceinline__ void l2_prefetch_rows(const double* __restrict__ A, int t, int64_t ld, int64_t b) {
+  // the C rows of the warp's step are one block of 2*C lines of 128 B: lane l names line l
+  const int lane = int(b & 31);
+  if (lane < 2 * C) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + soa(t, C, 0, ld, b & ~int64_t(31)) + lane * 16));
+}
+
+// compact discrete linearisation lin[t][10][ld]: a[0][0..3], a[1][0..3], b[0], b[1]
+// ld == 0 means a single shared linearisation stored plainly as lin[t][10]
+__device__ __forceinline__ LinD load_lin(const double* __restrict__ lin, int t, int64_t ld, int64_t b) {
+  LinD L;
+  if (ld == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      L.a[0][j] = __ldg(lin + t * 10 + j);
+      L.a[1][j] = __ldg(lin + t * 10 + 4 + j);
+    }
+    L.b[0] = __ldg(lin + t * 10 + 8);
+    L.b[1] = __ldg(lin + t * 10 + 9);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      L.a[0][j] = lin[soa(t, 10, j, ld, b)];
+      L.a[1][j] = lin[soa(t, 10, 4 + j, ld, b)];
+    }
+    L.b[0] = lin[soa(t, 10, 8, ld, b)];
+    L.b[1] = lin[soa(t, 10, 9, ld, b)];
+  }
+  L.b0[0] = L.b0[1] = 0.0;
+  return L;
+}
+__device__ __forceinline__ void store_lin(double* __restrict__ lin, int t, int64_t ld, int64_t b, const LinD& L) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    lin[soa(t, 10, j, ld, b)] = L.a[0][j];
+    lin[soa(t, 10, 4 + j, ld, b)] = L.a[1][j];
+  }
+  lin[soa(t, 10, 8, ld, b)] = L.b[0];
+  lin[soa(t, 10, 9, ld, b)] = L.b[1];
+}
+
 // ---------------------------------------------------------------------------------------
 // G2+G4+G5+G6 fused backward pass: linearise, discretise, cost blocks, affine Riccati.
 // Reads X, U of one problem (column b of leading dimension ld), writes K, S.
 // ---------------------------------------------------------------------------------------
-template <bool WPB, bool RPB>
+// HAVE_LIN: the discrete linearisation about (X, U) was already written by the forward pass that produced
+// the iterate (rk4_step_lin), so this pass is pure Riccati algebra on loaded operands.
+template <bool WPB, bool RPB, bool HAVE_LIN>
 __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, const RefV<RPB>& ref, int N,
                                               const double* __restrict__ X, const double* __restrict__ U,
-                                              double* __restrict__ K, double* __restrict__ S, int64_t ld,
-                                              int64_t b, double& dJ_out, double& sn_out) {
+                                              const double* __restrict__ lin, double* __restrict__ K,
+                                              double* __restrict__ S, int64_t ld, int64_t b, double& dJ_out,
+                                              double& sn_out) {
   double P[10], p[4];
   {
     double dx[4];
@@ -320,9 +368,18 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
     ur[c] = ref.U(N - 2, c);
   }
   const QhQ2<WV<WPB>> Qh{w};
+  LinD Lc, Ln;
+  if (HAVE_LIN) Lc = load_lin(lin, N - 2, ld, b);
   for (int t = N - 2; t >= 0; --t) {
     double nx[4] = {0, 0, 0, 0}, nu[2] = {0, 0}, nxr[4] = {0, 0, 0, 0}, nur[2] = {0, 0};
+    if (HAVE_LIN) Ln = Lc;
+    if (t > ACRO_PF_DIST) {
+      l2_prefetch_rows<4>(X, t - 1 - ACRO_PF_DIST, ld, b);
+      l2_prefetch_rows<2>(U, t - 1 - ACRO_PF_DIST, ld, b);
+      if (HAVE_LIN) l2_prefetch_rows<10>(lin, t - 1 - ACRO_PF_DIST, ld, b);
+    }
     if (t > 0) {
+      if (HAVE_LIN) Ln = load_lin(lin, t - 1, ld, b);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         nx[c] = X[soa(t - 1, 4, c, ld, b)];
@@ -334,7 +391,7 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
         nur[c] = ref.U(t - 1, c);
       }
     }
-    const LinD L = linearize_d(m, x, u[0], u[1]);
+    const LinD L = HAVE_LIN ? Lc : linearize_d(m, x, u[0], u[1]);
     double dx[4], du[2], q[4], r[2];
 #pragma unroll
     for (int c = 0; c < 4; ++c) dx[c] = x[c] - xr[c];
@@ -369,6 +426,7 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
       u[c] = nu[c];
       ur[c] = nur[c];
     }
+    if (HAVE_LIN) Lc = Ln;
   }
   dJ_out = dJ;
   sn_out = sn;
@@ -384,7 +442,7 @@ __global__ void k_riccati_affine(const __grid_constant__ Model m, const __grid_c
   const WV<WPB> w(kw, B, b);
   const RefV<RPB> ref{rx, ru, B, b};
   double d, s;
-  backward_pass(m, w, ref, N, X, U, K, S, B, b, d, s);
+  backward_pass<WPB, RPB, false>(m, w, ref, N, X, U, nullptr, K, S, B, b, d, s);
   dJ[b] = d;
   sn[b] = s;
 }
@@ -417,12 +475,13 @@ __device__ __forceinline__ StepIn load_step(const double* __restrict__ X, const 
   return in;
 }
 
-template <bool WPB, bool RPB, bool STORE>
+template <bool WPB, bool RPB, bool STORE, bool LIN = false>
 __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w, const RefV<RPB>& ref, int N,
                                                const double* __restrict__ X, const double* __restrict__ U,
                                                const double* __restrict__ K, const double* __restrict__ S,
                                                int64_t ld, int64_t b, double gamma, double* __restrict__ Xn,
-                                               double* __restrict__ Un, int64_t ldo, int64_t bo) {
+                                               double* __restrict__ Un, int64_t ldo, int64_t bo,
+                                               double* __restrict__ lin_out = nullptr) {
   double xp[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) xp[c] = X[soa(0, 4, c, ld, b)];
@@ -433,6 +492,12 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
   for (int c = 0; c < 4; ++c) xrT[c] = ref.X(N - 1, c);
   for (int t = 0; t < N - 1; ++t) {
     StepIn nx = in;
+    if (t + 1 + ACRO_PF_DIST < N - 1) {
+      l2_prefetch_rows<4>(X, t + 1 + ACRO_PF_DIST, ld, b);
+      l2_prefetch_rows<2>(U, t + 1 + ACRO_PF_DIST, ld, b);
+      l2_prefetch_rows<8>(K, t + 1 + ACRO_PF_DIST, ld, b);
+      l2_prefetch_rows<2>(S, t + 1 + ACRO_PF_DIST, ld, b);
+    }
     if (t + 1 < N - 1) nx = load_step(X, U, K, S, ref, t + 1, ld, b);
     double dx[4], up[2];
 #pragma unroll
@@ -458,7 +523,13 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
     cost += quad4(ex, [&](int i, int j) { return w.Q(i, j); });
     cost += quad2(eu, [&](int i, int j) { return w.R(i, j); });
     double xn[4];
-    rk4_step(m, xp, up[0], up[1], xn);
+    if (LIN) {
+      LinD L;
+      rk4_step_lin(m, xp, up[0], up[1], xn, L);
+      store_lin(lin_out, t, ldo, bo, L);
+    } else {
+      rk4_step(m, xp, up[0], up[1], xn);
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c) xp[c] = xn[c];
     in = nx;
@@ -488,8 +559,8 @@ __global__ void k_closed_loop(const __grid_constant__ Model m, const __grid_cons
   const double gamma = gpp ? gammas[int64_t(g) * B + b] : gammas[g];
   double c;
   if (Xn)
-    c = forward_pass<WPB, RPB, true>(m, w, ref, N, X, U, K, S, B, b, gamma, Xn + int64_t(g) * N * 4 * B,
-                                     Un + int64_t(g) * (N - 1) * 2 * B, B, b);
+    c = forward_pass<WPB, RPB, true>(m, w, ref, N, X, U, K, S, B, b, gamma, Xn + int64_t(g) * N * 4 * padded(B),
+                                     Un + int64_t(g) * (N - 1) * 2 * padded(B), B, b);
   else
     c = forward_pass<WPB, RPB, false>(m, w, ref, N, X, U, K, S, B, b, gamma, nullptr, nullptr, B, b);
   cost[int64_t(g) * B + b] = c;
@@ -539,7 +610,7 @@ struct NewtonArgs {
   int N;
   const double* x0;
   const double *rx, *ru;
-  double *X, *U, *Xw, *Uw, *K, *S;
+  double *X, *U, *Xw, *Uw, *lin, *K, *S;
   double *cost, *dJ, *sn, *gacc;
   int32_t *iters, *status;
   double *h_cost, *h_sn, *h_gamma;
@@ -556,7 +627,8 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
   int it, st;
   double cost_k;
   if (a.o.init) {
-    // u = 0, x = simulate_open_loop(x0, u), cost_k = total_cost(...)   (tg:311-319)
+    // u = 0 (init = 1; init = 2 keeps the caller's U as a warm start), x = simulate_open_loop(x0, u),
+    // cost_k = total_cost(...)   (tg:311-319); the rollout also leaves the linearisation for iteration 0
     double x[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -564,10 +636,18 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
       a.X[soa(0, 4, c, B, b)] = x[c];
     }
     for (int t = 0; t < N - 1; ++t) {
-      a.U[soa(t, 2, 0, B, b)] = 0.0;
-      a.U[soa(t, 2, 1, B, b)] = 0.0;
+      double u0 = 0.0, u1 = 0.0;
+      if (a.o.init == 2) {
+        u0 = a.U[soa(t, 2, 0, B, b)];
+        u1 = a.U[soa(t, 2, 1, B, b)];
+      } else {
+        a.U[soa(t, 2, 0, B, b)] = 0.0;
+        a.U[soa(t, 2, 1, B, b)] = 0.0;
+      }
       double xn[4];
-      rk4_step(a.m, x, 0.0, 0.0, xn);
+      LinD L;
+      rk4_step_lin(a.m, x, u0, u1, xn, L);
+      store_lin(a.lin, t, B, b, L);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         x[c] = xn[c];
@@ -590,13 +670,13 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
     const double* Uc = cur ? a.Uw : a.U;
     double* Xo = cur ? a.X : a.Xw;
     double* Uo = cur ? a.U : a.Uw;
-    backward_pass(a.m, w, ref, N, Xc, Uc, a.K, a.S, B, b, dJ, sn);
+    backward_pass<WPB, RPB, true>(a.m, w, ref, N, Xc, Uc, a.lin, a.K, a.S, B, b, dJ, sn);
     if (a.h_sn) a.h_sn[int64_t(it) * B + b] = sn;
     double gamma = a.o.gamma_0, cn = 0.0;
     int tries = 0;
     bool ok = false;
     for (int i = 0; i < a.o.max_line_search; ++i) {
-      cn = forward_pass<WPB, RPB, true>(a.m, w, ref, N, Xc, Uc, a.K, a.S, B, b, gamma, Xo, Uo, B, b);
+      cn = forward_pass<WPB, RPB, true, true>(a.m, w, ref, N, Xc, Uc, a.K, a.S, B, b, gamma, Xo, Uo, B, b, a.lin);
       ++tries;
       // accept iff cost_new < cost_k + c*gamma*delta_J  (strict, NaN rejects)   tg:361
       const double thr = __dadd_rn(cost_k, __dmul_rn(__dmul_rn(a.o.c, gamma), dJ));
@@ -639,6 +719,10 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
   a.iters[b] = it;
   a.status[b] = st;
 }
+
+}  // namespace acro
+#include "acro_newton_ring.cuh"
+namespace acro {
 
 // ---------------------------------------------------------------------------------------
 // Stand-alone pieces of the Newton iteration for the drop-in functions that expose them:
@@ -995,13 +1079,17 @@ __global__ void k_lin_compact(const __grid_constant__ Model m, int64_t B, int N,
 #pragma unroll
   for (int c = 0; c < 4; ++c) x[c] = ref.X(t, c);
   const LinD L = linearize_d(m, x, ref.U(t, 0), ref.U(t, 1));
+  if (RPB) {
+    store_lin(lin, t, B, b, L);
+  } else {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    lin[soa(t, 10, j, nb, b)] = L.a[0][j];
-    lin[soa(t, 10, 4 + j, nb, b)] = L.a[1][j];
+    for (int j = 0; j < 4; ++j) {
+      lin[t * 10 + j] = L.a[0][j];
+      lin[t * 10 + 4 + j] = L.a[1][j];
+    }
+    lin[t * 10 + 8] = L.b[0];
+    lin[t * 10 + 9] = L.b[1];
   }
-  lin[soa(t, 10, 8, nb, b)] = L.b[0];
-  lin[soa(t, 10, 9, nb, b)] = L.b[1];
 }
 
 struct MpcArgs {
@@ -1018,19 +1106,6 @@ struct MpcArgs {
   double* K0;         // shared mode: [(T-1)][8]
   double *Xr, *Ur;
 };
-
-__device__ __forceinline__ LinD load_lin(const double* __restrict__ lin, int t, int64_t ld, int64_t b) {
-  LinD L;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    L.a[0][j] = lin[soa(t, 10, j, ld, b)];
-    L.a[1][j] = lin[soa(t, 10, 4 + j, ld, b)];
-  }
-  L.b[0] = lin[soa(t, 10, 8, ld, b)];
-  L.b[1] = lin[soa(t, 10, 9, ld, b)];
-  L.b0[0] = L.b0[1] = 0.0;
-  return L;
-}
 
 // One receding-horizon solve: (H-1)-step Riccati sweep over the window starting at time t
 // (tt:50, 80-117 with the window/padding of tt:64-67) -> first-move gain K_0 (2x4).
@@ -1069,7 +1144,7 @@ __global__ void k_mpc_gains_shared(const __grid_constant__ MpcArgs a) {
 #pragma unroll
     for (int j = i; j < 4; ++j) QT[sym(i, j)] = a.QT[i * 4 + j];
   double K[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  mpc_sweep(w, a.m.dt, a.lin, 1, 0, a.N - 1, Lf, QT, t, a.H, K);
+  mpc_sweep(w, a.m.dt, a.lin, 0, 0, a.N - 1, Lf, QT, t, a.H, K);
 #pragma unroll
   for (int e = 0; e < 8; ++e) a.K0[t * 8 + e] = K[e];
 }
@@ -1156,7 +1231,7 @@ __global__ void k_mpc_track_pp(const __grid_constant__ MpcArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// layout helpers: (B, T*C) row-major <-> [T*C][B], tiled through shared memory
+// layout helpers, tiled through shared memory
 // ---------------------------------------------------------------------------------------
 __global__ void k_transpose(int64_t rows, int64_t cols, const double* __restrict__ src, double* __restrict__ dst) {
   // src (rows, cols) row-major -> dst (cols, rows) row-major
@@ -1171,6 +1246,34 @@ __global__ void k_transpose(int64_t rows, int64_t cols, const double* __restrict
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int64_t c = c0 + i, r = r0 + threadIdx.x;
     if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+// batch-major (B, T, C) <-> tiled [t][tile][c][lane].  One block = one tile of 32 problems x 32 consecutive
+// flattened (t, c) indices; both sides are read / written 256 bytes at a time.  Padding lanes are zero-filled.
+template <bool PACK>
+__global__ void k_tiled(int64_t B, int T, int C, const double* __restrict__ src, double* __restrict__ dst) {
+  __shared__ double tile[32][33];
+  const int64_t TC = int64_t(T) * C, chunks = (TC + 31) / 32;
+  const int64_t k0 = (blockIdx.x % chunks) * 32LL, b0 = (blockIdx.x / chunks) * 32LL;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    if (PACK) {  // row i = problem b0+i, column = flattened index k0 + x
+      const int64_t b = b0 + i, k = k0 + threadIdx.x;
+      tile[i][threadIdx.x] = (b < B && k < TC) ? src[b * TC + k] : 0.0;
+    } else {     // row i = flattened index k0+i, column = lane x
+      const int64_t k = k0 + i, b = b0 + threadIdx.x;
+      if (k < TC) tile[i][threadIdx.x] = src[soa(int(k / C), C, int(k % C), B, b)];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    if (PACK) {
+      const int64_t k = k0 + i, b = b0 + threadIdx.x;
+      if (k < TC) dst[soa(int(k / C), C, int(k % C), B, b)] = tile[threadIdx.x][i];
+    } else {
+      const int64_t b = b0 + i, k = k0 + threadIdx.x;
+      if (b < B && k < TC) dst[b * TC + k] = tile[threadIdx.x][i];
+    }
   }
 }
 
@@ -1352,11 +1455,11 @@ int acro_armijo_select(int64_t B, int G, const double* cost_k, const double* del
 }
 
 int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewtonOpts* opts, int64_t B, int N,
-                      const double* x0, const AcroRef* ref, double* X, double* U, double* Xw, double* Uw, double* K,
-                      double* S, double* cost, double* delta_J, double* sigma_norm, double* gamma_acc,
+                      const double* x0, const AcroRef* ref, double* X, double* U, double* Xw, double* Uw,
+                      double* lin_ws, double* K, double* S, double* cost, double* delta_J, double* sigma_norm, double* gamma_acc,
                       int32_t* iters, int32_t* status, double* hist_cost, double* hist_sigma_norm,
                       double* hist_gamma, int32_t* hist_ntry, void* stream) {
-  ACRO_REQUIRE(p && w && opts && ref && ref->x && ref->u && X && U && Xw && Uw && K && S && cost && delta_J &&
+  ACRO_REQUIRE(p && w && opts && ref && ref->x && ref->u && X && U && Xw && Uw && lin_ws && K && S && cost && delta_J &&
                    sigma_norm && gamma_acc && iters && status && B > 0 && N >= 2,
                "acro_newton_solve: bad argument");
   ACRO_REQUIRE(!opts->init || x0, "acro_newton_solve: x0 required when init");
@@ -1375,6 +1478,7 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
   a.U = U;
   a.Xw = Xw;
   a.Uw = Uw;
+  a.lin = lin_ws;
   a.K = K;
   a.S = S;
   a.cost = cost;
@@ -1387,10 +1491,33 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
   a.h_sn = hist_sigma_norm;
   a.h_gamma = hist_gamma;
   a.h_ntry = hist_ntry;
-  const Cfg c = cfg_for(B);
-#define EXPR(WPB, RPB) k_newton<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(a)
-  DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+  // Small and medium batches are latency bound: warp-synchronous kernel with TMA-fed shared-memory rings
+  // (one warp per block).  Large batches hide latency with occupancy: one thread per problem, register prefetch.
+  const int64_t tiles = (B + 31) / 32;
+  const char* force = getenv("ACRO_NEWTON_KERNEL");
+  auto aligned = [](const void* q, uintptr_t al) { return (reinterpret_cast<uintptr_t>(q) % al) == 0; };
+  bool ring = tiles <= 148 * 6 && aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) &&
+              aligned(lin_ws, 128) && aligned(K, 128) && aligned(S, 128) &&
+              aligned(ref->x, ref->per_problem ? 128 : 32) && aligned(ref->u, ref->per_problem ? 128 : 16);
+  if (force && !strcmp(force, "ldg")) ring = false;
+  if (force && !strcmp(force, "ring")) {
+    ACRO_REQUIRE(aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) && aligned(lin_ws, 128) &&
+                     aligned(K, 128) && aligned(S, 128),
+                 "acro_newton_solve: ring kernel needs 128-byte aligned buffers");
+    ring = true;
+  }
+  if (ring) {
+#define EXPR(WPB, RPB)                                                                                   \
+  k_newton_ring<WPB, RPB><<<(unsigned)tiles, 32, ACRO_RING_D * stage_bytes<RPB>() + ACRO_RING_D * 8, \
+                            (cudaStream_t)stream>>>(a)
+    DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
 #undef EXPR
+  } else {
+    const Cfg c = cfg_for(B);
+#define EXPR(WPB, RPB) k_newton<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(a)
+    DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+  }
   ACRO_LAUNCH_CHECK("acro_newton_solve");
   return ACRO_OK;
 }
@@ -1591,20 +1718,32 @@ int acro_bench_fp64_chain(int blocks, int threads, int iters, int chains, int ac
   return ACRO_OK;
 }
 
-static int transpose(int64_t rows, int64_t cols, const double* src, double* dst, void* stream, const char* name) {
-  ACRO_REQUIRE(src && dst && rows > 0 && cols > 0, "acro_pack/unpack: bad argument");
+int acro_transpose(int64_t rows, int64_t cols, const double* src, double* dst, void* stream) {
+  ACRO_REQUIRE(src && dst && rows > 0 && cols > 0, "acro_transpose: bad argument");
   const int64_t tiles = ((cols + 31) / 32) * ((rows + 31) / 32);
-  ACRO_REQUIRE(tiles < (1LL << 31), "acro_pack/unpack: array too large for one call");
+  ACRO_REQUIRE(tiles < (1LL << 31), "acro_transpose: array too large for one call");
   k_transpose<<<(unsigned)tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(rows, cols, src, dst);
+  ACRO_LAUNCH_CHECK("acro_transpose");
+  return ACRO_OK;
+}
+
+static int tiled(bool pack, int64_t B, int T, int C, const double* src, double* dst, void* stream, const char* name) {
+  ACRO_REQUIRE(src && dst && B > 0 && T > 0 && C > 0, "acro_pack_soa/acro_unpack_soa: bad argument");
+  const int64_t blocks = ((int64_t(T) * C + 31) / 32) * ((B + 31) / 32);
+  ACRO_REQUIRE(blocks < (1LL << 31), "acro_pack_soa/acro_unpack_soa: array too large for one call");
+  if (pack)
+    k_tiled<true><<<(unsigned)blocks, dim3(32, 8), 0, (cudaStream_t)stream>>>(B, T, C, src, dst);
+  else
+    k_tiled<false><<<(unsigned)blocks, dim3(32, 8), 0, (cudaStream_t)stream>>>(B, T, C, src, dst);
   ACRO_LAUNCH_CHECK(name);
   return ACRO_OK;
 }
 
 int acro_pack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream) {
-  return transpose(B, int64_t(T) * C, src, dst, stream, "acro_pack_soa");
+  return tiled(true, B, T, C, src, dst, stream, "acro_pack_soa");
 }
 int acro_unpack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream) {
-  return transpose(int64_t(T) * C, B, src, dst, stream, "acro_unpack_soa");
+  return tiled(false, B, T, C, src, dst, stream, "acro_unpack_soa");
 }
 
 }  // extern "C"

@@ -64,23 +64,27 @@ struct QhQ {
   __device__ __forceinline__ double operator()(int i, int j) const { return w.Q(i, j); }
 };
 
-// Reference trajectory: shared (N,4)/(N-1,2) row-major, or per problem [t][c][B].
+// Reference trajectory: shared (N,4)/(N-1,2) row-major, or per problem in the tiled layout of soa().
 template <bool RPB>
 struct RefV {
   const double* x;
   const double* u;
   int64_t B, b;
   __device__ __forceinline__ double X(int t, int c) const {
-    return RPB ? x[(int64_t(t) * 4 + c) * B + b] : __ldg(x + t * 4 + c);
+    return RPB ? x[(int64_t(t) * ((B + 31) & ~int64_t(31)) + (b & ~int64_t(31))) * 4 + (c << 5) + (b & 31)] : __ldg(x + t * 4 + c);
   }
   __device__ __forceinline__ double U(int t, int c) const {
-    return RPB ? u[(int64_t(t) * 2 + c) * B + b] : __ldg(u + t * 2 + c);
+    return RPB ? u[(int64_t(t) * ((B + 31) & ~int64_t(31)) + (b & ~int64_t(31))) * 2 + (c << 5) + (b & 31)] : __ldg(u + t * 2 + c);
   }
 };
 
-// SoA trajectory element [t][c][ld] at column b
+// Time-indexed batch arrays are tiled structure-of-arrays: A[t][tile][c][lane], tile = b / 32, lane = b % 32,
+// with the batch padded to a multiple of 32.  The C rows of one time step of one warp are one contiguous block
+// of C * 256 bytes (component c at a compile-time offset c * 256), so a step is streamed with one pointer per
+// array, 128-byte aligned, and a whole step can be moved by one bulk copy.  `ld` is the batch size (padded here).
+__device__ __forceinline__ int64_t padded(int64_t ld) { return (ld + 31) & ~int64_t(31); }
 __device__ __forceinline__ int64_t soa(int t, int C, int c, int64_t ld, int64_t b) {
-  return (int64_t(t) * C + c) * ld + b;
+  return (int64_t(t) * padded(ld) + (b & ~int64_t(31))) * C + (c << 5) + (b & 31);
 }
 
 // (v' W v) for a symmetric 4x4 / 2x2 given through an accessor

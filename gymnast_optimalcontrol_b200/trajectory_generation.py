@@ -40,10 +40,7 @@ def _weights(Qm=None, Rm=None, QTm=None):
 
 def _ref(x_ref, u_ref):
     """Shared (N,4)/(N-1,2) or per-problem (B,N,4)/(B,N-1,2) reference."""
-    xd, ud = bt.upload(x_ref), bt.upload(u_ref)
-    if xd.dim() == 3:
-        return bt.Ref(bt.pack_soa(xd), bt.pack_soa(ud))
-    return bt.Ref(xd, ud)
+    return bt.make_ref(x_ref, u_ref)
 
 
 def define_reference_piecewise(T, x_e1, x_e2, u_e1, u_e2):
@@ -70,7 +67,7 @@ def simulate_open_loop(x0, u_traj):
     """trajectory_generation.py:74-87"""
     x, kind = _io.state_in(x0, nx)
     U, ku = _io.traj_in(u_traj, nu)
-    if U.shape[2] != x.shape[1]:
+    if U.B != x.shape[1]:
         raise ValueError("batch sizes of x0 and u_traj differ")
     kind.batched = kind.batched or ku.batched
     return _io.out(bt.rollout_open_loop(x, U, params=active_params()), kind)
@@ -120,7 +117,7 @@ def build_stage_lists(x_traj, u_traj, x_ref, u_ref, lambda_seq=None):
     A, Bm, q, r, qT = bt.stage_lists(X, U, _ref(x_ref, u_ref), _weights(), active_params())
     A_, B_ = _io.out(A, kind, tail=(4, 4), key="A"), _io.out(Bm, kind, tail=(4, 2), key="B")
     q_, r_, qT_ = _io.out(q, kind, key="q"), _io.out(r, kind, key="r"), _io.out(qT, kind, key="qT")
-    n = X.shape[0] - 1
+    n = X.T - 1
     Q_t, R_t, S_t, QTb = 2 * np.asarray(Q), 2 * np.asarray(R), np.zeros((nu, nx)), 2 * np.asarray(Q_T)
     if kind.batched:
         return A_, B_, Q_t, R_t, S_t, q_, r_, QTb, qT_
@@ -132,14 +129,14 @@ def calculate_K_and_sigma(A_list, B_list, Q_list, R_list, S_list, q_list, r_list
     Tn = len(A_list)
 
     def dev(lst, shape):
-        a = np.asarray([np.asarray(v, dtype=np.float64) for v in lst]).reshape(Tn, shape, 1)
-        return bt.upload(a)
+        a = np.asarray([np.asarray(v, dtype=np.float64) for v in lst]).reshape(1, Tn, shape)
+        return bt.Traj.from_batch_major(bt.upload(a))
 
     K, S, dJ = bt.riccati_lists(dev(A_list, 16), dev(B_list, 8), dev(Q_list, 16), dev(R_list, 4), dev(q_list, 4),
                                 dev(r_list, 2), bt.upload(np.asarray(Q_T_block, dtype=np.float64).reshape(16, 1)),
                                 bt.upload(np.asarray(q_T, dtype=np.float64).reshape(4, 1)), S_cross=dev(S_list, 8))
-    Kh = K.cpu().numpy()[:, :, 0].reshape(Tn, 2, 4)
-    Sh = S.cpu().numpy()[:, :, 0]
+    Kh = K.batch_major()[0].cpu().numpy().reshape(Tn, 2, 4)
+    Sh = S.batch_major()[0].cpu().numpy()
     return list(Kh), list(Sh), float(dJ[0].item())
 
 
@@ -150,7 +147,7 @@ def forward_closed_loop_update(x_traj, u_traj, K, sigma, gamma=1.0):
     Kd, _ = _io.traj_in(K, 8)
     Sd, _ = _io.traj_in(sigma, nu)
     g = np.atleast_1d(np.asarray(gamma.detach().cpu() if isinstance(gamma, torch.Tensor) else gamma, dtype=np.float64))
-    gam = bt.upload(np.broadcast_to(g, (X.shape[2],)).reshape(1, -1).copy())
+    gam = bt.upload(np.broadcast_to(g, (X.B,)).reshape(1, -1).copy())
     ref = bt.Ref(X.clone(), U.clone())  # the cost the kernel also produces is not part of this call: any reference will do
     _, Xn, Un = bt.closed_loop_rollout_cost(X, U, Kd, Sd, ref, _weights(), gam, store=True, params=active_params())
     return _io.out(Xn[0], kind, key="xn"), _io.out(Un[0], kind, key="un")

@@ -70,12 +70,12 @@ def solver_mpc(x0, A_list, B_list, Q, R, Q_T, T_pred, u_ref=None):
     """trajectory_tracking.py:73-140 -> (U0 (2,), X_opt (T_pred,4), U_opt (T_pred,2)).  u_ref is unused, as in
     the reference when test_constraints is False (tt:87)."""
     H = int(T_pred)
-    A = np.asarray([np.asarray(a, dtype=np.float64) for a in A_list[:H - 1]]).reshape(H - 1, 4, 4, 1)
-    Bm = np.asarray([np.asarray(b, dtype=np.float64) for b in B_list[:H - 1]]).reshape(H - 1, 4, 2, 1)
+    A = np.asarray([np.asarray(a, dtype=np.float64) for a in A_list[:H - 1]]).reshape(1, H - 1, 16)
+    Bm = np.asarray([np.asarray(b, dtype=np.float64) for b in B_list[:H - 1]]).reshape(1, H - 1, 8)
     x0d, kind = _io.state_in(np.asarray(x0, dtype=np.float64).reshape(4), nx)
-    U0, Xo, Uo, _ = bt.mpc_solve(x0d, bt.upload(A), bt.upload(Bm), bt.upload(np.asarray(Q_T, dtype=np.float64).reshape(4, 4, 1)),
-                                 bt.Weights(Q, R), H)
-    return U0.cpu().numpy()[:, 0], Xo.cpu().numpy()[:, :, 0], Uo.cpu().numpy()[:, :, 0]
+    U0, Xo, Uo, _ = bt.mpc_solve(x0d, bt.Traj.from_batch_major(bt.upload(A)), bt.Traj.from_batch_major(bt.upload(Bm)),
+                                 bt.upload(np.asarray(Q_T, dtype=np.float64).reshape(4, 4, 1)), bt.Weights(Q, R), H)
+    return U0.cpu().numpy()[:, 0], Xo.batch_major()[0].cpu().numpy(), Uo.batch_major()[0].cpu().numpy()
 
 
 def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return_info=False):

@@ -14,14 +14,21 @@
  *    error string (acro_last_error_string).
  *  - All array pointers are caller-owned DEVICE pointers to FP64 (or int32 where stated)
  *    unless a parameter is documented as HOST.  The library allocates nothing.
- *  - Batch layout is structure-of-arrays with the problem index fastest:
+ *  - Point batches are structure-of-arrays with the problem index fastest:
  *        state batch      x[c][b]            c in 0..3            -> x[c*B + b]
  *        input batch      u[c][b]            c in 0..1
- *        state trajectory X[t][c][b]         t in 0..N-1          -> X[(t*4 + c)*B + b]
- *        input trajectory U[t][c][b]         t in 0..N-2
- *        gains            K[t][i*4+j][b]     K_t is 2x4 row-major
- *        feed-forward     S[t][i][b]         sigma_t, 2 entries
- *    so that the 32 problems of a warp touch 256 contiguous bytes per component per step.
+ *        per-problem scalars, int32 flags    v[b]
+ *    TIME-INDEXED batch arrays (trajectories, gains, ...) are TILED structure-of-arrays,
+ *        A[t][tile][c][lane],   tile = b / 32, lane = b % 32,   Bp = 32*ceil(B/32)
+ *        element (t, c, b)  ->  A[(t*Bp + 32*tile)*C + 32*c + lane]
+ *    so the C rows of one time step of one warp are ONE contiguous, 128-byte aligned block of
+ *    C*256 bytes (component c at the constant offset c*256): coalesced, vectorisable, and
+ *    movable by a single bulk copy.  Buffers hold T*Bp*C doubles; padding lanes are never read
+ *    for results.  In this notation:
+ *        state trajectory X[N][4]      input trajectory U[N-1][2]
+ *        gains            K[N-1][8]    (K_t is 2x4 row-major, component i*4+j)
+ *        feed-forward     S[N-1][2]    (sigma_t)
+ *    acro_pack_soa / acro_unpack_soa convert from / to batch-major (B, T, C) arrays.
  *  - "Shared" reference data (one trajectory for the whole batch) is plain row-major
  *    [t][c], i.e. exactly the NumPy arrays of the reference: x_ref (N,4), u_ref (N-1,2),
  *    K_reg (N-1,2,4).
@@ -89,7 +96,9 @@ typedef struct AcroNewtonOpts {
   int32_t chunk_iters;  /* at most this many iterations in THIS call (0 = no limit) */
   int32_t max_line_search; /* 20 in the reference (tg:345) */
   int32_t init;         /* 1: start from u = 0, roll out from x0, compute the initial cost
-                           (tg:311-319); 0: resume from X, U, cost, iters, status */
+                           (tg:311-319); 2: the same but keep the caller's U as the initial inputs
+                           (warm start); 0: resume - X, U, lin_ws, cost, delta_J, sigma_norm,
+                           gamma_acc, iters, status must be what the previous call left */
   double tol;           /* tg:394 */
   double beta;          /* tg:365 */
   double c;             /* tg:361 */
@@ -170,14 +179,16 @@ int acro_armijo_select(int64_t B, int G, const double* cost_k, const double* del
 /* newton_Algorithm  tg:298-398, one problem per thread, whole loop on the device.
  * In/out: X [N][4][B], U [N-1][2][B] (current iterate; written by init), cost [B],
  * iters [B] int32, status [B] int32.  x0 [4][B] is read when opts->init.
- * Workspace: Xw, Uw same sizes as X, U.  Out: K, S of the last computed iteration
+ * Workspace: Xw, Uw same sizes as X, U; lin_ws [N-1][10][B] holds the discrete linearisation about the
+ * current iterate (written by the rollouts, read by the next backward pass; part of the state to keep when
+ * resuming).  Out: K, S of the last computed iteration
  * (evaluated on the pre-update trajectory, as the reference returns them), delta_J [B],
  * sigma_norm [B], gamma_acc [B] (last accepted step).
  * Optional history (NULL to skip): hist_cost [(max_iters+1)][B], hist_sigma_norm
  * [max_iters][B], hist_gamma [max_iters][B], hist_ntry [max_iters][B] int32. */
 int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewtonOpts* opts, int64_t B,
                       int N, const double* x0, const AcroRef* ref, double* X, double* U, double* Xw,
-                      double* Uw, double* K, double* S, double* cost, double* delta_J,
+                      double* Uw, double* lin_ws, double* K, double* S, double* cost, double* delta_J,
                       double* sigma_norm, double* gamma_acc, int32_t* iters, int32_t* status,
                       double* hist_cost, double* hist_sigma_norm, double* hist_gamma,
                       int32_t* hist_ntry, void* stream);
@@ -237,11 +248,13 @@ int acro_bench_fp64_peak(int blocks, int threads, int iters, double* out, void* 
 int acro_bench_fp64_chain(int blocks, int threads, int iters, int chains, int active_lanes, double* out,
                           long long* cycles, void* stream);
 
-/* ---- layout helpers (batch-major <-> structure-of-arrays) -------------------------- */
-/* src (B, T, C) row-major  ->  dst [T][C][B] */
+/* ---- layout helpers ------------------------------------------------------------------ */
+/* batch-major src (B, T, C) row-major  ->  tiled dst [t][tile][c][lane] (padding lanes zero-filled) */
 int acro_pack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream);
-/* src [T][C][B]  ->  dst (B, T, C) row-major */
+/* tiled src [t][tile][c][lane]  ->  batch-major dst (B, T, C) row-major */
 int acro_unpack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream);
+/* plain matrix transpose src (rows, cols) -> dst (cols, rows): state batches (B, 4) <-> [4][B] */
+int acro_transpose(int64_t rows, int64_t cols, const double* src, double* dst, void* stream);
 
 #ifdef __cplusplus
 }

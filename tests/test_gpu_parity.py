@@ -26,15 +26,27 @@ def dev(a):
 
 
 def soa(a):
-    """batch-major (B,C) / (B,T,C) numpy -> SoA cuda (C,B) / (T,C,B)"""
+    """batch-major numpy (B,C) -> plain device (C,B);  (B,T,C) -> Traj in the tiled layout A[t][tile][c][lane].
+    The tiling is done here in NumPy, independently of the library's pack kernel."""
+    from gymnast_optimalcontrol_b200.batched import Traj
     a = np.asarray(a, dtype=np.float64)
-    return dev(a.T if a.ndim == 2 else np.transpose(a, (1, 2, 0)))
+    if a.ndim == 2:
+        return dev(a.T)
+    Bn, T, Cn = a.shape
+    nt = (Bn + 31) // 32
+    pad = np.zeros((nt * 32, T, Cn))
+    pad[:Bn] = a
+    return Traj(dev(np.transpose(pad.reshape(nt, 32, T, Cn), (2, 0, 3, 1))), Bn)
 
 
 def aos(t):
-    """SoA cuda -> batch-major numpy"""
-    a = t.detach().cpu().numpy()
-    return a.T if a.ndim == 2 else np.transpose(a, (2, 0, 1))
+    """plain device (C,B) -> numpy (B,C);  Traj -> numpy (B,T,C)  (un-tiled in NumPy)"""
+    from gymnast_optimalcontrol_b200.batched import Traj
+    if isinstance(t, Traj):
+        a = t.data.detach().cpu().numpy()  # (T, nt, C, 32)
+        T, nt, Cn, _ = a.shape
+        return np.transpose(a, (1, 3, 0, 2)).reshape(nt * 32, T, Cn)[:t.B]
+    return t.detach().cpu().numpy().T
 
 
 def assert_gain_parity(K_gpu, K_ref, x_prev, u_prev, x_ref, u_ref):
@@ -100,11 +112,13 @@ def test_param_sets(bt):
 
 def test_pack_unpack(bt):
     rng = np.random.default_rng(0)
-    for shape in ((1, 501, 4), (37, 500, 2), (300, 3, 8), (65, 4)):
+    for shape in ((1, 501, 4), (37, 500, 2), (300, 3, 8), (64, 7, 10), (65, 4)):
         a = rng.normal(size=shape)
         s = bt.pack_soa(dev(a))
         assert np.array_equal(aos(s), a)
         assert np.array_equal(bt.unpack_soa(s).cpu().numpy(), a)
+        if a.ndim == 3:  # the library's tiling == the NumPy tiling of the test helpers, padding lanes are zero
+            assert torch.equal(s.data, soa(a).data)
 
 
 # ------------------------------------------------------------------------------------- G1-G9
@@ -132,7 +146,7 @@ def test_first_iteration_blocks_golden(bt, fa_ref):
     w = bt.newton_weights()
     X = bt.rollout_open_loop(soa(g["x0"][None]), None, N=501)
     assert rel_err(aos(X)[0], g["x_open"]) < TOL
-    U = torch.zeros(500, 2, 1, dtype=torch.float64, device="cuda")
+    U = bt.Traj.zeros(500, 2, 1)
     K, S, dJ, sn = bt.riccati_affine(X, U, ref, w)
     assert rel_err(kmat(K)[0], g["K0"]) < TOL and rel_err(aos(S)[0], g["sigma0"]) < TOL
     assert abs(dJ.item() - g["delta_J0"]) < TOL * abs(g["delta_J0"])
@@ -326,7 +340,8 @@ def test_newton_resume_in_chunks_is_bitwise_identical(bt, fa_ref):
     for _ in range(7):
         st = bt.newton_solve(soa(x0s), ref, max_iters=7, tol=1e-4, gamma_0=0.5, state=st, chunk_iters=1)
     torch.cuda.synchronize()
-    assert torch.equal(a.X, st.X) and torch.equal(a.U, st.U) and torch.equal(a.hist_cost, st.hist_cost)
+    assert np.array_equal(aos(a.X), aos(st.X)) and np.array_equal(aos(a.U), aos(st.U))
+    assert torch.equal(a.hist_cost, st.hist_cost) and np.array_equal(aos(a.K), aos(st.K))
     assert torch.equal(a.iters, st.iters) and torch.equal(a.status, st.status)
     assert (st.status == 2).all() and (st.iters == 7).all()
 
@@ -352,7 +367,7 @@ def test_newton_line_search_failure_keeps_iterate(bt, fa_ref):
     assert (st.status == 3).all() and (st.iters == 1).all()
     assert (st.hist_ntry[0] == 20).all()
     Xo = O.simulate_open_loop(x0, np.zeros((2, 500, 2)))
-    assert rel_err(aos(st.X), Xo) < TOL and float(st.U.abs().max()) == 0.0
+    assert rel_err(aos(st.X), Xo) < TOL and float(np.abs(aos(st.U)).max()) == 0.0
 
 
 # ------------------------------------------------------------------------------------- G11
@@ -364,7 +379,7 @@ def test_stepsize_sweep_golden(bt, fa_ref):
     w = bt.newton_weights()
     # 5 copies of the same base iterate: every column must give the reference curve
     X = soa(np.repeat(b["x_open"][None], 5, 0))
-    U = torch.zeros(500, 2, 5, dtype=torch.float64, device="cuda")
+    U = bt.Traj.zeros(500, 2, 5)
     K = soa(np.repeat(b["K0"].reshape(1, 500, 8), 5, 0))
     S = soa(np.repeat(b["sigma0"][None], 5, 0))
     cost = bt.stepsize_sweep(X, U, K, S, ref, w, dev(g["steps"])).cpu().numpy()
@@ -428,8 +443,8 @@ def test_mpc_solve_vs_kkt_and_riccati(bt):
         Bw = np.array([Bd[t0 + j] if t0 + j < 500 else g["B_f"] for j in range(H - 1)])
         x0 = np.vstack([0.1 * np.ones(4), rng.uniform(-0.2, 0.2, (2, 4))])
         n = len(x0)
-        A_w = dev(np.repeat(Aw[..., None], n, -1))
-        B_w = dev(np.repeat(Bw[..., None], n, -1))
+        A_w = soa(np.repeat(Aw.reshape(1, H - 1, 16), n, 0))
+        B_w = soa(np.repeat(Bw.reshape(1, H - 1, 8), n, 0))
         QT = dev(np.repeat(g["P_inf"][..., None], n, -1))
         U0, Xo, Uo, Kws = bt.mpc_solve(soa(x0), A_w, B_w, QT, w, H)
         for b in range(n):
@@ -478,7 +493,7 @@ def test_full_size_c2_properties(bt, fa_ref):
     assert (st.iters == 3).all() and (st.status == 2).all()
     g = golden("newton_task2")
     assert rel_err(hc[:, 0], g["cost"][:4]) < TOL
-    assert rel_err(aos(st.X[:, :, :1])[0], g["x_trajs"][3]) < TOL
+    assert rel_err(aos(st.X)[0], g["x_trajs"][3]) < TOL
     # Armijo inequality holds for every problem at the accepted step (checked with the kernel's own outputs)
     ntry = st.hist_ntry[:3].cpu().numpy()
     assert (ntry >= 1).all() and (ntry <= 20).all()
@@ -497,9 +512,10 @@ def test_full_size_c3_properties(bt):
     traj = bt.make_ref(d["x"], d["u"])
     K = bt.lqr_gains(traj)
     Xt, Ut = bt.lqr_track(traj, K, soa(x0))
-    xe = Xt[-1].cpu().numpy().T
-    assert rel_err(aos(Xt[:, :, :2]), g["x_track"][:2]) < TOL
-    assert np.max(np.abs(aos(Xt[:, :, 2:3])[0] - d["x"])) < 1e-9
+    Xb = Xt.batch_major()  # (B, N, 4) on the device
+    xe = Xb[:, -1].cpu().numpy()
+    assert rel_err(Xb[:2].cpu().numpy(), g["x_track"][:2]) < TOL
+    assert np.max(np.abs(Xb[2].cpu().numpy() - d["x"])) < 1e-9
     ok = np.isfinite(xe).all(axis=1)
     assert ok.mean() > 0.99
     assert np.median(np.abs(xe[ok] - d["x"][-1]).max(axis=1)) < 1e-2
