@@ -45,6 +45,11 @@ struct Trig {
 // trick and the two-FMA Cody-Waite reduction (first FMA exact) leaves an error below 1e-24.
 #define ACRO_TRIG_FAST_MAX 1.0e9
 
+// x with its sign bit XORed with bit 31 of `bits`
+__device__ __forceinline__ double flip_sign(double x, int bits) {
+  return __hiloint2double(__double2hiint(x) ^ (bits & 0x80000000), __double2loint(x));
+}
+
 // sin and cos of two angles in lockstep (~1 ulp).  No branch: for |x| > ACRO_TRIG_FAST_MAX the result is
 // meaningless but finite, and callers that may see such angles check and redo with the library routine;
 // inf / nan propagate to nan like the library.
@@ -70,10 +75,11 @@ __device__ __forceinline__ void sincos2(const Model& m, double xa, double xb, do
   const double cra = fma(za * za, pca, fma(za, -0.5, 1.0)), crb = fma(zb * zb, pcb, fma(zb, -0.5, 1.0));
   const double s0a = (ja & 1) ? cra : sra, c0a = (ja & 1) ? sra : cra;
   const double s0b = (jb & 1) ? crb : srb, c0b = (jb & 1) ? srb : crb;
-  sa = (ja & 2) ? -s0a : s0a;
-  ca = ((ja + 1) & 2) ? -c0a : c0a;
-  sb = (jb & 2) ? -s0b : s0b;
-  cb = ((jb + 1) & 2) ? -c0b : c0b;
+  // quadrant signs: flip the sign bit with integer logic instead of spending FP64-pipe slots on negations
+  sa = flip_sign(s0a, ja << 30);
+  ca = flip_sign(c0a, (ja + 1) << 30);
+  sb = flip_sign(s0b, jb << 30);
+  cb = flip_sign(c0b, (jb + 1) << 30);
 }
 
 // FAST = true: polynomial path (caller guarantees or checks |angles| <= ACRO_TRIG_FAST_MAX);
@@ -142,9 +148,12 @@ __device__ __forceinline__ void f_eval_t(const Model& m, const double x[4], doub
   f[3] = e.dd2;
 }
 
-__device__ __forceinline__ bool angles_ok(double a, double b) {
-  return !(fmax(fabs(a), fabs(b)) > ACRO_TRIG_FAST_MAX);  // nan counts as ok: it propagates either way
-}
+// Range tracking on the high words (integer pipe): hi(|x|) as an int orders finite doubles like their magnitude.
+// "Too large" = finite and above ACRO_TRIG_FAST_MAX; inf / nan are left to propagate through the fast path.
+#define ACRO_TRIG_FAST_MAX_HI 0x41cdcd65  /* high word of 1.0e9 */
+__device__ __forceinline__ int abs_hi(double x) { return __double2hiint(x) & 0x7fffffff; }
+__device__ __forceinline__ bool hi_too_large(int h) { return h > ACRO_TRIG_FAST_MAX_HI && h < 0x7ff00000; }
+__device__ __forceinline__ bool angles_ok(double a, double b) { return !hi_too_large(max(abs_hi(a), abs_hi(b))); }
 
 __device__ __forceinline__ void f_eval(const Model& m, const double x[4], double u0, double u1, double f[4]) {
   if (angles_ok(x[0], x[1]))
@@ -154,24 +163,24 @@ __device__ __forceinline__ void f_eval(const Model& m, const double x[4], double
 }
 
 // dynamics(xx, uu): classic RK4, zero-order hold on u   dynamics.py:177-195.
-// Returns the largest |angle| any of the four stages saw.
+// Returns the largest high word of |angle| any of the four stages saw.
 template <bool FAST>
-__device__ __forceinline__ double rk4_step_t(const Model& m, const double x[4], double u0, double u1, double xn[4]) {
+__device__ __forceinline__ int rk4_step_t(const Model& m, const double x[4], double u0, double u1, double xn[4]) {
   const double h = m.dt, hh = 0.5 * m.dt;
   double k1[4], k2[4], k3[4], k4[4], y[4];
-  double amax = fmax(fabs(x[0]), fabs(x[1]));
+  int amax = max(abs_hi(x[0]), abs_hi(x[1]));
   f_eval_t<FAST>(m, x, u0, u1, k1);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = fma(hh, k1[i], x[i]);
-  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  amax = max(amax, max(abs_hi(y[0]), abs_hi(y[1])));
   f_eval_t<FAST>(m, y, u0, u1, k2);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = fma(hh, k2[i], x[i]);
-  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  amax = max(amax, max(abs_hi(y[0]), abs_hi(y[1])));
   f_eval_t<FAST>(m, y, u0, u1, k3);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = fma(h, k3[i], x[i]);
-  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  amax = max(amax, max(abs_hi(y[0]), abs_hi(y[1])));
   f_eval_t<FAST>(m, y, u0, u1, k4);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -184,8 +193,8 @@ __device__ __forceinline__ double rk4_step_t(const Model& m, const double x[4], 
 // One branch per step instead of one per sin/cos: run the polynomial path, and only if some stage angle
 // was beyond its range (a diverging rollout on its way to overflow) redo the step with the library routine.
 __device__ __forceinline__ void rk4_step(const Model& m, const double x[4], double u0, double u1, double xn[4]) {
-  const double amax = rk4_step_t<true>(m, x, u0, u1, xn);
-  if (amax > ACRO_TRIG_FAST_MAX) rk4_step_t<false>(m, x, u0, u1, xn);
+  const int amax = rk4_step_t<true>(m, x, u0, u1, xn);
+  if (hi_too_large(amax)) rk4_step_t<false>(m, x, u0, u1, xn);
 }
 
 // Lower two rows of the continuous Jacobians (dynamics.py:153-170, 217-226):
@@ -265,11 +274,11 @@ __device__ __forceinline__ LinD linearize_d(const Model& m, const double x[4], d
 // sines, cosines and accelerations the Jacobian needs, so the backward pass of the next Newton iteration can
 // read A_d, B_d instead of redoing two sincos and one evaluation of the equations of motion per step.
 template <bool FAST>
-__device__ __forceinline__ double rk4_step_lin_t(const Model& m, const double x[4], double u0, double u1,
+__device__ __forceinline__ int rk4_step_lin_t(const Model& m, const double x[4], double u0, double u1,
                                                  double xn[4], LinD& L) {
   const double h = m.dt, hh = 0.5 * m.dt;
   double k1[4], k2[4], k3[4], k4[4], y[4];
-  double amax = fmax(fabs(x[0]), fabs(x[1]));
+  int amax = max(abs_hi(x[0]), abs_hi(x[1]));
   {
     const Trig t = trig_of<FAST>(m, x[0], x[1]);
     const Eom e = eom(m, t, x[2], x[3], u0, u1);
@@ -281,15 +290,15 @@ __device__ __forceinline__ double rk4_step_lin_t(const Model& m, const double x[
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = fma(hh, k1[i], x[i]);
-  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  amax = max(amax, max(abs_hi(y[0]), abs_hi(y[1])));
   f_eval_t<FAST>(m, y, u0, u1, k2);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = fma(hh, k2[i], x[i]);
-  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  amax = max(amax, max(abs_hi(y[0]), abs_hi(y[1])));
   f_eval_t<FAST>(m, y, u0, u1, k3);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = fma(h, k3[i], x[i]);
-  amax = fmax(amax, fmax(fabs(y[0]), fabs(y[1])));
+  amax = max(amax, max(abs_hi(y[0]), abs_hi(y[1])));
   f_eval_t<FAST>(m, y, u0, u1, k4);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -301,8 +310,8 @@ __device__ __forceinline__ double rk4_step_lin_t(const Model& m, const double x[
 
 __device__ __forceinline__ void rk4_step_lin(const Model& m, const double x[4], double u0, double u1, double xn[4],
                                              LinD& L) {
-  const double amax = rk4_step_lin_t<true>(m, x, u0, u1, xn, L);
-  if (amax > ACRO_TRIG_FAST_MAX) rk4_step_lin_t<false>(m, x, u0, u1, xn, L);
+  const int amax = rk4_step_lin_t<true>(m, x, u0, u1, xn, L);
+  if (hi_too_large(amax)) rk4_step_lin_t<false>(m, x, u0, u1, xn, L);
 }
 
 // ---------------------------------------------------------------------------------------

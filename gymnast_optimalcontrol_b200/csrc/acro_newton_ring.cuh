@@ -75,28 +75,47 @@ struct TilePtrs {
   int64_t sx, su, sk, ss, sl;         // doubles per time step of the tiled arrays (Bp * C)
 };
 
+// Source pointers of the next fill; they walk forwards (forward pass) or backwards (backward pass) one time
+// step per fill, so issuing a stage needs no multiplications.
+struct FillPtrs {
+  const double *x, *u, *a0, *a1, *rx, *ru;
+};
 template <bool RPB, bool FWD>
-__device__ __forceinline__ void ring_fill(Ring& r, const TilePtrs& p, int t, int lane) {
+__device__ __forceinline__ FillPtrs fill_begin(const TilePtrs& p, int steps) {
+  const int64_t t0 = FWD ? 0 : steps - 1;
+  FillPtrs f;
+  f.x = p.x + t0 * p.sx;
+  f.u = p.u + t0 * p.su;
+  f.a0 = FWD ? p.k + t0 * p.sk : p.lin + t0 * p.sl;
+  f.a1 = p.s + t0 * p.ss;
+  f.rx = p.rx + t0 * (RPB ? p.sx : 4);
+  f.ru = p.ru + t0 * (RPB ? p.su : 2);
+  return f;
+}
+template <bool RPB, bool FWD>
+__device__ __forceinline__ void ring_fill(Ring& r, const TilePtrs& p, FillPtrs& f, int lane) {
   if (lane == 0) {
     const uint32_t st = r.iss & (ACRO_RING_D - 1);
     const uint32_t bar = r.bars + st * 8, dst = r.data + st * stage_bytes<RPB>();
     mbar_expect_tx(bar, tx_bytes<RPB>());
-    bulk_g2s(dst + kOffX, p.x + t * p.sx, 1024, bar);
-    bulk_g2s(dst + kOffU, p.u + t * p.su, 512, bar);
+    bulk_g2s(dst + kOffX, f.x, 1024, bar);
+    bulk_g2s(dst + kOffU, f.u, 512, bar);
     if (FWD) {
-      bulk_g2s(dst + kOffA, p.k + t * p.sk, 2048, bar);
-      bulk_g2s(dst + kOffA + 2048, p.s + t * p.ss, 512, bar);
+      bulk_g2s(dst + kOffA, f.a0, 2048, bar);
+      bulk_g2s(dst + kOffA + 2048, f.a1, 512, bar);
     } else {
-      bulk_g2s(dst + kOffA, p.lin + t * p.sl, 2560, bar);
+      bulk_g2s(dst + kOffA, f.a0, 2560, bar);
     }
-    if (RPB) {
-      bulk_g2s(dst + kOffRef, p.rx + t * p.sx, 1024, bar);
-      bulk_g2s(dst + kOffRef + 1024, p.ru + t * p.su, 512, bar);
-    } else {
-      bulk_g2s(dst + kOffRef, p.rx + t * 4, 32, bar);
-      bulk_g2s(dst + kOffRef + 32, p.ru + t * 2, 16, bar);
-    }
+    bulk_g2s(dst + kOffRef, f.rx, RPB ? 1024 : 32, bar);
+    bulk_g2s(dst + kOffRef + (RPB ? 1024 : 32), f.ru, RPB ? 512 : 16, bar);
   }
+  constexpr int dir = FWD ? 1 : -1;
+  f.x += dir * p.sx;
+  f.u += dir * p.su;
+  f.a0 += dir * (FWD ? p.sk : p.sl);
+  f.a1 += dir * p.ss;
+  f.rx += dir * (RPB ? p.sx : 4);
+  f.ru += dir * (RPB ? p.su : 2);
   ++r.iss;
 }
 
@@ -130,7 +149,8 @@ __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w,
                                                int lane, double gamma, bool store, double* __restrict__ Xo,
                                                double* __restrict__ Uo, double* __restrict__ Lo, const double xrT[4]) {
   const int steps = N - 1;
-  for (int i = 0; i < ACRO_RING_D && i < steps; ++i) ring_fill<RPB, true>(r, p, i, lane);
+  FillPtrs f = fill_begin<RPB, true>(p, steps);
+  for (int i = 0; i < ACRO_RING_D && i < steps; ++i) ring_fill<RPB, true>(r, p, f, lane);
   double xp[4];
   StepIn in;
   {
@@ -196,7 +216,7 @@ __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w,
     }
     // the stage read one iteration ago is free now: refill it with step t + D
     __syncwarp();
-    if (t + ACRO_RING_D < steps) ring_fill<RPB, true>(r, p, t + ACRO_RING_D, lane);
+    if (t + ACRO_RING_D < steps) ring_fill<RPB, true>(r, p, f, lane);
     double xn[4];
     LinD L;
     rk4_step_lin(m, xp, up[0], up[1], xn, L);
@@ -234,7 +254,8 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
                                               const double xT[4], const double xrT[4], double& dJ_out,
                                               double& sn_out) {
   const int steps = N - 1;
-  for (int i = 0; i < ACRO_RING_D && i < steps; ++i) ring_fill<RPB, false>(r, p, steps - 1 - i, lane);
+  FillPtrs f = fill_begin<RPB, false>(p, steps);
+  for (int i = 0; i < ACRO_RING_D && i < steps; ++i) ring_fill<RPB, false>(r, p, f, lane);
   double P[10], pv[4];
   {
     double dx[4];
@@ -292,16 +313,8 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
     }
     rr[0] = fma(w.R2(0, 1), du[1], w.R2(0, 0) * du[0]);
     rr[1] = fma(w.R2(1, 1), du[1], w.R2(1, 0) * du[0]);
-    const LinD Lc = L;
-    if (more) {  // operands of the next step (time index steps-2-i)
-      if (!ready) mbar_wait(ring_bar(r, r.seq), ring_parity(r.seq));
-      load(r.seq);
-      ++r.seq;
-    }
-    __syncwarp();
-    if (i + ACRO_RING_D < steps) ring_fill<RPB, false>(r, p, steps - 1 - (i + ACRO_RING_D), lane);
     double Kt[8], st[2];
-    riccati_step<true, false>(P, pv, Lc, m.dt, Qh, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, rr, Kt, st, dJ);
+    riccati_step<true, false>(P, pv, L, m.dt, Qh, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, rr, Kt, st, dJ);
     if (store) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) pk[e * 32] = Kt[e];
@@ -313,6 +326,14 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
       const double a = fabs(st[e]);
       sn = (a > sn || a != a) ? a : sn;  // NaN is sticky, like np.max(np.abs(sigma))
     }
+    if (more) {  // operands of the next step (time index steps-2-i), straight into the registers just used
+      if (!ready) mbar_wait(ring_bar(r, r.seq), ring_parity(r.seq));
+      load(r.seq);
+      ++r.seq;
+    }
+    // the stage read one iteration ago is free now: refill it
+    __syncwarp();
+    if (i + ACRO_RING_D < steps) ring_fill<RPB, false>(r, p, f, lane);
     pk -= p.sk;
     ps -= p.ss;
   }
