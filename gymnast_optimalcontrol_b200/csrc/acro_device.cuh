@@ -358,10 +358,23 @@ __device__ __forceinline__ void lu2_solve(const Lu2& f, double b0, double b1, do
 // -K'G sigma = K'g.  Qh/Rh are the blocks as used by the caller (2Q, 2R for Newton; Q, R
 // for tracking).  P is symmetric (10 values); K is 2x4 row-major.
 // ---------------------------------------------------------------------------------------
+// First column of G = Rh + B'PB when the first actuator does not exist: (Rh00, Rh01), constant over the sweep.
+struct Lu2Col {
+  double inv_p, l;
+  bool swap;
+};
+__device__ __forceinline__ Lu2Col lu2_col(double g00, double g10) {
+  Lu2Col c;
+  c.swap = fabs(g10) > fabs(g00);
+  c.inv_p = 1.0 / (c.swap ? g10 : g00);
+  c.l = (c.swap ? g00 : g10) * c.inv_p;
+  return c;
+}
+
 template <bool AFFINE, bool ACT0, class QH>
 __device__ __forceinline__ void riccati_step(double P[10], double p[4], const LinD& L, double dt,
-                                             const QH& Qh, double Rh00, double Rh01, double Rh11,
-                                             const double q[4], const double r[2], double K[8],
+                                             const QH& Qh, const Lu2Col& col, double Rh00, double Rh01, double Rh11,
+                                             const double qv[4], const double r[2], double K[8],
                                              double sig[2], double& dJ) {
   // M = P * A_d    (A_d rows 0-1 are [1 0 dt 0; 0 1 0 dt])
   double M[4][4];
@@ -400,15 +413,38 @@ __device__ __forceinline__ void riccati_step(double P[10], double p[4], const Li
     G00 += fma(L.b0[1], Pb0_3, L.b0[0] * Pb0_2);
     G01 += fma(L.b[1], Pb0_3, L.b[0] * Pb0_2);
   }
-  const Lu2 lu = lu2(G00, G01, G01, G11);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) lu2_solve(lu, -F0[j], -F1[j], K[j], K[4 + j]);
+  // 2x2 solve G [K | sigma] = -[F | g] by LU with partial pivoting (what LAPACK does).  Without the first
+  // actuator the first column of G is the constant (Rh00, Rh01): pivot choice, 1/pivot and the multiplier come
+  // precomputed in `col`, F has a zero first row, and only ONE reciprocal (of u11) sits on the P -> P chain.
   double g0 = 0.0, g1 = 0.0;
+  if (ACT0) {
+    const Lu2 lu = lu2(G00, G01, G01, G11);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lu2_solve(lu, -F0[j], -F1[j], K[j], K[4 + j]);
+    if (AFFINE) {
+      g0 = r[0] + fma(L.b0[1], p[3], L.b0[0] * p[2]);
+      g1 = r[1] + fma(L.b[1], p[3], L.b[0] * p[2]);
+      lu2_solve(lu, -g0, -g1, sig[0], sig[1]);
+    }
+  } else {
+    const double q = col.swap ? G11 : G01, s = col.swap ? G01 : G11;
+    const double inv_u11 = rcp_nr(fma(-col.l, q, s));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // right-hand side (0, -F1[j])
+      const double x1 = (col.swap ? col.l * F1[j] : -F1[j]) * inv_u11;
+      K[4 + j] = x1;
+      K[j] = (col.swap ? fma(-q, x1, -F1[j]) : -(q * x1)) * col.inv_p;
+    }
+    if (AFFINE) {
+      g0 = r[0];
+      g1 = r[1] + fma(L.b[1], p[3], L.b[0] * p[2]);
+      const double y0 = col.swap ? -g1 : -g0, y1 = col.swap ? -g0 : -g1;
+      sig[1] = fma(-col.l, y0, y1) * inv_u11;
+      sig[0] = fma(-q, sig[1], y0) * col.inv_p;
+    }
+  }
   if (AFFINE) {
-    g0 = r[0];
-    g1 = r[1] + fma(L.b[1], p[3], L.b[0] * p[2]);
-    if (ACT0) g0 += fma(L.b0[1], p[3], L.b0[0] * p[2]);
-    lu2_solve(lu, -g0, -g1, sig[0], sig[1]);
     dJ += fma(g1, sig[1], g0 * sig[0]);
     // p <- q + A_d' p + K' g
     const double p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
@@ -416,7 +452,7 @@ __device__ __forceinline__ void riccati_step(double P[10], double p[4], const Li
                           fma(L.a[1][2], p3, fma(L.a[0][2], p2, dt * p0)),
                           fma(L.a[1][3], p3, fma(L.a[0][3], p2, dt * p1))};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) p[i] = q[i] + ap[i] + fma(K[4 + i], g1, K[i] * g0);
+    for (int i = 0; i < 4; ++i) p[i] = qv[i] + ap[i] + fma(K[4 + i], g1, K[i] * g0);
   }
   // P <- Qh + S + K'F
 #pragma unroll

@@ -368,6 +368,7 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
     ur[c] = ref.U(N - 2, c);
   }
   const QhQ2<WV<WPB>> Qh{w};
+  const Lu2Col col = lu2_col(w.R2(0, 0), w.R2(0, 1));
   LinD Lc, Ln;
   if (HAVE_LIN) Lc = load_lin(lin, N - 2, ld, b);
   for (int t = N - 2; t >= 0; --t) {
@@ -407,7 +408,7 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
     r[0] = fma(w.R2(0, 1), du[1], w.R2(0, 0) * du[0]);
     r[1] = fma(w.R2(1, 1), du[1], w.R2(1, 0) * du[0]);
     double Kt[8], st[2];
-    riccati_step<true, false>(P, p, L, m.dt, Qh, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, r, Kt, st, dJ);
+    riccati_step<true, false>(P, p, L, m.dt, Qh, col, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, r, Kt, st, dJ);
 #pragma unroll
     for (int e = 0; e < 8; ++e) K[soa(t, 8, e, ld, b)] = Kt[e];
 #pragma unroll
@@ -891,6 +892,7 @@ __global__ void k_lqr_gains(const __grid_constant__ Model m, const __grid_consta
 #pragma unroll
     for (int j = i; j < 4; ++j) P[sym(i, j)] = w.Q2(i, j);  // Q_T_reg = 2 Q_reg  (tt:175)
   const QhQ<WV<WPB>> Qh{w};
+  const Lu2Col col = lu2_col(w.R(0, 0), w.R(0, 1));
   double dummy = 0.0;
   for (int t = N - 2; t >= 0; --t) {
     double x[4];
@@ -898,7 +900,7 @@ __global__ void k_lqr_gains(const __grid_constant__ Model m, const __grid_consta
     for (int c = 0; c < 4; ++c) x[c] = ref.X(t, c);
     const LinD L = linearize_d(m, x, ref.U(t, 0), ref.U(t, 1));
     double Kt[8], st[2];
-    riccati_step<false, false>(P, p, L, m.dt, Qh, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, Kt, st, dummy);
+    riccati_step<false, false>(P, p, L, m.dt, Qh, col, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, Kt, st, dummy);
     if (RPB) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) K[soa(t, 8, e, B, b)] = Kt[e];
@@ -1117,16 +1119,17 @@ __device__ __forceinline__ void mpc_sweep(const WV<WPB>& w, double dt, const dou
 #pragma unroll
   for (int e = 0; e < 10; ++e) P[e] = QT[e];
   const QhQ<WV<WPB>> Qh{w};
+  const Lu2Col col = lu2_col(w.R(0, 0), w.R(0, 1));
   int j = H - 2;
   // padded tail of the window: linearisation about (x_f, u_f)
   for (; j >= 0 && t + j >= n_lin; --j)
-    riccati_step<false, false>(P, p, Lf, dt, Qh, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, K, st, dummy);
+    riccati_step<false, false>(P, p, Lf, dt, Qh, col, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, K, st, dummy);
   if (j < 0) return;
   LinD L = load_lin(lin, t + j, ld, b);
   for (; j >= 0; --j) {
     LinD Ln = L;
     if (j > 0) Ln = load_lin(lin, t + j - 1, ld, b);  // prefetch
-    riccati_step<false, false>(P, p, L, dt, Qh, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, K, st, dummy);
+    riccati_step<false, false>(P, p, L, dt, Qh, col, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, K, st, dummy);
     L = Ln;
   }
 }

@@ -294,6 +294,7 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
   ++r.seq;
   double dJ = 0.0, sn = 0.0;
   const QhQ2<WV<WPB>> Qh{w};
+  const Lu2Col col = lu2_col(w.R2(0, 0), w.R2(0, 1));
   double* pk = K + (steps - 1) * p.sk + lane;
   double* ps = S + (steps - 1) * p.ss + lane;
   for (int i = 0; i < steps; ++i) {
@@ -314,7 +315,7 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
     rr[0] = fma(w.R2(0, 1), du[1], w.R2(0, 0) * du[0]);
     rr[1] = fma(w.R2(1, 1), du[1], w.R2(1, 0) * du[0]);
     double Kt[8], st[2];
-    riccati_step<true, false>(P, pv, L, m.dt, Qh, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, rr, Kt, st, dJ);
+    riccati_step<true, false>(P, pv, L, m.dt, Qh, col, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, rr, Kt, st, dJ);
     if (store) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) pk[e * 32] = Kt[e];
