@@ -194,6 +194,8 @@ def run_native(a):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the one JSON line: NCCL's version / debug banner goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/acro_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gymnast_optimalcontrol_b200 import _abi
     from gymnast_optimalcontrol_b200 import batched as bt

@@ -1,0 +1,138 @@
+#!/usr/bin/env python
+"""Secondary benchmark lines: configs 3, 4, 5 of BASELINE.json and config 2 in the throughput regime.
+
+    python bench_configs.py [--quick]
+
+One JSON line per config, device-resident timing with CUDA events (inputs in HBM), FP64 roofline by the flop
+convention of SURVEY 8(d).  bench.py (config 2, B = 4096) stays the headline the driver runs.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from gymnast_optimalcontrol_b200 import _abi  # noqa: E402
+from gymnast_optimalcontrol_b200 import batched as bt  # noqa: E402
+
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def timeit(f, n):
+    f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _abi.launch_count()
+    e0.record()
+    for _ in range(n):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / n, (_abi.launch_count() - l0) // n
+
+
+def fp64_peak():
+    blocks, threads, iters = 148 * 8, 256, 20000
+    out = torch.empty(blocks * threads, dtype=torch.float64, device="cuda")
+    best = 0.0
+    for i in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _abi.call("acro_bench_fp64_peak", blocks, threads, iters, C.c_void_p(out.data_ptr()), None)
+        e1.record()
+        torch.cuda.synchronize()
+        if i:
+            best = max(best, blocks * threads * iters * 16.0 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def line(name, metric, value, unit, flops_per_unit, t, launches, peak, extra=None):
+    ach = value * flops_per_unit / 1e12
+    d = {"config": name, "metric": metric, "value": value, "unit": unit, "seconds": t, "gpu_launches": launches,
+         "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                      "flops_per_unit": flops_per_unit}}
+    if extra:
+        d.update(extra)
+    print(json.dumps(d), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    reps = 2 if a.quick else 5
+    peak = fp64_peak()
+    opt = np.load(os.path.join(G, "acrobot_optimal_trajectory.npz"))
+    fa = np.load(os.path.join(G, "fully_actuated_trajectory.npz"))
+    u_ref = np.zeros(fa["u"].shape)
+    u_ref[:, 1] = 2.0 * fa["u"][:, 1]
+    N = 501
+
+    # ---- config 3: LQR tracking of the optimal trajectory from 65 536 perturbed initial conditions
+    B = 65536
+    traj = bt.make_ref(opt["x"], opt["u"])
+    K = bt.lqr_gains(traj)
+    x0 = bt.upload(np.ascontiguousarray((opt["x"][0] + np.random.default_rng(2).uniform(-0.3, 0.3, (B, 4))).T))
+    t, nl = timeit(lambda: bt.lqr_track(traj, K, x0), reps)
+    line("C3 LQR tracking, B=65536, N=501", "lqr_rollouts_per_sec", B / t, "tracked problems/s", 878.0 * (N - 1), t, nl, peak,
+         {"steps_per_sec": B * (N - 1) / t})
+    tg, _ = timeit(lambda: bt.lqr_gains(traj), reps)
+    print(json.dumps({"config": "C3 gains (one shared trajectory, 500 sequential Riccati steps, 1 thread)", "seconds": tg}))
+
+    # ---- config 4: receding-horizon MPC for 16 384 acrobots
+    B = 16384
+    w = bt.mpc_weights()
+    xf = bt.upload(np.array([[np.pi], [0], [0], [0]], dtype=np.float64))
+    A_f, B_f = bt.linearize(xf, bt.upload(np.zeros((2, 1))), discrete=True)
+    P, n = bt.p_inf(A_f, B_f, w)
+    QT = P[:, :, 0].contiguous()
+    x0 = bt.upload(np.ascontiguousarray((opt["x"][0] + np.random.default_rng(3).uniform(-0.1, 0.1, (B, 4))).T))
+    for H in ((75,) if a.quick else (50, 75, 100, 200)):
+        res = {}
+        t, nl = timeit(lambda: res.__setitem__("s", bt.mpc_track(x0, traj, QT, T=N, T_pred=H, w=w)), reps)
+        ns = res["s"][3]
+        line("C4 MPC tracking, shared reference, B=16384, H=%d" % H, "mpc_control_updates_per_sec", B * (N - 1) / t,
+             "closed-loop MPC steps/s (gains from %d Riccati sweeps shared by the batch)" % ns, 856.0 + 16.0, t, nl, peak,
+             {"riccati_sweeps_executed": ns})
+    refp = bt.Ref(bt.Traj.from_batch_major(bt.upload(np.repeat(opt["x"][None], B, 0))),
+                  bt.Traj.from_batch_major(bt.upload(np.repeat(opt["u"][None], B, 0))))
+    for H in ((75,) if a.quick else (50, 75, 100, 200)):
+        res = {}
+        t, nl = timeit(lambda: res.__setitem__("s", bt.mpc_track(x0, refp, QT, T=N, T_pred=H, w=w)), max(1, reps // 2))
+        ns = res["s"][3]
+        line("C4 MPC tracking, per-problem references, B=16384, H=%d" % H, "mpc_solves_per_sec", ns / t,
+             "MPC solves/s (one (H-1)-step Riccati sweep + plant step each)", 550.0 * (H - 1) + 16 + 856, t, nl, peak,
+             {"riccati_sweeps_executed": ns})
+
+    # ---- config 5: 5000 base iterates x 200 step sizes = 1M closed-loop rollouts
+    Pn = 5000 if not a.quick else 1000
+    ref = bt.make_ref(fa["x"], u_ref)
+    wn = bt.newton_weights()
+    x0 = bt.upload(np.ascontiguousarray(np.random.default_rng(1).uniform(-0.2, 0.2, (Pn, 4)).T))
+    st = bt.newton_solve(x0, ref, max_iters=3, tol=0.0, gamma_0=0.1, history=False)
+    Kd, Sd, dJ, sn = bt.riccati_affine(st.X, st.U, ref, wn)
+    steps = bt.upload(np.linspace(0, 1.25, 200))
+    t, nl = timeit(lambda: bt.stepsize_sweep(st.X, st.U, Kd, Sd, ref, wn, steps), reps)
+    line("C5 step-size sweep, %d iterates x 200 step sizes" % Pn, "sweep_rollouts_per_sec", Pn * 200 / t, "rollouts/s",
+         940.0 * (N - 1), t, nl, peak)
+
+    # ---- config 2 in the throughput regime
+    for B in ((65536,) if a.quick else (32768, 65536, 131072)):
+        x0 = bt.upload(np.ascontiguousarray(np.random.default_rng(1).uniform(-0.2, 0.2, (B, 4)).T))
+        state = bt.newton_alloc(B, N, 10, history=False)
+
+        def run():
+            state.initialised = False
+            bt.newton_solve(x0, ref, max_iters=10, tol=0.0, gamma_0=0.1, state=state)
+        t, nl = timeit(run, max(1, reps // 2))
+        line("C2 Newton, B=%d, 10 iterations" % B, "newton_iterations_per_sec", B * 10 / t, "Newton iterations/s",
+             2054.0 * (N - 1), t, nl, peak)
+
+
+if __name__ == "__main__":
+    main()

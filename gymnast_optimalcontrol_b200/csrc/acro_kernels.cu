@@ -369,28 +369,13 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
   }
   const QhQ2<WV<WPB>> Qh{w};
   const Lu2Col col = lu2_col(w.R2(0, 0), w.R2(0, 1));
-  LinD Lc, Ln;
+  LinD Lc;
   if (HAVE_LIN) Lc = load_lin(lin, N - 2, ld, b);
   for (int t = N - 2; t >= 0; --t) {
-    double nx[4] = {0, 0, 0, 0}, nu[2] = {0, 0}, nxr[4] = {0, 0, 0, 0}, nur[2] = {0, 0};
-    if (HAVE_LIN) Ln = Lc;
     if (t > ACRO_PF_DIST) {
       l2_prefetch_rows<4>(X, t - 1 - ACRO_PF_DIST, ld, b);
       l2_prefetch_rows<2>(U, t - 1 - ACRO_PF_DIST, ld, b);
       if (HAVE_LIN) l2_prefetch_rows<10>(lin, t - 1 - ACRO_PF_DIST, ld, b);
-    }
-    if (t > 0) {
-      if (HAVE_LIN) Ln = load_lin(lin, t - 1, ld, b);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        nx[c] = X[soa(t - 1, 4, c, ld, b)];
-        nxr[c] = ref.X(t - 1, c);
-      }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        nu[c] = U[soa(t - 1, 2, c, ld, b)];
-        nur[c] = ref.U(t - 1, c);
-      }
     }
     const LinD L = HAVE_LIN ? Lc : linearize_d(m, x, u[0], u[1]);
     double dx[4], du[2], q[4], r[2];
@@ -407,8 +392,23 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
     }
     r[0] = fma(w.R2(0, 1), du[1], w.R2(0, 0) * du[0]);
     r[1] = fma(w.R2(1, 1), du[1], w.R2(1, 0) * du[0]);
+    // operands of step t-1 into the registers step t has finished with (x, u, reference); the Riccati algebra
+    // below covers the load latency
+    if (t > 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        x[c] = X[soa(t - 1, 4, c, ld, b)];
+        xr[c] = ref.X(t - 1, c);
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        u[c] = U[soa(t - 1, 2, c, ld, b)];
+        ur[c] = ref.U(t - 1, c);
+      }
+    }
     double Kt[8], st[2];
     riccati_step<true, false>(P, p, L, m.dt, Qh, col, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, r, Kt, st, dJ);
+    if (HAVE_LIN && t > 0) Lc = load_lin(lin, t - 1, ld, b);
 #pragma unroll
     for (int e = 0; e < 8; ++e) K[soa(t, 8, e, ld, b)] = Kt[e];
 #pragma unroll
@@ -417,17 +417,6 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
       const double a = fabs(st[e]);
       sn = (a > sn || a != a) ? a : sn;  // NaN is sticky, like np.max(np.abs(sigma))
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      x[c] = nx[c];
-      xr[c] = nxr[c];
-    }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      u[c] = nu[c];
-      ur[c] = nur[c];
-    }
-    if (HAVE_LIN) Lc = Ln;
   }
   dJ_out = dJ;
   sn_out = sn;
@@ -492,14 +481,12 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
 #pragma unroll
   for (int c = 0; c < 4; ++c) xrT[c] = ref.X(N - 1, c);
   for (int t = 0; t < N - 1; ++t) {
-    StepIn nx = in;
     if (t + 1 + ACRO_PF_DIST < N - 1) {
       l2_prefetch_rows<4>(X, t + 1 + ACRO_PF_DIST, ld, b);
       l2_prefetch_rows<2>(U, t + 1 + ACRO_PF_DIST, ld, b);
       l2_prefetch_rows<8>(K, t + 1 + ACRO_PF_DIST, ld, b);
       l2_prefetch_rows<2>(S, t + 1 + ACRO_PF_DIST, ld, b);
     }
-    if (t + 1 < N - 1) nx = load_step(X, U, K, S, ref, t + 1, ld, b);
     double dx[4], up[2];
 #pragma unroll
     for (int c = 0; c < 4; ++c) dx[c] = xp[c] - in.x[c];
@@ -523,6 +510,9 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
     for (int c = 0; c < 2; ++c) eu[c] = up[c] - in.ur[c];
     cost += quad4(ex, [&](int i, int j) { return w.Q(i, j); });
     cost += quad2(eu, [&](int i, int j) { return w.R(i, j); });
+    // operands of step t+1 straight into the registers step t no longer needs; the four RK4 stages below
+    // (about a thousand cycles) cover the load latency
+    if (t + 1 < N - 1) in = load_step(X, U, K, S, ref, t + 1, ld, b);
     double xn[4];
     if (LIN) {
       LinD L;
@@ -533,7 +523,6 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) xp[c] = xn[c];
-    in = nx;
   }
   double ex[4];
 #pragma unroll
@@ -547,7 +536,7 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
 
 // one thread per (problem b, candidate g); lanes run over b
 template <bool WPB, bool RPB>
-__global__ void k_closed_loop(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B,
+__global__ void __launch_bounds__(128, 3) k_closed_loop(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B,
                               int N, const double* __restrict__ X, const double* __restrict__ U,
                               const double* __restrict__ K, const double* __restrict__ S, const double* rx,
                               const double* ru, int G, const double* __restrict__ gammas, int gpp,
@@ -571,7 +560,7 @@ __global__ void k_closed_loop(const __grid_constant__ Model m, const __grid_cons
 // iterate, so the 16 operand loads per step are warp-wide broadcasts; the 4 warps of a
 // block take 4 neighbouring iterates, i.e. whole 32-byte sectors of every SoA row.
 template <bool WPB, bool RPB>
-__global__ void k_sweep(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t P, int N,
+__global__ void __launch_bounds__(128, 3) k_sweep(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t P, int N,
                         const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ K,
                         const double* __restrict__ S, const double* rx, const double* ru, int S_n,
                         const double* __restrict__ steps, double* __restrict__ cost) {
