@@ -34,6 +34,10 @@ sys.path.insert(0, ROOT)
 N_STEPS = 501
 FLOPS_FIXED, FLOPS_PER_TRY = 1114.0, 940.0  # per problem-step-iteration, FMA = 2, sin/cos = 40
 BYTES_STEP_ITER = 304.0                      # read x,u; write K,sigma; read x,u,K,sigma; write x+,u+
+# dram__bytes_read+write of acro::k_newton_ring from the ncu --set full capture in profiles/ (4-iteration launch,
+# B = 4096: 3.67 GB): 404 B per problem-step-iteration (the kernel moves 464 B by design, L2 absorbs part of the
+# re-reads) + 176 B per problem-step for the initial rollout and cost
+TRAFFIC_STEP_ITER, TRAFFIC_STEP_INIT = 404.0, 176.0
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2
 
 
@@ -280,14 +284,16 @@ def run_native(a):
         ach_gbs = per_gpu_rate * BYTES_STEP_ITER * (N_STEPS - 1) / 1e9
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         roof = {"bound": "fp64", "achieved": ach_tflops, "peak": fp64_meas, "unit": "TFLOP/s", "frac": ach_tflops / fp64_meas,
-                "traffic": a.traffic_bytes,
+                "traffic": a.traffic_bytes if a.traffic_bytes else B * (N_STEPS - 1) * (TRAFFIC_STEP_ITER * iters + TRAFFIC_STEP_INIT),
+                "traffic_source": "profiles/r1_newton_ring_ncu_summary.txt (ncu --set full, 4-iteration launch) scaled to this launch",
                 "peak_source": "DFMA-chain microbenchmark (acro_bench_fp64_peak) run in this process; nominal %.1f" % FP64_NOMINAL_TFLOPS,
                 "frac_of_nominal": ach_tflops / FP64_NOMINAL_TFLOPS,
-                "kernel": "acro::k_newton<false,false>", "launch_ms": 1e3 * t_dev / max(launches, 1),
+                "kernel": "acro::k_newton_ring<false,false> (warp-synchronous, TMA-fed shared-memory ring)", "launch_ms": 1e3 * t_dev / max(launches, 1),
                 "algorithmic_flops_per_launch": flops_iter * B * iters, "algorithmic_bytes_per_launch": BYTES_STEP_ITER * (N_STEPS - 1) * B * iters,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650"},
-                "note": "latency bound at B=4096: 128 warps on 592 SM sub-partitions; see DESIGN.md"}
+                "note": "latency bound at B=4096: 128 warps on 592 SM sub-partitions, every problem a 1000-step dependent FP64 recurrence per "
+                        "iteration; the same code reaches 60% of the DFMA peak at B>=32k (bench_configs.py); see DESIGN.md section 4"}
         cpu = None
         if world == 1 and not a.no_cpu:
             cores = os.cpu_count() or 1

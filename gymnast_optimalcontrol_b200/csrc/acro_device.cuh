@@ -155,14 +155,11 @@ __device__ __forceinline__ int abs_hi(double x) { return __double2hiint(x) & 0x7
 __device__ __forceinline__ bool hi_too_large(int h) { return h > ACRO_TRIG_FAST_MAX_HI && h < 0x7ff00000; }
 __device__ __forceinline__ bool angles_ok(double a, double b) { return !hi_too_large(max(abs_hi(a), abs_hi(b))); }
 
-__device__ __noinline__ void f_eval_slow(const Model& m, const double x[4], double u0, double u1, double f[4]) {
-  f_eval_t<false>(m, x, u0, u1, f);
-}
 __device__ __forceinline__ void f_eval(const Model& m, const double x[4], double u0, double u1, double f[4]) {
   if (angles_ok(x[0], x[1]))
     f_eval_t<true>(m, x, u0, u1, f);
   else
-    f_eval_slow(m, x, u0, u1, f);
+    f_eval_t<false>(m, x, u0, u1, f);
 }
 
 // dynamics(xx, uu): classic RK4, zero-order hold on u   dynamics.py:177-195.
@@ -196,12 +193,24 @@ __device__ __forceinline__ int rk4_step_t(const Model& m, const double x[4], dou
 // One branch per step instead of one per sin/cos: run the polynomial path, and only if some stage angle
 // was beyond its range (a diverging rollout on its way to overflow) redo the step with the library routine.
 // the library-sincos version is a real function call: it keeps its registers and code out of the hot kernels
-__device__ __noinline__ void rk4_step_slow(const Model& m, const double x[4], double u0, double u1, double xn[4]) {
-  rk4_step_t<false>(m, x, u0, u1, xn);
+// (arguments and results by value, so the fast path never has to keep its arrays addressable in local memory)
+struct Vec4 {
+  double v[4];
+};
+__device__ __noinline__ Vec4 rk4_step_slow(const Model& m, double x0, double x1, double x2, double x3, double u0,
+                                           double u1) {
+  const double x[4] = {x0, x1, x2, x3};
+  Vec4 o;
+  rk4_step_t<false>(m, x, u0, u1, o.v);
+  return o;
 }
 __device__ __forceinline__ void rk4_step(const Model& m, const double x[4], double u0, double u1, double xn[4]) {
   const int amax = rk4_step_t<true>(m, x, u0, u1, xn);
-  if (hi_too_large(amax)) rk4_step_slow(m, x, u0, u1, xn);
+  if (hi_too_large(amax)) {
+    const Vec4 o = rk4_step_slow(m, x[0], x[1], x[2], x[3], u0, u1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xn[i] = o.v[i];
+  }
 }
 
 // Lower two rows of the continuous Jacobians (dynamics.py:153-170, 217-226):
@@ -248,12 +257,14 @@ __device__ __forceinline__ LinC linearize_c_t(const Model& m, const double x[4],
   return jacobian_from(m, t, e, x[2], x[3]);
 }
 
-__device__ __noinline__ LinC linearize_c_slow(const Model& m, const double x[4], double u0, double u1) {
+__device__ __noinline__ LinC linearize_c_slow(const Model& m, double x0, double x1, double x2, double x3, double u0,
+                                              double u1) {
+  const double x[4] = {x0, x1, x2, x3};
   return linearize_c_t<false>(m, x, u0, u1);
 }
 __device__ __forceinline__ LinC linearize_c(const Model& m, const double x[4], double u0, double u1) {
   if (angles_ok(x[0], x[1])) return linearize_c_t<true>(m, x, u0, u1);
-  return linearize_c_slow(m, x, u0, u1);
+  return linearize_c_slow(m, x[0], x[1], x[2], x[3], u0, u1);
 }
 
 // Forward-Euler discretisation (tg:161-164) of the lower block:
@@ -318,14 +329,26 @@ __device__ __forceinline__ int rk4_step_lin_t(const Model& m, const double x[4],
   return amax;
 }
 
-__device__ __noinline__ void rk4_step_lin_slow(const Model& m, const double x[4], double u0, double u1, double xn[4],
-                                               LinD& L) {
-  rk4_step_lin_t<false>(m, x, u0, u1, xn, L);
+struct StepLin {
+  double xn[4];
+  LinD L;
+};
+__device__ __noinline__ StepLin rk4_step_lin_slow(const Model& m, double x0, double x1, double x2, double x3, double u0,
+                                                  double u1) {
+  const double x[4] = {x0, x1, x2, x3};
+  StepLin o;
+  rk4_step_lin_t<false>(m, x, u0, u1, o.xn, o.L);
+  return o;
 }
 __device__ __forceinline__ void rk4_step_lin(const Model& m, const double x[4], double u0, double u1, double xn[4],
                                              LinD& L) {
   const int amax = rk4_step_lin_t<true>(m, x, u0, u1, xn, L);
-  if (hi_too_large(amax)) rk4_step_lin_slow(m, x, u0, u1, xn, L);
+  if (hi_too_large(amax)) {
+    const StepLin o = rk4_step_lin_slow(m, x[0], x[1], x[2], x[3], u0, u1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xn[i] = o.xn[i];
+    L = o.L;
+  }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -1488,7 +1488,9 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
   const int64_t tiles = (B + 31) / 32;
   const char* force = getenv("ACRO_NEWTON_KERNEL");
   auto aligned = [](const void* q, uintptr_t al) { return (reinterpret_cast<uintptr_t>(q) % al) == 0; };
-  bool ring = tiles <= 148 * 6 && aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) &&
+  // measured on B200 (profiles/newton_batch_sweep.py): the ring kernel wins up to one full wave of 148 x 6
+  // one-warp blocks and again from two waves on; in between its second wave is mostly empty
+  bool ring = (tiles <= 148 * 6 || tiles >= 2 * 148 * 6) && aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) &&
               aligned(lin_ws, 128) && aligned(K, 128) && aligned(S, 128) &&
               aligned(ref->x, ref->per_problem ? 128 : 32) && aligned(ref->u, ref->per_problem ? 128 : 16);
   if (force && !strcmp(force, "ldg")) ring = false;

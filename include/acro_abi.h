@@ -25,9 +25,11 @@
  *    C*256 bytes (component c at the constant offset c*256): coalesced, vectorisable, and
  *    movable by a single bulk copy.  Buffers hold T*Bp*C doubles; padding lanes are never read
  *    for results.  In this notation:
- *        state trajectory X[N][4]      input trajectory U[N-1][2]
- *        gains            K[N-1][8]    (K_t is 2x4 row-major, component i*4+j)
- *        feed-forward     S[N-1][2]    (sigma_t)
+ *    Below, a tiled array with T time steps and C components is written  name {T x C}:
+ *        state trajectory X {N x 4}     input trajectory U {N-1 x 2}
+ *        gains            K {N-1 x 8}   (K_t is 2x4 row-major, component i*4+j)
+ *        feed-forward     S {N-1 x 2}   (sigma_t)
+ *    and point batches keep the bracket notation  x [4][B].
  *    acro_pack_soa / acro_unpack_soa convert from / to batch-major (B, T, C) arrays.
  *  - "Shared" reference data (one trajectory for the whole batch) is plain row-major
  *    [t][c], i.e. exactly the NumPy arrays of the reference: x_ref (N,4), u_ref (N-1,2),
@@ -82,7 +84,7 @@ typedef struct AcroWeights {
 
 /* Reference trajectory handed to the optimiser / tracker.
  * per_problem = 0: x (N,4) and u (N-1,2) row-major, shared by the batch.
- * per_problem = 1: x [N][4][B], u [N-1][2][B]. */
+ * per_problem = 1: x {N x 4}, u {N-1 x 2}. */
 typedef struct AcroRef {
   const double* x;
   const double* u;
@@ -124,14 +126,14 @@ int acro_linearize(const AcroParams* p, int64_t B, const double* x, const double
                    double* Bm, int discrete, void* stream);
 
 /* ---- G1-G11: trajectory_generation.py ---------------------------------------------- */
-/* simulate_open_loop(x0, u_traj)  tg:74-87.  x0 [4][B], U [N-1][2][B] (NULL = zeros)
- * -> X [N][4][B] */
+/* simulate_open_loop(x0, u_traj)  tg:74-87.  x0 [4][B], U {N-1 x 2} (NULL = zeros)
+ * -> X {N x 4} */
 int acro_rollout_open_loop(const AcroParams* p, int64_t B, int N, const double* x0, const double* U,
                            double* X, void* stream);
 /* total_cost(x_traj, u_traj, x_ref, u_ref, Q, R, Q_T)  tg:231-252 -> cost [B] */
 int acro_total_cost(const AcroWeights* w, int64_t B, int N, const double* X, const double* U,
                     const AcroRef* ref, double* cost, void* stream);
-/* compute_costate_trajectory  tg:138-159 -> lam [N][4][B].  (Its result is not used by the
+/* compute_costate_trajectory  tg:138-159 -> lam {N x 4}.  (Its result is not used by the
  * reference's Newton loop; exposed for completeness.) */
 int acro_costate(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X,
                  const double* U, const AcroRef* ref, double* lam, void* stream);
@@ -145,26 +147,26 @@ int acro_cost_derivatives(const AcroWeights* w, int64_t B, const double* x, cons
 int acro_discretize(int64_t B, const double* Ac, const double* Bc, double dt, double* Ad, double* Bd,
                     void* stream);
 /* build_stage_lists(x_traj, u_traj, x_ref, u_ref, lambda_seq)  tg:166-181 (lambda_seq is ignored by the
- * reference, tg:116-129): -> A [N-1][16][B], Bm [N-1][8][B], q [N-1][4][B], r [N-1][2][B], q_T [4][B].
+ * reference, tg:116-129): -> A {N-1 x 16}, Bm {N-1 x 8}, q {N-1 x 4}, r {N-1 x 2}, q_T [4][B].
  * The quadratic blocks are the constants 2Q, 2R, S = 0 and 2Q_T. */
 int acro_stage_lists(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X,
                      const double* U, const AcroRef* ref, double* A, double* Bm, double* q, double* r,
                      double* q_T, void* stream);
 /* calculate_K_and_sigma(A_list, B_list, Q_list, R_list, S_list, q_list, r_list, Q_T_block, q_T)
- * tg:183-216 on caller-supplied dense lists: A [T][16][B], Bm [T][8][B], Q [T][16][B], R [T][4][B],
- * S_cross [T][8][B] (NULL = 0), q [T][4][B], r [T][2][B], Q_T [16][B], q_T [4][B]
- * -> K [T][8][B], S [T][2][B], delta_J [B]. */
+ * tg:183-216 on caller-supplied dense lists: A {T x 16}, Bm {T x 8}, Q {T x 16}, R {T x 4},
+ * S_cross {T x 8} (NULL = 0), q {T x 4}, r {T x 2}, Q_T [16][B], q_T [4][B]
+ * -> K {T x 8}, S {T x 2}, delta_J [B]. */
 int acro_riccati_lists(int64_t B, int T, const double* A, const double* Bm, const double* Q, const double* R,
                        const double* S_cross, const double* q, const double* r, const double* Q_T,
                        const double* q_T, double* K, double* S, double* delta_J, void* stream);
 /* build_stage_lists + calculate_K_and_sigma fused  tg:166-216:
- * -> K [N-1][8][B], S [N-1][2][B], delta_J [B] (expected_reduction), sigma_norm [B] = max|sigma| */
+ * -> K {N-1 x 8}, S {N-1 x 2}, delta_J [B] (expected_reduction), sigma_norm [B] = max|sigma| */
 int acro_riccati_affine(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X,
                         const double* U, const AcroRef* ref, double* K, double* S, double* delta_J,
                         double* sigma_norm, void* stream);
 /* forward_closed_loop_update + total_cost for a set of G step sizes  tg:218-252.
  * One rollout per (problem b, candidate g).  gammas: [G][B] if gammas_per_problem else [G].
- * cost out [G][B].  Xn [G][N][4][B] and Un [G][N-1][2][B] may be NULL (cost only). */
+ * cost out [G][B].  Xn [G]{N x 4} and Un [G]{N-1 x 2} may be NULL (cost only). */
 int acro_closed_loop_rollout_cost(const AcroParams* p, const AcroWeights* w, int64_t B, int N,
                                   const double* X, const double* U, const double* K, const double* S,
                                   const AcroRef* ref, int G, const double* gammas,
@@ -177,9 +179,9 @@ int acro_armijo_select(int64_t B, int G, const double* cost_k, const double* del
                        const double* gammas, int gammas_per_problem, const double* cost_cand,
                        double c, int32_t* accepted, void* stream);
 /* newton_Algorithm  tg:298-398, one problem per thread, whole loop on the device.
- * In/out: X [N][4][B], U [N-1][2][B] (current iterate; written by init), cost [B],
+ * In/out: X {N x 4}, U {N-1 x 2} (current iterate; written by init), cost [B],
  * iters [B] int32, status [B] int32.  x0 [4][B] is read when opts->init.
- * Workspace: Xw, Uw same sizes as X, U; lin_ws [N-1][10][B] holds the discrete linearisation about the
+ * Workspace: Xw, Uw same sizes as X, U; lin_ws {N-1 x 10} holds the discrete linearisation about the
  * current iterate (written by the rollouts, read by the next backward pass; part of the state to keep when
  * resuming).  Out: K, S of the last computed iteration
  * (evaluated on the pre-update trajectory, as the reference returns them), delta_J [B],
@@ -201,12 +203,12 @@ int acro_stepsize_sweep(const AcroParams* p, const AcroWeights* w, int64_t P, in
 /* ---- T1-T5: trajectory_tracking.py ------------------------------------------------- */
 /* solve_LQR_tracking(x_opt, u_opt)  tt:170-203 with weights w->Q (Q_reg), w->R (R_reg) and
  * P_T = 2 Q_reg.  traj = the trajectory linearised about (AcroRef layout; shared => B = 1
- * problem and K is (N-1,2,4) row-major, per-problem => K [N-1][8][B]). */
+ * problem and K is (N-1,2,4) row-major, per-problem => K {N-1 x 8}). */
 int acro_lqr_gains(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const AcroRef* traj,
                    double* K, void* stream);
 /* simulate_tracking(x_opt, u_opt, K_reg, x0_perturbed)  tt:206-216.
- * traj/K shared (K (N-1,2,4)) or per-problem (K [N-1][8][B]) following traj->per_problem.
- * x0 [4][B] -> Xt [N][4][B], Ut [N-1][2][B]. */
+ * traj/K shared (K (N-1,2,4)) or per-problem (K {N-1 x 8}) following traj->per_problem.
+ * x0 [4][B] -> Xt {N x 4}, Ut {N-1 x 2}. */
 int acro_lqr_track(const AcroParams* p, int64_t B, int N, const AcroRef* traj, const double* K,
                    const double* x0, double* Xt, double* Ut, void* stream);
 /* compute_P_inf(A, B, Q, R)  tt:144-165.  A [16][B], Bm [8][B], weights from w->Q, w->R
@@ -214,10 +216,10 @@ int acro_lqr_track(const AcroParams* p, int64_t B, int N, const AcroRef* traj, c
 int acro_p_inf(const AcroWeights* w, int64_t B, const double* A, const double* Bm, int max_iter,
                double tol, double* P, int32_t* n_iter, void* stream);
 /* solver_mpc(x0, A_list, B_list, Q, R, Q_T, T_pred)  tt:73-140 restated as the
- * equality-constrained LQ problem it is.  x0 [4][B]; window A_w [(T_pred-1)][16][B],
- * B_w [(T_pred-1)][8][B]; terminal weight QT [16][B]; w->Q, w->R stage weights.
- * -> U0 [2][B], X_opt [T_pred][4][B], U_opt [T_pred][2][B] (X_opt/U_opt may be NULL),
- * K_ws [(T_pred-1)][8][B]: the gains of the sweep (out; required when X_opt/U_opt are asked for,
+ * equality-constrained LQ problem it is.  x0 [4][B]; window A_w {T_pred-1 x 16},
+ * B_w {T_pred-1 x 8}; terminal weight QT [16][B]; w->Q, w->R stage weights.
+ * -> U0 [2][B], X_opt {T_pred x 4}, U_opt {T_pred x 2} (X_opt/U_opt may be NULL),
+ * K_ws {T_pred-1 x 8}: the gains of the sweep (out; required when X_opt/U_opt are asked for,
  * else may be NULL). */
 int acro_mpc_solve(const AcroWeights* w, int64_t B, int T_pred, const double* x0, const double* A_w,
                    const double* B_w, const double* QT, double* U0, double* X_opt, double* U_opt,
@@ -228,10 +230,10 @@ int acro_mpc_solve(const AcroWeights* w, int64_t B, int T_pred, const double* x0
  * ref shared: the first-move gains are computed once per time step by one sweep each
  * (K0 [(T-1)][8] workspace/out, row-major) and applied to every problem;
  * ref per problem: every problem runs its own sweeps.  lin_ws is a workspace for the compact
- * linearisation: [N-1][10] (shared) or [N-1][10][B] (per problem).
+ * linearisation: [N-1][10] (shared) or {N-1 x 10} (per problem).
  * x_f HOST [4], u_f HOST [2]  (tt:33-34).
  * QT_inf: DEVICE terminal weight (from acro_p_inf), [16] or, if qt_per_problem, [16][B].
- * -> Xr [T][4][B], Ur [T-1][2][B]; n_solves (HOST int64*, may be NULL) = Riccati sweeps run. */
+ * -> Xr {T x 4}, Ur {T-1 x 2}; n_solves (HOST int64*, may be NULL) = Riccati sweeps run. */
 int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
                    const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
                    int qt_per_problem, const double* x0, double* K0, double* lin_ws, double* Xr,
