@@ -519,3 +519,91 @@ def test_full_size_c3_properties(bt):
     ok = np.isfinite(xe).all(axis=1)
     assert ok.mean() > 0.99
     assert np.median(np.abs(xe[ok] - d["x"][-1]).max(axis=1)) < 1e-2
+
+
+# ------------------------------------------------------------------------------------- ragged batches (ring kernel)
+def _short_ref(fa_ref, N=61):
+    x_ref, u_ref, _ = fa_ref
+    return x_ref[:N].copy(), u_ref[:N - 1].copy()
+
+
+@pytest.mark.parametrize("kernel", ["ring", "ldg"])
+def test_newton_ragged_line_search_failures(bt, fa_ref, kernel, monkeypatch):
+    """gamma_0 = 1 on a short horizon: problems back-track up to 20 times and fail the line search at different
+    iterations (status 3 after 3-7 iterations).  A warp therefore holds finished and running problems side by
+    side; 40 problems = one full tile + a partial one.  Same tries, same accepted steps, same final iterates."""
+    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    xr, ur = _short_ref(fa_ref)
+    x0 = np.random.default_rng(11).uniform(-0.3, 0.3, (40, 4))
+    st = bt.newton_solve(soa(x0), bt.make_ref(xr, ur), max_iters=25, tol=2e-3, gamma_0=1.0)
+    torch.cuda.synchronize()
+    X, U, K, S = aos(st.X), aos(st.U), kmat(st.K), aos(st.S)
+    iters, status = st.iters.cpu().numpy(), st.status.cpu().numpy()
+    seen = set()
+    for b in (0, 1, 2, 5, 9, 31, 32, 39):
+        x, u, Ko, so, h = O.newton_Algorithm(x0[b], xr, ur, max_iters=25, tol=2e-3, gamma_0=1.0)
+        assert status[b] == h["status"] and iters[b] == h["iters"], (b, status[b], iters[b], h["status"], h["iters"])
+        n_acc = len(h["n_try"])
+        assert list(st.hist_ntry[:n_acc, b].cpu().numpy()) == h["n_try"]
+        assert list(st.hist_gamma[:n_acc, b].cpu().numpy()) == h["gamma"]
+        assert rel_err(st.hist_cost[:n_acc + 1, b].cpu().numpy(), h["cost"]) < TOL
+        assert rel_err(X[b], x) < TOL and rel_err(U[b], u) < TOL
+        assert rel_err(S[b], so) < TOL and rel_err(K[b], Ko) < 1e-7
+        seen.add((h["status"], h["iters"]))
+    assert len(seen) >= 3  # genuinely ragged
+
+
+@pytest.mark.parametrize("kernel", ["ring", "ldg"])
+def test_newton_ragged_convergence_per_problem_refs_and_weights(bt, fa_ref, kernel, monkeypatch):
+    """Per-problem reference trajectories (scaled copies) and per-problem weights: problems converge after different
+    numbers of iterations inside the same warp."""
+    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    xr0, ur0 = _short_ref(fa_ref)
+    n = 40
+    a = np.linspace(0.2, 1.5, n)
+    xr = xr0[None] * a[:, None, None]
+    ur = ur0[None] * a[:, None, None]
+    rng = np.random.default_rng(3)
+    x0 = rng.uniform(-0.1, 0.1, (n, 4))
+    Qs = np.array([np.diag([130.0, 30.0, 1e-4, 1e-4]) * (1 + 0.5 * rng.uniform()) for _ in range(n)])
+    Rs = np.array([np.diag([1e-6, 1.5]) * (1 + 0.5 * rng.uniform()) for _ in range(n)])
+    QTs = np.array([np.diag([130.0, 130.0, 1.0, 1.0]) * (1 + 0.5 * rng.uniform()) for _ in range(n)])
+    ref = bt.Ref(soa(xr), soa(ur))
+    for per_problem_w in (False, True):
+        if per_problem_w:
+            w = bt.Weights(Qs[0], Rs[0], QTs[0], Q_b=dev(Qs.reshape(n, 16).T), R_b=dev(Rs.reshape(n, 4).T),
+                           QT_b=dev(QTs.reshape(n, 16).T))
+        else:
+            w = bt.newton_weights()
+        st = bt.newton_solve(soa(x0), ref, max_iters=30, tol=0.3, gamma_0=0.5, w=w)
+        torch.cuda.synchronize()
+        X, U, K, S = aos(st.X), aos(st.U), kmat(st.K), aos(st.S)
+        iters, status = st.iters.cpu().numpy(), st.status.cpu().numpy()
+        seen = set()
+        for b in (0, 7, 19, 31, 32, 39):
+            kw = dict(Q=Qs[b], R=Rs[b], Q_T=QTs[b]) if per_problem_w else {}
+            x, u, Ko, so, h = O.newton_Algorithm(x0[b], xr[b], ur[b], max_iters=30, tol=0.3, gamma_0=0.5, **kw)
+            assert status[b] == h["status"] and iters[b] == h["iters"]
+            assert rel_err(X[b], x) < TOL and rel_err(U[b], u) < TOL and rel_err(S[b], so) < TOL
+            assert rel_err(K[b], Ko) < 1e-7
+            assert abs(st.cost[b].item() - h["cost"][-1]) < TOL * max(1.0, abs(h["cost"][-1]))
+            seen.add(h["iters"])
+        assert (status == 1).all() and len(seen) >= 3
+
+
+def test_newton_warm_start(bt, fa_ref):
+    """init = 2: start from caller-supplied inputs instead of u = 0 (the commented-out alternative at tg:310)."""
+    xr, ur = _short_ref(fa_ref)
+    x0 = np.random.default_rng(5).uniform(-0.1, 0.1, (3, 4))
+    U0 = np.repeat(ur[None], 3, 0) * 0.5
+    st = bt.newton_solve(soa(x0), bt.make_ref(xr, ur), max_iters=2, tol=0.0, gamma_0=0.2, warm_start_U=soa(U0))
+    torch.cuda.synchronize()
+    for b in range(3):
+        X0 = O.simulate_open_loop(x0[b], U0[b])
+        c0 = float(O.total_cost(X0, U0[b], xr, ur))
+        assert abs(st.hist_cost[0, b].item() - c0) < TOL * c0
+        x, u, cost = X0, U0[b], c0
+        for k in range(2):
+            it = O.newton_iteration(x, u, cost, xr, ur, 0.2)
+            x, u, cost = it["x"], it["u"], it["cost"]
+        assert rel_err(aos(st.X)[b], x) < TOL and rel_err(aos(st.U)[b], u) < TOL
