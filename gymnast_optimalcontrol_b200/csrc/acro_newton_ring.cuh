@@ -49,6 +49,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// One lane of the (fully active) warp, chosen by the hardware.  ptxas knows that exactly one lane follows the
+// branch on this predicate, so the bulk copies inside keep their uniform-register operands (a branch on
+// `lane == 0` makes it wrap every copy in an ELECT / R2UR.BROADCAST loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\telect.sync %%rx|%%px, %2;\n\t@%%px mov.s32 %1, 1;\n\tmov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 __device__ __forceinline__ double lds(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -94,7 +105,7 @@ __device__ __forceinline__ FillPtrs fill_begin(const TilePtrs& p, int steps) {
 }
 template <bool RPB, bool FWD>
 __device__ __forceinline__ void ring_fill(Ring& r, const TilePtrs& p, FillPtrs& f, int lane) {
-  if (lane == 0) {
+  if (elect_one()) {
     const uint32_t st = r.iss & (ACRO_RING_D - 1);
     const uint32_t bar = r.bars + st * 8, dst = r.data + st * stage_bytes<RPB>();
     mbar_expect_tx(bar, tx_bytes<RPB>());
