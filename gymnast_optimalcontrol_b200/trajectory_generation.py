@@ -43,6 +43,28 @@ def _ref(x_ref, u_ref):
     return bt.make_ref(x_ref, u_ref)
 
 
+def compute_equilibrium(u_target, theta_guess, version=1, tol=1e-14, max_iter=50):
+    """Equilibrium of the gravity vector, G(theta1, theta2) = u_target (trajectory_generation.py:22-39).
+
+    The reference calls SciPy's MINPACK `hybr` root finder; the system is two smooth equations in two unknowns,
+        g1 sin(th1) + g2 sin(th1 + th2) = u1,      g2 sin(th1 + th2) = u2,
+    so a Newton iteration from the same initial guess is used here (host side: this builds an input of the hot
+    path once per problem family).  Raises RuntimeError like the reference if it does not converge."""
+    p = bt.PARAM_SETS[version]
+    g1 = p["g"] * (p["lc1"] * p["m1"] + p["m2"] * p["l1"])
+    g2 = p["g"] * p["m2"] * p["lc2"]
+    u = np.asarray(u_target, dtype=float).reshape(-1)
+    th = np.asarray(theta_guess, dtype=float).reshape(2).copy()
+    for _ in range(max_iter):
+        s1, c1, s12, c12 = np.sin(th[0]), np.cos(th[0]), np.sin(th[0] + th[1]), np.cos(th[0] + th[1])
+        res = np.array([g1 * s1 + g2 * s12 - u[0], g2 * s12 - u[1]])
+        if np.max(np.abs(res)) < tol:
+            return np.array([th[0], th[1], 0.0, 0.0]), u.copy()
+        J = np.array([[g1 * c1 + g2 * c12, g2 * c12], [g2 * c12, g2 * c12]])
+        th = th - np.linalg.solve(J, res)
+    raise RuntimeError("Root finder failed: Newton iteration on G(theta) = u did not converge")
+
+
 def define_reference_piecewise(T, x_e1, x_e2, u_e1, u_e2):
     """Two constant segments, x_e1 for t < T/2 and x_e2 after (trajectory_generation.py:41-58).  Host-side
     construction of an input; not a compute kernel."""

@@ -93,6 +93,18 @@ def test_reference_builders_match_reference_shapes():
     assert np.array_equal(xr, g2["x_ref"]) and np.array_equal(ur, g2["u_ref"])
 
 
+def test_compute_equilibrium_matches_reference_root_finder():
+    """main.py:33-38 (task_1): the two equilibria the reference obtains with scipy.optimize.root(hybr)."""
+    from gymnast_optimalcontrol_b200 import trajectory_generation as tg
+    g = np.load(os.path.join(ROOT, "tests", "golden", "newton_task1.npz"))
+    x_e1, u_e1 = tg.compute_equilibrium(np.array([0.0, 0.0]), (0.1, -0.1))
+    x_e2, u_e2 = tg.compute_equilibrium(np.array([0.5, 0.5]), (0.35, -0.35))
+    assert np.max(np.abs(x_e1 - g["x_e1"])) < 1e-10 and np.max(np.abs(x_e2 - g["x_e2"])) < 1e-10
+    assert np.array_equal(u_e1, g["u_e1"]) and np.array_equal(u_e2, g["u_e2"])
+    with pytest.raises(RuntimeError, match="Root finder failed"):
+        tg.compute_equilibrium(np.array([1e3, 1e3]), (0.1, -0.1))
+
+
 def test_product_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "gymnast_optimalcontrol_b200")
     for dirpath, _, files in os.walk(pkg):

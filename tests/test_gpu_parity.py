@@ -607,3 +607,58 @@ def test_newton_warm_start(bt, fa_ref):
             it = O.newton_iteration(x, u, cost, xr, ur, 0.2)
             x, u, cost = it["x"], it["u"], it["cost"]
         assert rel_err(aos(st.X)[b], x) < TOL and rel_err(aos(st.U)[b], u) < TOL
+
+
+# ------------------------------------------------------------------------------------- properties / other parameter sets
+def test_jacobian_matches_finite_differences(bt):
+    """Calculate_A_B_matrixes is the Jacobian of continuous_dynamics (checked on the device against central differences)."""
+    rng = np.random.default_rng(17)
+    n = 64
+    x = np.concatenate([rng.uniform(-3, 3, (n, 2)), rng.uniform(-6, 6, (n, 2))], axis=1)
+    u = rng.uniform(-10, 10, (n, 2))
+    A, Bm = bt.linearize(soa(x), soa(u), discrete=False)
+    A = np.transpose(A.cpu().numpy(), (2, 0, 1))
+    Bm = np.transpose(Bm.cpu().numpy(), (2, 0, 1))
+    eps = 1e-6
+    for j in range(4):
+        dxp, dxm = x.copy(), x.copy()
+        dxp[:, j] += eps
+        dxm[:, j] -= eps
+        col = (aos(bt.continuous_dynamics(soa(dxp), soa(u))) - aos(bt.continuous_dynamics(soa(dxm), soa(u)))) / (2 * eps)
+        assert np.max(np.abs(col - A[:, :, j])) < 2e-7 * max(1.0, np.abs(A).max())
+    dup, dum = u.copy(), u.copy()
+    dup[:, 1] += eps
+    dum[:, 1] -= eps
+    col = (aos(bt.continuous_dynamics(soa(x), soa(dup))) - aos(bt.continuous_dynamics(soa(x), soa(dum)))) / (2 * eps)
+    assert np.max(np.abs(col - Bm[:, :, 1])) < 1e-7
+    assert np.all(Bm[:, :, 0] == 0.0)  # tau_1 is not an input of the plant (dynamics.py:205)
+
+
+def test_newton_other_parameter_sets(bt, fa_ref):
+    """params_2 / params_3 (dynamics.py:31-61) through the whole Newton iteration."""
+    xr, ur = _short_ref(fa_ref)
+    x0 = np.random.default_rng(9).uniform(-0.2, 0.2, (3, 4))
+    for v in (2, 3):
+        st = bt.newton_solve(soa(x0), bt.make_ref(xr, ur), max_iters=4, tol=0.0, gamma_0=0.3, params=bt.make_params(v))
+        torch.cuda.synchronize()
+        m = O.Model(O.PARAM_SETS[v])
+        for b in range(3):
+            x, u, K, s, h = O.newton_Algorithm(x0[b], xr, ur, max_iters=4, tol=0.0, gamma_0=0.3, m=m)
+            assert rel_err(aos(st.X)[b], x) < TOL and rel_err(aos(st.U)[b], u) < TOL
+            assert rel_err(kmat(st.K)[b], K) < TOL and rel_err(aos(st.S)[b], s) < TOL
+            assert rel_err(st.hist_cost[:5, b].cpu().numpy(), h["cost"]) < TOL
+
+
+def test_huge_angles_take_the_library_path(bt):
+    """|theta| > 1e9 (a diverging rollout) leaves the polynomial sin/cos range: the step is redone with the library
+    routine and still matches the oracle; inf / nan propagate."""
+    x = np.array([[3.0e9, -7.5e10, 0.3, -0.2], [1.0e15, 2.0, 1.0, 1.0], [0.5, 0.25, 0.1, 0.2], [np.inf, 0.0, 0.0, 0.0],
+                  [0.1, np.nan, 0.0, 0.0]])
+    u = np.array([[0.0, 1.0]] * 5)
+    f = aos(bt.continuous_dynamics(soa(x), soa(u)))
+    s = aos(bt.rk4_step(soa(x), soa(u)))
+    fo, so = O.continuous_dynamics(x[:3], u[:3]), O.dynamics(x[:3], u[:3])
+    assert np.max(np.abs(f[:3] - fo)) < 1e-6 * max(1.0, np.abs(fo).max())  # angle-addition vs sin(fl(th1+th2)) at 1e10
+    assert rel_err(s[2], so[2]) < TOL
+    assert np.isfinite(s[:2]).all() and not np.isfinite(s[3:]).all()
+    assert not np.isfinite(f[3]).all() and not np.isfinite(f[4]).all()
