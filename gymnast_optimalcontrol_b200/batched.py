@@ -4,8 +4,8 @@ Every function here is a thin wrapper that allocates outputs with torch and call
 entry point of libacro_b200.so on torch's current stream.
 
     point batches   plain tensors, problem index last:  state (4, B), input (2, B), scalars (B,)
-    time-indexed    ``Traj`` objects: a tensor of shape (T, ntiles, C, 32) in the tiled layout
-                    A[t][tile][c][lane] of include/acro_abi.h plus the true batch size B
+    time-indexed    ``Traj`` objects: a tensor of shape (ntiles, T, C, 32) in the tiled layout
+                    A[tile][t][c][lane] of include/acro_abi.h plus the true batch size B
                     (X: C=4, U: C=2, K: C=8 = 2x4 row-major, S: C=2)
 
 torch is used for device memory and streams only.  There is no CPU path: without a CUDA
@@ -57,24 +57,24 @@ def _stream():
 
 
 class Traj:
-    """A time-indexed batch array in the device layout A[t][tile][c][lane] (tile = b // 32, lane = b % 32)."""
+    """A time-indexed batch array in the device layout A[tile][t][c][lane] (tile = b // 32, lane = b % 32)."""
     __slots__ = ("data", "B")
 
     def __init__(self, data, B):
-        if data.dim() != 4 or data.shape[3] != 32 or data.shape[1] != ntiles(B):
-            raise ValueError("expected shape (T, %d, C, 32) for B = %d, got %r" % (ntiles(B), B, tuple(data.shape)))
+        if data.dim() != 4 or data.shape[3] != 32 or data.shape[0] != ntiles(B):
+            raise ValueError("expected shape (%d, T, C, 32) for B = %d, got %r" % (ntiles(B), B, tuple(data.shape)))
         self.data, self.B = data, int(B)
 
-    T = property(lambda self: self.data.shape[0])
+    T = property(lambda self: self.data.shape[1])
     C = property(lambda self: self.data.shape[2])
 
     @staticmethod
     def empty(T, C, B):
-        return Traj(_empty(T, ntiles(B), C, 32), B)
+        return Traj(_empty(ntiles(B), T, C, 32), B)
 
     @staticmethod
     def zeros(T, C, B):
-        return Traj(torch.zeros(T, ntiles(B), C, 32, dtype=F64, device=device()), B)
+        return Traj(torch.zeros(ntiles(B), T, C, 32, dtype=F64, device=device()), B)
 
     @staticmethod
     def from_batch_major(a):
@@ -278,8 +278,8 @@ def closed_loop_rollout_cost(X, U, K, S, ref, w, gammas, store=False, params=DEF
     N, Bn = X.T, X.B
     G = gammas.shape[0]
     cost = _empty(G, Bn)
-    Xn = _empty(G, N, ntiles(Bn), 4, 32) if store else None
-    Un = _empty(G, N - 1, ntiles(Bn), 2, 32) if store else None
+    Xn = _empty(G, ntiles(Bn), N, 4, 32) if store else None
+    Un = _empty(G, ntiles(Bn), N - 1, 2, 32) if store else None
     call("acro_closed_loop_rollout_cost", C.byref(params), w.ref(), Bn, N, _p(X), _p(U), _p(K), _p(S), ref.ref(), G,
          _p(gammas), int(gammas.dim() == 2), _p(Xn), _p(Un), _p(cost), _stream())
     if store:

@@ -184,21 +184,21 @@ __global__ void k_rollout_open(const __grid_constant__ Model m, int64_t B, int N
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     x[c] = x0[c * B + b];
-    X[soa(0, 4, c, B, b)] = x[c];
+    X[soa(0, 4, c, N, b)] = x[c];
   }
-  double u0 = U ? U[soa(0, 2, 0, B, b)] : 0.0, u1 = U ? U[soa(0, 2, 1, B, b)] : 0.0;
+  double u0 = U ? U[soa(0, 2, 0, N - 1, b)] : 0.0, u1 = U ? U[soa(0, 2, 1, N - 1, b)] : 0.0;
   for (int t = 0; t < N - 1; ++t) {
     double n0 = 0.0, n1 = 0.0;
     if (U && t + 1 < N - 1) {  // prefetch the next input while this step computes
-      n0 = U[soa(t + 1, 2, 0, B, b)];
-      n1 = U[soa(t + 1, 2, 1, B, b)];
+      n0 = U[soa(t + 1, 2, 0, N - 1, b)];
+      n1 = U[soa(t + 1, 2, 1, N - 1, b)];
     }
     double xn[4];
     rk4_step(m, x, u0, u1, xn);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       x[c] = xn[c];
-      X[soa(t + 1, 4, c, B, b)] = x[c];
+      X[soa(t + 1, 4, c, N, b)] = x[c];
     }
     u0 = n0;
     u1 = n1;
@@ -213,15 +213,15 @@ __device__ __forceinline__ double total_cost_dev(const WV<WPB>& w, const RefV<RP
   for (int t = 0; t < N - 1; ++t) {
     double dx[4], du[2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) dx[c] = X[soa(t, 4, c, ld, b)] - ref.X(t, c);
+    for (int c = 0; c < 4; ++c) dx[c] = X[soa(t, 4, c, N, b)] - ref.X(t, c);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) du[c] = U[soa(t, 2, c, ld, b)] - ref.U(t, c);
+    for (int c = 0; c < 2; ++c) du[c] = U[soa(t, 2, c, N - 1, b)] - ref.U(t, c);
     cost += quad4(dx, [&](int i, int j) { return w.Q(i, j); });
     cost += quad2(du, [&](int i, int j) { return w.R(i, j); });
   }
   double dx[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) dx[c] = X[soa(N - 1, 4, c, ld, b)] - ref.X(N - 1, c);
+  for (int c = 0; c < 4; ++c) dx[c] = X[soa(N - 1, 4, c, N, b)] - ref.X(N - 1, c);
   cost += quad4(dx, [&](int i, int j) { return w.QT(i, j); });
   return cost;
 }
@@ -233,7 +233,7 @@ __global__ void k_total_cost(const __grid_constant__ KWeights kw, int64_t B, int
   const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
   const WV<WPB> w(kw, B, b);
-  const RefV<RPB> ref{rx, ru, B, b};
+  const RefV<RPB> ref{rx, ru, N, b};
   cost[b] = total_cost_dev(w, ref, N, X, U, B, b);
 }
 
@@ -245,23 +245,23 @@ __global__ void k_costate(const __grid_constant__ Model m, const __grid_constant
   const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
   const WV<WPB> w(kw, B, b);
-  const RefV<RPB> ref{rx, ru, B, b};
+  const RefV<RPB> ref{rx, ru, N, b};
   double l[4], dx[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) dx[c] = X[soa(N - 1, 4, c, B, b)] - ref.X(N - 1, c);
+  for (int c = 0; c < 4; ++c) dx[c] = X[soa(N - 1, 4, c, N, b)] - ref.X(N - 1, c);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     double s = w.QT2(i, 0) * dx[0];
 #pragma unroll
     for (int j = 1; j < 4; ++j) s = fma(w.QT2(i, j), dx[j], s);
     l[i] = s;
-    lam[soa(N - 1, 4, i, B, b)] = s;
+    lam[soa(N - 1, 4, i, N, b)] = s;
   }
   for (int t = N - 2; t >= 0; --t) {
     double x[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) x[c] = X[soa(t, 4, c, B, b)];
-    const LinD L = linearize_d(m, x, U[soa(t, 2, 0, B, b)], U[soa(t, 2, 1, B, b)]);
+    for (int c = 0; c < 4; ++c) x[c] = X[soa(t, 4, c, N, b)];
+    const LinD L = linearize_d(m, x, U[soa(t, 2, 0, N - 1, b)], U[soa(t, 2, 1, N - 1, b)]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) dx[c] = x[c] - ref.X(t, c);
     double g[4];
@@ -278,7 +278,7 @@ __global__ void k_costate(const __grid_constant__ Model m, const __grid_constant
     l[2] = g[2] + fma(L.a[1][2], l3, fma(L.a[0][2], l2, m.dt * l0));
     l[3] = g[3] + fma(L.a[1][3], l3, fma(L.a[0][3], l2, m.dt * l1));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) lam[soa(t, 4, i, B, b)] = l[i];
+    for (int i = 0; i < 4; ++i) lam[soa(t, 4, i, N, b)] = l[i];
   }
 }
 
@@ -286,17 +286,17 @@ __global__ void k_costate(const __grid_constant__ Model m, const __grid_constant
 // own element, so one instruction covers the 256 B row of the warp; no register, no scoreboard.
 #define ACRO_PF_DIST 4
 template <int C>
-__device__ __forceinline__ void l2_prefetch_rows(const double* __restrict__ A, int t, int64_t ld, int64_t b) {
+__device__ __forceinline__ void l2_prefetch_rows(const double* __restrict__ A, int t, int64_t T, int64_t b) {
   // the C rows of the warp's step are one block of 2*C lines of 128 B: lane l names line l
   const int lane = int(b & 31);
-  if (lane < 2 * C) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + soa(t, C, 0, ld, b & ~int64_t(31)) + lane * 16));
+  if (lane < 2 * C) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + soa(t, C, 0, T, b & ~int64_t(31)) + lane * 16));
 }
 
 // compact discrete linearisation lin[t][10][ld]: a[0][0..3], a[1][0..3], b[0], b[1]
-// ld == 0 means a single shared linearisation stored plainly as lin[t][10]
-__device__ __forceinline__ LinD load_lin(const double* __restrict__ lin, int t, int64_t ld, int64_t b) {
+// T = number of time steps of the tiled array; T == 0 means a single shared linearisation stored plainly as lin[t][10]
+__device__ __forceinline__ LinD load_lin(const double* __restrict__ lin, int t, int64_t T, int64_t b) {
   LinD L;
-  if (ld == 0) {
+  if (T == 0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       L.a[0][j] = __ldg(lin + t * 10 + j);
@@ -307,23 +307,23 @@ __device__ __forceinline__ LinD load_lin(const double* __restrict__ lin, int t, 
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      L.a[0][j] = lin[soa(t, 10, j, ld, b)];
-      L.a[1][j] = lin[soa(t, 10, 4 + j, ld, b)];
+      L.a[0][j] = lin[soa(t, 10, j, T, b)];
+      L.a[1][j] = lin[soa(t, 10, 4 + j, T, b)];
     }
-    L.b[0] = lin[soa(t, 10, 8, ld, b)];
-    L.b[1] = lin[soa(t, 10, 9, ld, b)];
+    L.b[0] = lin[soa(t, 10, 8, T, b)];
+    L.b[1] = lin[soa(t, 10, 9, T, b)];
   }
   L.b0[0] = L.b0[1] = 0.0;
   return L;
 }
-__device__ __forceinline__ void store_lin(double* __restrict__ lin, int t, int64_t ld, int64_t b, const LinD& L) {
+__device__ __forceinline__ void store_lin(double* __restrict__ lin, int t, int64_t T, int64_t b, const LinD& L) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    lin[soa(t, 10, j, ld, b)] = L.a[0][j];
-    lin[soa(t, 10, 4 + j, ld, b)] = L.a[1][j];
+    lin[soa(t, 10, j, T, b)] = L.a[0][j];
+    lin[soa(t, 10, 4 + j, T, b)] = L.a[1][j];
   }
-  lin[soa(t, 10, 8, ld, b)] = L.b[0];
-  lin[soa(t, 10, 9, ld, b)] = L.b[1];
+  lin[soa(t, 10, 8, T, b)] = L.b[0];
+  lin[soa(t, 10, 9, T, b)] = L.b[1];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -342,7 +342,7 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
   {
     double dx[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) dx[c] = X[soa(N - 1, 4, c, ld, b)] - ref.X(N - 1, c);
+    for (int c = 0; c < 4; ++c) dx[c] = X[soa(N - 1, 4, c, N, b)] - ref.X(N - 1, c);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       double s = w.QT2(i, 0) * dx[0];
@@ -359,23 +359,23 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
   double x[4], u[2], xr[4], ur[2];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    x[c] = X[soa(N - 2, 4, c, ld, b)];
+    x[c] = X[soa(N - 2, 4, c, N, b)];
     xr[c] = ref.X(N - 2, c);
   }
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    u[c] = U[soa(N - 2, 2, c, ld, b)];
+    u[c] = U[soa(N - 2, 2, c, N - 1, b)];
     ur[c] = ref.U(N - 2, c);
   }
   const QhQ2<WV<WPB>> Qh{w};
   const Lu2Col col = lu2_col(w.R2(0, 0), w.R2(0, 1));
   LinD Lc;
-  if (HAVE_LIN) Lc = load_lin(lin, N - 2, ld, b);
+  if (HAVE_LIN) Lc = load_lin(lin, N - 2, N - 1, b);
   for (int t = N - 2; t >= 0; --t) {
     if (t > ACRO_PF_DIST) {
-      l2_prefetch_rows<4>(X, t - 1 - ACRO_PF_DIST, ld, b);
-      l2_prefetch_rows<2>(U, t - 1 - ACRO_PF_DIST, ld, b);
-      if (HAVE_LIN) l2_prefetch_rows<10>(lin, t - 1 - ACRO_PF_DIST, ld, b);
+      l2_prefetch_rows<4>(X, t - 1 - ACRO_PF_DIST, N, b);
+      l2_prefetch_rows<2>(U, t - 1 - ACRO_PF_DIST, N - 1, b);
+      if (HAVE_LIN) l2_prefetch_rows<10>(lin, t - 1 - ACRO_PF_DIST, N - 1, b);
     }
     const LinD L = HAVE_LIN ? Lc : linearize_d(m, x, u[0], u[1]);
     double dx[4], du[2], q[4], r[2];
@@ -397,23 +397,23 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
     if (t > 0) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        x[c] = X[soa(t - 1, 4, c, ld, b)];
+        x[c] = X[soa(t - 1, 4, c, N, b)];
         xr[c] = ref.X(t - 1, c);
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        u[c] = U[soa(t - 1, 2, c, ld, b)];
+        u[c] = U[soa(t - 1, 2, c, N - 1, b)];
         ur[c] = ref.U(t - 1, c);
       }
     }
     double Kt[8], st[2];
     riccati_step<true, false>(P, p, L, m.dt, Qh, col, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, r, Kt, st, dJ);
-    if (HAVE_LIN && t > 0) Lc = load_lin(lin, t - 1, ld, b);
+    if (HAVE_LIN && t > 0) Lc = load_lin(lin, t - 1, N - 1, b);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) K[soa(t, 8, e, ld, b)] = Kt[e];
+    for (int e = 0; e < 8; ++e) K[soa(t, 8, e, N - 1, b)] = Kt[e];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      S[soa(t, 2, e, ld, b)] = st[e];
+      S[soa(t, 2, e, N - 1, b)] = st[e];
       const double a = fabs(st[e]);
       sn = (a > sn || a != a) ? a : sn;  // NaN is sticky, like np.max(np.abs(sigma))
     }
@@ -430,7 +430,7 @@ __global__ void k_riccati_affine(const __grid_constant__ Model m, const __grid_c
   const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
   const WV<WPB> w(kw, B, b);
-  const RefV<RPB> ref{rx, ru, B, b};
+  const RefV<RPB> ref{rx, ru, N, b};
   double d, s;
   backward_pass<WPB, RPB, false>(m, w, ref, N, X, U, nullptr, K, S, B, b, d, s);
   dJ[b] = d;
@@ -448,20 +448,20 @@ struct StepIn {
 template <class REF>
 __device__ __forceinline__ StepIn load_step(const double* __restrict__ X, const double* __restrict__ U,
                                             const double* __restrict__ K, const double* __restrict__ S,
-                                            const REF& ref, int t, int64_t ld, int64_t b) {
+                                            const REF& ref, int t, int64_t N, int64_t b) {
   StepIn in;
 #pragma unroll
   for (int c = 0; c < 4; ++c) in.xr[c] = ref.X(t, c);
 #pragma unroll
   for (int c = 0; c < 2; ++c) in.ur[c] = ref.U(t, c);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) in.x[c] = X[soa(t, 4, c, ld, b)];
+  for (int c = 0; c < 4; ++c) in.x[c] = X[soa(t, 4, c, N, b)];
 #pragma unroll
-  for (int c = 0; c < 2; ++c) in.u[c] = U[soa(t, 2, c, ld, b)];
+  for (int c = 0; c < 2; ++c) in.u[c] = U[soa(t, 2, c, N - 1, b)];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) in.k[c] = K[soa(t, 8, c, ld, b)];
+  for (int c = 0; c < 8; ++c) in.k[c] = K[soa(t, 8, c, N - 1, b)];
 #pragma unroll
-  for (int c = 0; c < 2; ++c) in.s[c] = S[soa(t, 2, c, ld, b)];
+  for (int c = 0; c < 2; ++c) in.s[c] = S[soa(t, 2, c, N - 1, b)];
   return in;
 }
 
@@ -474,18 +474,18 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
                                                double* __restrict__ lin_out = nullptr) {
   double xp[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) xp[c] = X[soa(0, 4, c, ld, b)];
+  for (int c = 0; c < 4; ++c) xp[c] = X[soa(0, 4, c, N, b)];
   double cost = 0.0;
-  StepIn in = load_step(X, U, K, S, ref, 0, ld, b);
+  StepIn in = load_step(X, U, K, S, ref, 0, N, b);
   double xrT[4];  // terminal reference, loaded early
 #pragma unroll
   for (int c = 0; c < 4; ++c) xrT[c] = ref.X(N - 1, c);
   for (int t = 0; t < N - 1; ++t) {
     if (t + 1 + ACRO_PF_DIST < N - 1) {
-      l2_prefetch_rows<4>(X, t + 1 + ACRO_PF_DIST, ld, b);
-      l2_prefetch_rows<2>(U, t + 1 + ACRO_PF_DIST, ld, b);
-      l2_prefetch_rows<8>(K, t + 1 + ACRO_PF_DIST, ld, b);
-      l2_prefetch_rows<2>(S, t + 1 + ACRO_PF_DIST, ld, b);
+      l2_prefetch_rows<4>(X, t + 1 + ACRO_PF_DIST, N, b);
+      l2_prefetch_rows<2>(U, t + 1 + ACRO_PF_DIST, N - 1, b);
+      l2_prefetch_rows<8>(K, t + 1 + ACRO_PF_DIST, N - 1, b);
+      l2_prefetch_rows<2>(S, t + 1 + ACRO_PF_DIST, N - 1, b);
     }
     double dx[4], up[2];
 #pragma unroll
@@ -499,9 +499,9 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
     }
     if (STORE) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) Xn[soa(t, 4, c, ldo, bo)] = xp[c];
+      for (int c = 0; c < 4; ++c) Xn[soa(t, 4, c, N, bo)] = xp[c];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) Un[soa(t, 2, c, ldo, bo)] = up[c];
+      for (int c = 0; c < 2; ++c) Un[soa(t, 2, c, N - 1, bo)] = up[c];
     }
     double ex[4], eu[2];
 #pragma unroll
@@ -512,12 +512,12 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
     cost += quad2(eu, [&](int i, int j) { return w.R(i, j); });
     // operands of step t+1 straight into the registers step t no longer needs; the four RK4 stages below
     // (about a thousand cycles) cover the load latency
-    if (t + 1 < N - 1) in = load_step(X, U, K, S, ref, t + 1, ld, b);
+    if (t + 1 < N - 1) in = load_step(X, U, K, S, ref, t + 1, N, b);
     double xn[4];
     if (LIN) {
       LinD L;
       rk4_step_lin(m, xp, up[0], up[1], xn, L);
-      store_lin(lin_out, t, ldo, bo, L);
+      store_lin(lin_out, t, N - 1, bo, L);
     } else {
       rk4_step(m, xp, up[0], up[1], xn);
     }
@@ -527,7 +527,7 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
   double ex[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    if (STORE) Xn[soa(N - 1, 4, c, ldo, bo)] = xp[c];
+    if (STORE) Xn[soa(N - 1, 4, c, N, bo)] = xp[c];
     ex[c] = xp[c] - xrT[c];
   }
   cost += quad4(ex, [&](int i, int j) { return w.QT(i, j); });
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(128, 3) k_closed_loop(const __grid_constant__ 
   const int g = blockIdx.y;
   if (b >= B) return;
   const WV<WPB> w(kw, B, b);
-  const RefV<RPB> ref{rx, ru, B, b};
+  const RefV<RPB> ref{rx, ru, N, b};
   const double gamma = gpp ? gammas[int64_t(g) * B + b] : gammas[g];
   double c;
   if (Xn)
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(128, 3) k_sweep(const __grid_constant__ Model 
   const int s = blockIdx.y * 32 + (threadIdx.x & 31);
   if (p >= P || s >= S_n) return;
   const WV<WPB> w(kw, P, p);
-  const RefV<RPB> ref{rx, ru, P, p};
+  const RefV<RPB> ref{rx, ru, N, p};
   cost[int64_t(s) * P + p] =
       forward_pass<WPB, RPB, false>(m, w, ref, N, X, U, K, S, P, p, steps[s], nullptr, nullptr, P, p);
 }
@@ -613,7 +613,7 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
   if (b >= B) return;
   const int N = a.N;
   const WV<WPB> w(a.kw, B, b);
-  const RefV<RPB> ref{a.rx, a.ru, B, b};
+  const RefV<RPB> ref{a.rx, a.ru, N, b};
   int it, st;
   double cost_k;
   if (a.o.init) {
@@ -623,25 +623,25 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       x[c] = a.x0[c * B + b];
-      a.X[soa(0, 4, c, B, b)] = x[c];
+      a.X[soa(0, 4, c, N, b)] = x[c];
     }
     for (int t = 0; t < N - 1; ++t) {
       double u0 = 0.0, u1 = 0.0;
       if (a.o.init == 2) {
-        u0 = a.U[soa(t, 2, 0, B, b)];
-        u1 = a.U[soa(t, 2, 1, B, b)];
+        u0 = a.U[soa(t, 2, 0, N - 1, b)];
+        u1 = a.U[soa(t, 2, 1, N - 1, b)];
       } else {
-        a.U[soa(t, 2, 0, B, b)] = 0.0;
-        a.U[soa(t, 2, 1, B, b)] = 0.0;
+        a.U[soa(t, 2, 0, N - 1, b)] = 0.0;
+        a.U[soa(t, 2, 1, N - 1, b)] = 0.0;
       }
       double xn[4];
       LinD L;
       rk4_step_lin(a.m, x, u0, u1, xn, L);
-      store_lin(a.lin, t, B, b, L);
+      store_lin(a.lin, t, N - 1, b, L);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         x[c] = xn[c];
-        a.X[soa(t + 1, 4, c, B, b)] = x[c];
+        a.X[soa(t + 1, 4, c, N, b)] = x[c];
       }
     }
     cost_k = total_cost_dev(w, ref, N, a.X, a.U, B, b);
@@ -695,10 +695,10 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
   if (cur) {  // current iterate sits in the workspace: move it home
     for (int t = 0; t < N; ++t) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) a.X[soa(t, 4, c, B, b)] = a.Xw[soa(t, 4, c, B, b)];
+      for (int c = 0; c < 4; ++c) a.X[soa(t, 4, c, N, b)] = a.Xw[soa(t, 4, c, N, b)];
       if (t < N - 1) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) a.U[soa(t, 2, c, B, b)] = a.Uw[soa(t, 2, c, B, b)];
+        for (int c = 0; c < 2; ++c) a.U[soa(t, 2, c, N - 1, b)] = a.Uw[soa(t, 2, c, N - 1, b)];
       }
     }
   }
@@ -778,11 +778,11 @@ __global__ void k_stage_lists(const __grid_constant__ Model m, const __grid_cons
   const int t = int(idx / B);
   const int64_t b = idx % B;
   const WV<WPB> w(kw, B, b);
-  const RefV<RPB> ref{rx, ru, B, b};
+  const RefV<RPB> ref{rx, ru, N, b};
   double x[4], dx[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    x[c] = X[soa(t, 4, c, B, b)];
+    x[c] = X[soa(t, 4, c, N, b)];
     dx[c] = x[c] - ref.X(t, c);
   }
   if (t == N - 1) {
@@ -795,31 +795,31 @@ __global__ void k_stage_lists(const __grid_constant__ Model m, const __grid_cons
     }
     return;
   }
-  const double u0 = U[soa(t, 2, 0, B, b)], u1 = U[soa(t, 2, 1, B, b)];
+  const double u0 = U[soa(t, 2, 0, N - 1, b)], u1 = U[soa(t, 2, 1, N - 1, b)];
   const LinD L = linearize_d(m, x, u0, u1);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    A[soa(t, 16, 0 * 4 + j, B, b)] = (j == 0) ? 1.0 : (j == 2 ? m.dt : 0.0);
-    A[soa(t, 16, 1 * 4 + j, B, b)] = (j == 1) ? 1.0 : (j == 3 ? m.dt : 0.0);
-    A[soa(t, 16, 2 * 4 + j, B, b)] = L.a[0][j];
-    A[soa(t, 16, 3 * 4 + j, B, b)] = L.a[1][j];
+    A[soa(t, 16, 0 * 4 + j, N - 1, b)] = (j == 0) ? 1.0 : (j == 2 ? m.dt : 0.0);
+    A[soa(t, 16, 1 * 4 + j, N - 1, b)] = (j == 1) ? 1.0 : (j == 3 ? m.dt : 0.0);
+    A[soa(t, 16, 2 * 4 + j, N - 1, b)] = L.a[0][j];
+    A[soa(t, 16, 3 * 4 + j, N - 1, b)] = L.a[1][j];
   }
 #pragma unroll
-  for (int e = 0; e < 4; ++e) Bm[soa(t, 8, e, B, b)] = 0.0;
-  Bm[soa(t, 8, 4, B, b)] = L.b0[0];
-  Bm[soa(t, 8, 5, B, b)] = L.b[0];
-  Bm[soa(t, 8, 6, B, b)] = L.b0[1];
-  Bm[soa(t, 8, 7, B, b)] = L.b[1];
+  for (int e = 0; e < 4; ++e) Bm[soa(t, 8, e, N - 1, b)] = 0.0;
+  Bm[soa(t, 8, 4, N - 1, b)] = L.b0[0];
+  Bm[soa(t, 8, 5, N - 1, b)] = L.b[0];
+  Bm[soa(t, 8, 6, N - 1, b)] = L.b0[1];
+  Bm[soa(t, 8, 7, N - 1, b)] = L.b[1];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     double s = w.Q2(i, 0) * dx[0];
 #pragma unroll
     for (int j = 1; j < 4; ++j) s = fma(w.Q2(i, j), dx[j], s);
-    q[soa(t, 4, i, B, b)] = s;
+    q[soa(t, 4, i, N - 1, b)] = s;
   }
   const double du0 = u0 - ref.U(t, 0), du1 = u1 - ref.U(t, 1);
-  r[soa(t, 2, 0, B, b)] = fma(w.R2(0, 1), du1, w.R2(0, 0) * du0);
-  r[soa(t, 2, 1, B, b)] = fma(w.R2(1, 1), du1, w.R2(1, 0) * du0);
+  r[soa(t, 2, 0, N - 1, b)] = fma(w.R2(0, 1), du1, w.R2(0, 0) * du0);
+  r[soa(t, 2, 1, N - 1, b)] = fma(w.R2(1, 1), du1, w.R2(1, 0) * du0);
 }
 
 __global__ void k_riccati_lists(int64_t B, int T, const double* __restrict__ A, const double* __restrict__ Bm,
@@ -841,26 +841,26 @@ __global__ void k_riccati_lists(int64_t B, int T, const double* __restrict__ A, 
     double Am[16], Bv[8], Qm[16], Rm[4], Sm[8], qv[4], rv[2], Kt[8], st[2];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
-      Am[e] = A[soa(t, 16, e, B, b)];
-      Qm[e] = Q[soa(t, 16, e, B, b)];
+      Am[e] = A[soa(t, 16, e, T, b)];
+      Qm[e] = Q[soa(t, 16, e, T, b)];
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      Bv[e] = Bm[soa(t, 8, e, B, b)];
-      Sm[e] = Sx ? Sx[soa(t, 8, e, B, b)] : 0.0;
+      Bv[e] = Bm[soa(t, 8, e, T, b)];
+      Sm[e] = Sx ? Sx[soa(t, 8, e, T, b)] : 0.0;
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      Rm[e] = R[soa(t, 4, e, B, b)];
-      qv[e] = q[soa(t, 4, e, B, b)];
+      Rm[e] = R[soa(t, 4, e, T, b)];
+      qv[e] = q[soa(t, 4, e, T, b)];
     }
-    rv[0] = r[soa(t, 2, 0, B, b)];
-    rv[1] = r[soa(t, 2, 1, B, b)];
+    rv[0] = r[soa(t, 2, 0, T, b)];
+    rv[1] = r[soa(t, 2, 1, T, b)];
     riccati_step_lists(P, p, Am, Bv, Qm, Rm, Sm, qv, rv, Kt, st, d);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) K[soa(t, 8, e, B, b)] = Kt[e];
-    S[soa(t, 2, 0, B, b)] = st[0];
-    S[soa(t, 2, 1, B, b)] = st[1];
+    for (int e = 0; e < 8; ++e) K[soa(t, 8, e, T, b)] = Kt[e];
+    S[soa(t, 2, 0, T, b)] = st[0];
+    S[soa(t, 2, 1, T, b)] = st[1];
   }
   dJ[b] = d;
 }
@@ -874,7 +874,7 @@ __global__ void k_lqr_gains(const __grid_constant__ Model m, const __grid_consta
   const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
   const WV<WPB> w(kw, B, b);
-  const RefV<RPB> ref{rx, ru, B, b};
+  const RefV<RPB> ref{rx, ru, N, b};
   double P[10], p[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -892,7 +892,7 @@ __global__ void k_lqr_gains(const __grid_constant__ Model m, const __grid_consta
     riccati_step<false, false>(P, p, L, m.dt, Qh, col, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, Kt, st, dummy);
     if (RPB) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) K[soa(t, 8, e, B, b)] = Kt[e];
+      for (int e = 0; e < 8; ++e) K[soa(t, 8, e, N - 1, b)] = Kt[e];
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) K[t * 8 + e] = Kt[e];
@@ -906,12 +906,12 @@ __global__ void k_lqr_track(const __grid_constant__ Model m, int64_t B, int N, c
                             double* __restrict__ Ut) {
   const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
-  const RefV<RPB> ref{rx, ru, B, b};
+  const RefV<RPB> ref{rx, ru, N, b};
   double x[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     x[c] = x0[c * B + b];
-    Xt[soa(0, 4, c, B, b)] = x[c];
+    Xt[soa(0, 4, c, N, b)] = x[c];
   }
   for (int t = 0; t < N - 1; ++t) {
     double u[2];
@@ -920,18 +920,18 @@ __global__ void k_lqr_track(const __grid_constant__ Model m, int64_t B, int N, c
       double kd = 0.0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double k = RPB ? K[soa(t, 8, i * 4 + j, B, b)] : __ldg(K + t * 8 + i * 4 + j);
+        const double k = RPB ? K[soa(t, 8, i * 4 + j, N - 1, b)] : __ldg(K + t * 8 + i * 4 + j);
         kd = (j == 0) ? k * (x[0] - ref.X(t, 0)) : fma(k, x[j] - ref.X(t, j), kd);
       }
       u[i] = ref.U(t, i) + kd;
-      Ut[soa(t, 2, i, B, b)] = u[i];
+      Ut[soa(t, 2, i, N - 1, b)] = u[i];
     }
     double xn[4];
     rk4_step(m, x, u[0], u[1], xn);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       x[c] = xn[c];
-      Xt[soa(t + 1, 4, c, B, b)] = x[c];
+      Xt[soa(t + 1, 4, c, N, b)] = x[c];
     }
   }
 }
@@ -998,13 +998,13 @@ __global__ void k_mpc_solve(const __grid_constant__ KWeights kw, int64_t B, int 
   for (int j = H - 2; j >= 0; --j) {
     double Am[16], Bv[8];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) Am[e] = Aw[soa(j, 16, e, B, b)];
+    for (int e = 0; e < 16; ++e) Am[e] = Aw[soa(j, 16, e, H - 1, b)];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) Bv[e] = Bw[soa(j, 8, e, B, b)];
+    for (int e = 0; e < 8; ++e) Bv[e] = Bw[soa(j, 8, e, H - 1, b)];
     riccati_step_dense(P, Am, Bv, Qh, w.R(0, 0), w.R(0, 1), w.R(1, 1), K);
     if (Kws) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) Kws[soa(j, 8, e, B, b)] = K[e];
+      for (int e = 0; e < 8; ++e) Kws[soa(j, 8, e, H - 1, b)] = K[e];
     }
   }
   double x[4];
@@ -1022,29 +1022,29 @@ __global__ void k_mpc_solve(const __grid_constant__ KWeights kw, int64_t B, int 
   // forward pass of the predicted trajectory (X_opt, U_opt of tt:136-137)
   for (int j = 0; j < H; ++j) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) Xo[soa(j, 4, c, B, b)] = x[c];
+    for (int c = 0; c < 4; ++c) Xo[soa(j, 4, c, H, b)] = x[c];
     if (j == H - 1) {
-      Uo[soa(j, 2, 0, B, b)] = 0.0;  // free, unpenalised variable stays at its initial guess
-      Uo[soa(j, 2, 1, B, b)] = 0.0;
+      Uo[soa(j, 2, 0, H, b)] = 0.0;  // free, unpenalised variable stays at its initial guess
+      Uo[soa(j, 2, 1, H, b)] = 0.0;
       break;
     }
     double u[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      double s = Kws[soa(j, 8, i * 4, B, b)] * x[0];
+      double s = Kws[soa(j, 8, i * 4, H - 1, b)] * x[0];
 #pragma unroll
-      for (int jj = 1; jj < 4; ++jj) s = fma(Kws[soa(j, 8, i * 4 + jj, B, b)], x[jj], s);
+      for (int jj = 1; jj < 4; ++jj) s = fma(Kws[soa(j, 8, i * 4 + jj, H - 1, b)], x[jj], s);
       u[i] = s;
-      Uo[soa(j, 2, i, B, b)] = s;
+      Uo[soa(j, 2, i, H, b)] = s;
     }
     double xn[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double s = Aw[soa(j, 16, i * 4, B, b)] * x[0];
+      double s = Aw[soa(j, 16, i * 4, H - 1, b)] * x[0];
 #pragma unroll
-      for (int jj = 1; jj < 4; ++jj) s = fma(Aw[soa(j, 16, i * 4 + jj, B, b)], x[jj], s);
-      s = fma(Bw[soa(j, 8, i * 2, B, b)], u[0], s);
-      s = fma(Bw[soa(j, 8, i * 2 + 1, B, b)], u[1], s);
+      for (int jj = 1; jj < 4; ++jj) s = fma(Aw[soa(j, 16, i * 4 + jj, H - 1, b)], x[jj], s);
+      s = fma(Bw[soa(j, 8, i * 2, H - 1, b)], u[0], s);
+      s = fma(Bw[soa(j, 8, i * 2 + 1, H - 1, b)], u[1], s);
       xn[i] = s;
     }
 #pragma unroll
@@ -1065,13 +1065,13 @@ __global__ void k_lin_compact(const __grid_constant__ Model m, int64_t B, int N,
   if (idx >= int64_t(N - 1) * nb) return;
   const int t = int(idx / nb);
   const int64_t b = idx % nb;
-  const RefV<RPB> ref{rx, ru, B, b};
+  const RefV<RPB> ref{rx, ru, N, b};
   double x[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) x[c] = ref.X(t, c);
   const LinD L = linearize_d(m, x, ref.U(t, 0), ref.U(t, 1));
   if (RPB) {
-    store_lin(lin, t, B, b, L);
+    store_lin(lin, t, N - 1, b, L);
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -1150,7 +1150,7 @@ __global__ void k_mpc_track_shared(const __grid_constant__ MpcArgs a) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     x[c] = a.x0[c * B + b];
-    a.Xr[soa(0, 4, c, B, b)] = x[c];
+    a.Xr[soa(0, 4, c, a.T, b)] = x[c];
   }
   for (int t = 0; t < a.T - 1; ++t) {
     double u[2];
@@ -1165,14 +1165,14 @@ __global__ void k_mpc_track_shared(const __grid_constant__ MpcArgs a) {
       }
       const double ur = (t < a.N - 1) ? __ldg(a.ru + t * 2 + i) : a.uf[i];
       u[i] = ur + kd;
-      a.Ur[soa(t, 2, i, B, b)] = u[i];
+      a.Ur[soa(t, 2, i, a.T - 1, b)] = u[i];
     }
     double xn[4];
     rk4_step(a.m, x, u[0], u[1], xn);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       x[c] = xn[c];
-      a.Xr[soa(t + 1, 4, c, B, b)] = x[c];
+      a.Xr[soa(t + 1, 4, c, a.T, b)] = x[c];
     }
   }
 }
@@ -1183,7 +1183,7 @@ __global__ void k_mpc_track_pp(const __grid_constant__ MpcArgs a) {
   const int64_t B = a.B, b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
   const WV<WPB> w(a.kw, B, b);
-  const RefV<true> ref{a.rx, a.ru, B, b};
+  const RefV<true> ref{a.rx, a.ru, a.N, b};
   const LinD Lf = linearize_d(a.m, a.xf, a.uf[0], a.uf[1]);
   double QT[10];
 #pragma unroll
@@ -1194,11 +1194,11 @@ __global__ void k_mpc_track_pp(const __grid_constant__ MpcArgs a) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     x[c] = a.x0[c * B + b];
-    a.Xr[soa(0, 4, c, B, b)] = x[c];
+    a.Xr[soa(0, 4, c, a.T, b)] = x[c];
   }
   for (int t = 0; t < a.T - 1; ++t) {
     double K[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    mpc_sweep(w, a.m.dt, a.lin, B, b, a.N - 1, Lf, QT, t, a.H, K);
+    mpc_sweep(w, a.m.dt, a.lin, a.N - 1, b, a.N - 1, Lf, QT, t, a.H, K);
     double u[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -1210,14 +1210,14 @@ __global__ void k_mpc_track_pp(const __grid_constant__ MpcArgs a) {
       }
       const double ur = (t < a.N - 1) ? ref.U(t, i) : a.uf[i];
       u[i] = ur + kd;
-      a.Ur[soa(t, 2, i, B, b)] = u[i];
+      a.Ur[soa(t, 2, i, a.T - 1, b)] = u[i];
     }
     double xn[4];
     rk4_step(a.m, x, u[0], u[1], xn);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       x[c] = xn[c];
-      a.Xr[soa(t + 1, 4, c, B, b)] = x[c];
+      a.Xr[soa(t + 1, 4, c, a.T, b)] = x[c];
     }
   }
 }
@@ -1241,7 +1241,7 @@ __global__ void k_transpose(int64_t rows, int64_t cols, const double* __restrict
   }
 }
 
-// batch-major (B, T, C) <-> tiled [t][tile][c][lane].  One block = one tile of 32 problems x 32 consecutive
+// batch-major (B, T, C) <-> tiled [tile][t][c][lane].  One block = one tile of 32 problems x 32 consecutive
 // flattened (t, c) indices; both sides are read / written 256 bytes at a time.  Padding lanes are zero-filled.
 template <bool PACK>
 __global__ void k_tiled(int64_t B, int T, int C, const double* __restrict__ src, double* __restrict__ dst) {
@@ -1254,14 +1254,14 @@ __global__ void k_tiled(int64_t B, int T, int C, const double* __restrict__ src,
       tile[i][threadIdx.x] = (b < B && k < TC) ? src[b * TC + k] : 0.0;
     } else {     // row i = flattened index k0+i, column = lane x
       const int64_t k = k0 + i, b = b0 + threadIdx.x;
-      if (k < TC) tile[i][threadIdx.x] = src[soa(int(k / C), C, int(k % C), B, b)];
+      if (k < TC) tile[i][threadIdx.x] = src[soa(int(k / C), C, int(k % C), T, b)];
     }
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     if (PACK) {
       const int64_t k = k0 + i, b = b0 + threadIdx.x;
-      if (k < TC) dst[soa(int(k / C), C, int(k % C), B, b)] = tile[threadIdx.x][i];
+      if (k < TC) dst[soa(int(k / C), C, int(k % C), T, b)] = tile[threadIdx.x][i];
     } else {
       const int64_t b = b0 + i, k = k0 + threadIdx.x;
       if (b < B && k < TC) dst[b * TC + k] = tile[threadIdx.x][i];

@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
   extern __shared__ __align__(128) unsigned char ring_smem[];
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x;
-  const int64_t B = a.B, Bp = padded(B), b0 = blockIdx.x * 32LL, b = b0 + lane;
+  const int64_t B = a.B, tile = blockIdx.x, b0 = tile * 32LL, b = b0 + lane;
   const bool valid = b < B;
   const int64_t bs = valid ? b : B - 1;  // padding lanes shadow the last problem and never write per-problem scalars
   const int N = a.N;
@@ -377,24 +377,26 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
   }
   __syncwarp();
 
-  const int64_t sx = Bp * 4, su = Bp * 2, sk = Bp * 8, ss = Bp * 2, sl = Bp * 10;
-  double* const tX[2] = {a.X + b0 * 4, a.Xw + b0 * 4};
-  double* const tU[2] = {a.U + b0 * 2, a.Uw + b0 * 2};
-  double* const tK = a.K + b0 * 8;
-  double* const tS = a.S + b0 * 2;
-  double* const tL = a.lin + b0 * 10;
+  // doubles per time step of one tile (tile-major layout: compile-time strides)
+  constexpr int64_t sx = 4 * 32, su = 2 * 32, sk = 8 * 32, ss = 2 * 32, sl = 10 * 32;
+  const int64_t oN = tile * N, oM = tile * (N - 1);
+  double* const tX[2] = {a.X + oN * sx, a.Xw + oN * sx};
+  double* const tU[2] = {a.U + oM * su, a.Uw + oM * su};
+  double* const tK = a.K + oM * sk;
+  double* const tS = a.S + oM * ss;
+  double* const tL = a.lin + oM * sl;
   TilePtrs p;
   p.k = tK;
   p.s = tS;
   p.lin = tL;
-  p.rx = RPB ? a.rx + b0 * 4 : a.rx;
-  p.ru = RPB ? a.ru + b0 * 2 : a.ru;
+  p.rx = RPB ? a.rx + oN * sx : a.rx;
+  p.ru = RPB ? a.ru + oM * su : a.ru;
   p.sx = sx;
   p.su = su;
   p.sk = sk;
   p.ss = ss;
   p.sl = sl;
-  const RefV<RPB> ref{a.rx, a.ru, B, bs};
+  const RefV<RPB> ref{a.rx, a.ru, N, bs};
   double xrT[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) xrT[c] = ref.X(N - 1, c);

@@ -64,28 +64,27 @@ struct QhQ {
   __device__ __forceinline__ double operator()(int i, int j) const { return w.Q(i, j); }
 };
 
-// Reference trajectory: shared (N,4)/(N-1,2) row-major, or per problem in the tiled layout of soa().
+// Time-indexed batch arrays are tiled structure-of-arrays, tile-major:
+//     A[tile][t][c][lane],   tile = b / 32, lane = b % 32,   T time steps, C components
+//     element (t, c, b)  ->  A[((tile*T + t)*C + c)*32 + lane]
+// The whole trajectory of a warp's 32 problems is one contiguous block: the C rows of a time step are C*256
+// consecutive bytes (component c at the compile-time offset c*256), consecutive time steps follow each other
+// (compile-time stride C*256), so a pass streams through memory with one pointer per array and any number of
+// consecutive steps can be moved by ONE bulk copy.  `T` is the number of time steps the array holds.
+__device__ __forceinline__ int64_t padded(int64_t B) { return (B + 31) & ~int64_t(31); }
+__device__ __forceinline__ int64_t soa(int t, int C, int c, int64_t T, int64_t b) {
+  return (((b >> 5) * T + t) * C + c) * 32 + (b & 31);
+}
+
+// Reference trajectory: shared (N,4)/(N-1,2) row-major, or per problem in the tiled layout (x: T = N, u: T = N-1).
 template <bool RPB>
 struct RefV {
   const double* x;
   const double* u;
-  int64_t B, b;
-  __device__ __forceinline__ double X(int t, int c) const {
-    return RPB ? x[(int64_t(t) * ((B + 31) & ~int64_t(31)) + (b & ~int64_t(31))) * 4 + (c << 5) + (b & 31)] : __ldg(x + t * 4 + c);
-  }
-  __device__ __forceinline__ double U(int t, int c) const {
-    return RPB ? u[(int64_t(t) * ((B + 31) & ~int64_t(31)) + (b & ~int64_t(31))) * 2 + (c << 5) + (b & 31)] : __ldg(u + t * 2 + c);
-  }
+  int64_t N, b;
+  __device__ __forceinline__ double X(int t, int c) const { return RPB ? x[soa(t, 4, c, N, b)] : __ldg(x + t * 4 + c); }
+  __device__ __forceinline__ double U(int t, int c) const { return RPB ? u[soa(t, 2, c, N - 1, b)] : __ldg(u + t * 2 + c); }
 };
-
-// Time-indexed batch arrays are tiled structure-of-arrays: A[t][tile][c][lane], tile = b / 32, lane = b % 32,
-// with the batch padded to a multiple of 32.  The C rows of one time step of one warp are one contiguous block
-// of C * 256 bytes (component c at a compile-time offset c * 256), so a step is streamed with one pointer per
-// array, 128-byte aligned, and a whole step can be moved by one bulk copy.  `ld` is the batch size (padded here).
-__device__ __forceinline__ int64_t padded(int64_t ld) { return (ld + 31) & ~int64_t(31); }
-__device__ __forceinline__ int64_t soa(int t, int C, int c, int64_t ld, int64_t b) {
-  return (int64_t(t) * padded(ld) + (b & ~int64_t(31))) * C + (c << 5) + (b & 31);
-}
 
 // (v' W v) for a symmetric 4x4 / 2x2 given through an accessor
 template <class F>

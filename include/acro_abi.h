@@ -18,13 +18,14 @@
  *        state batch      x[c][b]            c in 0..3            -> x[c*B + b]
  *        input batch      u[c][b]            c in 0..1
  *        per-problem scalars, int32 flags    v[b]
- *    TIME-INDEXED batch arrays (trajectories, gains, ...) are TILED structure-of-arrays,
- *        A[t][tile][c][lane],   tile = b / 32, lane = b % 32,   Bp = 32*ceil(B/32)
- *        element (t, c, b)  ->  A[(t*Bp + 32*tile)*C + 32*c + lane]
- *    so the C rows of one time step of one warp are ONE contiguous, 128-byte aligned block of
- *    C*256 bytes (component c at the constant offset c*256): coalesced, vectorisable, and
- *    movable by a single bulk copy.  Buffers hold T*Bp*C doubles; padding lanes are never read
- *    for results.  In this notation:
+ *    TIME-INDEXED batch arrays (trajectories, gains, ...) are TILED structure-of-arrays, tile-major:
+ *        A[tile][t][c][lane],   tile = b / 32, lane = b % 32,   T time steps, C components
+ *        element (t, c, b)  ->  A[((tile*T + t)*C + c)*32 + lane]
+ *    so the whole trajectory of a warp's 32 problems is one contiguous block: the C rows of a time step
+ *    are C*256 consecutive, 128-byte aligned bytes (component c at the constant offset c*256) and
+ *    consecutive time steps follow each other: coalesced, vectorisable, streamed with one pointer per
+ *    array, and any run of consecutive steps is movable by a single bulk copy.  Buffers hold
+ *    32*ceil(B/32)*T*C doubles; padding lanes are never read for results.
  *    Below, a tiled array with T time steps and C components is written  name {T x C}:
  *        state trajectory X {N x 4}     input trajectory U {N-1 x 2}
  *        gains            K {N-1 x 8}   (K_t is 2x4 row-major, component i*4+j)
@@ -251,9 +252,9 @@ int acro_bench_fp64_chain(int blocks, int threads, int iters, int chains, int ac
                           long long* cycles, void* stream);
 
 /* ---- layout helpers ------------------------------------------------------------------ */
-/* batch-major src (B, T, C) row-major  ->  tiled dst [t][tile][c][lane] (padding lanes zero-filled) */
+/* batch-major src (B, T, C) row-major  ->  tiled dst [tile][t][c][lane] (padding lanes zero-filled) */
 int acro_pack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream);
-/* tiled src [t][tile][c][lane]  ->  batch-major dst (B, T, C) row-major */
+/* tiled src [tile][t][c][lane]  ->  batch-major dst (B, T, C) row-major */
 int acro_unpack_soa(int64_t B, int T, int C, const double* src, double* dst, void* stream);
 /* plain matrix transpose src (rows, cols) -> dst (cols, rows): state batches (B, 4) <-> [4][B] */
 int acro_transpose(int64_t rows, int64_t cols, const double* src, double* dst, void* stream);

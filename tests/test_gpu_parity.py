@@ -26,7 +26,7 @@ def dev(a):
 
 
 def soa(a):
-    """batch-major numpy (B,C) -> plain device (C,B);  (B,T,C) -> Traj in the tiled layout A[t][tile][c][lane].
+    """batch-major numpy (B,C) -> plain device (C,B);  (B,T,C) -> Traj in the tiled layout A[tile][t][c][lane].
     The tiling is done here in NumPy, independently of the library's pack kernel."""
     from gymnast_optimalcontrol_b200.batched import Traj
     a = np.asarray(a, dtype=np.float64)
@@ -36,16 +36,16 @@ def soa(a):
     nt = (Bn + 31) // 32
     pad = np.zeros((nt * 32, T, Cn))
     pad[:Bn] = a
-    return Traj(dev(np.transpose(pad.reshape(nt, 32, T, Cn), (2, 0, 3, 1))), Bn)
+    return Traj(dev(np.transpose(pad.reshape(nt, 32, T, Cn), (0, 2, 3, 1))), Bn)
 
 
 def aos(t):
     """plain device (C,B) -> numpy (B,C);  Traj -> numpy (B,T,C)  (un-tiled in NumPy)"""
     from gymnast_optimalcontrol_b200.batched import Traj
     if isinstance(t, Traj):
-        a = t.data.detach().cpu().numpy()  # (T, nt, C, 32)
-        T, nt, Cn, _ = a.shape
-        return np.transpose(a, (1, 3, 0, 2)).reshape(nt * 32, T, Cn)[:t.B]
+        a = t.data.detach().cpu().numpy()  # (nt, T, C, 32)
+        nt, T, Cn, _ = a.shape
+        return np.transpose(a, (0, 3, 1, 2)).reshape(nt * 32, T, Cn)[:t.B]
     return t.detach().cpu().numpy().T
 
 
