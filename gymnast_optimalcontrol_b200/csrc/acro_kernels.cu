@@ -1490,7 +1490,7 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
   auto aligned = [](const void* q, uintptr_t al) { return (reinterpret_cast<uintptr_t>(q) % al) == 0; };
   // measured on B200 (profiles/newton_batch_sweep.py): the ring kernel wins up to one full wave of 148 x 6
   // one-warp blocks and again from two waves on; in between its second wave is mostly empty
-  bool ring = (tiles <= 148 * 6 || tiles >= 2 * 148 * 6) && aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) &&
+  bool ring = (tiles <= 148 * 4 || tiles >= 2 * 148 * 4) && aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) &&
               aligned(lin_ws, 128) && aligned(K, 128) && aligned(S, 128) &&
               aligned(ref->x, ref->per_problem ? 128 : 32) && aligned(ref->u, ref->per_problem ? 128 : 16);
   if (force && !strcmp(force, "ldg")) ring = false;
@@ -1501,9 +1501,14 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
     ring = true;
   }
   if (ring) {
-#define EXPR(WPB, RPB)                                                                                   \
-  k_newton_ring<WPB, RPB><<<(unsigned)tiles, 32, ACRO_RING_D * stage_bytes<RPB>() + ACRO_RING_D * 8, \
-                            (cudaStream_t)stream>>>(a)
+#define EXPR(WPB, RPB)                                                                                          \
+  do {                                                                                                          \
+    constexpr int smem = ACRO_RING_D * stage_bytes<RPB>() + ACRO_RING_D * 8;                                    \
+    cudaError_t e_ = cudaFuncSetAttribute(k_newton_ring<WPB, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          smem);                                                                \
+    if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                      \
+    k_newton_ring<WPB, RPB><<<(unsigned)tiles, 32, smem, (cudaStream_t)stream>>>(a);                            \
+  } while (0)
     DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
 #undef EXPR
   } else {

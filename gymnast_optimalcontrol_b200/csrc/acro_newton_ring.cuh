@@ -19,7 +19,7 @@
 
 namespace acro {
 
-#define ACRO_RING_D 8  // power of two
+#define ACRO_RING_D 3  // stages per ring
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -66,89 +66,85 @@ __device__ __forceinline__ double lds(uint32_t addr) {
   return v;
 }
 
-// Stage layout (byte offsets).  Per-problem references add six tiled rows, shared ones 48 bytes.
-constexpr uint32_t kOffX = 0, kOffU = 1024, kOffA = 1536 /* K+S or lin: 2560 B */, kOffRef = 4096;
+// A stage holds ACRO_RING_SG consecutive time steps of every streamed array; a trajectory of a tile is contiguous
+// in memory (tile-major layout), so SG steps of one array are ONE bulk copy.  Byte offsets inside a stage:
+//     X: s*1024 + c*256   U: SG*1024 + s*512 + c*256   K: SG*1536 + s*2048 + c*256   S: SG*3584 + s*512 + c*256
+//     (backward pass: lin: SG*1536 + s*2560 + j*256)   reference block at SG*4096
+#define ACRO_RING_SG 4
+constexpr uint32_t kSG = ACRO_RING_SG;
+constexpr uint32_t kOffX = 0, kOffU = kSG * 1024, kOffA = kSG * 1536, kOffS = kSG * 3584, kOffRef = kSG * 4096;
 template <bool RPB>
-__host__ __device__ constexpr uint32_t stage_bytes() { return RPB ? 4096 + 1536 : 4096 + 128; }
-template <bool RPB>
-__host__ __device__ constexpr uint32_t tx_bytes() { return RPB ? 4096 + 1536 : 4096 + 48; }
+__host__ __device__ constexpr uint32_t stage_bytes() { return kSG * 4096 + (RPB ? kSG * 1536 : 256); }
 
 struct Ring {
-  uint32_t data, bars;  // shared addresses of stage 0 / barrier 0
-  uint32_t seq;         // fills consumed so far (warp-uniform); fills issued = seq + in-flight
-  uint32_t iss;         // fills issued so far
+  uint32_t data, bars;  // shared addresses of slot 0 / barrier 0
+  uint32_t base;        // stages consumed by earlier passes: stage k of this pass has sequence number base + k
 };
+__device__ __forceinline__ uint32_t ring_slot(uint32_t g) { return g % ACRO_RING_D; }
+__device__ __forceinline__ uint32_t ring_parity(uint32_t g) { return (g / ACRO_RING_D) & 1u; }
 
-// Everything a pass needs to find one warp's operands: tile base pointers (at t = 0) and per-step strides.
+// Tile base pointers (time step 0) of everything a pass streams.
 struct TilePtrs {
   const double *x, *u, *k, *s, *lin;  // source iterate (current), gains, feed-forward, linearisation
   const double *rx, *ru;              // reference (shared: plain arrays; per problem: tile bases)
-  int64_t sx, su, sk, ss, sl;         // doubles per time step of the tiled arrays (Bp * C)
 };
+constexpr int64_t kSX = 4 * 32, kSU = 2 * 32, kSK = 8 * 32, kSS = 2 * 32, kSL = 10 * 32;  // doubles per time step
 
-// Source pointers of the next fill; they walk forwards (forward pass) or backwards (backward pass) one time
-// step per fill, so issuing a stage needs no multiplications.
-struct FillPtrs {
-  const double *x, *u, *a0, *a1, *rx, *ru;
-};
+// Issue the bulk copies of stage k of a pass: time steps [t_lo, t_lo + cnt).
 template <bool RPB, bool FWD>
-__device__ __forceinline__ FillPtrs fill_begin(const TilePtrs& p, int steps) {
-  const int64_t t0 = FWD ? 0 : steps - 1;
-  FillPtrs f;
-  f.x = p.x + t0 * p.sx;
-  f.u = p.u + t0 * p.su;
-  f.a0 = FWD ? p.k + t0 * p.sk : p.lin + t0 * p.sl;
-  f.a1 = p.s + t0 * p.ss;
-  f.rx = p.rx + t0 * (RPB ? p.sx : 4);
-  f.ru = p.ru + t0 * (RPB ? p.su : 2);
-  return f;
-}
-template <bool RPB, bool FWD>
-__device__ __forceinline__ void ring_fill(Ring& r, const TilePtrs& p, FillPtrs& f, int lane) {
+__device__ __forceinline__ void ring_fill(const Ring& r, const TilePtrs& p, int k, int t_lo, int cnt) {
   if (elect_one()) {
-    const uint32_t st = r.iss & (ACRO_RING_D - 1);
-    const uint32_t bar = r.bars + st * 8, dst = r.data + st * stage_bytes<RPB>();
-    mbar_expect_tx(bar, tx_bytes<RPB>());
-    bulk_g2s(dst + kOffX, f.x, 1024, bar);
-    bulk_g2s(dst + kOffU, f.u, 512, bar);
+    const uint32_t g = r.base + k, slot = ring_slot(g);
+    const uint32_t bar = r.bars + slot * 8, dst = r.data + slot * stage_bytes<RPB>();
+    const uint32_t n = (uint32_t)cnt;
+    mbar_expect_tx(bar, n * (4096u + (RPB ? 1536u : 48u)));
+    bulk_g2s(dst + kOffX, p.x + t_lo * kSX, n * 1024, bar);
+    bulk_g2s(dst + kOffU, p.u + t_lo * kSU, n * 512, bar);
     if (FWD) {
-      bulk_g2s(dst + kOffA, f.a0, 2048, bar);
-      bulk_g2s(dst + kOffA + 2048, f.a1, 512, bar);
+      bulk_g2s(dst + kOffA, p.k + t_lo * kSK, n * 2048, bar);
+      bulk_g2s(dst + kOffS, p.s + t_lo * kSS, n * 512, bar);
     } else {
-      bulk_g2s(dst + kOffA, f.a0, 2560, bar);
+      bulk_g2s(dst + kOffA, p.lin + t_lo * kSL, n * 2560, bar);
     }
-    bulk_g2s(dst + kOffRef, f.rx, RPB ? 1024 : 32, bar);
-    bulk_g2s(dst + kOffRef + (RPB ? 1024 : 32), f.ru, RPB ? 512 : 16, bar);
+    if (RPB) {
+      bulk_g2s(dst + kOffRef, p.rx + t_lo * kSX, n * 1024, bar);
+      bulk_g2s(dst + kOffRef + kSG * 1024, p.ru + t_lo * kSU, n * 512, bar);
+    } else {
+      bulk_g2s(dst + kOffRef, p.rx + t_lo * 4, n * 32, bar);
+      bulk_g2s(dst + kOffRef + kSG * 32, p.ru + t_lo * 2, n * 16, bar);
+    }
   }
-  constexpr int dir = FWD ? 1 : -1;
-  f.x += dir * p.sx;
-  f.u += dir * p.su;
-  f.a0 += dir * (FWD ? p.sk : p.sl);
-  f.a1 += dir * p.ss;
-  f.rx += dir * (RPB ? p.sx : 4);
-  f.ru += dir * (RPB ? p.su : 2);
-  ++r.iss;
 }
 
-struct RingStage {
-  uint32_t base;  // shared address of the stage + lane * 8
-  uint32_t ref;   // shared address of the reference block (+ lane * 8 when per problem)
-};
+// reference of step s of a stage
 template <bool RPB>
-__device__ __forceinline__ RingStage ring_stage(const Ring& r, uint32_t n, int lane) {
-  const uint32_t st = n & (ACRO_RING_D - 1);
-  const uint32_t b = r.data + st * stage_bytes<RPB>();
-  return RingStage{b + lane * 8u, b + kOffRef + (RPB ? lane * 8u : 0u)};
+__device__ __forceinline__ void lds_ref(uint32_t stage, int s, int lane, double xr[4], double ur[2]) {
+  const uint32_t b = stage + kOffRef;
+  if (RPB) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xr[c] = lds(b + s * 1024 + c * 256 + lane * 8);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) ur[c] = lds(b + kSG * 1024 + s * 512 + c * 256 + lane * 8);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xr[c] = lds(b + s * 32 + c * 8);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) ur[c] = lds(b + kSG * 32 + s * 16 + c * 8);
+  }
 }
-__device__ __forceinline__ uint32_t ring_bar(const Ring& r, uint32_t n) { return r.bars + (n & (ACRO_RING_D - 1)) * 8; }
-__device__ __forceinline__ uint32_t ring_parity(uint32_t n) { return (n / ACRO_RING_D) & 1u; }
 
 template <bool RPB>
-__device__ __forceinline__ void lds_ref(const RingStage& s, double xr[4], double ur[2]) {
+__device__ __forceinline__ void lds_fwd(uint32_t stage, int s, int lane, StepIn& in) {
+  const uint32_t b = stage + lane * 8;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) xr[c] = lds(s.ref + (RPB ? c * 256 : c * 8));
+  for (int c = 0; c < 4; ++c) in.x[c] = lds(b + kOffX + s * 1024 + c * 256);
 #pragma unroll
-  for (int c = 0; c < 2; ++c) ur[c] = lds(s.ref + (RPB ? 1024 + c * 256 : 32 + c * 8));
+  for (int c = 0; c < 2; ++c) in.u[c] = lds(b + kOffU + s * 512 + c * 256);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) in.k[c] = lds(b + kOffA + s * 2048 + c * 256);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) in.s[c] = lds(b + kOffS + s * 512 + c * 256);
+  lds_ref<RPB>(stage, s, lane, in.xr, in.ur);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -159,93 +155,83 @@ template <bool WPB, bool RPB>
 __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w, int N, const TilePtrs& p, Ring& r,
                                                int lane, double gamma, bool store, double* __restrict__ Xo,
                                                double* __restrict__ Uo, double* __restrict__ Lo, const double xrT[4]) {
-  const int steps = N - 1;
-  FillPtrs f = fill_begin<RPB, true>(p, steps);
-  for (int i = 0; i < ACRO_RING_D && i < steps; ++i) ring_fill<RPB, true>(r, p, f, lane);
+  const int steps = N - 1, n_stages = (steps + kSG - 1) / kSG;
+  for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, true>(r, p, k, k * kSG, min((int)kSG, steps - k * (int)kSG));
   double xp[4];
   StepIn in;
-  {
-    mbar_wait(ring_bar(r, r.seq), ring_parity(r.seq));
-    const RingStage s = ring_stage<RPB>(r, r.seq, lane);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) in.x[c] = lds(s.base + kOffX + c * 256);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) in.u[c] = lds(s.base + kOffU + c * 256);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) in.k[c] = lds(s.base + kOffA + c * 256);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) in.s[c] = lds(s.base + kOffA + 2048 + c * 256);
-    lds_ref<RPB>(s, in.xr, in.ur);
-    ++r.seq;
-  }
+  mbar_wait(r.bars + ring_slot(r.base) * 8, ring_parity(r.base));
+  lds_fwd<RPB>(r.data + ring_slot(r.base) * stage_bytes<RPB>(), 0, lane, in);
 #pragma unroll
   for (int c = 0; c < 4; ++c) xp[c] = in.x[c];  // x+_0 = x_0
   double cost = 0.0;
   double* po_x = Xo + lane;
   double* po_u = Uo + lane;
   double* po_l = Lo + lane;
-  for (int t = 0; t < steps; ++t) {
-    const bool more = t + 1 < steps;
-    const uint32_t ready = more ? mbar_test(ring_bar(r, r.seq), ring_parity(r.seq)) : 1u;
-    double dx[4], up[2];
+  for (int k = 0; k < n_stages; ++k) {
+    const int cnt = min((int)kSG, steps - k * (int)kSG);
+    const uint32_t g = r.base + k;
+    const uint32_t stage = r.data + ring_slot(g) * stage_bytes<RPB>();
+    const uint32_t nstage = r.data + ring_slot(g + 1) * stage_bytes<RPB>();
+    const uint32_t nbar = r.bars + ring_slot(g + 1) * 8, npar = ring_parity(g + 1);
+    for (int s = 0; s < cnt; ++s) {
+      const bool cross = (s + 1 == cnt) && (k + 1 < n_stages);  // the next step lives in the next stage
+      const uint32_t ready = cross ? mbar_test(nbar, npar) : 1u;
+      double dx[4], up[2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) dx[c] = xp[c] - in.x[c];
+      for (int c = 0; c < 4; ++c) dx[c] = xp[c] - in.x[c];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      double kd = in.k[i * 4] * dx[0];
+      for (int i = 0; i < 2; ++i) {
+        double kd = in.k[i * 4] * dx[0];
 #pragma unroll
-      for (int j = 1; j < 4; ++j) kd = fma(in.k[i * 4 + j], dx[j], kd);
-      up[i] = (in.u[i] + kd) + gamma * in.s[i];
-    }
-    if (store) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) po_x[c * 32] = xp[c];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) po_u[c * 32] = up[c];
-    }
-    double ex[4], eu[2];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) ex[c] = xp[c] - in.xr[c];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) eu[c] = up[c] - in.ur[c];
-    cost += quad4(ex, [&](int i, int j) { return w.Q(i, j); });
-    cost += quad2(eu, [&](int i, int j) { return w.R(i, j); });
-    // operands of step t+1 straight into the registers that step t no longer needs
-    if (more) {
-      if (!ready) mbar_wait(ring_bar(r, r.seq), ring_parity(r.seq));
-      const RingStage s = ring_stage<RPB>(r, r.seq, lane);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) in.x[c] = lds(s.base + kOffX + c * 256);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) in.u[c] = lds(s.base + kOffU + c * 256);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) in.k[c] = lds(s.base + kOffA + c * 256);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) in.s[c] = lds(s.base + kOffA + 2048 + c * 256);
-      lds_ref<RPB>(s, in.xr, in.ur);
-      ++r.seq;
-    }
-    // the stage read one iteration ago is free now: refill it with step t + D
-    __syncwarp();
-    if (t + ACRO_RING_D < steps) ring_fill<RPB, true>(r, p, f, lane);
-    double xn[4];
-    LinD L;
-    rk4_step_lin(m, xp, up[0], up[1], xn, L);
-    if (store) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        po_l[j * 32] = L.a[0][j];
-        po_l[(4 + j) * 32] = L.a[1][j];
+        for (int j = 1; j < 4; ++j) kd = fma(in.k[i * 4 + j], dx[j], kd);
+        up[i] = (in.u[i] + kd) + gamma * in.s[i];
       }
-      po_l[8 * 32] = L.b[0];
-      po_l[9 * 32] = L.b[1];
-    }
+      if (store) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) xp[c] = xn[c];
-    po_x += p.sx;
-    po_u += p.su;
-    po_l += p.sl;
+        for (int c = 0; c < 4; ++c) po_x[c * 32] = xp[c];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) po_u[c * 32] = up[c];
+      }
+      double ex[4], eu[2];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ex[c] = xp[c] - in.xr[c];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) eu[c] = up[c] - in.ur[c];
+      cost += quad4(ex, [&](int i, int j) { return w.Q(i, j); });
+      cost += quad2(eu, [&](int i, int j) { return w.R(i, j); });
+      // operands of the next step straight into the registers this step no longer needs
+      if (s + 1 < cnt) {
+        lds_fwd<RPB>(stage, s + 1, lane, in);
+      } else if (cross) {
+        if (!ready) mbar_wait(nbar, npar);
+        lds_fwd<RPB>(nstage, 0, lane, in);
+      }
+      // first step of a stage: every read of the previous stage has completed, its slot can be refilled
+      if (s == 0 && k >= 1 && k - 1 + ACRO_RING_D < n_stages) {
+        __syncwarp();
+        const int kk = k - 1 + ACRO_RING_D;
+        ring_fill<RPB, true>(r, p, kk, kk * kSG, min((int)kSG, steps - kk * (int)kSG));
+      }
+      double xn[4];
+      LinD L;
+      rk4_step_lin(m, xp, up[0], up[1], xn, L);
+      if (store) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          po_l[j * 32] = L.a[0][j];
+          po_l[(4 + j) * 32] = L.a[1][j];
+        }
+        po_l[8 * 32] = L.b[0];
+        po_l[9 * 32] = L.b[1];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) xp[c] = xn[c];
+      po_x += kSX;
+      po_u += kSU;
+      po_l += kSL;
+    }
   }
+  r.base += n_stages;
   double ex[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -258,15 +244,17 @@ __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w,
 
 // ---------------------------------------------------------------------------------------------------------
 // backward pass (tg:166-216): affine Riccati sweep on the stored linearisation; writes K, S when `store`.
+// Stage k of this pass holds the time steps [t_lo, t_hi] with t_hi = steps-1 - k*SG, walked downwards.
 // ---------------------------------------------------------------------------------------------------------
 template <bool WPB, bool RPB>
 __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, int N, const TilePtrs& p, Ring& r,
                                               int lane, bool store, double* __restrict__ K, double* __restrict__ S,
                                               const double xT[4], const double xrT[4], double& dJ_out,
                                               double& sn_out) {
-  const int steps = N - 1;
-  FillPtrs f = fill_begin<RPB, false>(p, steps);
-  for (int i = 0; i < ACRO_RING_D && i < steps; ++i) ring_fill<RPB, false>(r, p, f, lane);
+  const int steps = N - 1, n_stages = (steps + kSG - 1) / kSG;
+  auto t_lo_of = [&](int k) { return max(0, steps - (k + 1) * (int)kSG); };
+  auto cnt_of = [&](int k) { return (steps - k * (int)kSG) - t_lo_of(k); };
+  for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, false>(r, p, k, t_lo_of(k), cnt_of(k));
   double P[10], pv[4];
   {
     double dx[4];
@@ -285,70 +273,83 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
   double x[4], u[2], xr[4], ur[2];
   LinD L;
   L.b0[0] = L.b0[1] = 0.0;
-  auto load = [&](uint32_t n) {
-    const RingStage s = ring_stage<RPB>(r, n, lane);
+  auto load = [&](uint32_t stage, int s) {
+    const uint32_t b = stage + lane * 8;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) x[c] = lds(s.base + kOffX + c * 256);
+    for (int c = 0; c < 4; ++c) x[c] = lds(b + kOffX + s * 1024 + c * 256);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) u[c] = lds(s.base + kOffU + c * 256);
+    for (int c = 0; c < 2; ++c) u[c] = lds(b + kOffU + s * 512 + c * 256);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      L.a[0][j] = lds(s.base + kOffA + j * 256);
-      L.a[1][j] = lds(s.base + kOffA + (4 + j) * 256);
+      L.a[0][j] = lds(b + kOffA + s * 2560 + j * 256);
+      L.a[1][j] = lds(b + kOffA + s * 2560 + (4 + j) * 256);
     }
-    L.b[0] = lds(s.base + kOffA + 8 * 256);
-    L.b[1] = lds(s.base + kOffA + 9 * 256);
-    lds_ref<RPB>(s, xr, ur);
+    L.b[0] = lds(b + kOffA + s * 2560 + 8 * 256);
+    L.b[1] = lds(b + kOffA + s * 2560 + 9 * 256);
+    lds_ref<RPB>(stage, s, lane, xr, ur);
   };
-  mbar_wait(ring_bar(r, r.seq), ring_parity(r.seq));
-  load(r.seq);
-  ++r.seq;
+  mbar_wait(r.bars + ring_slot(r.base) * 8, ring_parity(r.base));
+  load(r.data + ring_slot(r.base) * stage_bytes<RPB>(), cnt_of(0) - 1);
   double dJ = 0.0, sn = 0.0;
   const QhQ2<WV<WPB>> Qh{w};
   const Lu2Col col = lu2_col(w.R2(0, 0), w.R2(0, 1));
-  double* pk = K + (steps - 1) * p.sk + lane;
-  double* ps = S + (steps - 1) * p.ss + lane;
-  for (int i = 0; i < steps; ++i) {
-    const bool more = i + 1 < steps;
-    const uint32_t ready = more ? mbar_test(ring_bar(r, r.seq), ring_parity(r.seq)) : 1u;
-    double dx[4], du[2], q[4], rr[2];
+  double* pk = K + (steps - 1) * kSK + lane;
+  double* ps = S + (steps - 1) * kSS + lane;
+  for (int k = 0; k < n_stages; ++k) {
+    const int cnt = cnt_of(k);
+    const uint32_t g = r.base + k;
+    const uint32_t stage = r.data + ring_slot(g) * stage_bytes<RPB>();
+    const uint32_t nstage = r.data + ring_slot(g + 1) * stage_bytes<RPB>();
+    const uint32_t nbar = r.bars + ring_slot(g + 1) * 8, npar = ring_parity(g + 1);
+    const int ncnt = (k + 1 < n_stages) ? cnt_of(k + 1) : 0;
+    for (int s = cnt - 1; s >= 0; --s) {
+      const bool cross = (s == 0) && (k + 1 < n_stages);
+      const uint32_t ready = cross ? mbar_test(nbar, npar) : 1u;
+      double dx[4], du[2], q[4], rr[2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) dx[c] = x[c] - xr[c];
+      for (int c = 0; c < 4; ++c) dx[c] = x[c] - xr[c];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) du[c] = u[c] - ur[c];
+      for (int c = 0; c < 2; ++c) du[c] = u[c] - ur[c];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      double s = w.Q2(a, 0) * dx[0];
+      for (int a = 0; a < 4; ++a) {
+        double acc = w.Q2(a, 0) * dx[0];
 #pragma unroll
-      for (int j = 1; j < 4; ++j) s = fma(w.Q2(a, j), dx[j], s);
-      q[a] = s;
+        for (int j = 1; j < 4; ++j) acc = fma(w.Q2(a, j), dx[j], acc);
+        q[a] = acc;
+      }
+      rr[0] = fma(w.R2(0, 1), du[1], w.R2(0, 0) * du[0]);
+      rr[1] = fma(w.R2(1, 1), du[1], w.R2(1, 0) * du[0]);
+      double Kt[8], st[2];
+      riccati_step<true, false>(P, pv, L, m.dt, Qh, col, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, rr, Kt, st, dJ);
+      if (store) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pk[e * 32] = Kt[e];
+        ps[0] = st[0];
+        ps[32] = st[1];
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double a = fabs(st[e]);
+        sn = (a > sn || a != a) ? a : sn;  // NaN is sticky, like np.max(np.abs(sigma))
+      }
+      // operands of the next (earlier) time step into the registers just used
+      if (s > 0) {
+        load(stage, s - 1);
+      } else if (cross) {
+        if (!ready) mbar_wait(nbar, npar);
+        load(nstage, ncnt - 1);
+      }
+      // last step of the first stage-visit: refill the slot of the previous stage (all of its reads are done)
+      if (s == cnt - 1 && k >= 1 && k - 1 + ACRO_RING_D < n_stages) {
+        __syncwarp();
+        const int kk = k - 1 + ACRO_RING_D;
+        ring_fill<RPB, false>(r, p, kk, t_lo_of(kk), cnt_of(kk));
+      }
+      pk -= kSK;
+      ps -= kSS;
     }
-    rr[0] = fma(w.R2(0, 1), du[1], w.R2(0, 0) * du[0]);
-    rr[1] = fma(w.R2(1, 1), du[1], w.R2(1, 0) * du[0]);
-    double Kt[8], st[2];
-    riccati_step<true, false>(P, pv, L, m.dt, Qh, col, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, rr, Kt, st, dJ);
-    if (store) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) pk[e * 32] = Kt[e];
-      ps[0] = st[0];
-      ps[32] = st[1];
-    }
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const double a = fabs(st[e]);
-      sn = (a > sn || a != a) ? a : sn;  // NaN is sticky, like np.max(np.abs(sigma))
-    }
-    if (more) {  // operands of the next step (time index steps-2-i), straight into the registers just used
-      if (!ready) mbar_wait(ring_bar(r, r.seq), ring_parity(r.seq));
-      load(r.seq);
-      ++r.seq;
-    }
-    // the stage read one iteration ago is free now: refill it
-    __syncwarp();
-    if (i + ACRO_RING_D < steps) ring_fill<RPB, false>(r, p, f, lane);
-    pk -= p.sk;
-    ps -= p.ss;
   }
+  r.base += n_stages;
   dJ_out = dJ;
   sn_out = sn;
 }
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
   Ring r;
   r.data = smem_u32(ring_smem);
   r.bars = r.data + ACRO_RING_D * stage_bytes<RPB>();
-  r.seq = r.iss = 0;
+  r.base = 0;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < ACRO_RING_D; ++s) mbar_init(r.bars + s * 8, 1);
@@ -391,11 +392,6 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
   p.lin = tL;
   p.rx = RPB ? a.rx + oN * sx : a.rx;
   p.ru = RPB ? a.ru + oM * su : a.ru;
-  p.sx = sx;
-  p.su = su;
-  p.sk = sk;
-  p.ss = ss;
-  p.sl = sl;
   const RefV<RPB> ref{a.rx, a.ru, N, bs};
   double xrT[4];
 #pragma unroll
