@@ -1483,14 +1483,13 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
   a.h_sn = hist_sigma_norm;
   a.h_gamma = hist_gamma;
   a.h_ntry = hist_ntry;
-  // Small and medium batches are latency bound: warp-synchronous kernel with TMA-fed shared-memory rings
-  // (one warp per block).  Large batches hide latency with occupancy: one thread per problem, register prefetch.
+  // Default: the warp-synchronous kernel with TMA-fed shared-memory rings (one warp per block); it is the faster
+  // one at every batch size measured on B200 (profiles/newton_batch_sweep.py).  The one-thread-per-problem
+  // kernel with register prefetch remains for buffers that are not 128-byte aligned and for A/B runs.
   const int64_t tiles = (B + 31) / 32;
   const char* force = getenv("ACRO_NEWTON_KERNEL");
   auto aligned = [](const void* q, uintptr_t al) { return (reinterpret_cast<uintptr_t>(q) % al) == 0; };
-  // measured on B200 (profiles/newton_batch_sweep.py): the ring kernel wins up to one full wave of 148 x 6
-  // one-warp blocks and again from two waves on; in between its second wave is mostly empty
-  bool ring = (tiles <= 148 * 4 || tiles >= 2 * 148 * 4) && aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) &&
+  bool ring = aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) &&
               aligned(lin_ws, 128) && aligned(K, 128) && aligned(S, 128) &&
               aligned(ref->x, ref->per_problem ? 128 : 32) && aligned(ref->u, ref->per_problem ? 128 : 16);
   if (force && !strcmp(force, "ldg")) ring = false;
@@ -1501,16 +1500,26 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
     ring = true;
   }
   if (ring) {
-#define EXPR(WPB, RPB)                                                                                          \
-  do {                                                                                                          \
-    constexpr int smem = ACRO_RING_D * stage_bytes<RPB>() + ACRO_RING_D * 8;                                    \
-    cudaError_t e_ = cudaFuncSetAttribute(k_newton_ring<WPB, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          smem);                                                                \
-    if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                      \
-    k_newton_ring<WPB, RPB><<<(unsigned)tiles, 32, smem, (cudaStream_t)stream>>>(a);                            \
+#define LAUNCH_RING(WPB, RPB, SG)                                                                                   \
+  do {                                                                                                              \
+    constexpr int smem = ACRO_RING_D * stage_bytes<RPB, SG>() + ACRO_RING_D * 8;                                    \
+    cudaError_t e_ = cudaFuncSetAttribute(k_newton_ring<WPB, RPB, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          smem);                                                                    \
+    if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                          \
+    k_newton_ring<WPB, RPB, SG><<<(unsigned)tiles, 32, smem, (cudaStream_t)stream>>>(a);                            \
   } while (0)
-    DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+    // at most one block per SM: deep stages (16 steps per bulk copy); otherwise 4 steps per stage, 4 blocks per SM.
+    // Per-problem references need 50 % more shared memory per stage: they always use the 4-step stages.
+    if (tiles <= 148 && !ref->per_problem) {
+#define EXPR(WPB, RPB) LAUNCH_RING(WPB, false, 16)
+      DISPATCH2(per_problem_weights(*w), false, EXPR);
 #undef EXPR
+    } else {
+#define EXPR(WPB, RPB) LAUNCH_RING(WPB, RPB, 4)
+      DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+    }
+#undef LAUNCH_RING
   } else {
     const Cfg c = cfg_for(B);
 #define EXPR(WPB, RPB) k_newton<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(a)

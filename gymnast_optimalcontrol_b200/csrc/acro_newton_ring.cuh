@@ -66,15 +66,18 @@ __device__ __forceinline__ double lds(uint32_t addr) {
   return v;
 }
 
-// A stage holds ACRO_RING_SG consecutive time steps of every streamed array; a trajectory of a tile is contiguous
+// A stage holds SG consecutive time steps of every streamed array; a trajectory of a tile is contiguous
 // in memory (tile-major layout), so SG steps of one array are ONE bulk copy.  Byte offsets inside a stage:
 //     X: s*1024 + c*256   U: SG*1024 + s*512 + c*256   K: SG*1536 + s*2048 + c*256   S: SG*3584 + s*512 + c*256
 //     (backward pass: lin: SG*1536 + s*2560 + j*256)   reference block at SG*4096
-#define ACRO_RING_SG 4
-constexpr uint32_t kSG = ACRO_RING_SG;
-constexpr uint32_t kOffX = 0, kOffU = kSG * 1024, kOffA = kSG * 1536, kOffS = kSG * 3584, kOffRef = kSG * 4096;
-template <bool RPB>
-__host__ __device__ constexpr uint32_t stage_bytes() { return kSG * 4096 + (RPB ? kSG * 1536 : 256); }
+// SG is a template parameter: 16 when every SM holds at most one block (B <= 4736: 199 KB of shared memory per
+// block), 4 otherwise (50 KB, four blocks per SM).
+template <int SG>
+struct StageOff {
+  static constexpr uint32_t X = 0, U = SG * 1024, A = SG * 1536, S = SG * 3584, Ref = SG * 4096;
+};
+template <bool RPB, int SG>
+__host__ __device__ constexpr uint32_t stage_bytes() { return SG * 4096 + (RPB ? SG * 1536 : ((SG * 48 + 127) / 128) * 128); }
 
 struct Ring {
   uint32_t data, bars;  // shared addresses of slot 0 / barrier 0
@@ -91,76 +94,76 @@ struct TilePtrs {
 constexpr int64_t kSX = 4 * 32, kSU = 2 * 32, kSK = 8 * 32, kSS = 2 * 32, kSL = 10 * 32;  // doubles per time step
 
 // Issue the bulk copies of stage k of a pass: time steps [t_lo, t_lo + cnt).
-template <bool RPB, bool FWD>
+template <bool RPB, bool FWD, int SG>
 __device__ __forceinline__ void ring_fill(const Ring& r, const TilePtrs& p, int k, int t_lo, int cnt) {
   if (elect_one()) {
     const uint32_t g = r.base + k, slot = ring_slot(g);
-    const uint32_t bar = r.bars + slot * 8, dst = r.data + slot * stage_bytes<RPB>();
+    const uint32_t bar = r.bars + slot * 8, dst = r.data + slot * stage_bytes<RPB, SG>();
     const uint32_t n = (uint32_t)cnt;
     mbar_expect_tx(bar, n * (4096u + (RPB ? 1536u : 48u)));
-    bulk_g2s(dst + kOffX, p.x + t_lo * kSX, n * 1024, bar);
-    bulk_g2s(dst + kOffU, p.u + t_lo * kSU, n * 512, bar);
+    bulk_g2s(dst + StageOff<SG>::X, p.x + t_lo * kSX, n * 1024, bar);
+    bulk_g2s(dst + StageOff<SG>::U, p.u + t_lo * kSU, n * 512, bar);
     if (FWD) {
-      bulk_g2s(dst + kOffA, p.k + t_lo * kSK, n * 2048, bar);
-      bulk_g2s(dst + kOffS, p.s + t_lo * kSS, n * 512, bar);
+      bulk_g2s(dst + StageOff<SG>::A, p.k + t_lo * kSK, n * 2048, bar);
+      bulk_g2s(dst + StageOff<SG>::S, p.s + t_lo * kSS, n * 512, bar);
     } else {
-      bulk_g2s(dst + kOffA, p.lin + t_lo * kSL, n * 2560, bar);
+      bulk_g2s(dst + StageOff<SG>::A, p.lin + t_lo * kSL, n * 2560, bar);
     }
     if (RPB) {
-      bulk_g2s(dst + kOffRef, p.rx + t_lo * kSX, n * 1024, bar);
-      bulk_g2s(dst + kOffRef + kSG * 1024, p.ru + t_lo * kSU, n * 512, bar);
+      bulk_g2s(dst + StageOff<SG>::Ref, p.rx + t_lo * kSX, n * 1024, bar);
+      bulk_g2s(dst + StageOff<SG>::Ref + SG * 1024, p.ru + t_lo * kSU, n * 512, bar);
     } else {
-      bulk_g2s(dst + kOffRef, p.rx + t_lo * 4, n * 32, bar);
-      bulk_g2s(dst + kOffRef + kSG * 32, p.ru + t_lo * 2, n * 16, bar);
+      bulk_g2s(dst + StageOff<SG>::Ref, p.rx + t_lo * 4, n * 32, bar);
+      bulk_g2s(dst + StageOff<SG>::Ref + SG * 32, p.ru + t_lo * 2, n * 16, bar);
     }
   }
 }
 
 // reference of step s of a stage
-template <bool RPB>
+template <bool RPB, int SG>
 __device__ __forceinline__ void lds_ref(uint32_t stage, int s, int lane, double xr[4], double ur[2]) {
-  const uint32_t b = stage + kOffRef;
+  const uint32_t b = stage + StageOff<SG>::Ref;
   if (RPB) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) xr[c] = lds(b + s * 1024 + c * 256 + lane * 8);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) ur[c] = lds(b + kSG * 1024 + s * 512 + c * 256 + lane * 8);
+    for (int c = 0; c < 2; ++c) ur[c] = lds(b + SG * 1024 + s * 512 + c * 256 + lane * 8);
   } else {
 #pragma unroll
     for (int c = 0; c < 4; ++c) xr[c] = lds(b + s * 32 + c * 8);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) ur[c] = lds(b + kSG * 32 + s * 16 + c * 8);
+    for (int c = 0; c < 2; ++c) ur[c] = lds(b + SG * 32 + s * 16 + c * 8);
   }
 }
 
-template <bool RPB>
+template <bool RPB, int SG>
 __device__ __forceinline__ void lds_fwd(uint32_t stage, int s, int lane, StepIn& in) {
   const uint32_t b = stage + lane * 8;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) in.x[c] = lds(b + kOffX + s * 1024 + c * 256);
+  for (int c = 0; c < 4; ++c) in.x[c] = lds(b + StageOff<SG>::X + s * 1024 + c * 256);
 #pragma unroll
-  for (int c = 0; c < 2; ++c) in.u[c] = lds(b + kOffU + s * 512 + c * 256);
+  for (int c = 0; c < 2; ++c) in.u[c] = lds(b + StageOff<SG>::U + s * 512 + c * 256);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) in.k[c] = lds(b + kOffA + s * 2048 + c * 256);
+  for (int c = 0; c < 8; ++c) in.k[c] = lds(b + StageOff<SG>::A + s * 2048 + c * 256);
 #pragma unroll
-  for (int c = 0; c < 2; ++c) in.s[c] = lds(b + kOffS + s * 512 + c * 256);
-  lds_ref<RPB>(stage, s, lane, in.xr, in.ur);
+  for (int c = 0; c < 2; ++c) in.s[c] = lds(b + StageOff<SG>::S + s * 512 + c * 256);
+  lds_ref<RPB, SG>(stage, s, lane, in.xr, in.ur);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // forward pass (tg:218-252): closed-loop rollout with step size gamma + its cost; writes the candidate
 // (Xo, Uo) and the linearisation about it when `store`.
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB>
+template <bool WPB, bool RPB, int SG>
 __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w, int N, const TilePtrs& p, Ring& r,
                                                int lane, double gamma, bool store, double* __restrict__ Xo,
                                                double* __restrict__ Uo, double* __restrict__ Lo, const double xrT[4]) {
-  const int steps = N - 1, n_stages = (steps + kSG - 1) / kSG;
-  for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, true>(r, p, k, k * kSG, min((int)kSG, steps - k * (int)kSG));
+  const int steps = N - 1, n_stages = (steps + SG - 1) / SG;
+  for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, true, SG>(r, p, k, k * SG, min(SG, steps - k * SG));
   double xp[4];
   StepIn in;
   mbar_wait(r.bars + ring_slot(r.base) * 8, ring_parity(r.base));
-  lds_fwd<RPB>(r.data + ring_slot(r.base) * stage_bytes<RPB>(), 0, lane, in);
+  lds_fwd<RPB, SG>(r.data + ring_slot(r.base) * stage_bytes<RPB, SG>(), 0, lane, in);
 #pragma unroll
   for (int c = 0; c < 4; ++c) xp[c] = in.x[c];  // x+_0 = x_0
   double cost = 0.0;
@@ -168,10 +171,10 @@ __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w,
   double* po_u = Uo + lane;
   double* po_l = Lo + lane;
   for (int k = 0; k < n_stages; ++k) {
-    const int cnt = min((int)kSG, steps - k * (int)kSG);
+    const int cnt = min(SG, steps - k * SG);
     const uint32_t g = r.base + k;
-    const uint32_t stage = r.data + ring_slot(g) * stage_bytes<RPB>();
-    const uint32_t nstage = r.data + ring_slot(g + 1) * stage_bytes<RPB>();
+    const uint32_t stage = r.data + ring_slot(g) * stage_bytes<RPB, SG>();
+    const uint32_t nstage = r.data + ring_slot(g + 1) * stage_bytes<RPB, SG>();
     const uint32_t nbar = r.bars + ring_slot(g + 1) * 8, npar = ring_parity(g + 1);
     for (int s = 0; s < cnt; ++s) {
       const bool cross = (s + 1 == cnt) && (k + 1 < n_stages);  // the next step lives in the next stage
@@ -201,16 +204,16 @@ __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w,
       cost += quad2(eu, [&](int i, int j) { return w.R(i, j); });
       // operands of the next step straight into the registers this step no longer needs
       if (s + 1 < cnt) {
-        lds_fwd<RPB>(stage, s + 1, lane, in);
+        lds_fwd<RPB, SG>(stage, s + 1, lane, in);
       } else if (cross) {
         if (!ready) mbar_wait(nbar, npar);
-        lds_fwd<RPB>(nstage, 0, lane, in);
+        lds_fwd<RPB, SG>(nstage, 0, lane, in);
       }
       // first step of a stage: every read of the previous stage has completed, its slot can be refilled
       if (s == 0 && k >= 1 && k - 1 + ACRO_RING_D < n_stages) {
         __syncwarp();
         const int kk = k - 1 + ACRO_RING_D;
-        ring_fill<RPB, true>(r, p, kk, kk * kSG, min((int)kSG, steps - kk * (int)kSG));
+        ring_fill<RPB, true, SG>(r, p, kk, kk * SG, min(SG, steps - kk * SG));
       }
       double xn[4];
       LinD L;
@@ -246,15 +249,15 @@ __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w,
 // backward pass (tg:166-216): affine Riccati sweep on the stored linearisation; writes K, S when `store`.
 // Stage k of this pass holds the time steps [t_lo, t_hi] with t_hi = steps-1 - k*SG, walked downwards.
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB>
+template <bool WPB, bool RPB, int SG>
 __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, int N, const TilePtrs& p, Ring& r,
                                               int lane, bool store, double* __restrict__ K, double* __restrict__ S,
                                               const double xT[4], const double xrT[4], double& dJ_out,
                                               double& sn_out) {
-  const int steps = N - 1, n_stages = (steps + kSG - 1) / kSG;
-  auto t_lo_of = [&](int k) { return max(0, steps - (k + 1) * (int)kSG); };
-  auto cnt_of = [&](int k) { return (steps - k * (int)kSG) - t_lo_of(k); };
-  for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, false>(r, p, k, t_lo_of(k), cnt_of(k));
+  const int steps = N - 1, n_stages = (steps + SG - 1) / SG;
+  auto t_lo_of = [&](int k) { return max(0, steps - (k + 1) * SG); };
+  auto cnt_of = [&](int k) { return (steps - k * SG) - t_lo_of(k); };
+  for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, false, SG>(r, p, k, t_lo_of(k), cnt_of(k));
   double P[10], pv[4];
   {
     double dx[4];
@@ -276,20 +279,20 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
   auto load = [&](uint32_t stage, int s) {
     const uint32_t b = stage + lane * 8;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) x[c] = lds(b + kOffX + s * 1024 + c * 256);
+    for (int c = 0; c < 4; ++c) x[c] = lds(b + StageOff<SG>::X + s * 1024 + c * 256);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) u[c] = lds(b + kOffU + s * 512 + c * 256);
+    for (int c = 0; c < 2; ++c) u[c] = lds(b + StageOff<SG>::U + s * 512 + c * 256);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      L.a[0][j] = lds(b + kOffA + s * 2560 + j * 256);
-      L.a[1][j] = lds(b + kOffA + s * 2560 + (4 + j) * 256);
+      L.a[0][j] = lds(b + StageOff<SG>::A + s * 2560 + j * 256);
+      L.a[1][j] = lds(b + StageOff<SG>::A + s * 2560 + (4 + j) * 256);
     }
-    L.b[0] = lds(b + kOffA + s * 2560 + 8 * 256);
-    L.b[1] = lds(b + kOffA + s * 2560 + 9 * 256);
-    lds_ref<RPB>(stage, s, lane, xr, ur);
+    L.b[0] = lds(b + StageOff<SG>::A + s * 2560 + 8 * 256);
+    L.b[1] = lds(b + StageOff<SG>::A + s * 2560 + 9 * 256);
+    lds_ref<RPB, SG>(stage, s, lane, xr, ur);
   };
   mbar_wait(r.bars + ring_slot(r.base) * 8, ring_parity(r.base));
-  load(r.data + ring_slot(r.base) * stage_bytes<RPB>(), cnt_of(0) - 1);
+  load(r.data + ring_slot(r.base) * stage_bytes<RPB, SG>(), cnt_of(0) - 1);
   double dJ = 0.0, sn = 0.0;
   const QhQ2<WV<WPB>> Qh{w};
   const Lu2Col col = lu2_col(w.R2(0, 0), w.R2(0, 1));
@@ -298,8 +301,8 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
   for (int k = 0; k < n_stages; ++k) {
     const int cnt = cnt_of(k);
     const uint32_t g = r.base + k;
-    const uint32_t stage = r.data + ring_slot(g) * stage_bytes<RPB>();
-    const uint32_t nstage = r.data + ring_slot(g + 1) * stage_bytes<RPB>();
+    const uint32_t stage = r.data + ring_slot(g) * stage_bytes<RPB, SG>();
+    const uint32_t nstage = r.data + ring_slot(g + 1) * stage_bytes<RPB, SG>();
     const uint32_t nbar = r.bars + ring_slot(g + 1) * 8, npar = ring_parity(g + 1);
     const int ncnt = (k + 1 < n_stages) ? cnt_of(k + 1) : 0;
     for (int s = cnt - 1; s >= 0; --s) {
@@ -343,7 +346,7 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
       if (s == cnt - 1 && k >= 1 && k - 1 + ACRO_RING_D < n_stages) {
         __syncwarp();
         const int kk = k - 1 + ACRO_RING_D;
-        ring_fill<RPB, false>(r, p, kk, t_lo_of(kk), cnt_of(kk));
+        ring_fill<RPB, false, SG>(r, p, kk, t_lo_of(kk), cnt_of(kk));
       }
       pk -= kSK;
       ps -= kSS;
@@ -357,7 +360,7 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
 // ---------------------------------------------------------------------------------------------------------
 // kernel: one warp per block, block = tile of 32 problems
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB>
+template <bool WPB, bool RPB, int SG>
 __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ NewtonArgs a) {
   extern __shared__ __align__(128) unsigned char ring_smem[];
   constexpr unsigned FULL = 0xffffffffu;
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
   const WV<WPB> w(a.kw, B, bs);
   Ring r;
   r.data = smem_u32(ring_smem);
-  r.bars = r.data + ACRO_RING_D * stage_bytes<RPB>();
+  r.bars = r.data + ACRO_RING_D * stage_bytes<RPB, SG>();
   r.base = 0;
   if (lane == 0) {
 #pragma unroll
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
 #pragma unroll
     for (int c = 0; c < 4; ++c) xT[c] = p.x[(N - 1) * sx + c * 32 + lane];
     double dJn, snn;
-    backward_ring<WPB, RPB>(a.m, w, N, p, r, lane, run, tK, tS, xT, xrT, dJn, snn);
+    backward_ring<WPB, RPB, SG>(a.m, w, N, p, r, lane, run, tK, tS, xT, xrT, dJn, snn);
     if (run) {
       dJ = dJn;
       sn = snn;
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
     double gamma = a.o.gamma_0, cn = 0.0;
     int tries = 0;
     for (int i = 0; i < a.o.max_line_search && __any_sync(FULL, need); ++i) {
-      const double c = forward_ring<WPB, RPB>(a.m, w, N, p, r, lane, gamma, need, Xo, Uo, tL, xrT);
+      const double c = forward_ring<WPB, RPB, SG>(a.m, w, N, p, r, lane, gamma, need, Xo, Uo, tL, xrT);
       if (need) {
         ++tries;
         // accept iff cost_new < cost_k + c*gamma*delta_J  (strict, NaN rejects)   tg:361
