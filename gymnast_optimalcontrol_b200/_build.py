@@ -7,7 +7,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libacro_b200.so")
 SOURCES = ["acro_kernels.cu"]
-HEADERS = ["acro_device.cuh", "acro_views.cuh", "acro_newton_ring.cuh", os.path.join("..", "..", "include", "acro_abi.h")]
+HEADERS = ["acro_device.cuh", "acro_views.cuh", "acro_newton_ring.cuh", "acro_newton_duo.cuh", os.path.join("..", "..", "include", "acro_abi.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

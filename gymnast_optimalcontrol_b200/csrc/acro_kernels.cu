@@ -712,6 +712,7 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
 
 }  // namespace acro
 #include "acro_newton_ring.cuh"
+#include "acro_newton_duo.cuh"
 namespace acro {
 
 // ---------------------------------------------------------------------------------------
@@ -1499,7 +1500,33 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
                  "acro_newton_solve: ring kernel needs 128-byte aligned buffers");
     ring = true;
   }
-  if (ring) {
+  // At most one tile per SM (config 2: 128 tiles): split every tile between two warps on two SM sub-partitions.
+  bool duo = ring && tiles <= 148;
+  if (force && !strcmp(force, "ring")) duo = false;
+  if (force && !strcmp(force, "duo")) {
+    ACRO_REQUIRE(ring, "acro_newton_solve: duo kernel needs 128-byte aligned buffers");
+    duo = true;
+  }
+  if (duo) {
+#define LAUNCH_DUO(WPB, RPB, SG)                                                                                   \
+  do {                                                                                                             \
+    constexpr int smem = DuoSmem<RPB, SG>::total;                                                                  \
+    cudaError_t e_ = cudaFuncSetAttribute(k_newton_duo<WPB, RPB, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          smem);                                                                   \
+    if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                         \
+    k_newton_duo<WPB, RPB, SG><<<(unsigned)tiles, 64, smem, (cudaStream_t)stream>>>(a);                            \
+  } while (0)
+    if (!ref->per_problem) {
+#define EXPR(WPB, RPB) LAUNCH_DUO(WPB, false, 16)
+      DISPATCH2(per_problem_weights(*w), false, EXPR);
+#undef EXPR
+    } else {
+#define EXPR(WPB, RPB) LAUNCH_DUO(WPB, true, 8)
+      DISPATCH2(per_problem_weights(*w), true, EXPR);
+#undef EXPR
+    }
+#undef LAUNCH_DUO
+  } else if (ring) {
 #define LAUNCH_RING(WPB, RPB, SG)                                                                                   \
   do {                                                                                                              \
     constexpr int smem = ACRO_RING_D * stage_bytes<RPB, SG>() + ACRO_RING_D * 8;                                    \

@@ -527,7 +527,7 @@ def _short_ref(fa_ref, N=61):
     return x_ref[:N].copy(), u_ref[:N - 1].copy()
 
 
-@pytest.mark.parametrize("kernel", ["ring", "ldg"])
+@pytest.mark.parametrize("kernel", ["duo", "ring", "ldg"])
 def test_newton_ragged_line_search_failures(bt, fa_ref, kernel, monkeypatch):
     """gamma_0 = 1 on a short horizon: problems back-track up to 20 times and fail the line search at different
     iterations (status 3 after 3-7 iterations).  A warp therefore holds finished and running problems side by
@@ -553,7 +553,7 @@ def test_newton_ragged_line_search_failures(bt, fa_ref, kernel, monkeypatch):
     assert len(seen) >= 3  # genuinely ragged
 
 
-@pytest.mark.parametrize("kernel", ["ring", "ldg"])
+@pytest.mark.parametrize("kernel", ["duo", "ring", "ldg"])
 def test_newton_ragged_convergence_per_problem_refs_and_weights(bt, fa_ref, kernel, monkeypatch):
     """Per-problem reference trajectories (scaled copies) and per-problem weights: problems converge after different
     numbers of iterations inside the same warp."""
@@ -589,6 +589,31 @@ def test_newton_ragged_convergence_per_problem_refs_and_weights(bt, fa_ref, kern
             assert abs(st.cost[b].item() - h["cost"][-1]) < TOL * max(1.0, abs(h["cost"][-1]))
             seen.add(h["iters"])
         assert (status == 1).all() and len(seen) >= 3
+
+
+def test_newton_kernels_agree(bt, fa_ref, monkeypatch):
+    """The three Newton kernels (two warps per tile / one warp per tile with the TMA ring / one thread per problem
+    with register prefetch) evaluate the same expressions: same Armijo decisions, iterates equal to rounding,
+    on a batch with a partial tile, back-tracking (gamma_0 = 1) and a resume in the middle."""
+    x_ref, u_ref, _ = fa_ref
+    x0s = np.random.default_rng(8).uniform(-0.2, 0.2, (45, 4))
+    ref = bt.make_ref(x_ref, u_ref)
+    out = {}
+    for kernel in ("duo", "ring", "ldg"):
+        monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+        st = bt.newton_solve(soa(x0s), ref, max_iters=6, tol=1e-4, gamma_0=1.0, chunk_iters=3)
+        st = bt.newton_solve(soa(x0s), ref, max_iters=6, tol=1e-4, gamma_0=1.0, state=st)
+        torch.cuda.synchronize()
+        out[kernel] = (aos(st.X), aos(st.U), kmat(st.K), aos(st.S), st.hist_cost[:7].cpu().numpy(),
+                       st.hist_ntry[:6].cpu().numpy(), st.hist_gamma[:6].cpu().numpy(), st.iters.cpu().numpy(),
+                       st.status.cpu().numpy(), st.sigma_norm.cpu().numpy(), st.delta_J.cpu().numpy())
+    for kernel in ("duo", "ldg"):
+        a, b = out[kernel], out["ring"]
+        for i in (5, 6, 7, 8):
+            assert np.array_equal(a[i], b[i]), (kernel, i)
+        for i in (0, 1, 3, 4, 9, 10):
+            assert rel_err(a[i], b[i]) < 1e-11, (kernel, i)
+        assert rel_err(a[2], b[2]) < 1e-8
 
 
 def test_newton_warm_start(bt, fa_ref):
