@@ -351,6 +351,98 @@ __device__ __forceinline__ void rk4_step_lin(const Model& m, const double x[4], 
   }
 }
 
+// sincos2 for NA angles in lockstep: 2*NA independent polynomial chains cover the 8-cycle DFMA latency.
+template <int NA>
+__device__ __forceinline__ void sincos_n(const Model& m, const double x[NA], double s[NA], double c[NA]) {
+  double qm[NA], q[NA], r[NA], z[NA], ps[NA], pc[NA];
+  int j[NA];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) qm[a] = fma(x[a], m.tc[0], m.tc[3]);
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    j[a] = __double2loint(qm[a]);
+    q[a] = qm[a] - m.tc[3];
+  }
+#pragma unroll
+  for (int a = 0; a < NA; ++a) r[a] = fma(q[a], m.tc[1], x[a]);
+#pragma unroll
+  for (int a = 0; a < NA; ++a) r[a] = fma(q[a], m.tc[2], r[a]);
+#pragma unroll
+  for (int a = 0; a < NA; ++a) z[a] = r[a] * r[a];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    ps[a] = fma(z[a], m.tc[9], m.tc[8]);
+    pc[a] = fma(z[a], m.tc[15], m.tc[14]);
+  }
+#pragma unroll
+  for (int k = 3; k >= 0; --k) {
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      ps[a] = fma(z[a], ps[a], m.tc[4 + k]);
+      pc[a] = fma(z[a], pc[a], m.tc[10 + k]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    const double sr = fma(r[a] * z[a], ps[a], r[a]);
+    const double cr = fma(z[a] * z[a], pc[a], fma(z[a], -0.5, 1.0));
+    const double s0 = (j[a] & 1) ? cr : sr, c0 = (j[a] & 1) ? sr : cr;
+    s[a] = flip_sign(s0, j[a] << 30);
+    c[a] = flip_sign(c0, (j[a] + 1) << 30);
+  }
+}
+
+__device__ __forceinline__ Trig trig_from(double s1, double c1, double s2, double c2) {
+  Trig t;
+  t.s1 = s1;
+  t.c1 = c1;
+  t.s2 = s2;
+  t.c2 = c2;
+  t.s12 = fma(t.s1, t.c2, t.c1 * t.s2);
+  t.c12 = fma(t.c1, t.c2, -(t.s1 * t.s2));
+  return t;
+}
+
+// The RK4 step of rk4_step_t<true>, same expressions, written in the order of its data dependencies instead of
+// stage by stage: the angles of a stage depend on the velocities of the previous stage, i.e. on the accelerations
+// of the stage before that, so the sines and cosines of stage s+1 do not wait for the equations of motion of
+// stage s.  Stages 1 and 2 (whose angles need nothing but x) share one lockstep sincos of four angles; the
+// sincos of stages 3 and 4 stand before the equations of motion of stages 2 and 3, which fill their latency.
+// `mid` is a hook for the caller's loads of the next step: issued here they hide behind FP64 instructions.
+template <class Mid>
+__device__ __forceinline__ int rk4_step_overlap(const Model& m, const double x[4], double u0, double u1,
+                                                double xn[4], Mid mid) {
+  const double h = m.dt, hh = 0.5 * m.dt;
+  const double th[4] = {x[0], x[1], fma(hh, x[2], x[0]), fma(hh, x[3], x[1])};
+  int amax = max(max(abs_hi(th[0]), abs_hi(th[1])), max(abs_hi(th[2]), abs_hi(th[3])));
+  double sn[4], cs[4];
+  sincos_n<4>(m, th, sn, cs);
+  const Trig t1 = trig_from(sn[0], cs[0], sn[1], cs[1]);
+  const Trig t2 = trig_from(sn[2], cs[2], sn[3], cs[3]);
+  const Eom e1 = eom(m, t1, x[2], x[3], u0, u1);
+  const double w21 = fma(hh, e1.dd1, x[2]), w22 = fma(hh, e1.dd2, x[3]);
+  const double th3a = fma(hh, w21, x[0]), th3b = fma(hh, w22, x[1]);
+  amax = max(amax, max(abs_hi(th3a), abs_hi(th3b)));
+  const Trig t3 = trig_of<true>(m, th3a, th3b);
+  mid();
+  const Eom e2 = eom(m, t2, w21, w22, u0, u1);
+  const double w31 = fma(hh, e2.dd1, x[2]), w32 = fma(hh, e2.dd2, x[3]);
+  const double th4a = fma(h, w31, x[0]), th4b = fma(h, w32, x[1]);
+  amax = max(amax, max(abs_hi(th4a), abs_hi(th4b)));
+  const Trig t4 = trig_of<true>(m, th4a, th4b);
+  const Eom e3 = eom(m, t3, w31, w32, u0, u1);
+  const double w41 = fma(h, e3.dd1, x[2]), w42 = fma(h, e3.dd2, x[3]);
+  const Eom e4 = eom(m, t4, w41, w42, u0, u1);
+  const double k1[4] = {x[2], x[3], e1.dd1, e1.dd2}, k2[4] = {w21, w22, e2.dd1, e2.dd2};
+  const double k3[4] = {w31, w32, e3.dd1, e3.dd2}, k4[4] = {w41, w42, e4.dd1, e4.dd2};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double s = k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i];
+    xn[i] = x[i] + (h * s) * (1.0 / 6.0);
+  }
+  return amax;
+}
+
 // ---------------------------------------------------------------------------------------
 // Symmetric 4x4 in 10 registers: index of (i,j), i<=j
 // ---------------------------------------------------------------------------------------

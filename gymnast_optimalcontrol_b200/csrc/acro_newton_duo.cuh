@@ -149,6 +149,8 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
   in.load(r.data + ring_slot(r.base) * stage_bytes<RPB, SG>(), 0, lane);
 #pragma unroll
   for (int c = 0; c < 4; ++c) xp[c] = in.x[c];  // x+_0 = x_0
+  uint32_t hready = 1u;
+  mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);  // the hand-off slot of the first step is free (all are, between passes)
   for (int k = 0; k < n_stages; ++k) {
     const int cnt = min(SG, steps - k * SG);
     const uint32_t g = r.base + k;
@@ -156,10 +158,16 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
     const uint32_t nstage = r.data + ring_slot(g + 1) * stage_bytes<RPB, SG>();
     const uint32_t nbar = r.bars + ring_slot(g + 1) * 8, npar = ring_parity(g + 1);
     for (int s = 0; s < cnt; ++s) {
+      // where the operands of the next step live: this stage, the next stage (whose bulk copies were issued at
+      // least a stage ago; the wait is a formality, done here at the top where it splits no straight-line code),
+      // or nowhere (last step of the pass: reload this step's, harmlessly)
       const bool cross = (s + 1 == cnt) && (k + 1 < n_stages);
-      const uint32_t ready = cross ? mbar_test(nbar, npar) : 1u;
-      const uint32_t slot = hd.slot(), fbar = hd.full_bar(), ebar = hd.empty_bar(), epar = hd.phase() ^ 1u;
-      const uint32_t hready = mbar_test(ebar, epar);
+      if (cross) mbar_wait(nbar, npar);
+      const uint32_t nsrc = cross ? nstage : stage;
+      const int ns = (s + 1 < cnt) ? s + 1 : (cross ? 0 : s);
+      const uint32_t slot = hd.slot(), fbar = hd.full_bar();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sts(slot + c * 256 + lane * 8, xp[c]);  // (the slot is free: checked last step)
       double dx[4], up[2];
 #pragma unroll
       for (int c = 0; c < 4; ++c) dx[c] = xp[c] - in.x[c];
@@ -170,30 +178,32 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
         for (int j = 1; j < 4; ++j) kd = fma(in.k[i * 4 + j], dx[j], kd);
         up[i] = (in.u[i] + kd) + gamma * in.s[i];
       }
-      if (!hready) mbar_wait(ebar, epar);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) sts(slot + c * 256 + lane * 8, xp[c]);
 #pragma unroll
       for (int c = 0; c < 2; ++c) sts(slot + (4 + c) * 256 + lane * 8, up[c]);
       __syncwarp();
       mbar_arrive_lane0(fbar, lane);
       ++hd.h;
-      if (s + 1 < cnt) {
-        in.load(stage, s + 1, lane);
-      } else if (cross) {
-        if (!ready) mbar_wait(nbar, npar);
-        in.load(nstage, 0, lane);
-      }
       double xn[4];
-      rk4_step(m, xp, up[0], up[1], xn);
+      const uint32_t nebar = hd.empty_bar(), nepar = hd.phase() ^ 1u;
+      const int amax = rk4_step_overlap(m, xp, up[0], up[1], xn, [&]() {
+        // operands of the next step, and the state of the next hand-off slot, while the FP64 pipe is busy
+        // (no branch in here: a branch would cut the step's straight-line code into two scheduling regions)
+        in.load(nsrc, ns, lane);
+        hready = mbar_test(nebar, nepar);
+      });
+      if (hi_too_large(amax)) {
+        const Vec4 o = rk4_step_slow(m, xp[0], xp[1], xp[2], xp[3], up[0], up[1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xn[i] = o.v[i];
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) xp[c] = xn[c];
+      if (!hready) mbar_wait(nebar, nepar);  // the trailer is ACRO_DUO_R steps behind: wait for it
     }
   }
   r.base += n_stages;
-  {  // terminal state
-    const uint32_t slot = hd.slot(), fbar = hd.full_bar(), ebar = hd.empty_bar(), epar = hd.phase() ^ 1u;
-    mbar_wait(ebar, epar);
+  {  // terminal state (its slot was checked at the end of the last step)
+    const uint32_t slot = hd.slot(), fbar = hd.full_bar();
 #pragma unroll
     for (int c = 0; c < 4; ++c) sts(slot + c * 256 + lane * 8, xp[c]);
     __syncwarp();
