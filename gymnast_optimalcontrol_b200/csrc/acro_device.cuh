@@ -352,15 +352,16 @@ __device__ __forceinline__ void rk4_step_lin(const Model& m, const double x[4], 
 }
 
 // sincos2 for NA angles in lockstep: 2*NA independent polynomial chains cover the 8-cycle DFMA latency.
+// `jz` is added to the quadrant index: callers pass 0, or an opaque zero that carries a scheduling dependency.
 template <int NA>
-__device__ __forceinline__ void sincos_n(const Model& m, const double x[NA], double s[NA], double c[NA]) {
+__device__ __forceinline__ void sincos_n(const Model& m, const double x[NA], double s[NA], double c[NA], int jz = 0) {
   double qm[NA], q[NA], r[NA], z[NA], ps[NA], pc[NA];
   int j[NA];
 #pragma unroll
   for (int a = 0; a < NA; ++a) qm[a] = fma(x[a], m.tc[0], m.tc[3]);
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
-    j[a] = __double2loint(qm[a]);
+    j[a] = __double2loint(qm[a]) + jz;
     q[a] = qm[a] - m.tc[3];
   }
 #pragma unroll
@@ -408,7 +409,10 @@ __device__ __forceinline__ Trig trig_from(double s1, double c1, double s2, doubl
 // of the stage before that, so the sines and cosines of stage s+1 do not wait for the equations of motion of
 // stage s.  Stages 1 and 2 (whose angles need nothing but x) share one lockstep sincos of four angles; the
 // sincos of stages 3 and 4 stand before the equations of motion of stages 2 and 3, which fill their latency.
-// `mid` is a hook for the caller's loads of the next step: issued here they hide behind FP64 instructions.
+// `mid` is a hook for the caller's loads of the next step: issued in the middle of the step they hide behind FP64
+// instructions.  It returns an (opaque) zero derived from what it loaded, which is added to the quadrant index of
+// the stage-4 sines: the instruction scheduler, which would otherwise push loads nobody needs before the next
+// step to the very end of this one (where nothing is left to overlap them with), has to complete them by then.
 template <class Mid>
 __device__ __forceinline__ int rk4_step_overlap(const Model& m, const double x[4], double u0, double u1,
                                                 double xn[4], Mid mid) {
@@ -424,12 +428,15 @@ __device__ __forceinline__ int rk4_step_overlap(const Model& m, const double x[4
   const double th3a = fma(hh, w21, x[0]), th3b = fma(hh, w22, x[1]);
   amax = max(amax, max(abs_hi(th3a), abs_hi(th3b)));
   const Trig t3 = trig_of<true>(m, th3a, th3b);
-  mid();
+  const int jz = mid();
   const Eom e2 = eom(m, t2, w21, w22, u0, u1);
   const double w31 = fma(hh, e2.dd1, x[2]), w32 = fma(hh, e2.dd2, x[3]);
   const double th4a = fma(h, w31, x[0]), th4b = fma(h, w32, x[1]);
   amax = max(amax, max(abs_hi(th4a), abs_hi(th4b)));
-  const Trig t4 = trig_of<true>(m, th4a, th4b);
+  const double th4[2] = {th4a, th4b};
+  double s4[2], c4[2];
+  sincos_n<2>(m, th4, s4, c4, jz);
+  const Trig t4 = trig_from(s4[0], c4[0], s4[1], c4[1]);
   const Eom e3 = eom(m, t3, w31, w32, u0, u1);
   const double w41 = fma(h, e3.dd1, x[2]), w42 = fma(h, e3.dd2, x[3]);
   const Eom e4 = eom(m, t4, w41, w42, u0, u1);

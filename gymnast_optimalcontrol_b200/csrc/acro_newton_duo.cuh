@@ -45,6 +45,8 @@ __device__ __forceinline__ void duo_bar() {
 struct Hand {
   uint32_t data, full, empty;  // shared addresses: slot 0, full barrier 0, empty barrier 0
   uint32_t h;                  // hand-offs so far (identical in both warps)
+  int zmask;                   // 0, read from shared memory at run time: `v & zmask` is a zero that depends on v
+                               // as far as nvcc and ptxas can tell (a scheduling dependency without arithmetic)
   __device__ __forceinline__ uint32_t slot() const { return data + (h & (ACRO_DUO_R - 1)) * ACRO_DUO_SLOT_BYTES; }
   __device__ __forceinline__ uint32_t full_bar() const { return full + (h & (ACRO_DUO_R - 1)) * 8; }
   __device__ __forceinline__ uint32_t empty_bar() const { return empty + (h & (ACRO_DUO_R - 1)) * 8; }
@@ -142,6 +144,7 @@ struct FwdIn {
 
 template <bool RPB, int SG>
 __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r, Hand& hd, int lane, double gamma) {
+  constexpr unsigned FULL = 0xffffffffu;
   const int steps = N - 1, n_stages = (steps + SG - 1) / SG;
   double xp[4];
   FwdIn<SG> in;
@@ -149,8 +152,11 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
   in.load(r.data + ring_slot(r.base) * stage_bytes<RPB, SG>(), 0, lane);
 #pragma unroll
   for (int c = 0; c < 4; ++c) xp[c] = in.x[c];  // x+_0 = x_0
-  uint32_t hready = 1u;
   mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);  // the hand-off slot of the first step is free (all are, between passes)
+  // State carried into the next step's single "anything unusual?" branch, so that the step itself is straight-line
+  // code: is the next hand-off slot free, and did the step just taken leave the range of the polynomial sincos.
+  uint32_t hready = 1u;
+  bool bad = false;
   for (int k = 0; k < n_stages; ++k) {
     const int cnt = min(SG, steps - k * SG);
     const uint32_t g = r.base + k;
@@ -159,15 +165,29 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
     const uint32_t nbar = r.bars + ring_slot(g + 1) * 8, npar = ring_parity(g + 1);
     for (int s = 0; s < cnt; ++s) {
       // where the operands of the next step live: this stage, the next stage (whose bulk copies were issued at
-      // least a stage ago; the wait is a formality, done here at the top where it splits no straight-line code),
-      // or nowhere (last step of the pass: reload this step's, harmlessly)
+      // least a stage ago: the wait is a formality), or nowhere (last step of the pass: reload this step's)
       const bool cross = (s + 1 == cnt) && (k + 1 < n_stages);
-      if (cross) mbar_wait(nbar, npar);
+      if (__builtin_expect(__any_sync(FULL, cross || bad || !hready), 0)) {
+        if (bad) {  // a diverging rollout on its way to overflow: redo the last step with the library sincos
+          double xo[4], uo[2];  // its inputs are still in the hand-off slot they were written to
+          const uint32_t pslot = hd.data + ((hd.h - 1) & (ACRO_DUO_R - 1)) * ACRO_DUO_SLOT_BYTES + lane * 8;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) xo[c] = lds(pslot + c * 256);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) uo[c] = lds(pslot + (4 + c) * 256);
+          const Vec4 o = rk4_step_slow(m, xo[0], xo[1], xo[2], xo[3], uo[0], uo[1]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xp[i] = o.v[i];
+        }
+        __syncwarp();
+        if (cross) mbar_wait(nbar, npar);
+        if (!hready) mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);  // the trailer is ACRO_DUO_R steps behind
+      }
       const uint32_t nsrc = cross ? nstage : stage;
       const int ns = (s + 1 < cnt) ? s + 1 : (cross ? 0 : s);
       const uint32_t slot = hd.slot(), fbar = hd.full_bar();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) sts(slot + c * 256 + lane * 8, xp[c]);  // (the slot is free: checked last step)
+      for (int c = 0; c < 4; ++c) sts(slot + c * 256 + lane * 8, xp[c]);
       double dx[4], up[2];
 #pragma unroll
       for (int c = 0; c < 4; ++c) dx[c] = xp[c] - in.x[c];
@@ -186,23 +206,38 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
       double xn[4];
       const uint32_t nebar = hd.empty_bar(), nepar = hd.phase() ^ 1u;
       const int amax = rk4_step_overlap(m, xp, up[0], up[1], xn, [&]() {
-        // operands of the next step, and the state of the next hand-off slot, while the FP64 pipe is busy
+        // operands of the next step and the state of the next hand-off slot, while the FP64 pipe is busy
         // (no branch in here: a branch would cut the step's straight-line code into two scheduling regions)
         in.load(nsrc, ns, lane);
         hready = mbar_test(nebar, nepar);
-      });
-      if (hi_too_large(amax)) {
-        const Vec4 o = rk4_step_slow(m, xp[0], xp[1], xp[2], xp[3], up[0], up[1]);
+        int acc = __double2loint(in.x[0]) | __double2loint(in.x[1]) | __double2loint(in.x[2]) | __double2loint(in.x[3]) |
+                  __double2loint(in.u[0]) | __double2loint(in.u[1]) | __double2loint(in.s[0]) | __double2loint(in.s[1]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xn[i] = o.v[i];
-      }
+        for (int e = 0; e < 8; ++e) acc |= __double2loint(in.k[e]);
+        return acc & hd.zmask;
+      });
+      bad = hi_too_large(amax);
 #pragma unroll
       for (int c = 0; c < 4; ++c) xp[c] = xn[c];
-      if (!hready) mbar_wait(nebar, nepar);  // the trailer is ACRO_DUO_R steps behind: wait for it
     }
   }
   r.base += n_stages;
-  {  // terminal state (its slot was checked at the end of the last step)
+  if (__any_sync(FULL, bad || !hready)) {
+    if (bad) {
+      double xo[4], uo[2];
+      const uint32_t pslot = hd.data + ((hd.h - 1) & (ACRO_DUO_R - 1)) * ACRO_DUO_SLOT_BYTES + lane * 8;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) xo[c] = lds(pslot + c * 256);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) uo[c] = lds(pslot + (4 + c) * 256);
+      const Vec4 o = rk4_step_slow(m, xo[0], xo[1], xo[2], xo[3], uo[0], uo[1]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xp[i] = o.v[i];
+    }
+    __syncwarp();
+    if (!hready) mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);
+  }
+  {  // terminal state
     const uint32_t slot = hd.slot(), fbar = hd.full_bar();
 #pragma unroll
     for (int c = 0; c < 4; ++c) sts(slot + c * 256 + lane * 8, xp[c]);
@@ -469,7 +504,7 @@ struct DuoSmem {
   static constexpr uint32_t hand = ACRO_RING_D * stage_bytes<RPB, SG>();
   static constexpr uint32_t res = hand + ACRO_DUO_R * ACRO_DUO_SLOT_BYTES;  // 3 rows of 32 doubles
   static constexpr uint32_t flags = res + 3 * 256;                          // 32 ints
-  static constexpr uint32_t cmd = flags + 128;                              // 2 ints (+ padding)
+  static constexpr uint32_t cmd = flags + 128;                              // 2 ints + the zero word (+ padding)
   static constexpr uint32_t bars = cmd + 16;  // ring full[D], hand full[R], hand empty[R]
   static constexpr uint32_t total = bars + (ACRO_RING_D + 2 * ACRO_DUO_R) * 8;
 };
@@ -503,8 +538,10 @@ __global__ void __launch_bounds__(64) k_newton_duo(const __grid_constant__ Newto
 #pragma unroll
     for (int s = 0; s < ACRO_RING_D + 2 * ACRO_DUO_R; ++s) mbar_init(r.bars + s * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    reinterpret_cast<volatile int*>(ring_smem + SM::cmd)[2] = 0;
   }
   __syncthreads();
+  hd.zmask = reinterpret_cast<volatile int*>(ring_smem + SM::cmd)[2];
   volatile double* const res = reinterpret_cast<volatile double*>(ring_smem + SM::res);
   volatile int* const flags = reinterpret_cast<volatile int*>(ring_smem + SM::flags);
   volatile int* const cmd = reinterpret_cast<volatile int*>(ring_smem + SM::cmd);
