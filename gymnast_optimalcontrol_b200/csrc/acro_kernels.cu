@@ -1500,8 +1500,8 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
                  "acro_newton_solve: ring kernel needs 128-byte aligned buffers");
     ring = true;
   }
-  // At most one tile per SM (config 2: 128 tiles): split every tile between two warps on two SM sub-partitions.
-  bool duo = ring && tiles <= 148;
+  // At most two tiles per SM (config 2: 128 tiles): split every tile between two warps on two SM sub-partitions.
+  bool duo = ring && tiles <= 296;
   if (force && !strcmp(force, "ring")) duo = false;
   if (force && !strcmp(force, "duo")) {
     ACRO_REQUIRE(ring, "acro_newton_solve: duo kernel needs 128-byte aligned buffers");
@@ -1516,7 +1516,11 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
     if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                         \
     k_newton_duo<WPB, RPB, SG><<<(unsigned)tiles, 64, smem, (cudaStream_t)stream>>>(a);                            \
   } while (0)
-    if (!ref->per_problem) {
+    if (tiles > 148) {  // two blocks per SM: 4-step stages (70-90 KB per block)
+#define EXPR(WPB, RPB) LAUNCH_DUO(WPB, RPB, 4)
+      DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+    } else if (!ref->per_problem) {
 #define EXPR(WPB, RPB) LAUNCH_DUO(WPB, false, 16)
       DISPATCH2(per_problem_weights(*w), false, EXPR);
 #undef EXPR
@@ -1537,9 +1541,16 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
   } while (0)
     // at most one block per SM: deep stages (16 steps per bulk copy); otherwise 4 steps per stage, 4 blocks per SM.
     // Per-problem references need 50 % more shared memory per stage: they always use the 4-step stages.
-    if (tiles <= 148 && !ref->per_problem) {
+    const char* sg_env = getenv("ACRO_RING_SG");
+    const int sg_force = sg_env ? atoi(sg_env) : 0;
+    if ((tiles <= 148 && !ref->per_problem && !sg_force) || sg_force == 16) {
 #define EXPR(WPB, RPB) LAUNCH_RING(WPB, false, 16)
       DISPATCH2(per_problem_weights(*w), false, EXPR);
+#undef EXPR
+    } else if ((tiles > 592 && !sg_force) || sg_force == 2) {
+      // more tiles than SM sub-partitions: 2-step stages (25 KB per block), eight blocks = two warps per sub-partition
+#define EXPR(WPB, RPB) LAUNCH_RING(WPB, RPB, 2)
+      DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
 #undef EXPR
     } else {
 #define EXPR(WPB, RPB) LAUNCH_RING(WPB, RPB, 4)

@@ -1,4 +1,5 @@
-"""Newton iterations/s versus batch size for the two kernels (ACRO_NEWTON_KERNEL=ring|ldg)."""
+"""Newton iterations/s versus batch size for the Newton kernels.
+Columns: default dispatch (duo <= 148 tiles, ring with 16/4/2-step stages beyond), and forced variants."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, '.')
@@ -6,10 +7,19 @@ from gymnast_optimalcontrol_b200 import batched as bt
 d = np.load('tests/golden/fully_actuated_trajectory.npz')
 u_ref = np.zeros(d['u'].shape); u_ref[:, 1] = 2 * d['u'][:, 1]
 ref = bt.make_ref(d['x'], u_ref)
-for B in (512, 1024, 2048, 4096, 8192, 16384, 28416, 32768, 65536):
+VARIANTS = (("default", None, None), ("duo", "duo", None), ("ring16", "ring", "16"), ("ring4", "ring", "4"),
+            ("ring2", "ring", "2"), ("ldg", "ldg", None))
+sizes = [int(v) for v in sys.argv[1:]] or [2048, 4096, 4736, 8192, 9472, 16384, 18944, 32768, 37888, 65536, 131072]
+for B in sizes:
     out = []
-    for k in ("ring", "ldg"):
-        os.environ["ACRO_NEWTON_KERNEL"] = k
+    for name, k, sg in VARIANTS:
+        if name == "duo" and B > 4736 * 4:
+            out.append(float('nan')); continue
+        if name == "ring16" and B > 4736 * 2:
+            out.append(float('nan')); continue
+        for key, val in (("ACRO_NEWTON_KERNEL", k), ("ACRO_RING_SG", sg)):
+            if val is None: os.environ.pop(key, None)
+            else: os.environ[key] = val
         x0 = torch.from_numpy(np.random.default_rng(1).uniform(-0.2, 0.2, (4, B))).cuda()
         st = bt.newton_alloc(B, 501, 10, history=False)
         def run():
@@ -19,4 +29,5 @@ for B in (512, 1024, 2048, 4096, 8192, 16384, 28416, 32768, 65536):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); run(); run(); e1.record(); torch.cuda.synchronize()
         out.append(B * 20 / (e0.elapsed_time(e1) * 1e-3))
-    print("B=%6d  ring %.3e it/s   ldg %.3e it/s" % (B, out[0], out[1]), flush=True)
+        del st
+    print("B=%6d  " % B + "  ".join("%s %.2fM" % (v[0], o / 1e6) for v, o in zip(VARIANTS, out)), flush=True)
