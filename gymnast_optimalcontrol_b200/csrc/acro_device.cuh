@@ -116,6 +116,10 @@ struct Eom {
 };
 
 // qdd = M^-1 (tau - (C+F) qd - G), tau = [tau1*u0, u1]   (dynamics.py:197-213, 64-90)
+// ACT = false: the caller knows that the first joint is not actuated (m.tau1 == 0; the Newton solver refuses the
+// fully-actuated plant), so the torque term and its run-time select disappear.  x + 0.0 == x except for the sign of
+// a zero, so the result is the same number.
+template <bool ACT = true>
 __device__ __forceinline__ Eom eom(const Model& m, const Trig& t, double w1, double w2, double u0,
                                    double u1) {
   Eom e;
@@ -125,9 +129,14 @@ __device__ __forceinline__ Eom eom(const Model& m, const Trig& t, double w1, dou
   const double hs2 = m.h * t.s2;
   const double grav2 = m.g2 * t.s12;
   const double grav1 = fma(m.g1, t.s1, grav2);
-  const double tau1 = (m.tau1 != 0.0) ? m.tau1 * u0 : 0.0;
   // r1 = tau1 + h s2 w2 w1 + h s2 (w1+w2) w2 - f1 w1 - G1 ; r2 = u1 - h s2 w1^2 - f2 w2 - G2
-  const double r1 = tau1 + hs2 * w2 * w1 + hs2 * (w1 + w2) * w2 - m.f1 * w1 - grav1;
+  double r1;
+  if (ACT) {
+    const double tau1 = (m.tau1 != 0.0) ? m.tau1 * u0 : 0.0;
+    r1 = tau1 + hs2 * w2 * w1 + hs2 * (w1 + w2) * w2 - m.f1 * w1 - grav1;
+  } else {
+    r1 = hs2 * w2 * w1 + hs2 * (w1 + w2) * w2 - m.f1 * w1 - grav1;
+  }
   const double r2 = u1 - hs2 * w1 * w1 - m.f2 * w2 - grav2;
   // det M = M11 M22 - M12^2 = (a1 a3 - a3^2) - h^2 cos^2(th2): two dependent operations after cos(th2)
   const double det = fma(-m.hsq, t.c2 * t.c2, m.det0);
@@ -423,13 +432,13 @@ __device__ __forceinline__ int rk4_step_overlap(const Model& m, const double x[4
   sincos_n<4>(m, th, sn, cs);
   const Trig t1 = trig_from(sn[0], cs[0], sn[1], cs[1]);
   const Trig t2 = trig_from(sn[2], cs[2], sn[3], cs[3]);
-  const Eom e1 = eom(m, t1, x[2], x[3], u0, u1);
+  const Eom e1 = eom<false>(m, t1, x[2], x[3], u0, u1);
   const double w21 = fma(hh, e1.dd1, x[2]), w22 = fma(hh, e1.dd2, x[3]);
   const double th3a = fma(hh, w21, x[0]), th3b = fma(hh, w22, x[1]);
   amax = max(amax, max(abs_hi(th3a), abs_hi(th3b)));
   const Trig t3 = trig_of<true>(m, th3a, th3b);
   const int jz = mid();
-  const Eom e2 = eom(m, t2, w21, w22, u0, u1);
+  const Eom e2 = eom<false>(m, t2, w21, w22, u0, u1);
   const double w31 = fma(hh, e2.dd1, x[2]), w32 = fma(hh, e2.dd2, x[3]);
   const double th4a = fma(h, w31, x[0]), th4b = fma(h, w32, x[1]);
   amax = max(amax, max(abs_hi(th4a), abs_hi(th4b)));
@@ -437,9 +446,9 @@ __device__ __forceinline__ int rk4_step_overlap(const Model& m, const double x[4
   double s4[2], c4[2];
   sincos_n<2>(m, th4, s4, c4, jz);
   const Trig t4 = trig_from(s4[0], c4[0], s4[1], c4[1]);
-  const Eom e3 = eom(m, t3, w31, w32, u0, u1);
+  const Eom e3 = eom<false>(m, t3, w31, w32, u0, u1);
   const double w41 = fma(h, e3.dd1, x[2]), w42 = fma(h, e3.dd2, x[3]);
-  const Eom e4 = eom(m, t4, w41, w42, u0, u1);
+  const Eom e4 = eom<false>(m, t4, w41, w42, u0, u1);
   const double k1[4] = {x[2], x[3], e1.dd1, e1.dd2}, k2[4] = {w21, w22, e2.dd1, e2.dd2};
   const double k3[4] = {w31, w32, e3.dd1, e3.dd2}, k4[4] = {w41, w42, e4.dd1, e4.dd2};
 #pragma unroll
