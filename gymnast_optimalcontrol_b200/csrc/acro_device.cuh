@@ -460,6 +460,141 @@ __device__ __forceinline__ int rk4_step_overlap(const Model& m, const double x[4
 }
 
 // ---------------------------------------------------------------------------------------
+// RK4 step with incremental sines and cosines.
+//
+// With dt = 0.02 the four stage angles of a step and the first angle of the next step lie within a fraction of a
+// radian of each other, so only ONE stage per step needs a full (range-reduced, degree-13/14) sincos: stage 2,
+// whose angle x + dt/2 * omega is known when the step starts and whose sines are not needed before the second
+// evaluation of the equations of motion.  The others follow by rotating a known (sin, cos) pair through the small
+// angle difference d, with sin d and cos d - 1 from short Taylor polynomials (no range reduction, no quadrant
+// logic, half the dependency chain):
+//     stage 1 of a step  <- stage 4 of the previous step   |d| = O(dt^2 * second difference of the accelerations)
+//     stage 3            <- stage 2                        |d| = dt^2/4 * |acceleration|
+//     stage 4            <- stage 2                        |d| ~ dt/2 * |omega|
+// Truncation errors are below 1e-19 (small: |d| <= 2^-6, terms to d^7 / d^6) and 3e-17 (medium: |d| <= 2^-3,
+// terms to d^9 / d^10); a rotated pair is never rotated more than twice before the next full sincos, so nothing
+// accumulates.  A step whose differences exceed the bounds (|omega| > 12 rad/s, |acceleration| > 150 rad/s^2:
+// a diverging candidate) reports `bad` and the caller redoes it with rk4_step_redo.
+// ---------------------------------------------------------------------------------------
+struct TrigCarry {
+  double th[2], s[2], c[2];  // stage-4 angles of the previous step, their sines and cosines
+};
+
+// (s, c) = (sin, cos)(theta)  ->  (sin, cos)(theta + d)
+__device__ __forceinline__ void rot_small(double d, double s, double c, double& so, double& co) {
+  const double d2 = d * d;
+  double ps = fma(d2, -1.0 / 5040.0, 1.0 / 120.0);
+  double pc = fma(d2, -1.0 / 720.0, 1.0 / 24.0);
+  ps = fma(d2, ps, -1.0 / 6.0);
+  pc = fma(d2, pc, -0.5);
+  const double sd = fma(d * d2, ps, d);  // sin d
+  const double cm = d2 * pc;             // cos d - 1
+  so = s + fma(s, cm, c * sd);
+  co = c + fma(c, cm, -(s * sd));
+}
+__device__ __forceinline__ void rot_medium(double d, double s, double c, double& so, double& co) {
+  const double d2 = d * d;
+  double ps = fma(d2, 1.0 / 362880.0, -1.0 / 5040.0);
+  double pc = fma(d2, -1.0 / 3628800.0, 1.0 / 40320.0);
+  ps = fma(d2, ps, 1.0 / 120.0);
+  pc = fma(d2, pc, -1.0 / 720.0);
+  ps = fma(d2, ps, -1.0 / 6.0);
+  pc = fma(d2, pc, 1.0 / 24.0);
+  pc = fma(d2, pc, -0.5);
+  const double sd = fma(d * d2, ps, d);
+  const double cm = d2 * pc;
+  so = s + fma(s, cm, c * sd);
+  co = c + fma(c, cm, -(s * sd));
+}
+#define ACRO_ROT_SMALL_HI 0x3f900000   /* high word of 2^-6 */
+#define ACRO_ROT_MEDIUM_HI 0x3fc00000  /* high word of 2^-3 */
+
+// x + 0 in a way that carries a scheduling dependency on `jz` (an opaque zero, see rk4_step_overlap)
+__device__ __forceinline__ double tie(double x, int jz) {
+  return __hiloint2double(__double2hiint(x) + jz, __double2loint(x));
+}
+
+// Returns true when the step left the validity range of the incremental formulas (then xn and tc are garbage).
+template <class Mid>
+__device__ __forceinline__ bool rk4_step_rot(const Model& m, const double x[4], double u0, double u1, double xn[4],
+                                             TrigCarry& tc, Mid mid) {
+  const double h = m.dt, hh = 0.5 * m.dt;
+  // stage 2: the one full sincos
+  const double th2[2] = {fma(hh, x[2], x[0]), fma(hh, x[3], x[1])};
+  double s2[2], c2[2];
+  sincos_n<2>(m, th2, s2, c2);
+  // stage 1 from the previous step's stage 4
+  const double d1[2] = {x[0] - tc.th[0], x[1] - tc.th[1]};
+  double s1[2], c1[2];
+  rot_small(d1[0], tc.s[0], tc.c[0], s1[0], c1[0]);
+  rot_small(d1[1], tc.s[1], tc.c[1], s1[1], c1[1]);
+  const Trig t1 = trig_from(s1[0], c1[0], s1[1], c1[1]);
+  const Eom e1 = eom<false>(m, t1, x[2], x[3], u0, u1);
+  const double w21 = fma(hh, e1.dd1, x[2]), w22 = fma(hh, e1.dd2, x[3]);
+  // stage 3 from stage 2
+  const double d3[2] = {fma(hh, w21, x[0]) - th2[0], fma(hh, w22, x[1]) - th2[1]};
+  double s3[2], c3[2];
+  rot_small(d3[0], s2[0], c2[0], s3[0], c3[0]);
+  rot_small(d3[1], s2[1], c2[1], s3[1], c3[1]);
+  const Trig t3 = trig_from(s3[0], c3[0], s3[1], c3[1]);
+  const int jz = mid();
+  const Trig t2 = trig_from(s2[0], c2[0], s2[1], c2[1]);
+  const Eom e2 = eom<false>(m, t2, w21, w22, u0, u1);
+  const double w31 = fma(hh, e2.dd1, x[2]), w32 = fma(hh, e2.dd2, x[3]);
+  // stage 4 from stage 2
+  const double th4[2] = {fma(h, w31, x[0]), fma(h, w32, x[1])};
+  const double d4[2] = {tie(th4[0] - th2[0], jz), th4[1] - th2[1]};
+  double s4[2], c4[2];
+  rot_medium(d4[0], s2[0], c2[0], s4[0], c4[0]);
+  rot_medium(d4[1], s2[1], c2[1], s4[1], c4[1]);
+  const Trig t4 = trig_from(s4[0], c4[0], s4[1], c4[1]);
+  const Eom e3 = eom<false>(m, t3, w31, w32, u0, u1);
+  const double w41 = fma(h, e3.dd1, x[2]), w42 = fma(h, e3.dd2, x[3]);
+  const Eom e4 = eom<false>(m, t4, w41, w42, u0, u1);
+  const double k1[4] = {x[2], x[3], e1.dd1, e1.dd2}, k2[4] = {w21, w22, e2.dd1, e2.dd2};
+  const double k3[4] = {w31, w32, e3.dd1, e3.dd2}, k4[4] = {w41, w42, e4.dd1, e4.dd2};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double s = k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i];
+    xn[i] = x[i] + (h * s) * (1.0 / 6.0);
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    tc.th[a] = th4[a];
+    tc.s[a] = s4[a];
+    tc.c[a] = c4[a];
+  }
+  const int small = max(max(abs_hi(d1[0]), abs_hi(d1[1])), max(abs_hi(d3[0]), abs_hi(d3[1])));
+  const int medium = max(abs_hi(d4[0]), abs_hi(d4[1]));
+  const int range = max(abs_hi(th2[0]), abs_hi(th2[1]));
+  // (non-finite differences have high words >= 0x7ff00000 and land here too)
+  return small >= ACRO_ROT_SMALL_HI || medium >= ACRO_ROT_MEDIUM_HI || range > ACRO_TRIG_FAST_MAX_HI;
+}
+
+// start of a pass, or after a redone step: carry = (angles of x, their sines and cosines), so that the next
+// step's stage-1 rotation is through d = 0 exactly
+__device__ __noinline__ TrigCarry trig_carry_at(const Model& m, double th1, double th2) {
+  TrigCarry tc;
+  tc.th[0] = th1;
+  tc.th[1] = th2;
+  if (angles_ok(th1, th2)) {
+    sincos2(m, th1, th2, tc.s[0], tc.c[0], tc.s[1], tc.c[1]);
+  } else {
+    sincos(th1, &tc.s[0], &tc.c[0]);
+    sincos(th2, &tc.s[1], &tc.c[1]);
+  }
+  return tc;
+}
+// the step again, with a full sincos per stage (and the library routine beyond its range)
+__device__ __noinline__ Vec4 rk4_step_redo(const Model& m, double x0, double x1, double x2, double x3, double u0,
+                                           double u1) {
+  const double x[4] = {x0, x1, x2, x3};
+  Vec4 o;
+  rk4_step(m, x, u0, u1, o.v);
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------
 // Symmetric 4x4 in 10 registers: index of (i,j), i<=j
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ constexpr int sym(int i, int j) {

@@ -1520,6 +1520,10 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
 #define EXPR(WPB, RPB) LAUNCH_DUO(WPB, RPB, 4)
       DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
 #undef EXPR
+    } else if (!ref->per_problem && getenv("ACRO_DUO_SG") && atoi(getenv("ACRO_DUO_SG")) == 8) {
+#define EXPR(WPB, RPB) LAUNCH_DUO(WPB, false, 8)
+      DISPATCH2(per_problem_weights(*w), false, EXPR);
+#undef EXPR
     } else if (!ref->per_problem) {
 #define EXPR(WPB, RPB) LAUNCH_DUO(WPB, false, 16)
       DISPATCH2(per_problem_weights(*w), false, EXPR);

@@ -25,7 +25,9 @@
 
 namespace acro {
 
-#define ACRO_DUO_R 8              // hand-off slots (power of two)
+#ifndef ACRO_DUO_R
+#define ACRO_DUO_R 8  // hand-off slots (power of two)
+#endif
 #define ACRO_DUO_SLOT_BYTES 2560  // 10 rows of 32 doubles
 
 __device__ __forceinline__ void sts(uint32_t addr, double v) {
@@ -157,6 +159,7 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
   // code: is the next hand-off slot free, and did the step just taken leave the range of the polynomial sincos.
   uint32_t hready = 1u;
   bool bad = false;
+  TrigCarry tc = trig_carry_at(m, xp[0], xp[1]);
   for (int k = 0; k < n_stages; ++k) {
     const int cnt = min(SG, steps - k * SG);
     const uint32_t g = r.base + k;
@@ -167,17 +170,18 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
       // where the operands of the next step live: this stage, the next stage (whose bulk copies were issued at
       // least a stage ago: the wait is a formality), or nowhere (last step of the pass: reload this step's)
       const bool cross = (s + 1 == cnt) && (k + 1 < n_stages);
-      if (__builtin_expect(__any_sync(FULL, cross || bad || !hready), 0)) {
-        if (bad) {  // a diverging rollout on its way to overflow: redo the last step with the library sincos
+      if (__any_sync(FULL, cross || bad || !hready)) {
+        if (bad) {  // the last step left the range of the incremental sincos: redo it with a full sincos per stage
           double xo[4], uo[2];  // its inputs are still in the hand-off slot they were written to
           const uint32_t pslot = hd.data + ((hd.h - 1) & (ACRO_DUO_R - 1)) * ACRO_DUO_SLOT_BYTES + lane * 8;
 #pragma unroll
           for (int c = 0; c < 4; ++c) xo[c] = lds(pslot + c * 256);
 #pragma unroll
           for (int c = 0; c < 2; ++c) uo[c] = lds(pslot + (4 + c) * 256);
-          const Vec4 o = rk4_step_slow(m, xo[0], xo[1], xo[2], xo[3], uo[0], uo[1]);
+          const Vec4 o = rk4_step_redo(m, xo[0], xo[1], xo[2], xo[3], uo[0], uo[1]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) xp[i] = o.v[i];
+          tc = trig_carry_at(m, xp[0], xp[1]);
         }
         __syncwarp();
         if (cross) mbar_wait(nbar, npar);
@@ -205,7 +209,7 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
       ++hd.h;
       double xn[4];
       const uint32_t nebar = hd.empty_bar(), nepar = hd.phase() ^ 1u;
-      const int amax = rk4_step_overlap(m, xp, up[0], up[1], xn, [&]() {
+      bad = rk4_step_rot(m, xp, up[0], up[1], xn, tc, [&]() {
         // operands of the next step and the state of the next hand-off slot, while the FP64 pipe is busy
         // (no branch in here: a branch would cut the step's straight-line code into two scheduling regions)
         in.load(nsrc, ns, lane);
@@ -216,7 +220,6 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
         for (int e = 0; e < 8; ++e) acc |= __double2loint(in.k[e]);
         return acc & hd.zmask;
       });
-      bad = hi_too_large(amax);
 #pragma unroll
       for (int c = 0; c < 4; ++c) xp[c] = xn[c];
     }
@@ -230,7 +233,7 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
       for (int c = 0; c < 4; ++c) xo[c] = lds(pslot + c * 256);
 #pragma unroll
       for (int c = 0; c < 2; ++c) uo[c] = lds(pslot + (4 + c) * 256);
-      const Vec4 o = rk4_step_slow(m, xo[0], xo[1], xo[2], xo[3], uo[0], uo[1]);
+      const Vec4 o = rk4_step_redo(m, xo[0], xo[1], xo[2], xo[3], uo[0], uo[1]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) xp[i] = o.v[i];
     }
@@ -350,6 +353,7 @@ __device__ __forceinline__ void lds_lin(uint32_t stage, int s, int lane, LinD& L
 
 template <bool WPB, bool RPB, int SG>
 __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>& w, int N, Ring& r, Hand& hd, int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
   const int steps = N - 1, n_stages = (steps + SG - 1) / SG;
   auto t_lo_of = [&](int k) { return max(0, steps - (k + 1) * SG); };
   auto cnt_of = [&](int k) { return (steps - k * SG) - t_lo_of(k); };
@@ -364,6 +368,8 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
   lds_lin<SG>(r.data + ring_slot(r.base) * stage_bytes<RPB, SG>(), cnt_of(0) - 1, lane, L);
   const QhQ2<WV<WPB>> Qh{w};
   const Lu2Col col = lu2_col(w.R2(0, 0), w.R2(0, 1));
+  mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);  // the hand-off slot of the first step is free (all are, between passes)
+  uint32_t hready = 1u;
   for (int k = 0; k < n_stages; ++k) {
     const int cnt = cnt_of(k);
     const uint32_t g = r.base + k;
@@ -372,13 +378,28 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
     const uint32_t nbar = r.bars + ring_slot(g + 1) * 8, npar = ring_parity(g + 1);
     const int ncnt = (k + 1 < n_stages) ? cnt_of(k + 1) : 0;
     for (int s = cnt - 1; s >= 0; --s) {
+      // one branch per step for everything unusual, so that the step itself is straight-line code (see the
+      // forward pass): the next stage's bulk copies (a formality) and a trailer that is ACRO_DUO_R steps behind
       const bool cross = (s == 0) && (k + 1 < n_stages);
-      const uint32_t ready = cross ? mbar_test(nbar, npar) : 1u;
-      const uint32_t slot = hd.slot(), fbar = hd.full_bar(), ebar = hd.empty_bar(), epar = hd.phase() ^ 1u;
-      const uint32_t hready = mbar_test(ebar, epar);
+      // (no vote here: with __any_sync in this loop ptxas puts a YIELD at the head of both chain loops, 50 cycles
+      // per step; the condition is the same in every lane)
+      if (cross || !hready) {
+        if (cross) mbar_wait(nbar, npar);
+        if (!hready) mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);
+      }
+      const uint32_t nsrc = cross ? nstage : stage;
+      const int ns = (s > 0) ? s - 1 : (cross ? ncnt - 1 : s);
       double Kt[8], inv_u11, qsel;
       riccati_chain_step(P, L, m.dt, Qh, col, w.R2(0, 1), w.R2(1, 1), Kt, inv_u11, qsel);
-      if (!hready) mbar_wait(ebar, epar);
+      // the linearisation of the next (earlier) time step, tied to the hand-off stores by an opaque zero so that
+      // the loads are issued while the P update keeps the FP64 pipe busy
+      LinD Ln;
+      Ln.b0[0] = Ln.b0[1] = 0.0;
+      lds_lin<SG>(nsrc, ns, lane, Ln);
+      int acc = __double2loint(Ln.b[0]) | __double2loint(Ln.b[1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc |= __double2loint(Ln.a[0][j]) | __double2loint(Ln.a[1][j]);
+      const uint32_t slot = hd.slot() + uint32_t(acc & hd.zmask), fbar = hd.full_bar();
 #pragma unroll
       for (int e = 0; e < 8; ++e) sts(slot + e * 256 + lane * 8, Kt[e]);
       sts(slot + 8 * 256 + lane * 8, inv_u11);
@@ -386,12 +407,8 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
       __syncwarp();
       mbar_arrive_lane0(fbar, lane);
       ++hd.h;
-      if (s > 0) {
-        lds_lin<SG>(stage, s - 1, lane, L);
-      } else if (cross) {
-        if (!ready) mbar_wait(nbar, npar);
-        lds_lin<SG>(nstage, ncnt - 1, lane, L);
-      }
+      hready = mbar_test(hd.empty_bar(), hd.phase() ^ 1u);
+      L = Ln;
     }
   }
   r.base += n_stages;
