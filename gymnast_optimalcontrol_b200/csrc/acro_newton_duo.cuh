@@ -60,10 +60,15 @@ enum { DUO_EXIT = 0, DUO_BACKWARD = 1, DUO_FORWARD = 2 };
 // ---------------------------------------------------------------------------------------------------------
 // The two halves of riccati_step<true, false> (acro_device.cuh), same expressions in the same order.
 // ---------------------------------------------------------------------------------------------------------
-template <class QH>
+// SW: which row of the constant first column of G is the pivot (lu2_col): 0 = the first, 1 = the second (rows
+// swapped), 2 = decided per lane at run time (per-problem weights).  With shared weights the choice is the same
+// for every problem and every step, so the caller branches once per pass and the selects (two dozen per step)
+// disappear from the step.
+template <int SW, class QH>
 __device__ __forceinline__ void riccati_chain_step(double P[10], const LinD& L, double dt, const QH& Qh,
                                                    const Lu2Col& col, double Rh01, double Rh11, double K[8],
                                                    double& inv_u11, double& qsel) {
+  const bool swap = (SW == 2) ? col.swap : (SW == 1);
   double M[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -88,14 +93,14 @@ __device__ __forceinline__ void riccati_chain_step(double P[10], const LinD& L, 
   const double Pb1_2 = fma(P[sym(2, 3)], L.b[1], P[sym(2, 2)] * L.b[0]);
   const double Pb1_3 = fma(P[sym(3, 3)], L.b[1], P[sym(2, 3)] * L.b[0]);
   const double G01 = Rh01, G11 = Rh11 + fma(L.b[1], Pb1_3, L.b[0] * Pb1_2);
-  const double q = col.swap ? G11 : G01, s = col.swap ? G01 : G11;
+  const double q = swap ? G11 : G01, s = swap ? G01 : G11;
   inv_u11 = rcp_nr(fma(-col.l, q, s));
   qsel = q;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const double x1 = (col.swap ? col.l * F1[j] : -F1[j]) * inv_u11;
+    const double x1 = (swap ? col.l * F1[j] : -F1[j]) * inv_u11;
     K[4 + j] = x1;
-    K[j] = (col.swap ? fma(-q, x1, -F1[j]) : -(q * x1)) * col.inv_p;
+    K[j] = (swap ? fma(-q, x1, -F1[j]) : -(q * x1)) * col.inv_p;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -107,13 +112,15 @@ __device__ __forceinline__ void riccati_chain_step(double P[10], const LinD& L, 
   }
 }
 
+template <int SW>
 __device__ __forceinline__ void riccati_trailer_step(double p[4], const LinD& L, double dt, const Lu2Col& col,
                                                      const double K[8], double inv_u11, double qsel,
                                                      const double qv[4], const double r[2], double sig[2],
                                                      double& dJ) {
   const double g0 = r[0];
   const double g1 = r[1] + fma(L.b[1], p[3], L.b[0] * p[2]);
-  const double y0 = col.swap ? -g1 : -g0, y1 = col.swap ? -g0 : -g1;
+  const bool swap = (SW == 2) ? col.swap : (SW == 1);
+  const double y0 = swap ? -g1 : -g0, y1 = swap ? -g0 : -g1;
   sig[1] = fma(-col.l, y0, y1) * inv_u11;
   sig[0] = fma(-qsel, sig[1], y0) * col.inv_p;
   dJ += fma(g1, sig[1], g0 * sig[0]);
@@ -351,7 +358,7 @@ __device__ __forceinline__ void lds_lin(uint32_t stage, int s, int lane, LinD& L
   L.b[1] = lds(b + 9 * 256);
 }
 
-template <bool WPB, bool RPB, int SG>
+template <bool WPB, bool RPB, int SG, int SW>
 __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>& w, int N, Ring& r, Hand& hd, int lane) {
   constexpr unsigned FULL = 0xffffffffu;
   const int steps = N - 1, n_stages = (steps + SG - 1) / SG;
@@ -390,7 +397,7 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
       const uint32_t nsrc = cross ? nstage : stage;
       const int ns = (s > 0) ? s - 1 : (cross ? ncnt - 1 : s);
       double Kt[8], inv_u11, qsel;
-      riccati_chain_step(P, L, m.dt, Qh, col, w.R2(0, 1), w.R2(1, 1), Kt, inv_u11, qsel);
+      riccati_chain_step<SW>(P, L, m.dt, Qh, col, w.R2(0, 1), w.R2(1, 1), Kt, inv_u11, qsel);
       // the linearisation of the next (earlier) time step, tied to the hand-off stores by an opaque zero so that
       // the loads are issued while the P update keeps the FP64 pipe busy
       LinD Ln;
@@ -417,7 +424,7 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
 // ---------------------------------------------------------------------------------------------------------
 // backward pass, trailer warp: cost gradients, sigma, delta_J, costate, stores, ring refills
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB, int SG>
+template <bool WPB, bool RPB, int SG, int SW>
 __device__ __forceinline__ void duo_backward_trailer(const Model& m, const WV<WPB>& w, int N, const TilePtrs& p, Ring& r,
                                                      Hand& hd, int lane, bool store, double* __restrict__ K,
                                                      double* __restrict__ S, const double xT[4], const double xrT[4],
@@ -487,7 +494,7 @@ __device__ __forceinline__ void duo_backward_trailer(const Model& m, const WV<WP
         mbar_arrive_lane0(hd.empty_bar(), lane);
         ++hd.h;
       }
-      riccati_trailer_step(pv, L, m.dt, col, Kt, inv_u11, qsel, q, rr, st, dJ);
+      riccati_trailer_step<SW>(pv, L, m.dt, col, Kt, inv_u11, qsel, q, rr, st, dJ);
       if (store) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) pk[e * 32] = Kt[e];
@@ -574,6 +581,8 @@ __global__ void __launch_bounds__(64) k_newton_duo(const __grid_constant__ Newto
   double xrT[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) xrT[c] = ref.X(N - 1, c);
+  // pivot row of the 2x2 factorisation for shared weights (the same for the whole batch, from the constant bank)
+  const bool swap_shared = fabs(a.kw.R2[1]) > fabs(a.kw.R2[0]);
 
   if (!chain) {
     // ------------------------------------------------------------------------------ trailer warp
@@ -595,7 +604,12 @@ __global__ void __launch_bounds__(64) k_newton_duo(const __grid_constant__ Newto
         double xT[4], dJ, sn;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) xT[cc] = p.x[(N - 1) * sx + cc * 32 + lane];
-        duo_backward_trailer<WPB, RPB, SG>(a.m, w, N, p, r, hd, lane, store, tK, tS, xT, xrT, dJ, sn);
+        if (WPB)
+          duo_backward_trailer<WPB, RPB, SG, 2>(a.m, w, N, p, r, hd, lane, store, tK, tS, xT, xrT, dJ, sn);
+        else if (swap_shared)
+          duo_backward_trailer<WPB, RPB, SG, 1>(a.m, w, N, p, r, hd, lane, store, tK, tS, xT, xrT, dJ, sn);
+        else
+          duo_backward_trailer<WPB, RPB, SG, 0>(a.m, w, N, p, r, hd, lane, store, tK, tS, xT, xrT, dJ, sn);
         res[lane] = dJ;
         res[32 + lane] = sn;
       } else {
@@ -687,7 +701,12 @@ __global__ void __launch_bounds__(64) k_newton_duo(const __grid_constant__ Newto
       cmd[1] = cur;
     }
     duo_bar();  // A
-    duo_backward_chain<WPB, RPB, SG>(a.m, w, N, r, hd, lane);
+    if (WPB)
+      duo_backward_chain<WPB, RPB, SG, 2>(a.m, w, N, r, hd, lane);
+    else if (swap_shared)
+      duo_backward_chain<WPB, RPB, SG, 1>(a.m, w, N, r, hd, lane);
+    else
+      duo_backward_chain<WPB, RPB, SG, 0>(a.m, w, N, r, hd, lane);
     duo_bar();  // B
     if (run) {
       dJ = res[lane];
