@@ -616,6 +616,34 @@ def test_newton_kernels_agree(bt, fa_ref, monkeypatch):
         assert rel_err(a[2], b[2]) < 1e-8
 
 
+@pytest.mark.parametrize("kernel", ["duo", "ring", "ldg"])
+def test_newton_pivot_swap_and_fast_spins(bt, fa_ref, kernel, monkeypatch):
+    """(i) A control weight whose off-diagonal exceeds R[0,0]: the 2x2 factorisation pivots on the second row
+    (the duo kernel compiles that choice in for shared weights).  (ii) Initial velocities of 15-25 rad/s: the stage
+    angles of a step differ by more than the incremental sincos of the duo kernel accepts (2^-3 rad), so its
+    redo-with-full-sincos path runs in some lanes of a warp and not in others."""
+    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    xr, ur = _short_ref(fa_ref, N=81)
+    rng = np.random.default_rng(17)
+    x0 = rng.uniform(-0.2, 0.2, (36, 4))
+    x0[::3, 2] = rng.uniform(15.0, 25.0, 12)   # every third problem spins fast
+    x0[1::6, 3] = -rng.uniform(15.0, 25.0, 6)
+    Q, QT = np.diag([130.0, 30.0, 1e-4, 1e-4]), np.diag([130.0, 130.0, 1.0, 1.0])
+    for R in (np.array([[1e-3, 0.02], [0.02, 1.5]]), np.diag([1e-6, 1.5])):
+        w = bt.Weights(Q, R, QT)
+        st = bt.newton_solve(soa(x0), bt.make_ref(xr, ur), max_iters=4, tol=1e-6, gamma_0=0.3, w=w)
+        torch.cuda.synchronize()
+        X, U, K, S = aos(st.X), aos(st.U), kmat(st.K), aos(st.S)
+        for b in (0, 1, 2, 3, 7, 31, 32, 35):
+            x, u, Ko, so, h = O.newton_Algorithm(x0[b], xr, ur, max_iters=4, tol=1e-6, gamma_0=0.3, Q=Q, R=R, Q_T=QT)
+            assert int(st.status[b]) == h["status"] and int(st.iters[b]) == h["iters"]
+            n_acc = len(h["n_try"])
+            assert list(st.hist_ntry[:n_acc, b].cpu().numpy()) == h["n_try"]
+            assert rel_err(st.hist_cost[:len(h["cost"]), b].cpu().numpy(), h["cost"]) < TOL
+            assert rel_err(X[b], x) < TOL and rel_err(U[b], u) < TOL
+            assert rel_err(S[b], so) < TOL and rel_err(K[b], Ko) < 1e-7
+
+
 def test_newton_warm_start(bt, fa_ref):
     """init = 2: start from caller-supplied inputs instead of u = 0 (the commented-out alternative at tg:310)."""
     xr, ur = _short_ref(fa_ref)
