@@ -34,10 +34,10 @@ sys.path.insert(0, ROOT)
 N_STEPS = 501
 FLOPS_FIXED, FLOPS_PER_TRY = 1114.0, 940.0  # per problem-step-iteration, FMA = 2, sin/cos = 40
 BYTES_STEP_ITER = 304.0                      # read x,u; write K,sigma; read x,u,K,sigma; write x+,u+
-# dram__bytes_read+write of acro::k_newton_ring from the ncu --set full capture in profiles/ (4-iteration launch,
-# B = 4096: 3.67 GB): 404 B per problem-step-iteration (the kernel moves 464 B by design, L2 absorbs part of the
+# dram__bytes_read+write of acro::k_newton_duo from the ncu --set full capture in profiles/ (4-iteration launch,
+# B = 4096: 3.60 GB): 396 B per problem-step-iteration (the kernel moves 464 B by design, L2 absorbs part of the
 # re-reads) + 176 B per problem-step for the initial rollout and cost
-TRAFFIC_STEP_ITER, TRAFFIC_STEP_INIT = 404.0, 176.0
+TRAFFIC_STEP_ITER, TRAFFIC_STEP_INIT = 396.0, 176.0
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2
 
 
@@ -170,6 +170,13 @@ def workload_config(a, sample_note=None):
     return c
 
 
+def kernel_name(batch):
+    tiles = (batch + 31) // 32
+    if tiles <= 296:
+        return "acro::k_newton_duo<false,false,%d> (two warps per tile: recurrence warp + trailer warp, TMA-fed ring)" % (16 if tiles <= 148 else 4)
+    return "acro::k_newton_ring<false,false,%d> (one warp per tile, TMA-fed shared-memory ring)" % (4 if tiles <= 592 else 2)
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def fp64_peak_tflops(bt, torch):
     """DFMA-chain microbenchmark (acro_bench_fp64_peak): achievable FP64 pipe rate of this GPU."""
@@ -285,15 +292,17 @@ def run_native(a):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         roof = {"bound": "fp64", "achieved": ach_tflops, "peak": fp64_meas, "unit": "TFLOP/s", "frac": ach_tflops / fp64_meas,
                 "traffic": a.traffic_bytes if a.traffic_bytes else B * (N_STEPS - 1) * (TRAFFIC_STEP_ITER * iters + TRAFFIC_STEP_INIT),
-                "traffic_source": "profiles/r1_newton_ring_ncu_summary.txt (ncu --set full, 4-iteration launch) scaled to this launch",
+                "traffic_source": "profiles/r1_newton_duo_ncu_summary.txt (ncu --set full, 4-iteration launch) scaled to this launch",
                 "peak_source": "DFMA-chain microbenchmark (acro_bench_fp64_peak) run in this process; nominal %.1f" % FP64_NOMINAL_TFLOPS,
                 "frac_of_nominal": ach_tflops / FP64_NOMINAL_TFLOPS,
-                "kernel": "acro::k_newton_ring<false,false> (warp-synchronous, TMA-fed shared-memory ring)", "launch_ms": 1e3 * t_dev / max(launches, 1),
+                "kernel": kernel_name(B), "launch_ms": 1e3 * t_dev / max(launches, 1),
                 "algorithmic_flops_per_launch": flops_iter * B * iters, "algorithmic_bytes_per_launch": BYTES_STEP_ITER * (N_STEPS - 1) * B * iters,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650"},
-                "note": "latency bound at B=4096: 128 warps on 592 SM sub-partitions, every problem a 1000-step dependent FP64 recurrence per "
-                        "iteration; the same code reaches 60% of the DFMA peak at B>=32k (bench_configs.py); see DESIGN.md section 4"}
+                "note": "B=4096 is 128 tiles of 32 problems on 148 SMs: every tile is a 1000-step dependent FP64 recurrence per iteration, "
+                        "split between two warps on two SM sub-partitions; the warp that carries the recurrence issues one FP64 "
+                        "instruction every 2 cycles and is the bound (see DESIGN.md section 4). Large batches (bench_configs.py) "
+                        "are HBM bound at 89% of the measured copy bandwidth"}
         cpu = None
         if world == 1 and not a.no_cpu:
             cores = os.cpu_count() or 1

@@ -122,7 +122,12 @@ def main():
          940.0 * (N - 1), t, nl, peak)
 
     # ---- config 2 in the throughput regime
-    for B in ((65536,) if a.quick else (32768, 65536, 131072)):
+    hbm = 6551.4
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    for B in ((65536,) if a.quick else (8192, 16384, 32768, 65536, 131072)):
         x0 = bt.upload(np.ascontiguousarray(np.random.default_rng(1).uniform(-0.2, 0.2, (B, 4)).T))
         state = bt.newton_alloc(B, N, 10, history=False)
 
@@ -130,8 +135,14 @@ def main():
             state.initialised = False
             bt.newton_solve(x0, ref, max_iters=10, tol=0.0, gamma_0=0.1, state=state)
         t, nl = timeit(run, max(1, reps // 2))
-        line("C2 Newton, B=%d, 10 iterations" % B, "newton_iterations_per_sec", B * 10 / t, "Newton iterations/s",
-             2054.0 * (N - 1), t, nl, peak)
+        rate = B * 10 / t
+        line("C2 Newton, B=%d, 10 iterations" % B, "newton_iterations_per_sec", rate, "Newton iterations/s",
+             2054.0 * (N - 1), t, nl, peak,
+             {"hbm": {"algorithmic_gbs": rate * (N - 1) * 304.0 / 1e9, "implementation_gbs": rate * (N - 1) * 464.0 / 1e9,
+                      "peak_gbs": hbm, "frac_algorithmic": rate * (N - 1) * 304.0 / 1e9 / hbm,
+                      "frac_implementation": rate * (N - 1) * 464.0 / 1e9 / hbm,
+                      "note": "304 B per problem-step-iteration by the SURVEY 8(d) count; the kernels move 464 B (they store and "
+                              "re-read the 80 B linearisation instead of recomputing it)"}})
 
 
 if __name__ == "__main__":
