@@ -74,7 +74,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -203,10 +203,13 @@ def run_native(a):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # stdout carries the one JSON line and nothing else: whatever libraries print to file descriptor 1 (NCCL's
+    # version banner when NCCL_DEBUG is set in the environment) goes to stderr; the line is written to the saved fd
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL's version / debug banner goes to a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/acro_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gymnast_optimalcontrol_b200 import _abi
     from gymnast_optimalcontrol_b200 import batched as bt
@@ -322,7 +325,8 @@ def run_native(a):
             "check": {"iterations_done_last_step_rank0": done_iters, "armijo_tries_mean": ntry_mean, "mean_final_cost": cost_mean,
                       "e2e_mean_final_cost": e2e_cost_mean},
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
