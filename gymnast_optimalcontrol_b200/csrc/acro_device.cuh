@@ -515,7 +515,7 @@ __device__ __forceinline__ double tie(double x, int jz) {
 }
 
 // Returns true when the step left the validity range of the incremental formulas (then xn and tc are garbage).
-template <class Mid>
+template <bool ACT, class Mid>
 __device__ __forceinline__ bool rk4_step_rot(const Model& m, const double x[4], double u0, double u1, double xn[4],
                                              TrigCarry& tc, Mid mid) {
   const double h = m.dt, hh = 0.5 * m.dt;
@@ -529,7 +529,7 @@ __device__ __forceinline__ bool rk4_step_rot(const Model& m, const double x[4], 
   rot_small(d1[0], tc.s[0], tc.c[0], s1[0], c1[0]);
   rot_small(d1[1], tc.s[1], tc.c[1], s1[1], c1[1]);
   const Trig t1 = trig_from(s1[0], c1[0], s1[1], c1[1]);
-  const Eom e1 = eom<false>(m, t1, x[2], x[3], u0, u1);
+  const Eom e1 = eom<ACT>(m, t1, x[2], x[3], u0, u1);
   const double w21 = fma(hh, e1.dd1, x[2]), w22 = fma(hh, e1.dd2, x[3]);
   // stage 3 from stage 2
   const double d3[2] = {fma(hh, w21, x[0]) - th2[0], fma(hh, w22, x[1]) - th2[1]};
@@ -539,7 +539,7 @@ __device__ __forceinline__ bool rk4_step_rot(const Model& m, const double x[4], 
   const Trig t3 = trig_from(s3[0], c3[0], s3[1], c3[1]);
   const int jz = mid();
   const Trig t2 = trig_from(s2[0], c2[0], s2[1], c2[1]);
-  const Eom e2 = eom<false>(m, t2, w21, w22, u0, u1);
+  const Eom e2 = eom<ACT>(m, t2, w21, w22, u0, u1);
   const double w31 = fma(hh, e2.dd1, x[2]), w32 = fma(hh, e2.dd2, x[3]);
   // stage 4 from stage 2
   const double th4[2] = {fma(h, w31, x[0]), fma(h, w32, x[1])};
@@ -548,9 +548,9 @@ __device__ __forceinline__ bool rk4_step_rot(const Model& m, const double x[4], 
   rot_medium(d4[0], s2[0], c2[0], s4[0], c4[0]);
   rot_medium(d4[1], s2[1], c2[1], s4[1], c4[1]);
   const Trig t4 = trig_from(s4[0], c4[0], s4[1], c4[1]);
-  const Eom e3 = eom<false>(m, t3, w31, w32, u0, u1);
+  const Eom e3 = eom<ACT>(m, t3, w31, w32, u0, u1);
   const double w41 = fma(h, e3.dd1, x[2]), w42 = fma(h, e3.dd2, x[3]);
-  const Eom e4 = eom<false>(m, t4, w41, w42, u0, u1);
+  const Eom e4 = eom<ACT>(m, t4, w41, w42, u0, u1);
   const double k1[4] = {x[2], x[3], e1.dd1, e1.dd2}, k2[4] = {w21, w22, e2.dd1, e2.dd2};
   const double k3[4] = {w31, w32, e3.dd1, e3.dd2}, k4[4] = {w41, w42, e4.dd1, e4.dd2};
 #pragma unroll
@@ -592,6 +592,19 @@ __device__ __noinline__ Vec4 rk4_step_redo(const Model& m, double x0, double x1,
   Vec4 o;
   rk4_step(m, x, u0, u1, o.v);
   return o;
+}
+
+// One step of a rollout with the incremental sincos and its fallback; `tc` is carried from step to step
+// (initialise with trig_carry_at(m, x[0], x[1])).  One thread per problem: the redo is an ordinary divergent branch.
+__device__ __forceinline__ void rk4_step_inc(const Model& m, const double x[4], double u0, double u1, double xn[4],
+                                             TrigCarry& tc) {
+  const bool bad = rk4_step_rot<true>(m, x, u0, u1, xn, tc, []() { return 0; });
+  if (bad) {
+    const Vec4 o = rk4_step_redo(m, x[0], x[1], x[2], x[3], u0, u1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xn[i] = o.v[i];
+    tc = trig_carry_at(m, xn[0], xn[1]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------

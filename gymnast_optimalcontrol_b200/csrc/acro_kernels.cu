@@ -19,6 +19,10 @@
 #include "acro_device.cuh"
 #include "acro_views.cuh"
 
+#ifndef ACRO_ROLLOUT_MINB
+#define ACRO_ROLLOUT_MINB 3  // resident blocks of 128 threads per SM the closed-loop rollout kernels are compiled for
+#endif
+
 namespace acro {
 
 // ---------------------------------------------------------------------------------------
@@ -187,6 +191,7 @@ __global__ void k_rollout_open(const __grid_constant__ Model m, int64_t B, int N
     X[soa(0, 4, c, N, b)] = x[c];
   }
   double u0 = U ? U[soa(0, 2, 0, N - 1, b)] : 0.0, u1 = U ? U[soa(0, 2, 1, N - 1, b)] : 0.0;
+  TrigCarry tc = trig_carry_at(m, x[0], x[1]);
   for (int t = 0; t < N - 1; ++t) {
     double n0 = 0.0, n1 = 0.0;
     if (U && t + 1 < N - 1) {  // prefetch the next input while this step computes
@@ -194,7 +199,7 @@ __global__ void k_rollout_open(const __grid_constant__ Model m, int64_t B, int N
       n1 = U[soa(t + 1, 2, 1, N - 1, b)];
     }
     double xn[4];
-    rk4_step(m, x, u0, u1, xn);
+    rk4_step_inc(m, x, u0, u1, xn, tc);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       x[c] = xn[c];
@@ -477,6 +482,8 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
   for (int c = 0; c < 4; ++c) xp[c] = X[soa(0, 4, c, N, b)];
   double cost = 0.0;
   StepIn in = load_step(X, U, K, S, ref, 0, N, b);
+  TrigCarry tc;
+  if (!LIN) tc = trig_carry_at(m, xp[0], xp[1]);
   double xrT[4];  // terminal reference, loaded early
 #pragma unroll
   for (int c = 0; c < 4; ++c) xrT[c] = ref.X(N - 1, c);
@@ -519,7 +526,7 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
       rk4_step_lin(m, xp, up[0], up[1], xn, L);
       store_lin(lin_out, t, N - 1, bo, L);
     } else {
-      rk4_step(m, xp, up[0], up[1], xn);
+      rk4_step_inc(m, xp, up[0], up[1], xn, tc);
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) xp[c] = xn[c];
@@ -536,7 +543,7 @@ __device__ __forceinline__ double forward_pass(const Model& m, const WV<WPB>& w,
 
 // one thread per (problem b, candidate g); lanes run over b
 template <bool WPB, bool RPB>
-__global__ void __launch_bounds__(128, 3) k_closed_loop(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B,
+__global__ void __launch_bounds__(128, ACRO_ROLLOUT_MINB) k_closed_loop(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B,
                               int N, const double* __restrict__ X, const double* __restrict__ U,
                               const double* __restrict__ K, const double* __restrict__ S, const double* rx,
                               const double* ru, int G, const double* __restrict__ gammas, int gpp,
@@ -560,7 +567,7 @@ __global__ void __launch_bounds__(128, 3) k_closed_loop(const __grid_constant__ 
 // iterate, so the 16 operand loads per step are warp-wide broadcasts; the 4 warps of a
 // block take 4 neighbouring iterates, i.e. whole 32-byte sectors of every SoA row.
 template <bool WPB, bool RPB>
-__global__ void __launch_bounds__(128, 3) k_sweep(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t P, int N,
+__global__ void __launch_bounds__(128, ACRO_ROLLOUT_MINB) k_sweep(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t P, int N,
                         const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ K,
                         const double* __restrict__ S, const double* rx, const double* ru, int S_n,
                         const double* __restrict__ steps, double* __restrict__ cost) {
@@ -914,6 +921,7 @@ __global__ void k_lqr_track(const __grid_constant__ Model m, int64_t B, int N, c
     x[c] = x0[c * B + b];
     Xt[soa(0, 4, c, N, b)] = x[c];
   }
+  TrigCarry tc = trig_carry_at(m, x[0], x[1]);
   for (int t = 0; t < N - 1; ++t) {
     double u[2];
 #pragma unroll
@@ -928,7 +936,7 @@ __global__ void k_lqr_track(const __grid_constant__ Model m, int64_t B, int N, c
       Ut[soa(t, 2, i, N - 1, b)] = u[i];
     }
     double xn[4];
-    rk4_step(m, x, u[0], u[1], xn);
+    rk4_step_inc(m, x, u[0], u[1], xn, tc);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       x[c] = xn[c];
@@ -1153,6 +1161,7 @@ __global__ void k_mpc_track_shared(const __grid_constant__ MpcArgs a) {
     x[c] = a.x0[c * B + b];
     a.Xr[soa(0, 4, c, a.T, b)] = x[c];
   }
+  TrigCarry tc = trig_carry_at(a.m, x[0], x[1]);
   for (int t = 0; t < a.T - 1; ++t) {
     double u[2];
 #pragma unroll
@@ -1169,7 +1178,7 @@ __global__ void k_mpc_track_shared(const __grid_constant__ MpcArgs a) {
       a.Ur[soa(t, 2, i, a.T - 1, b)] = u[i];
     }
     double xn[4];
-    rk4_step(a.m, x, u[0], u[1], xn);
+    rk4_step_inc(a.m, x, u[0], u[1], xn, tc);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       x[c] = xn[c];
