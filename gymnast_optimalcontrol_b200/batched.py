@@ -324,6 +324,10 @@ def newton_alloc(Bn, N, max_iters, history=True):
         cost=_empty(Bn), delta_J=_empty(Bn), sigma_norm=_empty(Bn), gamma_acc=_empty(Bn),
         iters=_empty(Bn, dtype=torch.int32), status=_empty(Bn, dtype=torch.int32), Xw=Traj.empty(N, 4, Bn),
         Uw=Traj.empty(N - 1, 2, Bn), lin=Traj.empty(N - 1, 10, Bn))
+    if Bn % 32:
+        # the padding lanes of the last tile compute in lockstep and never store: give them defined operands
+        for t in (st.X, st.U, st.K, st.S, st.Xw, st.Uw, st.lin):
+            t.data[-1].zero_()
     if history:
         st.hist_cost = torch.full((max_iters + 1, Bn), float("nan"), dtype=F64, device=device())
         st.hist_sigma_norm = torch.full((max_iters, Bn), float("nan"), dtype=F64, device=device())

@@ -644,6 +644,30 @@ def test_newton_pivot_swap_and_fast_spins(bt, fa_ref, kernel, monkeypatch):
             assert rel_err(S[b], so) < TOL and rel_err(K[b], Ko) < 1e-7
 
 
+@pytest.mark.parametrize("kernel", ["duo", "ring"])
+def test_newton_repeated_launches_are_bitwise_identical(bt, fa_ref, kernel, monkeypatch):
+    """The warp-specialised kernels synchronise through mbarriers, a hand-off ring and proxy fences: a missing
+    ordering would show up as run-to-run differences.  12 launches of a back-tracking batch (two tiles + a partial
+    one, shared and per-problem references) must give the same bits."""
+    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    xr, ur = _short_ref(fa_ref, N=101)
+    n = 70
+    x0 = np.random.default_rng(23).uniform(-0.3, 0.3, (n, 4))
+    refs = (bt.make_ref(xr, ur), bt.Ref(soa(np.repeat(xr[None], n, 0)), soa(np.repeat(ur[None], n, 0))))
+    for ref in refs:
+        first = None
+        for rep in range(12):
+            st = bt.newton_solve(soa(x0), ref, max_iters=5, tol=1e-6, gamma_0=1.0)
+            torch.cuda.synchronize()
+            cur = (aos(st.X), aos(st.U), aos(st.K), aos(st.S), st.hist_cost.cpu().numpy(), st.hist_ntry.cpu().numpy(),
+                   st.iters.cpu().numpy(), st.status.cpu().numpy())  # (aos drops the padding lanes of the last tile)
+            if first is None:
+                first = cur
+            else:
+                for i, (a, b) in enumerate(zip(first, cur)):
+                    assert np.array_equal(a, b, equal_nan=True), (rep, i)
+
+
 def test_newton_warm_start(bt, fa_ref):
     """init = 2: start from caller-supplied inputs instead of u = 0 (the commented-out alternative at tg:310)."""
     xr, ur = _short_ref(fa_ref)
