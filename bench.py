@@ -129,6 +129,85 @@ def cpu_newton_rate(pool, cores, iters_per_problem, seed=0):
     return done / wall, wall, done
 
 
+def _cpu_mpc_worker(args):
+    """`n_steps` receding-horizon MPC solves (tt:43-67) of one problem with the oracle: (H-1)-step Riccati sweep on the
+    sliding window + plant step."""
+    x0, n_steps, H = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import acro_oracle as O
+    d = np.load(os.path.join(ROOT, "tests", "golden", "acrobot_optimal_trajectory.npz"))
+    x_ref, u_ref = d["x"], d["u"]
+    N = x_ref.shape[0]
+    Ad, Bd = O.linearize_discrete(x_ref[:-1], u_ref)
+    A_f, B_f = O.linearize_discrete(O.X_F, O.U_F)
+    Q_T = O.compute_P_inf(A_f, B_f, O.Q_MPC, O.R_MPC)
+    x = np.array(x0, dtype=float)
+    t0 = time.perf_counter()
+    for t in range(n_steps):
+        Aw = [Ad[t + j] if t + j < N - 1 else A_f for j in range(H - 1)]
+        Bw = [Bd[t + j] if t + j < N - 1 else B_f for j in range(H - 1)]
+        K0 = O.mpc_gains(Aw, Bw, O.Q_MPC, O.R_MPC, Q_T, H)[0]
+        u = u_ref[t] + K0 @ (x - x_ref[t])
+        x = O.dynamics(x, u)
+    return time.perf_counter() - t0, n_steps
+
+
+def measure_mpc(bt, torch, dist, rank, world, steps, with_cpu):
+    """Second half of the BASELINE.json metric: MPC solves/s on config 4 (B = 16 384 acrobots per GPU, horizon 75,
+    500 receding-horizon steps, every problem its own reference copy so that every problem runs its own Riccati
+    sweeps: 8.19 M solves per run and GPU)."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "acrobot_optimal_trajectory.npz"))
+    B, H, N = 16384, 75, 501
+    w = bt.mpc_weights()
+    xf = bt.upload(np.array([[np.pi], [0], [0], [0]], dtype=np.float64))
+    A_f, B_f = bt.linearize(xf, bt.upload(np.zeros((2, 1))), discrete=True)
+    P, _ = bt.p_inf(A_f, B_f, w)
+    QT = P[:, :, 0].contiguous()
+    x0h = d["x"][0] + np.random.default_rng(3 + rank).uniform(-0.1, 0.1, (B, 4))
+    x0 = bt.upload(np.ascontiguousarray(x0h.T))
+    refp = bt.Ref(bt.Traj.from_batch_major(bt.upload(np.repeat(d["x"][None], B, 0))),
+                  bt.Traj.from_batch_major(bt.upload(np.repeat(d["u"][None], B, 0))))
+    res = {}
+
+    def run():
+        res["s"] = bt.mpc_track(x0, refp, QT, T=N, T_pred=H, w=w)
+    for _ in range(2):
+        run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ns = res["s"][3]
+    value = ns * steps * world / float(t[0])
+    flops = 550.0 * (H - 1) + 16 + 856  # SURVEY 8(d)
+    out = {"metric": "mpc_solves_per_sec", "value": value,
+           "unit": "MPC solves/s (one (H-1)-step Riccati sweep on the sliding window + plant step each)",
+           "config": {"workload": "config 4: receding-horizon MPC tracking of acrobot_optimal_trajectory.npz, B=16384 acrobots per GPU, "
+                                  "horizon 75, 500 steps, per-problem references (every solve executed)",
+                      "solves_per_run_per_gpu": ns},
+           "ms_per_run": 1e3 * float(t[0]) / steps, "flops_per_solve": flops,
+           "achieved_tflops_per_gpu": value / world * flops / 1e12}
+    if with_cpu:
+        cores = os.cpu_count() or 1
+        n_steps = 400
+        with mp.get_context("fork").Pool(cores) as pool:
+            t0 = time.perf_counter()
+            r = pool.map(_cpu_mpc_worker, [(x0h[i], n_steps, H) for i in range(cores)])
+            wall = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": sum(x[1] for x in r) / wall, "unit": "MPC solves/s", "cores": cores, "kind": "port",
+                               "sample": "%d problems (one per core) x %d MPC steps, horizon 75, %.1f s of wall time; the reference "
+                                         "solves each QP with CasADi/IPOPT (absent here): the port is the Riccati restatement" % (cores, n_steps, wall)}
+    return out
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -285,9 +364,15 @@ def run_native(a):
     value = total_iters / t_dev
     e2e_value = total_iters / t_e2e
 
+    mpc = None if a.no_mpc else measure_mpc(bt, torch, dist, rank, world, max(2, a.steps), with_cpu=(world == 1 and rank == 0 and not a.no_cpu))
     if rank == 0:
         peaks = measured_peaks()
         fp64_meas = fp64_peak_tflops(_abi, torch)
+        if mpc:
+            ach = mpc.pop("achieved_tflops_per_gpu")
+            mpc["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fp64_meas, "unit": "TFLOP/s", "frac": ach / fp64_meas,
+                               "note": "550 (H-1) + 16 + 856 flops per solve (SURVEY 8d); the sweeps re-read 80 B of compact "
+                                       "linearisation per window step from L2"}
         flops_iter = (FLOPS_FIXED + FLOPS_PER_TRY * ntry_mean) * (N_STEPS - 1)
         per_gpu_rate = value / world
         ach_tflops = per_gpu_rate * flops_iter / 1e12
@@ -321,7 +406,7 @@ def run_native(a):
             "step_iters_per_sec": value * (N_STEPS - 1), "newton_iters_per_sec_10k_step_equivalent": value * (N_STEPS - 1) / 1e4,
             "e2e": {"value": e2e_value, "unit": "Newton iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / a.steps, "api": "trajectory_generation.newton_Algorithm(x0[B,4] pinned host, x_ref, u_ref)"},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(), "mpc": mpc,
             "check": {"iterations_done_last_step_rank0": done_iters, "armijo_tries_mean": ntry_mean, "mean_final_cost": cost_mean,
                       "e2e_mean_final_cost": e2e_cost_mean},
         }
@@ -342,6 +427,7 @@ def main():
     ap.add_argument("--iters", type=int, default=50, help="Newton iterations per problem per step")
     ap.add_argument("--cpu-iters", type=int, default=40, help="Newton iterations per problem in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-mpc", action="store_true", help="skip the secondary MPC solves/s measurement")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes per launch from the ncu capture (profiles/)")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -759,6 +759,62 @@ __device__ __forceinline__ void riccati_step(double P[10], double p[4], const Li
   }
 }
 
+// The P half of riccati_step<*, false> alone (same expressions in the same order): what the recursion itself needs.
+// Used by the chain warp of k_newton_duo and by the MPC sweeps.
+// SW: which row of the constant first column of G is the pivot (lu2_col): 0 = the first, 1 = the second (rows
+// swapped), 2 = decided per lane at run time (per-problem weights).  With shared weights the choice is the same
+// for every problem and every step, so the caller branches once per pass and the selects (two dozen per step)
+// disappear from the step.
+// ROW0 = false skips the first row of K (the gain of the input that does not act on the plant, needed by the callers
+// that output K but not by the P recursion itself: the inner steps of an MPC sweep).
+template <int SW, bool ROW0 = true, class QH>
+__device__ __forceinline__ void riccati_chain_step(double P[10], const LinD& L, double dt, const QH& Qh,
+                                                   const Lu2Col& col, double Rh01, double Rh11, double K[8],
+                                                   double& inv_u11, double& qsel) {
+  const bool swap = (SW == 2) ? col.swap : (SW == 1);
+  double M[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double pi0 = P[sym(i, 0)], pi1 = P[sym(i, 1)], pi2 = P[sym(i, 2)], pi3 = P[sym(i, 3)];
+    M[i][0] = fma(pi3, L.a[1][0], fma(pi2, L.a[0][0], pi0));
+    M[i][1] = fma(pi3, L.a[1][1], fma(pi2, L.a[0][1], pi1));
+    M[i][2] = fma(pi3, L.a[1][2], fma(pi2, L.a[0][2], dt * pi0));
+    M[i][3] = fma(pi3, L.a[1][3], fma(pi2, L.a[0][3], dt * pi1));
+  }
+  double S[10];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = i; j < 4; ++j) {
+      const double top = (i < 2) ? M[i][j] : dt * M[i - 2][j];
+      S[sym(i, j)] = fma(L.a[1][i], M[3][j], fma(L.a[0][i], M[2][j], top));
+    }
+  }
+  double F1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) F1[j] = fma(L.b[1], M[3][j], L.b[0] * M[2][j]);
+  const double Pb1_2 = fma(P[sym(2, 3)], L.b[1], P[sym(2, 2)] * L.b[0]);
+  const double Pb1_3 = fma(P[sym(3, 3)], L.b[1], P[sym(2, 3)] * L.b[0]);
+  const double G01 = Rh01, G11 = Rh11 + fma(L.b[1], Pb1_3, L.b[0] * Pb1_2);
+  const double q = swap ? G11 : G01, s = swap ? G01 : G11;
+  inv_u11 = rcp_nr(fma(-col.l, q, s));
+  qsel = q;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double x1 = (swap ? col.l * F1[j] : -F1[j]) * inv_u11;
+    K[4 + j] = x1;
+    if (ROW0) K[j] = (swap ? fma(-q, x1, -F1[j]) : -(q * x1)) * col.inv_p;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = i; j < 4; ++j) {
+      const double kf = K[4 + i] * F1[j];
+      P[sym(i, j)] = Qh(i, j) + S[sym(i, j)] + kf;
+    }
+  }
+}
+
 // Dense variant for caller-supplied A (4x4) and B (4x2): compute_P_inf (tt:144-165) and
 // solver_mpc (tt:73-140) take arbitrary matrices.  P <- Q + A'PA + (A'PB)K, K = -(R+B'PB)^-1 B'PA.
 template <class QH>

@@ -1109,27 +1109,65 @@ struct MpcArgs {
 
 // One receding-horizon solve: (H-1)-step Riccati sweep over the window starting at time t
 // (tt:50, 80-117 with the window/padding of tt:64-67) -> first-move gain K_0 (2x4).
-template <bool WPB>
-__device__ __forceinline__ void mpc_sweep(const WV<WPB>& w, double dt, const double* __restrict__ lin, int64_t ld,
-                                          int64_t b, int n_lin, const LinD& Lf, const double QT[10], int t, int H,
-                                          double K[8]) {
-  double P[10], p[4] = {0, 0, 0, 0}, st[2], dummy = 0.0;
+template <bool WPB, int SW>
+__device__ __forceinline__ void mpc_sweep_sw(const WV<WPB>& w, double dt, const double* __restrict__ lin, int64_t ld,
+                                             int64_t b, int n_lin, const LinD& Lf, const double QT[10], int t, int H,
+                                             double K[8]) {
+  double P[10], inv_u11, qsel;
 #pragma unroll
   for (int e = 0; e < 10; ++e) P[e] = QT[e];
   const QhQ<WV<WPB>> Qh{w};
   const Lu2Col col = lu2_col(w.R(0, 0), w.R(0, 1));
   int j = H - 2;
-  // padded tail of the window: linearisation about (x_f, u_f)
-  for (; j >= 0 && t + j >= n_lin; --j)
-    riccati_step<false, false>(P, p, Lf, dt, Qh, col, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, K, st, dummy);
-  if (j < 0) return;
-  LinD L = load_lin(lin, t + j, ld, b);
-  for (; j >= 0; --j) {
-    LinD Ln = L;
-    if (j > 0) Ln = load_lin(lin, t + j - 1, ld, b);  // prefetch
-    riccati_step<false, false>(P, p, L, dt, Qh, col, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, K, st, dummy);
-    L = Ln;
+  // padded tail of the window: linearisation about (x_f, u_f).  Only the last step of a sweep (j = 0) needs the
+  // complete gain; the steps before it advance P.
+  for (; j >= 1 && t + j >= n_lin; --j)
+    riccati_chain_step<SW, false>(P, Lf, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+  if (j == 0 && t >= n_lin) {
+    riccati_chain_step<SW, true>(P, Lf, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+    return;
   }
+  if (j < 0) return;
+  // Window steps t+j, j downwards: the loads run three steps ahead of the arithmetic (a step is ~250 cycles of one
+  // warp, a load from L2 under load takes longer), in a rotating set of three register buffers.
+  LinD L0 = load_lin(lin, t + j, ld, b);
+  LinD L1 = load_lin(lin, t + max(j - 1, 0), ld, b);
+  LinD L2 = load_lin(lin, t + max(j - 2, 0), ld, b);
+  for (; j >= 3; j -= 3) {
+    LinD Ln = load_lin(lin, t + j - 3, ld, b);
+    riccati_chain_step<SW, false>(P, L0, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+    L0 = Ln;
+    Ln = load_lin(lin, t + max(j - 4, 0), ld, b);
+    riccati_chain_step<SW, false>(P, L1, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+    L1 = Ln;
+    Ln = load_lin(lin, t + max(j - 5, 0), ld, b);
+    riccati_chain_step<SW, false>(P, L2, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+    L2 = Ln;
+  }
+  // j in {0, 1, 2} steps left: L0 = step t+j, L1 = t+j-1, L2 = t+j-2
+  if (j == 2) {
+    riccati_chain_step<SW, false>(P, L0, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+    riccati_chain_step<SW, false>(P, L1, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+    riccati_chain_step<SW, true>(P, L2, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+  } else if (j == 1) {
+    riccati_chain_step<SW, false>(P, L0, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+    riccati_chain_step<SW, true>(P, L1, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+  } else {
+    riccati_chain_step<SW, true>(P, L0, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
+  }
+}
+// The pivot row of the 2x2 factorisation is the same for every step of every sweep: decide it once (per thread with
+// per-problem weights, for the whole batch otherwise).
+template <bool WPB>
+__device__ __forceinline__ void mpc_sweep(const WV<WPB>& w, double dt, const double* __restrict__ lin, int64_t ld,
+                                          int64_t b, int n_lin, const LinD& Lf, const double QT[10], int t, int H,
+                                          double K[8]) {
+  if (WPB)
+    mpc_sweep_sw<WPB, 2>(w, dt, lin, ld, b, n_lin, Lf, QT, t, H, K);
+  else if (fabs(w.R(0, 1)) > fabs(w.R(0, 0)))
+    mpc_sweep_sw<WPB, 1>(w, dt, lin, ld, b, n_lin, Lf, QT, t, H, K);
+  else
+    mpc_sweep_sw<WPB, 0>(w, dt, lin, ld, b, n_lin, Lf, QT, t, H, K);
 }
 
 // shared reference: one thread per time step computes K0[t]
