@@ -43,6 +43,11 @@ SIGNATURES = {
     "acro_rk4_step": [PP, I64, P, P, P, P],
     "acro_linearize": [PP, I64, P, P, P, P, I32, P],
     "acro_rollout_open_loop": [PP, I64, I32, P, P, P, P],
+    "acro_continuous_dynamics_pp": [PP, P, I64, P, P, P, P],
+    "acro_rk4_step_pp": [PP, P, I64, P, P, P, P],
+    "acro_linearize_pp": [PP, P, I64, P, P, P, P, I32, P],
+    "acro_rollout_open_loop_pp": [PP, P, I64, I32, P, P, P, P],
+    "acro_lqr_track_pp": [PP, P, I64, I32, PR, P, P, P, P, P],
     "acro_total_cost": [PW, I64, I32, P, P, PR, P, P],
     "acro_costate": [PP, PW, I64, I32, P, P, PR, P, P],
     "acro_cost_derivatives": [PW, I64, P, P, P, P, I32, P, P, P, P],

@@ -220,35 +220,56 @@ def unpack_soa(a):
 # ------------------------------------------------------------------------------------------
 # D1-D3
 # ------------------------------------------------------------------------------------------
-def continuous_dynamics(x, u, params=DEFAULT_PARAMS):
+PHYS_FIELDS = ("m1", "m2", "l1", "lc1", "l2", "lc2", "I1", "I2", "g", "f1", "f2")
+
+
+def phys_params(rows, Bn=None):
+    """Per-problem physical parameters for the *_pp entry points: a (B, 11) / (11, B) array-like in the order of
+    PHYS_FIELDS, or a dict field -> (B,) values (missing fields from params_1) -> device tensor (11, B)."""
+    if isinstance(rows, dict):
+        n = Bn or max(np.size(v) for v in rows.values())
+        rows = np.stack([np.broadcast_to(np.asarray(rows.get(f, getattr(DEFAULT_PARAMS, f)), dtype=np.float64), (n,))
+                         for f in PHYS_FIELDS])
+    if isinstance(rows, torch.Tensor):
+        t = rows.to(device=device(), dtype=F64)
+    else:
+        t = upload(np.asarray(rows, dtype=np.float64))
+    if t.shape[0] != len(PHYS_FIELDS):
+        t = t.T
+    if t.shape[0] != len(PHYS_FIELDS):
+        raise ValueError("physical parameters: expected 11 values per problem (%s)" % ", ".join(PHYS_FIELDS))
+    return t.contiguous()
+
+
+def continuous_dynamics(x, u, params=DEFAULT_PARAMS, params_b=None):
     out = torch.empty_like(x)
-    call("acro_continuous_dynamics", C.byref(params), x.shape[1], _p(x), _p(u), _p(out), _stream())
+    call("acro_continuous_dynamics_pp", C.byref(params), _p(params_b), x.shape[1], _p(x), _p(u), _p(out), _stream())
     return out
 
 
-def rk4_step(x, u, params=DEFAULT_PARAMS):
+def rk4_step(x, u, params=DEFAULT_PARAMS, params_b=None):
     out = torch.empty_like(x)
-    call("acro_rk4_step", C.byref(params), x.shape[1], _p(x), _p(u), _p(out), _stream())
+    call("acro_rk4_step_pp", C.byref(params), _p(params_b), x.shape[1], _p(x), _p(u), _p(out), _stream())
     return out
 
 
-def linearize(x, u, discrete=False, params=DEFAULT_PARAMS):
+def linearize(x, u, discrete=False, params=DEFAULT_PARAMS, params_b=None):
     """-> A (4,4,B), Bm (4,2,B)"""
     Bn = x.shape[1]
     A, Bm = _empty(4, 4, Bn), _empty(4, 2, Bn)
-    call("acro_linearize", C.byref(params), Bn, _p(x), _p(u), _p(A), _p(Bm), int(discrete), _stream())
+    call("acro_linearize_pp", C.byref(params), _p(params_b), Bn, _p(x), _p(u), _p(A), _p(Bm), int(discrete), _stream())
     return A, Bm
 
 
 # ------------------------------------------------------------------------------------------
 # G1-G11
 # ------------------------------------------------------------------------------------------
-def rollout_open_loop(x0, U=None, N=None, params=DEFAULT_PARAMS):
+def rollout_open_loop(x0, U=None, N=None, params=DEFAULT_PARAMS, params_b=None):
     """x0 (4,B), U Traj (C=2) or None (zeros, N given) -> X Traj"""
     Bn = x0.shape[1]
     N = U.T + 1 if U is not None else N
     X = Traj.empty(N, 4, Bn)
-    call("acro_rollout_open_loop", C.byref(params), Bn, N, _p(x0), _p(U), _p(X), _stream())
+    call("acro_rollout_open_loop_pp", C.byref(params), _p(params_b), Bn, N, _p(x0), _p(U), _p(X), _stream())
     return X
 
 
@@ -389,11 +410,11 @@ def lqr_gains(traj, w=None, params=DEFAULT_PARAMS):
     return K
 
 
-def lqr_track(traj, K, x0, params=DEFAULT_PARAMS):
-    """-> Xt Traj (C=4), Ut Traj (C=2)"""
+def lqr_track(traj, K, x0, params=DEFAULT_PARAMS, params_b=None):
+    """-> Xt Traj (C=4), Ut Traj (C=2).  params_b (11,B): every plant its own physical parameters (phys_params)."""
     N, Bn = traj.N, x0.shape[1]
     Xt, Ut = Traj.empty(N, 4, Bn), Traj.empty(N - 1, 2, Bn)
-    call("acro_lqr_track", C.byref(params), Bn, N, traj.ref(), _p(K), _p(x0), _p(Xt), _p(Ut), _stream())
+    call("acro_lqr_track_pp", C.byref(params), _p(params_b), Bn, N, traj.ref(), _p(K), _p(x0), _p(Xt), _p(Ut), _stream())
     return Xt, Ut
 
 

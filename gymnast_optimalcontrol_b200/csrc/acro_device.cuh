@@ -28,6 +28,27 @@ struct Model {
   double tc[16];
 };
 
+// Per-problem physical parameters (dynamics.py:15-61: params_1/2/3 are three such sets): rows m1, m2, l1, lc1, l2,
+// lc2, I1, I2, g, f1, f2 of an (11, B) array.  dt, the actuation flag and the trig constants stay those of the shared
+// model.  Same expressions as make_model() on the host.
+#define ACRO_N_PHYS 11
+__device__ __forceinline__ Model model_per_problem(const Model& base, const double* __restrict__ pb, int64_t B, int64_t b) {
+  const double m1 = pb[0 * B + b], m2 = pb[1 * B + b], l1 = pb[2 * B + b], lc1 = pb[3 * B + b], lc2 = pb[5 * B + b];
+  const double I1 = pb[6 * B + b], I2 = pb[7 * B + b], g = pb[8 * B + b];
+  Model m = base;
+  m.a1 = I1 + I2 + lc1 * lc1 * m1 + m2 * (l1 * l1 + lc2 * lc2);
+  m.h = m2 * l1 * lc2;
+  m.a3 = I2 + lc2 * lc2 * m2;
+  m.g1 = g * (lc1 * m1 + m2 * l1);
+  m.g2 = g * m2 * lc2;
+  m.f1 = pb[9 * B + b];
+  m.f2 = pb[10 * B + b];
+  m.h2 = 2.0 * m.h;
+  m.det0 = m.a1 * m.a3 - m.a3 * m.a3;
+  m.hsq = m.h * m.h;
+  return m;
+}
+
 // 2/pi, -pi/2 split in two, 1.5*2^52, then the minimax coefficients of fdlibm's __kernel_sin / __kernel_cos
 // on [-pi/4, pi/4]:  sin r = r + r^3 (S1 + z (S2 + ... z S6)),  cos r = 1 - z/2 + z^2 (C1 + z (C2 + ... z C6)),  z = r^2
 #define ACRO_TRIG_CONSTANTS                                                                                  \

@@ -113,11 +113,18 @@ static Cfg cfg_for(int64_t n) {
 // ---------------------------------------------------------------------------------------
 enum { PT_F = 0, PT_RK4 = 1 };
 
-template <int MODE>
-__global__ void k_point(const __grid_constant__ Model m, int64_t B, const double* __restrict__ x,
-                        const double* __restrict__ u, double* __restrict__ out) {
+// PPB: physical parameters per problem (`pb`, see model_per_problem); otherwise the shared model in the constant bank
+#define ACRO_MODEL(PPB, m0, pb, B, b) \
+  Model m_loc_;                        \
+  if (PPB) m_loc_ = model_per_problem(m0, pb, B, b); \
+  const Model& m = PPB ? m_loc_ : m0
+
+template <int MODE, bool PPB>
+__global__ void k_point(const __grid_constant__ Model m0, const double* __restrict__ pb, int64_t B,
+                        const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ out) {
   const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
+  ACRO_MODEL(PPB, m0, pb, B, b);
   double xs[4], o[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) xs[c] = x[c * B + b];
@@ -130,11 +137,13 @@ __global__ void k_point(const __grid_constant__ Model m, int64_t B, const double
   for (int c = 0; c < 4; ++c) out[c * B + b] = o[c];
 }
 
-__global__ void k_linearize(const __grid_constant__ Model m, int64_t B, const double* __restrict__ x,
-                            const double* __restrict__ u, double* __restrict__ A, double* __restrict__ Bm,
-                            int discrete) {
+template <bool PPB>
+__global__ void k_linearize(const __grid_constant__ Model m0, const double* __restrict__ pb, int64_t B,
+                            const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ A,
+                            double* __restrict__ Bm, int discrete) {
   const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
+  ACRO_MODEL(PPB, m0, pb, B, b);
   double xs[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) xs[c] = x[c * B + b];
@@ -180,10 +189,12 @@ __global__ void k_linearize(const __grid_constant__ Model m, int64_t B, const do
 // ---------------------------------------------------------------------------------------
 // G1 open-loop rollout, G8 cost, G3 costate
 // ---------------------------------------------------------------------------------------
-__global__ void k_rollout_open(const __grid_constant__ Model m, int64_t B, int N, const double* __restrict__ x0,
-                               const double* __restrict__ U, double* __restrict__ X) {
+template <bool PPB>
+__global__ void k_rollout_open(const __grid_constant__ Model m0, const double* __restrict__ pb, int64_t B, int N,
+                               const double* __restrict__ x0, const double* __restrict__ U, double* __restrict__ X) {
   const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
+  ACRO_MODEL(PPB, m0, pb, B, b);
   double x[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -908,12 +919,13 @@ __global__ void k_lqr_gains(const __grid_constant__ Model m, const __grid_consta
   }
 }
 
-template <bool RPB>
-__global__ void k_lqr_track(const __grid_constant__ Model m, int64_t B, int N, const double* rx, const double* ru,
-                            const double* __restrict__ K, const double* __restrict__ x0, double* __restrict__ Xt,
-                            double* __restrict__ Ut) {
+template <bool RPB, bool PPB>
+__global__ void k_lqr_track(const __grid_constant__ Model m0, const double* __restrict__ pb, int64_t B, int N,
+                            const double* rx, const double* ru, const double* __restrict__ K,
+                            const double* __restrict__ x0, double* __restrict__ Xt, double* __restrict__ Ut) {
   const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
+  ACRO_MODEL(PPB, m0, pb, B, b);
   const RefV<RPB> ref{rx, ru, N, b};
   double x[4];
 #pragma unroll
@@ -1381,39 +1393,68 @@ const char* acro_version(void) { return "acro_b200 0.1.0 (sm_100a, abi 1)"; }
 const char* acro_last_error_string(void) { return g_err; }
 int64_t acro_launch_count(void) { return g_launches.load(); }
 
-int acro_continuous_dynamics(const AcroParams* p, int64_t B, const double* x, const double* u, double* xdot,
-                             void* stream) {
+// ---- D1-D3, G1, T2 with shared (params_b = NULL) or per-problem physical parameters
+int acro_continuous_dynamics_pp(const AcroParams* p, const double* params_b, int64_t B, const double* x, const double* u,
+                                double* xdot, void* stream) {
   ACRO_REQUIRE(p && x && u && xdot && B > 0, "acro_continuous_dynamics: bad argument");
   const Cfg c = cfg_for(B);
-  k_point<PT_F><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), B, x, u, xdot);
+  if (params_b)
+    k_point<PT_F, true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), params_b, B, x, u, xdot);
+  else
+    k_point<PT_F, false><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), nullptr, B, x, u, xdot);
   ACRO_LAUNCH_CHECK("acro_continuous_dynamics");
   return ACRO_OK;
 }
+int acro_continuous_dynamics(const AcroParams* p, int64_t B, const double* x, const double* u, double* xdot,
+                             void* stream) {
+  return acro_continuous_dynamics_pp(p, nullptr, B, x, u, xdot, stream);
+}
 
-int acro_rk4_step(const AcroParams* p, int64_t B, const double* x, const double* u, double* xnext, void* stream) {
+int acro_rk4_step_pp(const AcroParams* p, const double* params_b, int64_t B, const double* x, const double* u,
+                     double* xnext, void* stream) {
   ACRO_REQUIRE(p && x && u && xnext && B > 0, "acro_rk4_step: bad argument");
   const Cfg c = cfg_for(B);
-  k_point<PT_RK4><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), B, x, u, xnext);
+  if (params_b)
+    k_point<PT_RK4, true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), params_b, B, x, u, xnext);
+  else
+    k_point<PT_RK4, false><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), nullptr, B, x, u, xnext);
   ACRO_LAUNCH_CHECK("acro_rk4_step");
   return ACRO_OK;
 }
+int acro_rk4_step(const AcroParams* p, int64_t B, const double* x, const double* u, double* xnext, void* stream) {
+  return acro_rk4_step_pp(p, nullptr, B, x, u, xnext, stream);
+}
 
-int acro_linearize(const AcroParams* p, int64_t B, const double* x, const double* u, double* A, double* Bm,
-                   int discrete, void* stream) {
+int acro_linearize_pp(const AcroParams* p, const double* params_b, int64_t B, const double* x, const double* u,
+                      double* A, double* Bm, int discrete, void* stream) {
   ACRO_REQUIRE(p && x && u && A && Bm && B > 0, "acro_linearize: bad argument");
   const Cfg c = cfg_for(B);
-  k_linearize<<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), B, x, u, A, Bm, discrete);
+  if (params_b)
+    k_linearize<true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), params_b, B, x, u, A, Bm, discrete);
+  else
+    k_linearize<false><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), nullptr, B, x, u, A, Bm, discrete);
   ACRO_LAUNCH_CHECK("acro_linearize");
   return ACRO_OK;
 }
+int acro_linearize(const AcroParams* p, int64_t B, const double* x, const double* u, double* A, double* Bm,
+                   int discrete, void* stream) {
+  return acro_linearize_pp(p, nullptr, B, x, u, A, Bm, discrete, stream);
+}
 
-int acro_rollout_open_loop(const AcroParams* p, int64_t B, int N, const double* x0, const double* U, double* X,
-                           void* stream) {
+int acro_rollout_open_loop_pp(const AcroParams* p, const double* params_b, int64_t B, int N, const double* x0,
+                              const double* U, double* X, void* stream) {
   ACRO_REQUIRE(p && x0 && X && B > 0 && N >= 1, "acro_rollout_open_loop: bad argument");
   const Cfg c = cfg_for(B);
-  k_rollout_open<<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), B, N, x0, U, X);
+  if (params_b)
+    k_rollout_open<true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), params_b, B, N, x0, U, X);
+  else
+    k_rollout_open<false><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), nullptr, B, N, x0, U, X);
   ACRO_LAUNCH_CHECK("acro_rollout_open_loop");
   return ACRO_OK;
+}
+int acro_rollout_open_loop(const AcroParams* p, int64_t B, int N, const double* x0, const double* U, double* X,
+                           void* stream) {
+  return acro_rollout_open_loop_pp(p, nullptr, B, N, x0, U, X, stream);
 }
 
 int acro_total_cost(const AcroWeights* w, int64_t B, int N, const double* X, const double* U, const AcroRef* ref,
@@ -1702,17 +1743,21 @@ int acro_lqr_gains(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
   return ACRO_OK;
 }
 
-int acro_lqr_track(const AcroParams* p, int64_t B, int N, const AcroRef* traj, const double* K, const double* x0,
-                   double* Xt, double* Ut, void* stream) {
+int acro_lqr_track_pp(const AcroParams* p, const double* params_b, int64_t B, int N, const AcroRef* traj,
+                      const double* K, const double* x0, double* Xt, double* Ut, void* stream) {
   ACRO_REQUIRE(p && traj && traj->x && traj->u && K && x0 && Xt && Ut && B > 0 && N >= 2, "acro_lqr_track: bad argument");
   const Cfg c = cfg_for(B);
   const Model m = make_model(*p);
-  if (traj->per_problem)
-    k_lqr_track<true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, B, N, traj->x, traj->u, K, x0, Xt, Ut);
-  else
-    k_lqr_track<false><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, B, N, traj->x, traj->u, K, x0, Xt, Ut);
+#define EXPR(RPB, PPB) \
+  k_lqr_track<RPB, PPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, params_b, B, N, traj->x, traj->u, K, x0, Xt, Ut)
+  DISPATCH2(traj->per_problem != 0, params_b != nullptr, EXPR);
+#undef EXPR
   ACRO_LAUNCH_CHECK("acro_lqr_track");
   return ACRO_OK;
+}
+int acro_lqr_track(const AcroParams* p, int64_t B, int N, const AcroRef* traj, const double* K, const double* x0,
+                   double* Xt, double* Ut, void* stream) {
+  return acro_lqr_track_pp(p, nullptr, B, N, traj, K, x0, Xt, Ut, stream);
 }
 
 int acro_p_inf(const AcroWeights* w, int64_t B, const double* A, const double* Bm, int max_iter, double tol,

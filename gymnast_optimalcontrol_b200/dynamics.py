@@ -55,21 +55,32 @@ def _xu(xx, uu):
     return x, u, kind
 
 
-def dynamics(xx, uu):
+def _pb(params_b, Bn):
+    """Keyword-only extension of the functions below: physical parameters per problem, (B, 11) in the order
+    m1, m2, l1, lc1, l2, lc2, I1, I2, g, f1, f2, or a dict of per-problem arrays (see batched.phys_params)."""
+    if params_b is None:
+        return None
+    t = bt.phys_params(params_b, Bn)
+    if t.shape[1] != Bn:
+        raise ValueError("params_b: %d parameter sets for %d problems" % (t.shape[1], Bn))
+    return t
+
+
+def dynamics(xx, uu, *, params_b=None):
     """One RK4 step of the acrobot (dynamics.py:177-195)."""
     x, u, kind = _xu(xx, uu)
-    return _io.out(bt.rk4_step(x, u, _active["params"]), kind)
+    return _io.out(bt.rk4_step(x, u, _active["params"], _pb(params_b, x.shape[1])), kind)
 
 
-def continuous_dynamics(xx, uu):
+def continuous_dynamics(xx, uu, *, params_b=None):
     """x_dot = f(x, u) (dynamics.py:197-213)."""
     x, u, kind = _xu(xx, uu)
-    return _io.out(bt.continuous_dynamics(x, u, _active["params"]), kind)
+    return _io.out(bt.continuous_dynamics(x, u, _active["params"], _pb(params_b, x.shape[1])), kind)
 
 
-def Calculate_A_B_matrixes(x_t, u_t):
+def Calculate_A_B_matrixes(x_t, u_t, *, params_b=None):
     """Continuous Jacobians A_c (4,4), B_c (4,2) (dynamics.py:217-226); batched input -> (B,4,4), (B,4,2)."""
     x, u, kind = _xu(x_t, u_t)
-    A, Bm = bt.linearize(x, u, False, _active["params"])
+    A, Bm = bt.linearize(x, u, False, _active["params"], _pb(params_b, x.shape[1]))
     Bn = x.shape[1]
     return (_io.out(A.reshape(16, Bn), kind, tail=(4, 4), key="A"), _io.out(Bm.reshape(8, Bn), kind, tail=(4, 2), key="B"))

@@ -85,14 +85,15 @@ def get_fully_actuated_ref(path="trajectories_npz/fully_actuated_trajectory.npz"
 
 
 # ---------------------------------------------------------------------------------------------------------
-def simulate_open_loop(x0, u_traj):
-    """trajectory_generation.py:74-87"""
+def simulate_open_loop(x0, u_traj, *, params_b=None):
+    """trajectory_generation.py:74-87.  params_b (B, 11): physical parameters per problem."""
     x, kind = _io.state_in(x0, nx)
     U, ku = _io.traj_in(u_traj, nu)
     if U.B != x.shape[1]:
         raise ValueError("batch sizes of x0 and u_traj differ")
     kind.batched = kind.batched or ku.batched
-    return _io.out(bt.rollout_open_loop(x, U, params=active_params()), kind)
+    pb = None if params_b is None else bt.phys_params(params_b, x.shape[1])
+    return _io.out(bt.rollout_open_loop(x, U, params=active_params(), params_b=pb), kind)
 
 
 def derivatives_Cost(x, x_ref, u, u_ref, Q, R, Q_T=None, terminal=False):

@@ -32,8 +32,9 @@ def solve_LQR_tracking(x_opt, u_opt):
     return list(Kh)
 
 
-def simulate_tracking(x_opt, u_opt, K_reg, x0_perturbed):
-    """trajectory_tracking.py:206-216.  x0_perturbed (4,) or (B,4); trajectory and gains shared or per problem."""
+def simulate_tracking(x_opt, u_opt, K_reg, x0_perturbed, *, params_b=None):
+    """trajectory_tracking.py:206-216.  x0_perturbed (4,) or (B,4); trajectory and gains shared or per problem.
+    params_b (B, 11): every plant its own physical parameters (tracking under model mismatch)."""
     x0, kind = _io.state_in(x0_perturbed, nx)
     traj = _ref(x_opt, u_opt)
     if traj.per_problem:
@@ -41,18 +42,20 @@ def simulate_tracking(x_opt, u_opt, K_reg, x0_perturbed):
     else:
         Kd = bt.upload(np.asarray([np.asarray(k, dtype=np.float64).reshape(8) for k in K_reg])
                        if isinstance(K_reg, (list, tuple)) else K_reg).reshape(-1, 8).contiguous()
-    Xt, Ut = bt.lqr_track(traj, Kd, x0, active_params())
+    pb = None if params_b is None else bt.phys_params(params_b, x0.shape[1])
+    Xt, Ut = bt.lqr_track(traj, Kd, x0, active_params(), pb)
     return _io.out(Xt, kind, key="xt"), _io.out(Ut, kind, key="ut")
 
 
-def LQR_tracking(x_ref, u_ref, t_ref, x0_perturbed=None):
-    """trajectory_tracking.py:219-249"""
+def LQR_tracking(x_ref, u_ref, t_ref, x0_perturbed=None, *, params_b=None):
+    """trajectory_tracking.py:219-249.  params_b: the gains are those of the active (nominal) model, the plants differ."""
     if x0_perturbed is None:
         x0_perturbed = x_ref[0].copy() if not isinstance(x_ref, torch.Tensor) else x_ref[0].clone()
     traj = _ref(x_ref, u_ref)
     K = bt.lqr_gains(traj, bt.Weights(Q_reg, R_Reg), active_params())
     x0, kind = _io.state_in(x0_perturbed, nx)
-    Xt, Ut = bt.lqr_track(traj, K, x0, active_params())
+    pb = None if params_b is None else bt.phys_params(params_b, x0.shape[1])
+    Xt, Ut = bt.lqr_track(traj, K, x0, active_params(), pb)
     return _io.out(Xt, kind, key="xt"), _io.out(Ut, kind, key="ut")
 
 

@@ -207,6 +207,23 @@ int acro_stepsize_sweep(const AcroParams* p, const AcroWeights* w, int64_t P, in
  * problem and K is (N-1,2,4) row-major, per-problem => K {N-1 x 8}). */
 int acro_lqr_gains(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const AcroRef* traj,
                    double* K, void* stream);
+/* ---- per-problem physical parameters (dynamics.py:15-61 defines three parameter sets,
+ * set_params dynamics.py:117-144 selects one for the whole program).  params_b [11][B] (device): rows m1, m2, l1,
+ * lc1, l2, lc2, I1, I2, g, f1, f2 per problem; dt and actuated_tau1 from p.  params_b = NULL is the shared-parameter
+ * call above.  Everything else as in the function without the suffix. */
+int acro_continuous_dynamics_pp(const AcroParams* p, const double* params_b, int64_t B, const double* x,
+                                const double* u, double* xdot, void* stream);
+int acro_rk4_step_pp(const AcroParams* p, const double* params_b, int64_t B, const double* x, const double* u,
+                     double* xnext, void* stream);
+int acro_linearize_pp(const AcroParams* p, const double* params_b, int64_t B, const double* x, const double* u,
+                      double* A, double* Bm, int discrete, void* stream);
+int acro_rollout_open_loop_pp(const AcroParams* p, const double* params_b, int64_t B, int N, const double* x0,
+                              const double* U, double* X, void* stream);
+/* the plant of every problem has its own parameters, the gains are the caller's (e.g. those of the nominal model:
+ * tracking under model mismatch) */
+int acro_lqr_track_pp(const AcroParams* p, const double* params_b, int64_t B, int N, const AcroRef* traj,
+                      const double* K, const double* x0, double* Xt, double* Ut, void* stream);
+
 /* simulate_tracking(x_opt, u_opt, K_reg, x0_perturbed)  tt:206-216.
  * traj/K shared (K (N-1,2,4)) or per-problem (K {N-1 x 8}) following traj->per_problem.
  * x0 [4][B] -> Xt {N x 4}, Ut {N-1 x 2}. */

@@ -150,3 +150,32 @@ def test_task4_recipe(mods):
     assert X.shape == (75, 4) and U.shape == (75, 2)
     assert rel_err(U0, U0o) < 1e-7 and rel_err(X, Xo) < 1e-7 and rel_err(U, Uo) < 1e-7
     assert rel_err(ur[0] - u_ref[0], U0) < TOL
+
+
+def test_per_problem_parameters_through_the_dropins(mods):
+    """Keyword-only extension params_b (B, 11) or a dict of per-problem arrays."""
+    dyn, tg, tt = mods
+    from gymnast_optimalcontrol_b200.batched import PARAM_SETS, PHYS_FIELDS
+    rng = np.random.default_rng(12)
+    n = 9
+    x, u = rng.uniform(-1, 1, (n, 4)), rng.uniform(-2, 2, (n, 2))
+    sets = [dict(PARAM_SETS[1 + b % 3]) for b in range(n)]
+    rows = np.array([[s[f] for f in PHYS_FIELDS] for s in sets])
+    step = dyn.dynamics(x, u, params_b=rows)
+    A, B = dyn.Calculate_A_B_matrixes(x, u, params_b=rows)
+    for b in range(n):
+        m = O.Model(sets[b])
+        assert rel_err(step[b], O.dynamics(x[b], u[b], m)) < TOL
+        Ac, Bc = O.Calculate_A_B_matrixes(x[b], u[b], m)
+        assert rel_err(A[b], Ac) < TOL and rel_err(B[b], Bc) < TOL
+    # dict form: only the masses vary
+    m2 = rng.uniform(0.8, 1.2, n)
+    step = dyn.dynamics(x, u, params_b={"m2": m2})
+    Ut = rng.uniform(-1, 1, (n, 20, 2))
+    Xo = tg.simulate_open_loop(x, Ut, params_b={"m2": m2})
+    for b in range(n):
+        m = O.Model(dict(PARAM_SETS[1], m2=m2[b]))
+        assert rel_err(step[b], O.dynamics(x[b], u[b], m)) < TOL
+        assert rel_err(Xo[b], O.simulate_open_loop(x[b], Ut[b], m)) < TOL
+    with pytest.raises(ValueError):
+        dyn.dynamics(x, u, params_b=rows[:3])

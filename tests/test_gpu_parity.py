@@ -110,6 +110,63 @@ def test_param_sets(bt):
         assert rel_err(aos(bt.rk4_step(soa(x), soa(u), params=bt.make_params(v))), O.dynamics(x, u, m)) < TOL
 
 
+def _random_phys(n, seed):
+    """n physical parameter sets within +-25 % of params_1 (+ the three sets the reference defines, dynamics.py:15-61)"""
+    from gymnast_optimalcontrol_b200.batched import PHYS_FIELDS, PARAM_SETS
+    rng = np.random.default_rng(seed)
+    sets = []
+    for b in range(n):
+        if b < 3:
+            sets.append(dict(PARAM_SETS[b + 1]))
+        else:
+            sets.append({f: PARAM_SETS[1][f] * (1.0 if f == "g" else rng.uniform(0.75, 1.25)) for f in PHYS_FIELDS})
+    rows = np.array([[s_[f] for f in PHYS_FIELDS] for s_ in sets])
+    return sets, rows
+
+
+def test_per_problem_physical_parameters(bt):
+    """every problem its own (m, l, lc, I, g, f): dynamics, Jacobians, open-loop rollouts and LQR
+    tracking under model mismatch against the oracle evaluated problem by problem."""
+    n = 37
+    sets, rows = _random_phys(n, 4)
+    pb = bt.phys_params(rows)
+    assert pb.shape == (11, n)
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-2.0, 2.0, (n, 4))
+    u = rng.uniform(-5.0, 5.0, (n, 2))
+    f = aos(bt.continuous_dynamics(soa(x), soa(u), params_b=pb))
+    s1 = aos(bt.rk4_step(soa(x), soa(u), params_b=pb))
+    A, Bm = bt.linearize(soa(x), soa(u), discrete=False, params_b=pb)
+    Ad, Bd = bt.linearize(soa(x), soa(u), discrete=True, params_b=pb)
+    A, Bm, Ad, Bd = (t.cpu().numpy() for t in (A, Bm, Ad, Bd))
+    U = rng.uniform(-3.0, 3.0, (n, 60, 2))
+    X = aos(bt.rollout_open_loop(soa(x), soa(U), params_b=pb))
+    d = golden("acrobot_optimal_trajectory")
+    traj = bt.make_ref(d["x"], d["u"])
+    K = bt.lqr_gains(traj)  # nominal model
+    x0 = d["x"][0] + rng.uniform(-0.05, 0.05, (n, 4))
+    Xt, Ut = bt.lqr_track(traj, K, soa(x0), params_b=pb)
+    Xt, Ut = aos(Xt), aos(Ut)
+    Kn = K.cpu().numpy().reshape(500, 2, 4)
+    for b in range(n):
+        m = O.Model(sets[b])
+        assert rel_err(f[b], O.continuous_dynamics(x[b], u[b], m)) < TOL
+        assert rel_err(s1[b], O.dynamics(x[b], u[b], m)) < TOL
+        Ac, Bc = O.Calculate_A_B_matrixes(x[b], u[b], m)
+        assert rel_err(A[:, :, b], Ac) < TOL and rel_err(Bm[:, :, b], Bc) < TOL
+        Ado, Bdo = O.linearize_discrete(x[b], u[b], m)
+        assert rel_err(Ad[:, :, b], Ado) < TOL and rel_err(Bd[:, :, b], Bdo) < TOL
+        assert rel_err(X[b], O.simulate_open_loop(x[b], U[b], m)) < TOL
+        if b < 12:
+            xo, uo = O.simulate_tracking(d["x"], d["u"], Kn, x0[b], m)
+            if np.isfinite(xo).all() and np.abs(xo).max() < 50:
+                assert rel_err(Xt[b], xo) < TOL and rel_err(Ut[b], uo) < TOL
+            else:
+                assert not (np.isfinite(Xt[b]).all() and np.abs(Xt[b]).max() < 50)
+    # problem 0 carries params_1: same bits as the shared-parameter call
+    assert np.array_equal(s1[0], aos(bt.rk4_step(soa(x[:1]), soa(u[:1])))[0])
+
+
 def test_pack_unpack(bt):
     rng = np.random.default_rng(0)
     for shape in ((1, 501, 4), (37, 500, 2), (300, 3, 8), (64, 7, 10), (65, 4)):
