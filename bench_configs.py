@@ -81,6 +81,14 @@ def main():
     t, nl = timeit(lambda: bt.lqr_track(traj, K, x0), reps)
     line("C3 LQR tracking, B=65536, N=501", "lqr_rollouts_per_sec", B / t, "tracked problems/s", 878.0 * (N - 1), t, nl, peak,
          {"steps_per_sec": B * (N - 1) / t})
+    # the same with every plant its own physical parameters: nominal gains, mismatched plants
+    rng = np.random.default_rng(7)
+    rows = np.array([[getattr(bt.DEFAULT_PARAMS, f) * (1.0 if f == "g" else 1.0) for f in bt.PHYS_FIELDS]] * B)
+    rows[:, :8] *= rng.uniform(0.97, 1.03, (B, 8))
+    pb = bt.phys_params(rows)
+    t, nl = timeit(lambda: bt.lqr_track(traj, K, x0, params_b=pb), reps)
+    line("C3 LQR tracking with per-problem physical parameters (+-3 %), B=65536, N=501", "lqr_rollouts_per_sec", B / t,
+         "tracked problems/s", 878.0 * (N - 1), t, nl, peak, {"steps_per_sec": B * (N - 1) / t})
     tg, _ = timeit(lambda: bt.lqr_gains(traj), reps)
     print(json.dumps({"config": "C3 gains (one shared trajectory, 500 sequential Riccati steps, 1 thread)", "seconds": tg}))
 
