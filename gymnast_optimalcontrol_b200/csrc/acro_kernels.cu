@@ -1631,6 +1631,14 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
     if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                          \
     k_newton_ring<WPB, RPB, SG><<<(unsigned)tiles, 32, smem, (cudaStream_t)stream>>>(a);                            \
   } while (0)
+#define LAUNCH_RING_RL(WPB, RPB, SG)                                                                                \
+  do {                                                                                                              \
+    constexpr int smem = ACRO_RING_D * stage_bytes<RPB, SG>() + ACRO_RING_D * 8;                                    \
+    cudaError_t e_ = cudaFuncSetAttribute(k_newton_ring<WPB, RPB, SG, true>,                                        \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
+    if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                          \
+    k_newton_ring<WPB, RPB, SG, true><<<(unsigned)tiles, 32, smem, (cudaStream_t)stream>>>(a);                      \
+  } while (0)
     // at most one block per SM: deep stages (16 steps per bulk copy); otherwise 4 steps per stage, 4 blocks per SM.
     // Per-problem references need 50 % more shared memory per stage: they always use the 4-step stages.
     const char* sg_env = getenv("ACRO_RING_SG");
@@ -1640,16 +1648,27 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
       DISPATCH2(per_problem_weights(*w), false, EXPR);
 #undef EXPR
     } else if ((tiles > 592 && !sg_force) || sg_force == 2) {
-      // more tiles than SM sub-partitions: 2-step stages (25 KB per block), eight blocks = two warps per sub-partition
+      // more tiles than SM sub-partitions: 2-step stages (25 KB per block), eight blocks = two warps per sub-partition.
+      // This regime is HBM bound: the backward pass recomputes the linearisation about (x_t, u_t) instead of
+      // streaming the 80 B the forward pass would have stored for it (304 instead of 464 B per problem-step-iteration;
+      // ACRO_RING_RL=0 keeps the stored linearisation for A/B runs).
+      const char* rl_env = getenv("ACRO_RING_RL");
+      if (rl_env && atoi(rl_env) == 0) {
 #define EXPR(WPB, RPB) LAUNCH_RING(WPB, RPB, 2)
-      DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+        DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
 #undef EXPR
+      } else {
+#define EXPR(WPB, RPB) LAUNCH_RING_RL(WPB, RPB, 2)
+        DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+      }
     } else {
 #define EXPR(WPB, RPB) LAUNCH_RING(WPB, RPB, 4)
       DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
 #undef EXPR
     }
 #undef LAUNCH_RING
+#undef LAUNCH_RING_RL
   } else {
     const Cfg c = cfg_for(B);
 #define EXPR(WPB, RPB) k_newton<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(a)

@@ -94,19 +94,20 @@ struct TilePtrs {
 constexpr int64_t kSX = 4 * 32, kSU = 2 * 32, kSK = 8 * 32, kSS = 2 * 32, kSL = 10 * 32;  // doubles per time step
 
 // Issue the bulk copies of stage k of a pass: time steps [t_lo, t_lo + cnt).
-template <bool RPB, bool FWD, int SG>
+// RL ("recompute the linearisation"): the backward pass does not stream lin[t]; it linearises about (x_t, u_t) itself.
+template <bool RPB, bool FWD, int SG, bool RL = false>
 __device__ __forceinline__ void ring_fill(const Ring& r, const TilePtrs& p, int k, int t_lo, int cnt) {
   if (elect_one()) {
     const uint32_t g = r.base + k, slot = ring_slot(g);
     const uint32_t bar = r.bars + slot * 8, dst = r.data + slot * stage_bytes<RPB, SG>();
     const uint32_t n = (uint32_t)cnt;
-    mbar_expect_tx(bar, n * (4096u + (RPB ? 1536u : 48u)));
+    mbar_expect_tx(bar, n * ((!FWD && RL ? 1536u : 4096u) + (RPB ? 1536u : 48u)));
     bulk_g2s(dst + StageOff<SG>::X, p.x + t_lo * kSX, n * 1024, bar);
     bulk_g2s(dst + StageOff<SG>::U, p.u + t_lo * kSU, n * 512, bar);
     if (FWD) {
       bulk_g2s(dst + StageOff<SG>::A, p.k + t_lo * kSK, n * 2048, bar);
       bulk_g2s(dst + StageOff<SG>::S, p.s + t_lo * kSS, n * 512, bar);
-    } else {
+    } else if (!RL) {
       bulk_g2s(dst + StageOff<SG>::A, p.lin + t_lo * kSL, n * 2560, bar);
     }
     if (RPB) {
@@ -154,18 +155,20 @@ __device__ __forceinline__ void lds_fwd(uint32_t stage, int s, int lane, StepIn&
 // forward pass (tg:218-252): closed-loop rollout with step size gamma + its cost; writes the candidate
 // (Xo, Uo) and the linearisation about it when `store`.
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB, int SG>
+template <bool WPB, bool RPB, int SG, bool RL>
 __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w, int N, const TilePtrs& p, Ring& r,
                                                int lane, double gamma, bool store, double* __restrict__ Xo,
                                                double* __restrict__ Uo, double* __restrict__ Lo, const double xrT[4]) {
   const int steps = N - 1, n_stages = (steps + SG - 1) / SG;
-  for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, true, SG>(r, p, k, k * SG, min(SG, steps - k * SG));
+  for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, true, SG, RL>(r, p, k, k * SG, min(SG, steps - k * SG));
   double xp[4];
   StepIn in;
   mbar_wait(r.bars + ring_slot(r.base) * 8, ring_parity(r.base));
   lds_fwd<RPB, SG>(r.data + ring_slot(r.base) * stage_bytes<RPB, SG>(), 0, lane, in);
 #pragma unroll
   for (int c = 0; c < 4; ++c) xp[c] = in.x[c];  // x+_0 = x_0
+  TrigCarry tc;
+  if (RL) tc = trig_carry_at(m, xp[0], xp[1]);
   double cost = 0.0;
   double* po_x = Xo + lane;
   double* po_u = Uo + lane;
@@ -213,19 +216,23 @@ __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w,
       if (s == 0 && k >= 1 && k - 1 + ACRO_RING_D < n_stages) {
         __syncwarp();
         const int kk = k - 1 + ACRO_RING_D;
-        ring_fill<RPB, true, SG>(r, p, kk, kk * SG, min(SG, steps - kk * SG));
+        ring_fill<RPB, true, SG, RL>(r, p, kk, kk * SG, min(SG, steps - kk * SG));
       }
       double xn[4];
-      LinD L;
-      rk4_step_lin(m, xp, up[0], up[1], xn, L);
-      if (store) {
+      if (RL) {
+        rk4_step_inc(m, xp, up[0], up[1], xn, tc);
+      } else {
+        LinD L;
+        rk4_step_lin(m, xp, up[0], up[1], xn, L);
+        if (store) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          po_l[j * 32] = L.a[0][j];
-          po_l[(4 + j) * 32] = L.a[1][j];
+          for (int j = 0; j < 4; ++j) {
+            po_l[j * 32] = L.a[0][j];
+            po_l[(4 + j) * 32] = L.a[1][j];
+          }
+          po_l[8 * 32] = L.b[0];
+          po_l[9 * 32] = L.b[1];
         }
-        po_l[8 * 32] = L.b[0];
-        po_l[9 * 32] = L.b[1];
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) xp[c] = xn[c];
@@ -249,7 +256,7 @@ __device__ __forceinline__ double forward_ring(const Model& m, const WV<WPB>& w,
 // backward pass (tg:166-216): affine Riccati sweep on the stored linearisation; writes K, S when `store`.
 // Stage k of this pass holds the time steps [t_lo, t_hi] with t_hi = steps-1 - k*SG, walked downwards.
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB, int SG>
+template <bool WPB, bool RPB, int SG, bool RL>
 __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, int N, const TilePtrs& p, Ring& r,
                                               int lane, bool store, double* __restrict__ K, double* __restrict__ S,
                                               const double xT[4], const double xrT[4], double& dJ_out,
@@ -257,7 +264,7 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
   const int steps = N - 1, n_stages = (steps + SG - 1) / SG;
   auto t_lo_of = [&](int k) { return max(0, steps - (k + 1) * SG); };
   auto cnt_of = [&](int k) { return (steps - k * SG) - t_lo_of(k); };
-  for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, false, SG>(r, p, k, t_lo_of(k), cnt_of(k));
+  for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, false, SG, RL>(r, p, k, t_lo_of(k), cnt_of(k));
   double P[10], pv[4];
   {
     double dx[4];
@@ -282,13 +289,15 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
     for (int c = 0; c < 4; ++c) x[c] = lds(b + StageOff<SG>::X + s * 1024 + c * 256);
 #pragma unroll
     for (int c = 0; c < 2; ++c) u[c] = lds(b + StageOff<SG>::U + s * 512 + c * 256);
+    if (!RL) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      L.a[0][j] = lds(b + StageOff<SG>::A + s * 2560 + j * 256);
-      L.a[1][j] = lds(b + StageOff<SG>::A + s * 2560 + (4 + j) * 256);
+      for (int j = 0; j < 4; ++j) {
+        L.a[0][j] = lds(b + StageOff<SG>::A + s * 2560 + j * 256);
+        L.a[1][j] = lds(b + StageOff<SG>::A + s * 2560 + (4 + j) * 256);
+      }
+      L.b[0] = lds(b + StageOff<SG>::A + s * 2560 + 8 * 256);
+      L.b[1] = lds(b + StageOff<SG>::A + s * 2560 + 9 * 256);
     }
-    L.b[0] = lds(b + StageOff<SG>::A + s * 2560 + 8 * 256);
-    L.b[1] = lds(b + StageOff<SG>::A + s * 2560 + 9 * 256);
     lds_ref<RPB, SG>(stage, s, lane, xr, ur);
   };
   mbar_wait(r.bars + ring_slot(r.base) * 8, ring_parity(r.base));
@@ -322,6 +331,16 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
       }
       rr[0] = fma(w.R2(0, 1), du[1], w.R2(0, 0) * du[0]);
       rr[1] = fma(w.R2(1, 1), du[1], w.R2(1, 0) * du[0]);
+      if (RL) {
+        const LinD Lr = linearize_d(m, x, u[0], u[1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          L.a[0][j] = Lr.a[0][j];
+          L.a[1][j] = Lr.a[1][j];
+        }
+        L.b[0] = Lr.b[0];
+        L.b[1] = Lr.b[1];
+      }
       double Kt[8], st[2];
       riccati_step<true, false>(P, pv, L, m.dt, Qh, col, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, rr, Kt, st, dJ);
       if (store) {
@@ -346,7 +365,7 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
       if (s == cnt - 1 && k >= 1 && k - 1 + ACRO_RING_D < n_stages) {
         __syncwarp();
         const int kk = k - 1 + ACRO_RING_D;
-        ring_fill<RPB, false, SG>(r, p, kk, t_lo_of(kk), cnt_of(kk));
+        ring_fill<RPB, false, SG, RL>(r, p, kk, t_lo_of(kk), cnt_of(kk));
       }
       pk -= kSK;
       ps -= kSS;
@@ -360,7 +379,7 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
 // ---------------------------------------------------------------------------------------------------------
 // kernel: one warp per block, block = tile of 32 problems
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB, int SG>
+template <bool WPB, bool RPB, int SG, bool RL = false>
 __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ NewtonArgs a) {
   extern __shared__ __align__(128) unsigned char ring_smem[];
   constexpr unsigned FULL = 0xffffffffu;
@@ -429,15 +448,19 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
       c_acc += quad4(ex, [&](int i, int j) { return w.Q(i, j); });
       c_acc += quad2(eu, [&](int i, int j) { return w.R(i, j); });
       double xn[4];
-      LinD L;
-      rk4_step_lin(a.m, x, u0, u1, xn, L);
+      if (RL) {
+        rk4_step(a.m, x, u0, u1, xn);
+      } else {
+        LinD L;
+        rk4_step_lin(a.m, x, u0, u1, xn, L);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        pl[j * 32] = L.a[0][j];
-        pl[(4 + j) * 32] = L.a[1][j];
+        for (int j = 0; j < 4; ++j) {
+          pl[j * 32] = L.a[0][j];
+          pl[(4 + j) * 32] = L.a[1][j];
+        }
+        pl[8 * 32] = L.b[0];
+        pl[9 * 32] = L.b[1];
       }
-      pl[8 * 32] = L.b[0];
-      pl[9 * 32] = L.b[1];
       px += sx;
       pu += su;
       pl += sl;
@@ -476,7 +499,7 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
 #pragma unroll
     for (int c = 0; c < 4; ++c) xT[c] = p.x[(N - 1) * sx + c * 32 + lane];
     double dJn, snn;
-    backward_ring<WPB, RPB, SG>(a.m, w, N, p, r, lane, run, tK, tS, xT, xrT, dJn, snn);
+    backward_ring<WPB, RPB, SG, RL>(a.m, w, N, p, r, lane, run, tK, tS, xT, xrT, dJn, snn);
     if (run) {
       dJ = dJn;
       sn = snn;
@@ -490,7 +513,7 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
     double gamma = a.o.gamma_0, cn = 0.0;
     int tries = 0;
     for (int i = 0; i < a.o.max_line_search && __any_sync(FULL, need); ++i) {
-      const double c = forward_ring<WPB, RPB, SG>(a.m, w, N, p, r, lane, gamma, need, Xo, Uo, tL, xrT);
+      const double c = forward_ring<WPB, RPB, SG, RL>(a.m, w, N, p, r, lane, gamma, need, Xo, Uo, tL, xrT);
       if (need) {
         ++tries;
         // accept iff cost_new < cost_k + c*gamma*delta_J  (strict, NaN rejects)   tg:361

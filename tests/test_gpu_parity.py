@@ -656,15 +656,20 @@ def test_newton_kernels_agree(bt, fa_ref, monkeypatch):
     x0s = np.random.default_rng(8).uniform(-0.2, 0.2, (45, 4))
     ref = bt.make_ref(x_ref, u_ref)
     out = {}
-    for kernel in ("duo", "ring", "ldg"):
-        monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    for kernel in ("duo", "ring", "ldg", "ring-rl"):
+        # "ring-rl": the large-batch variant (2-step stages, linearisation recomputed in the backward pass)
+        monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel.split("-")[0])
+        if kernel == "ring-rl":
+            monkeypatch.setenv("ACRO_RING_SG", "2")
+        else:
+            monkeypatch.delenv("ACRO_RING_SG", raising=False)
         st = bt.newton_solve(soa(x0s), ref, max_iters=6, tol=1e-4, gamma_0=1.0, chunk_iters=3)
         st = bt.newton_solve(soa(x0s), ref, max_iters=6, tol=1e-4, gamma_0=1.0, state=st)
         torch.cuda.synchronize()
         out[kernel] = (aos(st.X), aos(st.U), kmat(st.K), aos(st.S), st.hist_cost[:7].cpu().numpy(),
                        st.hist_ntry[:6].cpu().numpy(), st.hist_gamma[:6].cpu().numpy(), st.iters.cpu().numpy(),
                        st.status.cpu().numpy(), st.sigma_norm.cpu().numpy(), st.delta_J.cpu().numpy())
-    for kernel in ("duo", "ldg"):
+    for kernel in ("duo", "ldg", "ring-rl"):
         a, b = out[kernel], out["ring"]
         for i in (5, 6, 7, 8):
             assert np.array_equal(a[i], b[i]), (kernel, i)
