@@ -730,6 +730,26 @@ def test_newton_repeated_launches_are_bitwise_identical(bt, fa_ref, kernel, monk
                     assert np.array_equal(a, b, equal_nan=True), (rep, i)
 
 
+@pytest.mark.parametrize("kernel", ["duo", "ring", "ldg"])
+@pytest.mark.parametrize("N", [2, 3, 16, 17, 18, 33, 49])
+def test_newton_short_horizons(bt, fa_ref, kernel, N, monkeypatch):
+    """Horizons around the stage sizes of the TMA rings (16 steps per stage; fewer steps than one stage, exactly
+    one stage, one step more) and the degenerate N = 2 (a single time step)."""
+    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    x_ref, u_ref, _ = fa_ref
+    t0 = 150  # a stretch of the reference where the inputs are large
+    xr, ur = x_ref[t0:t0 + N].copy(), u_ref[t0:t0 + N - 1].copy()
+    x0 = xr[0] + np.random.default_rng(N).uniform(-0.1, 0.1, (5, 4))
+    st = bt.newton_solve(soa(x0), bt.make_ref(xr, ur), max_iters=3, tol=1e-9, gamma_0=0.5)
+    torch.cuda.synchronize()
+    for b in (0, 4):
+        x, u, Ko, so, h = O.newton_Algorithm(x0[b], xr, ur, max_iters=3, tol=1e-9, gamma_0=0.5)
+        assert int(st.status[b]) == h["status"] and int(st.iters[b]) == h["iters"]
+        assert rel_err(aos(st.X)[b], x) < TOL and rel_err(aos(st.U)[b], u) < TOL
+        assert rel_err(aos(st.S)[b], so) < TOL and rel_err(kmat(st.K)[b], Ko) < 1e-7
+        assert rel_err(st.hist_cost[:len(h["cost"]), b].cpu().numpy(), h["cost"]) < TOL
+
+
 def test_newton_warm_start(bt, fa_ref):
     """init = 2: start from caller-supplied inputs instead of u = 0 (the commented-out alternative at tg:310)."""
     xr, ur = _short_ref(fa_ref)
