@@ -58,6 +58,7 @@ SIGNATURES = {
     "acro_closed_loop_rollout_cost": [PP, PW, I64, I32, P, P, P, P, PR, I32, P, I32, P, P, P, P],
     "acro_armijo_select": [I64, I32, P, P, P, I32, P, F64, P, P],
     "acro_newton_solve": [PP, PW, PO, I64, I32, P, PR] + [P] * 17 + [P],
+    "acro_newton_solve_pp": [PP, P, PW, PO, I64, I32, P, PR] + [P] * 17 + [P],
     "acro_stepsize_sweep": [PP, PW, I64, I32, P, P, P, P, PR, I32, P, P, P],
     "acro_lqr_gains": [PP, PW, I64, I32, PR, P, P],
     "acro_lqr_track": [PP, I64, I32, PR, P, P, P, P, P],

@@ -358,12 +358,12 @@ def newton_alloc(Bn, N, max_iters, history=True):
 
 
 def newton_solve(x0, ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, w=None, params=DEFAULT_PARAMS,
-                 state=None, chunk_iters=0, max_line_search=20, history=True, warm_start_U=None):
+                 state=None, chunk_iters=0, max_line_search=20, history=True, warm_start_U=None, params_b=None):
     """newton_Algorithm (trajectory_generation.py:298-398) for a batch, x0 (4,B).
 
     One kernel launch runs the whole loop for every problem.  Pass the returned state back
     (with chunk_iters) to continue a solve in pieces.  warm_start_U (Traj, C=2) replaces the reference's
-    u = 0 initial guess (tg:311)."""
+    u = 0 initial guess (tg:311).  params_b (11,B): physical parameters per problem (phys_params)."""
     w = newton_weights() if w is None else w
     Bn = x0.shape[1]
     N = ref.N
@@ -376,7 +376,7 @@ def newton_solve(x0, ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, w=N
     o = AcroNewtonOpts(max_iters=int(max_iters), chunk_iters=int(chunk_iters), max_line_search=int(max_line_search),
                        init=init, tol=float(tol), beta=float(beta), c=float(c), gamma_0=float(gamma_0))
     s = state
-    call("acro_newton_solve", C.byref(params), w.ref(), C.byref(o), Bn, N, _p(x0), ref.ref(), _p(s.X), _p(s.U), _p(s.Xw),
+    call("acro_newton_solve_pp", C.byref(params), _p(params_b), w.ref(), C.byref(o), Bn, N, _p(x0), ref.ref(), _p(s.X), _p(s.U), _p(s.Xw),
          _p(s.Uw), _p(s.lin), _p(s.K), _p(s.S), _p(s.cost), _p(s.delta_J), _p(s.sigma_norm), _p(s.gamma_acc),
          _p(s.iters, torch.int32), _p(s.status, torch.int32), _p(s.hist_cost), _p(s.hist_sigma_norm), _p(s.hist_gamma),
          _p(s.hist_ntry, torch.int32), _stream())

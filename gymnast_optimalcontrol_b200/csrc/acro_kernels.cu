@@ -617,6 +617,7 @@ struct NewtonArgs {
   int64_t B;
   int N;
   const double* x0;
+  const double* pb;  // per-problem physical parameters [11][B] or nullptr (k_newton<.., PPB = true> only)
   const double *rx, *ru;
   double *X, *U, *Xw, *Uw, *lin, *K, *S;
   double *cost, *dJ, *sn, *gacc;
@@ -625,10 +626,11 @@ struct NewtonArgs {
   int32_t* h_ntry;
 };
 
-template <bool WPB, bool RPB>
+template <bool WPB, bool RPB, bool PPB = false>
 __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
   const int64_t B = a.B, b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
+  ACRO_MODEL(PPB, a.m, a.pb, B, b);
   const int N = a.N;
   const WV<WPB> w(a.kw, B, b);
   const RefV<RPB> ref{a.rx, a.ru, N, b};
@@ -654,7 +656,7 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
       }
       double xn[4];
       LinD L;
-      rk4_step_lin(a.m, x, u0, u1, xn, L);
+      rk4_step_lin(m, x, u0, u1, xn, L);
       store_lin(a.lin, t, N - 1, b, L);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -678,13 +680,13 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
     const double* Uc = cur ? a.Uw : a.U;
     double* Xo = cur ? a.X : a.Xw;
     double* Uo = cur ? a.U : a.Uw;
-    backward_pass<WPB, RPB, true>(a.m, w, ref, N, Xc, Uc, a.lin, a.K, a.S, B, b, dJ, sn);
+    backward_pass<WPB, RPB, true>(m, w, ref, N, Xc, Uc, a.lin, a.K, a.S, B, b, dJ, sn);
     if (a.h_sn) a.h_sn[int64_t(it) * B + b] = sn;
     double gamma = a.o.gamma_0, cn = 0.0;
     int tries = 0;
     bool ok = false;
     for (int i = 0; i < a.o.max_line_search; ++i) {
-      cn = forward_pass<WPB, RPB, true, true>(a.m, w, ref, N, Xc, Uc, a.K, a.S, B, b, gamma, Xo, Uo, B, b, a.lin);
+      cn = forward_pass<WPB, RPB, true, true>(m, w, ref, N, Xc, Uc, a.K, a.S, B, b, gamma, Xo, Uo, B, b, a.lin);
       ++tries;
       // accept iff cost_new < cost_k + c*gamma*delta_J  (strict, NaN rejects)   tg:361
       const double thr = __dadd_rn(cost_k, __dmul_rn(__dmul_rn(a.o.c, gamma), dJ));
@@ -1540,6 +1542,15 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
                       double* lin_ws, double* K, double* S, double* cost, double* delta_J, double* sigma_norm, double* gamma_acc,
                       int32_t* iters, int32_t* status, double* hist_cost, double* hist_sigma_norm,
                       double* hist_gamma, int32_t* hist_ntry, void* stream) {
+  return acro_newton_solve_pp(p, nullptr, w, opts, B, N, x0, ref, X, U, Xw, Uw, lin_ws, K, S, cost, delta_J, sigma_norm,
+                              gamma_acc, iters, status, hist_cost, hist_sigma_norm, hist_gamma, hist_ntry, stream);
+}
+
+int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const AcroWeights* w, const AcroNewtonOpts* opts,
+                         int64_t B, int N, const double* x0, const AcroRef* ref, double* X, double* U, double* Xw,
+                         double* Uw, double* lin_ws, double* K, double* S, double* cost, double* delta_J,
+                         double* sigma_norm, double* gamma_acc, int32_t* iters, int32_t* status, double* hist_cost,
+                         double* hist_sigma_norm, double* hist_gamma, int32_t* hist_ntry, void* stream) {
   ACRO_REQUIRE(p && w && opts && ref && ref->x && ref->u && X && U && Xw && Uw && lin_ws && K && S && cost && delta_J &&
                    sigma_norm && gamma_acc && iters && status && B > 0 && N >= 2,
                "acro_newton_solve: bad argument");
@@ -1553,6 +1564,7 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
   a.B = B;
   a.N = N;
   a.x0 = x0;
+  a.pb = params_b;
   a.rx = ref->x;
   a.ru = ref->u;
   a.X = X;
@@ -1582,6 +1594,15 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
               aligned(lin_ws, 128) && aligned(K, 128) && aligned(S, 128) &&
               aligned(ref->x, ref->per_problem ? 128 : 32) && aligned(ref->u, ref->per_problem ? 128 : 16);
   if (force && !strcmp(force, "ldg")) ring = false;
+  if (params_b) {
+    // per-problem physical parameters: the one-thread-per-problem kernel derives its model per thread
+    const Cfg c = cfg_for(B);
+#define EXPR(WPB, RPB) k_newton<WPB, RPB, true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(a)
+    DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+    ACRO_LAUNCH_CHECK("acro_newton_solve");
+    return ACRO_OK;
+  }
   if (force && !strcmp(force, "ring")) {
     ACRO_REQUIRE(aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) && aligned(lin_ws, 128) &&
                      aligned(K, 128) && aligned(S, 128),

@@ -204,7 +204,7 @@ def plot_armijo_line_search(*args, **kwargs):
 
 def newton_Algorithm(x0, x_ref, u_ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1, plot_armijo_iters=10, *,
                      Q=None, R=None, Q_T=None, return_history=False, history_stride=1, verbose=True,
-                     return_state=False):
+                     return_state=False, params_b=None):
     """Regularised Newton method with Armijo line search (trajectory_generation.py:298-398).
 
     One problem: returns ``(x_traj, u_traj, K, sigma, history)`` with the reference's types (K and sigma
@@ -212,6 +212,7 @@ def newton_Algorithm(x0, x_ref, u_ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gam
     it needs one launch per stored iterate - 'x_trajs' and 'sigmas').
     Batch (x0 of shape (B,4)): arrays with a leading batch axis; history['cost'] is (B, iters+1) padded with
     NaN past each problem's last iteration, plus 'iters', 'status', 'n_try', 'gamma'.
+    params_b (B, 11): every problem its own physical parameters (domain randomisation).
     """
     u_ref_n = u_ref.shape[0] if u_ref.ndim == 2 else u_ref.shape[1]
     x_ref_n = x_ref.shape[0] if x_ref.ndim == 2 else x_ref.shape[1]
@@ -227,6 +228,8 @@ def newton_Algorithm(x0, x_ref, u_ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gam
     ref = _ref(x_ref, u_ref)
     w = _weights(Q, R, Q_T)
     kw = dict(max_iters=max_iters, tol=tol, beta=beta, c=c, gamma_0=gamma_0, w=w, params=active_params())
+    if params_b is not None:  # physical parameters per problem (B, 11): see batched.phys_params
+        kw["params_b"] = bt.phys_params(params_b, x0d.shape[1])
     x_trajs, sigmas = [], []
 
     def snap(t, key):
@@ -235,7 +238,8 @@ def newton_Algorithm(x0, x_ref, u_ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gam
 
     if return_history:
         # history['x_trajs'][0] is the initial open-loop rollout (tg:322-327); one launch per stored iterate after that
-        x_trajs.append(snap(bt.rollout_open_loop(x0d, None, N=ref.N, params=active_params()), "hx"))
+        x_trajs.append(snap(bt.rollout_open_loop(x0d, None, N=ref.N, params=active_params(),
+                                                 params_b=kw.get("params_b")), "hx"))
         st, done = None, 0
         while True:
             st = bt.newton_solve(x0d, ref, state=st, chunk_iters=history_stride, **kw)

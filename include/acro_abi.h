@@ -219,6 +219,12 @@ int acro_linearize_pp(const AcroParams* p, const double* params_b, int64_t B, co
                       double* A, double* Bm, int discrete, void* stream);
 int acro_rollout_open_loop_pp(const AcroParams* p, const double* params_b, int64_t B, int N, const double* x0,
                               const double* U, double* X, void* stream);
+/* acro_newton_solve with per-problem physical parameters (one thread per problem; params_b = NULL: acro_newton_solve) */
+int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const AcroWeights* w, const AcroNewtonOpts* opts,
+                         int64_t B, int N, const double* x0, const AcroRef* ref, double* X, double* U, double* Xw,
+                         double* Uw, double* lin_ws, double* K, double* S, double* cost, double* delta_J,
+                         double* sigma_norm, double* gamma_acc, int32_t* iters, int32_t* status, double* hist_cost,
+                         double* hist_sigma_norm, double* hist_gamma, int32_t* hist_ntry, void* stream);
 /* the plant of every problem has its own parameters, the gains are the caller's (e.g. those of the nominal model:
  * tracking under model mismatch) */
 int acro_lqr_track_pp(const AcroParams* p, const double* params_b, int64_t B, int N, const AcroRef* traj,

@@ -167,6 +167,24 @@ def test_per_problem_physical_parameters(bt):
     assert np.array_equal(s1[0], aos(bt.rk4_step(soa(x[:1]), soa(u[:1])))[0])
 
 
+def test_newton_per_problem_physical_parameters(bt, fa_ref):
+    """The Newton / Armijo loop with every problem its own plant (domain randomisation) against the oracle."""
+    xr, ur = _short_ref(fa_ref, N=81)
+    n = 35
+    sets, rows = _random_phys(n, 9)
+    x0 = np.random.default_rng(10).uniform(-0.2, 0.2, (n, 4))
+    st = bt.newton_solve(soa(x0), bt.make_ref(xr, ur), max_iters=4, tol=1e-6, gamma_0=0.5, params_b=bt.phys_params(rows))
+    torch.cuda.synchronize()
+    X, U, K, S = aos(st.X), aos(st.U), kmat(st.K), aos(st.S)
+    for b in (0, 1, 2, 3, 17, 31, 32, 34):
+        x, u, Ko, so, h = O.newton_Algorithm(x0[b], xr, ur, max_iters=4, tol=1e-6, gamma_0=0.5, m=O.Model(sets[b]))
+        assert int(st.status[b]) == h["status"] and int(st.iters[b]) == h["iters"]
+        assert list(st.hist_ntry[:len(h["n_try"]), b].cpu().numpy()) == h["n_try"]
+        assert rel_err(st.hist_cost[:len(h["cost"]), b].cpu().numpy(), h["cost"]) < TOL
+        assert rel_err(X[b], x) < TOL and rel_err(U[b], u) < TOL
+        assert rel_err(S[b], so) < TOL and rel_err(K[b], Ko) < 1e-7
+
+
 def test_pack_unpack(bt):
     rng = np.random.default_rng(0)
     for shape in ((1, 501, 4), (37, 500, 2), (300, 3, 8), (64, 7, 10), (65, 4)):
