@@ -66,6 +66,8 @@ SIGNATURES = {
     "acro_mpc_solve": [PW, I64, I32, P, P, P, P, P, P, P, P, P],
     "acro_mpc_track": [PP, PW, I64, I32, I32, I32, PR, C.POINTER(C.c_double), C.POINTER(C.c_double), P, I32, P, P, P,
                        P, P, C.POINTER(C.c_int64), P],
+    "acro_mpc_track_box": [PP, PW, I64, I32, I32, I32, PR, C.POINTER(C.c_double), C.POINTER(C.c_double), P, I32, P, F64, I32,
+                           P, P, P, P, P, P, P, P],
     "acro_bench_fp64_peak": [I32, I32, I32, P, P],
     "acro_bench_fp64_chain": [I32, I32, I32, I32, I32, P, P, P],
     "acro_transpose": [I64, I64, P, P, P],
@@ -73,6 +75,7 @@ SIGNATURES = {
     "acro_unpack_soa": [I64, I32, I32, P, P, P],
 }
 QUERIES = {"acro_version": C.c_char_p, "acro_last_error_string": C.c_char_p, "acro_launch_count": C.c_int64}
+SIZES = {"acro_mpc_box_ws_doubles": ([I64, I32], C.c_int64)}
 
 
 class AcroError(RuntimeError):
@@ -92,6 +95,10 @@ def _load():
     for name, res in QUERIES.items():
         f = getattr(lib, name)
         f.argtypes = []
+        f.restype = res
+    for name, (args, res) in SIZES.items():
+        f = getattr(lib, name)
+        f.argtypes = args
         f.restype = res
     return lib
 

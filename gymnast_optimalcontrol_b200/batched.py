@@ -458,6 +458,29 @@ def mpc_track(x0, ref, QT_inf, T=None, T_pred=75, w=None, x_f=(np.pi, 0.0, 0.0, 
     return Xr, Ur, K0, int(ns.value)
 
 
+def mpc_track_box(x0, ref, QT_inf, tau_max=18.0, T=None, T_pred=75, w=None, x_f=(np.pi, 0.0, 0.0, 0.0), u_f=(0.0, 0.0),
+                  params=DEFAULT_PARAMS, max_iter=0):
+    """solve_mpc_tracking with the input box -tau_max <= u + u_ref <= tau_max of tt:87-91, 112-114 switched on; every
+    step is solved exactly (active set on Riccati sweeps).  -> Xr Traj, Ur Traj, info {n_sweeps (B,), n_active (T-1,B),
+    status (B,)}"""
+    from ._abi import lib
+    w = mpc_weights() if w is None else w
+    N, Bn = ref.N, x0.shape[1]
+    T = N if T is None else T
+    qt_pp = QT_inf.dim() == 3
+    Xr, Ur = Traj.empty(T, 4, Bn), Traj.empty(T - 1, 2, Bn)
+    lin = Traj.empty(N - 1, 10, Bn) if ref.per_problem else _empty(N - 1, 10)
+    ws = _empty(int(lib.acro_mpc_box_ws_doubles(Bn, int(T_pred))))
+    ns, st = _empty(Bn, dtype=torch.int32), _empty(Bn, dtype=torch.int32)
+    na = _empty(T - 1, Bn, dtype=torch.int32)
+    xf = (C.c_double * 4)(*[float(v) for v in x_f])
+    uf = (C.c_double * 2)(*[float(v) for v in u_f])
+    call("acro_mpc_track_box", C.byref(params), w.ref(), Bn, N, int(T), int(T_pred), ref.ref(), xf, uf, _p(QT_inf), int(qt_pp),
+         _p(x0), float(tau_max), int(max_iter), _p(lin), _p(ws), _p(Xr), _p(Ur), _p(ns, torch.int32), _p(na, torch.int32),
+         _p(st, torch.int32), _stream())
+    return Xr, Ur, {"n_sweeps": ns, "n_active": na, "status": st}
+
+
 # ------------------------------------------------------------------------------------------
 # stand-alone pieces of the Newton iteration (for the drop-in functions that expose them)
 # ------------------------------------------------------------------------------------------

@@ -1284,6 +1284,10 @@ __global__ void k_mpc_track_pp(const __grid_constant__ MpcArgs a) {
   }
 }
 
+}  // namespace acro
+#include "acro_mpc_box.cuh"
+namespace acro {
+
 // ---------------------------------------------------------------------------------------
 // layout helpers, tiled through shared memory
 // ---------------------------------------------------------------------------------------
@@ -1882,6 +1886,57 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
     ACRO_LAUNCH_CHECK("acro_mpc_track/track");
     if (n_solves) *n_solves = int64_t(T - 1) * B;
   }
+  return ACRO_OK;
+}
+
+int64_t acro_mpc_box_ws_doubles(int64_t B, int T_pred) { return mpc_box_ws_per_problem(T_pred) * B; }
+
+int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
+                       const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                       int qt_per_problem, const double* x0, double tau_max, int max_iter, double* lin_ws, double* ws,
+                       double* Xr, double* Ur, int32_t* n_sweeps, int32_t* n_active, int32_t* status, void* stream) {
+  ACRO_REQUIRE(p && w && ref && ref->x && ref->u && x_f && u_f && QT_inf && x0 && lin_ws && ws && Xr && Ur && B > 0 &&
+                   N >= 2 && T >= 2 && T <= N && T_pred >= 2 && tau_max > 0.0,
+               "acro_mpc_track_box: bad argument");
+  ACRO_REQUIRE(!p->actuated_tau1, "acro_mpc_track_box: fully-actuated plant not supported here");
+  ACRO_REQUIRE(!per_problem_weights(*w), "acro_mpc_track_box: per-problem weights not supported here");
+  ACRO_REQUIRE(w->R[1] == 0.0 && w->R[2] == 0.0, "acro_mpc_track_box: R must be diagonal");
+  MpcBoxArgs a;
+  a.m = make_model(*p);
+  a.kw = make_weights(*w);
+  a.B = B;
+  a.N = N;
+  a.T = T;
+  a.H = T_pred;
+  a.rx = ref->x;
+  a.ru = ref->u;
+  for (int i = 0; i < 4; ++i) a.xf[i] = x_f[i];
+  for (int i = 0; i < 2; ++i) a.uf[i] = u_f[i];
+  a.QT = QT_inf;
+  a.qt_per_problem = qt_per_problem;
+  a.x0 = x0;
+  a.lin = lin_ws;
+  a.ws = ws;
+  a.tau = tau_max;
+  a.max_iter = max_iter > 0 ? max_iter : 6 * (T_pred - 1) + 20;
+  a.Xr = Xr;
+  a.Ur = Ur;
+  a.n_sweeps = n_sweeps;
+  a.n_active = n_active;
+  a.status = status;
+  cudaStream_t s = (cudaStream_t)stream;
+  const Cfg c = cfg_for(B);
+  if (ref->per_problem) {
+    const int64_t n = int64_t(N - 1) * B;
+    k_lin_compact<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
+    ACRO_LAUNCH_CHECK("acro_mpc_track_box/linearize");
+    k_mpc_track_box<true><<<c.grid, c.block, 0, s>>>(a);
+  } else {
+    k_lin_compact<false><<<(N - 1 + 63) / 64, 64, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
+    ACRO_LAUNCH_CHECK("acro_mpc_track_box/linearize");
+    k_mpc_track_box<false><<<c.grid, c.block, 0, s>>>(a);
+  }
+  ACRO_LAUNCH_CHECK("acro_mpc_track_box");
   return ACRO_OK;
 }
 

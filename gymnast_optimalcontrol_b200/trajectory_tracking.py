@@ -81,8 +81,11 @@ def solver_mpc(x0, A_list, B_list, Q, R, Q_T, T_pred, u_ref=None):
     return U0.cpu().numpy()[:, 0], Xo.batch_major()[0].cpu().numpy(), Uo.batch_major()[0].cpu().numpy()
 
 
-def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return_info=False):
-    """trajectory_tracking.py:8-69.  x0 (4,) or (B,4); reference shared (N,4) or per problem (B,N,4)."""
+def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return_info=False, tau_max=None):
+    """trajectory_tracking.py:8-69.  x0 (4,) or (B,4); reference shared (N,4) or per problem (B,N,4).
+
+    tau_max: switches on the input box the reference keeps behind `test_constraints` (tt:87-91, 112-114; 18 there):
+    -tau_max <= u + u_ref <= tau_max at every step of every horizon, each QP solved exactly."""
     w = bt.Weights(Q_mpc if Q is None else Q, R_mpc if R is None else R)
     p = active_params()
     x0d, kind = _io.state_in(x0, nx)
@@ -94,6 +97,17 @@ def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return
     P, n = bt.p_inf(A_f, B_f, w)
     if int(n[0]) < 0:
         print("P_inf did not converge!!!")
+    if tau_max is not None:
+        Xr, Ur, info = bt.mpc_track_box(x0d, ref, P[:, :, 0].contiguous(), tau_max=float(tau_max), T=int(T),
+                                        T_pred=int(T_pred), w=w, x_f=x_f, u_f=u_f, params=p)
+        if int(info["status"].max()) != 0:
+            print("Attention! mpc solver: active-set iteration limit reached for %d problem(s)" % int((info["status"] != 0).sum()))
+        xr, ur = _io.out(Xr, kind, key="xr"), _io.out(Ur, kind, key="ur")
+        if return_info:
+            return xr, ur, dict(n_solves=(int(T) - 1) * x0d.shape[1], n_sweeps=info["n_sweeps"].cpu().numpy(),
+                                n_active=info["n_active"].cpu().numpy().T, status=info["status"].cpu().numpy(),
+                                P_inf=P.cpu().numpy()[:, :, 0])
+        return xr, ur
     Xr, Ur, K0, n_solves = bt.mpc_track(x0d, ref, P[:, :, 0].contiguous(), T=int(T), T_pred=int(T_pred), w=w,
                                         x_f=x_f, u_f=u_f, params=p)
     xr, ur = _io.out(Xr, kind, key="xr"), _io.out(Ur, kind, key="ur")

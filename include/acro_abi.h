@@ -264,6 +264,21 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
                    double* Ur, int64_t* n_solves, void* stream);
 
 /* ---- measurement helper ------------------------------------------------------------- */
+/* solve_mpc_tracking with the input box of trajectory_tracking.py:87-91, 102-104, 112-114 switched on
+ * (`test_constraints`): every receding-horizon step solves
+ *     min sum_{j<T_pred-1} x_j'Q x_j + u_j'R u_j + x_{T_pred-1}' Q_T x_{T_pred-1},  x_{j+1} = A_j x_j + B_j u_j,
+ *     -tau_max <= u_j + u_ref[t+j] <= tau_max
+ * exactly (primal active-set method on Riccati sweeps, csrc/acro_mpc_box.cuh) and applies u_ref[t] + u_0 to the plant.
+ * R must be diagonal, weights shared.  Reference shared or per problem; lin_ws as in acro_mpc_track;
+ * ws: acro_mpc_box_ws_doubles(B, T_pred) doubles of scratch.  max_iter <= 0: 6 (T_pred-1) + 20 iterations per step.
+ * Out: Xr {T x 4}, Ur {T-1 x 2}; optional n_sweeps [B] (active-set iterations of the problem), n_active [T-1][B]
+ * (inputs at a bound in the solution of step t), status [B] (1 if a step hit max_iter, else 0). */
+int64_t acro_mpc_box_ws_doubles(int64_t B, int T_pred);
+int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
+                       const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                       int qt_per_problem, const double* x0, double tau_max, int max_iter, double* lin_ws, double* ws,
+                       double* Xr, double* Ur, int32_t* n_sweeps, int32_t* n_active, int32_t* status, void* stream);
+
 /* Runs blocks x threads threads, each doing iters x 8 independent dependent-chain DFMAs
  * (16 flops per thread per iteration); out [blocks*threads].  Timed by bench.py to get the
  * achievable FP64 pipe peak of the device it runs on. */

@@ -484,6 +484,107 @@ def solver_mpc(x0, A_list, B_list, Q, R, Q_T, T_pred, u_ref=None):
     return U[0].copy(), X, U
 
 
+def solver_mpc_box(x0, A_list, B_list, Q, R, Q_T, T_pred, u_ref, tau_max=18.0, return_info=False):
+    """solver_mpc with the input constraints the reference keeps behind `test_constraints` (tt:87-91, 112-114):
+    -tau_max <= U[:, t] + u_ref[t] <= tau_max for t < T_pred - 1.
+
+    The reference hands this QP to IPOPT (tol 1e-6).  Here it is solved exactly: states eliminated (condensed QP in
+    the inputs), primal active-set method with dense solves.  R must be diagonal; the first input does not act on
+    the plant (B[:, 0] = 0, dynamics.py:153), so it is min R00 u0^2 on its interval, i.e. the point closest to 0.
+    Returns (U0, X_opt (T_pred,4), U_opt (T_pred,2)); U_opt[T_pred-1] = 0 as in solver_mpc."""
+    H = T_pred
+    n = H - 1
+    Q, R, Q_T = (np.asarray(M, dtype=float) for M in (Q, R, Q_T))
+    assert R[0, 1] == 0.0 and R[1, 0] == 0.0, "solver_mpc_box: R must be diagonal"
+    u_ref = np.asarray(u_ref, dtype=float)[:n]
+    A = [np.asarray(a, dtype=float) for a in A_list[:n]]
+    b = [np.asarray(Bm, dtype=float)[:, 1] for Bm in B_list[:n]]
+    assert all(np.all(np.asarray(Bm)[:, 0] == 0.0) for Bm in B_list[:n]), "solver_mpc_box: B[:, 0] must vanish"
+    x0 = np.asarray(x0, dtype=float)
+    Phi = [np.eye(4)]
+    for j in range(n):
+        Phi.append(A[j] @ Phi[-1])
+    G = np.zeros((H, 4, n))
+    for j in range(n):
+        col = b[j]
+        G[j + 1, :, j] = col
+        for t in range(j + 2, H):
+            col = A[t - 1] @ col
+            G[t, :, j] = col
+    Hq = np.eye(n) * R[1, 1]
+    f = np.zeros(n)
+    for t in range(H):
+        W = Q_T if t == H - 1 else Q
+        Hq += G[t].T @ W @ G[t]
+        f += G[t].T @ W @ (Phi[t] @ x0)
+    lo, hi = -tau_max - u_ref[:, 1], tau_max - u_ref[:, 1]
+    v = np.clip(np.zeros(n), lo, hi)
+    act = np.where(v >= hi, 1, np.where(v <= lo, -1, 0))
+    iters = 0
+    for iters in range(1, 20 * n + 20):
+        F = act == 0
+        vA = np.where(act == 1, hi, np.where(act == -1, lo, 0.0))
+        vn = vA.copy()
+        if F.any():
+            vn[F] = np.linalg.solve(Hq[np.ix_(F, F)], -(f[F] + Hq[np.ix_(F, ~F)] @ vA[~F]))
+        dv = vn - v
+        alpha, jb, sg = 1.0, -1, 0
+        for j in np.where(F)[0]:
+            if vn[j] > hi[j] and dv[j] > 0:
+                a_ = (hi[j] - v[j]) / dv[j]
+                if a_ < alpha:
+                    alpha, jb, sg = a_, j, 1
+            elif vn[j] < lo[j] and dv[j] < 0:
+                a_ = (lo[j] - v[j]) / dv[j]
+                if a_ < alpha:
+                    alpha, jb, sg = a_, j, -1
+        if jb >= 0:
+            v = v + alpha * dv
+            act[jb] = sg
+            v[jb] = hi[jb] if sg == 1 else lo[jb]
+            continue
+        v = vn
+        grad = 2.0 * (Hq @ v + f)
+        scale = 2.0 * (np.abs(Hq) @ np.abs(v) + np.abs(f))
+        wrong = ((act == 1) & (grad > 1e-10 * scale)) | ((act == -1) & (grad < -1e-10 * scale))
+        if not wrong.any():
+            break
+        jw = np.where(wrong)[0][np.argmax((np.abs(grad) / scale)[wrong])]
+        act[jw] = 0
+    X = np.array([Phi[t] @ x0 + G[t] @ v for t in range(H)])
+    U = np.zeros((H, 2))
+    U[:n, 1] = v
+    U[:n, 0] = np.clip(0.0, -tau_max - u_ref[:, 0], tau_max - u_ref[:, 0])
+    if return_info:
+        return U[0].copy(), X, U, {"active": act, "iterations": iters, "H": Hq, "f": f, "lo": lo, "hi": hi}
+    return U[0].copy(), X, U
+
+
+def solve_mpc_tracking_box(x0, x_ref, u_ref, T, T_pred=75, tau_max=18.0, Q=Q_MPC, R=R_MPC, m=DEFAULT, Q_T=None):
+    """solve_mpc_tracking (tt:8-69) with the input box of tt:112-114 switched on, ONE problem (x0 (4,)):
+    every step solves solver_mpc_box on the sliding window and applies u_ref[t] + U0 to the plant."""
+    x_ref = np.asarray(x_ref, dtype=float)
+    u_ref = np.asarray(u_ref, dtype=float)
+    N = x_ref.shape[0]
+    Ad, Bd = linearize_discrete(x_ref[:-1], u_ref, m)
+    A_f, B_f = linearize_discrete(X_F, U_F, m)
+    Q_T = compute_P_inf(A_f, B_f, Q, R) if Q_T is None else np.asarray(Q_T, dtype=float)
+    xr = np.zeros((T, 4))
+    ur = np.zeros((T - 1, 2))
+    xr[0] = x0
+    n_active = np.zeros(T - 1, dtype=int)
+    for t in range(T - 1):
+        Aw = [Ad[t + j] if t + j < N - 1 else A_f for j in range(T_pred - 1)]
+        Bw = [Bd[t + j] if t + j < N - 1 else B_f for j in range(T_pred - 1)]
+        uw = np.array([u_ref[t + j] if t + j < N - 1 else U_F for j in range(T_pred - 1)])
+        xw = x_ref[t] if t < N else X_F
+        U0, _, _, info = solver_mpc_box(xr[t] - xw, Aw, Bw, Q, R, Q_T, T_pred, uw, tau_max, return_info=True)
+        n_active[t] = int((info["active"] != 0).sum())
+        ur[t] = uw[0] + U0
+        xr[t + 1] = dynamics(xr[t], ur[t], m)
+    return xr, ur, n_active
+
+
 def solve_mpc_tracking(x0, x_ref, u_ref, T, T_pred=75, Q=Q_MPC, R=R_MPC, m=DEFAULT, return_gains=False):
     """Receding-horizon tracking loop (tt:8-69) for ONE reference; x0 may carry batch axes.
 

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     for n in names:
         assert hasattr(lib, n), "libacro_b200.so does not export %s" % n
-    bound = set(_abi.SIGNATURES) | set(_abi.QUERIES)
+    bound = set(_abi.SIGNATURES) | set(_abi.QUERIES) | set(_abi.SIZES)
     assert set(names) == bound, (set(names) ^ bound)
     assert b"sm_100a" in lib.acro_version.__call__.__self__.acro_version() if False else True
     assert "sm_100a" in _abi.version()

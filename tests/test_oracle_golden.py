@@ -202,3 +202,38 @@ def test_reference_gains_carry_rounding_noise_near_convergence(fa_ref):
     b = golden("newton_task2_blocks")
     K0, S0 = riccati_ld(b["x_open"], np.zeros((500, 2)), x_ref, u_ref)
     assert rel_err(b["K0"], K0.astype(float)) < 1e-12
+
+
+def test_box_constrained_mpc_oracle_against_scipy_bvls():
+    """solver_mpc_box (dense primal active set) against SciPy's bounded-variable least squares on the same condensed
+    QP: min v'Hv + 2f'v = |L'v + L^-1 f|^2, lo <= v <= hi.  Windows of the shipped trajectory where the box binds."""
+    from scipy.optimize import lsq_linear
+    d = golden("acrobot_optimal_trajectory")
+    g = golden("p_inf")
+    x_ref, u_ref = d["x"], d["u"]
+    N = 501
+    Ad, Bd = O.linearize_discrete(x_ref[:-1], u_ref)
+    rng = np.random.default_rng(1)
+    n_bound = 0
+    for t0, H, tau in ((170, 40, 18.0), (227, 50, 12.0), (60, 30, 18.0), (410, 75, 18.0), (300, 20, 8.0)):
+        Aw = [Ad[t0 + j] if t0 + j < N - 1 else g["A_f"] for j in range(H - 1)]
+        Bw = [Bd[t0 + j] if t0 + j < N - 1 else g["B_f"] for j in range(H - 1)]
+        uw = np.array([u_ref[t0 + j] if t0 + j < N - 1 else O.U_F for j in range(H - 1)])
+        x0 = rng.uniform(-0.1, 0.1, 4)
+        U0, X, U, info = O.solver_mpc_box(x0, Aw, Bw, O.Q_MPC, O.R_MPC, g["P_inf"], H, uw, tau, return_info=True)
+        L = np.linalg.cholesky(info["H"])
+        r = lsq_linear(L.T, -np.linalg.solve(L, info["f"]), bounds=(info["lo"], info["hi"]), method="bvls", tol=1e-15,
+                       max_iter=5000)
+        assert np.abs(r.x - U[:H - 1, 1]).max() <= 1e-9 * max(1.0, np.abs(r.x).max())
+        assert (np.abs(U[:H - 1] + uw) <= tau * (1 + 1e-12)).all()
+        # the states are those of the window dynamics under U
+        x = x0.copy()
+        for j in range(H - 1):
+            assert np.abs(X[j] - x).max() < 1e-9 * max(1.0, np.abs(x).max())
+            x = Aw[j] @ x + Bw[j] @ U[j]
+        n_bound += int((info["active"] != 0).sum())
+        # a box that cannot bind gives solver_mpc
+        U0u, Xu, Uu = O.solver_mpc(x0, Aw, Bw, O.Q_MPC, O.R_MPC, g["P_inf"], H)
+        U0b, Xb, Ub = O.solver_mpc_box(x0, Aw, Bw, O.Q_MPC, O.R_MPC, g["P_inf"], H, uw, 1e9)
+        assert rel_err(Ub, Uu) < 1e-8 and rel_err(Xb, Xu) < 1e-8
+    assert n_bound > 20
