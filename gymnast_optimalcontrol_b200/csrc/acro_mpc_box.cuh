@@ -19,8 +19,8 @@
 //
 // Finite termination, no tolerance on the answer other than rounding; consecutive MPC steps warm-start from the
 // shifted solution (typically one or two sweeps per step).  Per-problem scratch lives in a caller-supplied workspace
-// ws[e][B] (e fastest across problems: coalesced).  The oracle (oracle/acro_oracle.py: solver_mpc_box) solves the same
-// QP with dense matrices; the reference itself would hand it to IPOPT (tol 1e-6): parity against IPOPT is unpinned.
+// ws[e][B] (e fastest across problems: coalesced).  The tests compare it with the same QP condensed and solved with
+// dense matrices; the reference itself would hand it to IPOPT (tol 1e-6): parity against IPOPT is unpinned.
 #pragma once
 #include "acro_device.cuh"
 #include "acro_views.cuh"
