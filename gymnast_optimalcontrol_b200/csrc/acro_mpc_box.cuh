@@ -230,13 +230,14 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
       }
       // ---- forward sweep (closed loop): minimiser over the free inputs, blocking input
       double alpha = 1.0, dmax = 0.0, vmax = 0.0;
-      int jb = -1;
+      int jb = -1, nheld = 0;
       double sb = 0.0;
       {
         double xs[4] = {x0w[0], x0w[1], x0w[2], x0w[3]};
         for (int j = 0; j < n; ++j) {
           const double vj = V(j), wj = Wk(j);
           double vs = vj;
+          nheld += (wj != 0.0);
           if (wj == 0.0) {
             vs = fma(Kg(j, 3), xs[3], fma(Kg(j, 2), xs[2], fma(Kg(j, 1), xs[1], fma(Kg(j, 0), xs[0], kg(j)))));
             const double ur = uref1(t + j), lo = -tau - ur, hi = tau - ur, d = vs - vj;
@@ -276,6 +277,7 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
       }
       if (dmax > 1e-11 * (1.0 + vmax)) {  // full step to the minimiser of the current working set
         for (int j = 0; j < n; ++j) V(j) = Vs(j);
+        if (nheld == 0) break;  // nothing is held: the unconstrained minimiser lies inside the box, done
         rollout();
         continue;
       }
