@@ -102,12 +102,15 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
   for (int t = 0; t < a.T - 1; ++t) {
     // ---- start: the previous solution shifted by one step (same absolute times, hence still feasible), the new last
     // input at the point of its interval closest to 0; W = the inputs that sit on a bound
+    int held = 0;  // inputs in the working set
     for (int j = 0; j < n; ++j) {
       const double ur = uref1(t + j), lo = -tau - ur, hi = tau - ur;
       double v = (t > 0 && j + 1 < n) ? V(j + 1) : 0.0;
       v = fmin(fmax(v, lo), hi);
       V(j) = v;
-      Wk(j) = (v >= hi) ? 1.0 : ((v <= lo) ? -1.0 : 0.0);
+      const double wj = (v >= hi) ? 1.0 : ((v <= lo) ? -1.0 : 0.0);
+      Wk(j) = wj;
+      held += (wj != 0.0);
     }
     double x0w[4];
 #pragma unroll
@@ -126,14 +129,16 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) Xb(n, c) = xs[c];
     };
-    rollout();
+    // the state trajectory of v is only needed for the multipliers of held inputs
+    if (held > 0) rollout();
     int it = 0;
     for (; it < a.max_iter; ++it) {
+      const bool need_lam = held > 0;
       // ---- backward sweep
       double P[10], p[4] = {0.0, 0.0, 0.0, 0.0}, lam[4];
 #pragma unroll
       for (int e = 0; e < 10; ++e) P[e] = QT[e];
-      {
+      if (need_lam) {
         double xe[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) xe[c] = Xb(n, c);
@@ -144,6 +149,9 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
           for (int c = 1; c < 4; ++c) s = fma(P[sym(i, c)], xe[c], s);
           lam[i] = s;  // half the gradient of the cost with respect to the state
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lam[i] = 0.0;
       }
       int jw = -1;
       double worst = 0.0;
@@ -216,28 +224,29 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) p[c] = pn[c];
         // costate: lam_j = Q xb_j + A_d' lam_{j+1}
-        double xe[4], al[4];
+        if (need_lam) {
+          double xe[4], al[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) xe[c] = Xb(j, c);
-        box_At(L, dt, lam, al);
+          for (int c = 0; c < 4; ++c) xe[c] = Xb(j, c);
+          box_At(L, dt, lam, al);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          double s = w.Q(i, 0) * xe[0];
+          for (int i = 0; i < 4; ++i) {
+            double s = w.Q(i, 0) * xe[0];
 #pragma unroll
-          for (int c = 1; c < 4; ++c) s = fma(w.Q(i, c), xe[c], s);
-          lam[i] = s + al[i];
+            for (int c = 1; c < 4; ++c) s = fma(w.Q(i, c), xe[c], s);
+            lam[i] = s + al[i];
+          }
         }
       }
       // ---- forward sweep (closed loop): minimiser over the free inputs, blocking input
       double alpha = 1.0, dmax = 0.0, vmax = 0.0;
-      int jb = -1, nheld = 0;
+      int jb = -1;
       double sb = 0.0;
       {
         double xs[4] = {x0w[0], x0w[1], x0w[2], x0w[3]};
         for (int j = 0; j < n; ++j) {
           const double vj = V(j), wj = Wk(j);
           double vs = vj;
-          nheld += (wj != 0.0);
           if (wj == 0.0) {
             vs = fma(Kg(j, 3), xs[3], fma(Kg(j, 2), xs[2], fma(Kg(j, 1), xs[1], fma(Kg(j, 0), xs[0], kg(j)))));
             const double ur = uref1(t + j), lo = -tau - ur, hi = tau - ur, d = vs - vj;
@@ -272,17 +281,19 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         const double ur = uref1(t + jb);
         V(jb) = (sb > 0.0) ? tau - ur : -tau - ur;
         Wk(jb) = sb;
+        ++held;
         rollout();
         continue;
       }
       if (dmax > 1e-11 * (1.0 + vmax)) {  // full step to the minimiser of the current working set
         for (int j = 0; j < n; ++j) V(j) = Vs(j);
-        if (nheld == 0) break;  // nothing is held: the unconstrained minimiser lies inside the box, done
+        if (held == 0) break;  // nothing is held: the unconstrained minimiser lies inside the box, done
         rollout();
         continue;
       }
       if (jw >= 0) {  // at the minimiser: release the input whose multiplier has the wrong sign
         Wk(jw) = 0.0;
+        --held;
         continue;
       }
       break;  // optimal
