@@ -92,9 +92,29 @@ class ClockSampler:
             self.proc.terminate()
             self.thread.join(timeout=2)
 
-    def summary(self):
+    def wait_first_row(self, timeout=8.0):
+        """nvidia-smi needs a second or more to start on an 8-GPU box: block until it streams."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        return len(self.rows)
+
+    def summary(self, lo=0, hi=None):
+        """Rows lo:hi (the timed region); if the region was too short to be sampled, every row so far (the warm-up
+        steps before it run the same kernels on the same inputs)."""
+        rows = self.rows[lo:hi]
+        window = "timed region"
+        if not rows:
+            rows, window = list(self.rows), "warm-up + timed region (timed region shorter than the sampling interval)"
+        out = self._summary(rows)
+        out["window"] = window
+        return out
+
+    def _summary(self, rows):
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -316,18 +336,22 @@ def run_native(a):
             summ = sharding.pack_summary(state.cost, state.status, state.iters, state.gamma_acc, state.sigma_norm)
             gathered["summary"] = sharding.gather_summary(summ, B * world)
 
-    # ---- device-resident throughput
-    for _ in range(a.warmup):
-        step_device()
-    barrier()
-    l0 = _abi.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- device-resident throughput (the clock sampler runs from before the warm-up: nvidia-smi takes its time to start)
     with ClockSampler(local) as clk:
+        clk.wait_first_row()
+        for _ in range(a.warmup):
+            step_device()
+        barrier()
+        l0 = _abi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = clk.mark()
         e0.record()
         for _ in range(a.steps):
             step_device()
         e1.record()
         barrier()
+        c1 = clk.mark()
+    clocks = clk.summary(c0, c1)
     launches = _abi.launch_count() - l0
     t_dev = e0.elapsed_time(e1) * 1e-3
     done_iters = int(state.iters.sum().item())
@@ -406,7 +430,7 @@ def run_native(a):
             "step_iters_per_sec": value * (N_STEPS - 1), "newton_iters_per_sec_10k_step_equivalent": value * (N_STEPS - 1) / 1e4,
             "e2e": {"value": e2e_value, "unit": "Newton iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / a.steps, "api": "trajectory_generation.newton_Algorithm(x0[B,4] pinned host, x_ref, u_ref)"},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(), "mpc": mpc,
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "mpc": mpc,
             "check": {"iterations_done_last_step_rank0": done_iters, "armijo_tries_mean": ntry_mean, "mean_final_cost": cost_mean,
                       "e2e_mean_final_cost": e2e_cost_mean},
         }
