@@ -571,14 +571,16 @@ def test_mpc_tracking_with_input_box(bt):
     refs = bt.make_ref(xs, us)
     x0 = xs[0] + rng.uniform(-0.05, 0.05, (5, 4))
     x0[0] = xs[0]
-    for tau, H in ((18.0, 30), (12.0, 20)):
+    for tau, H in ((18.0, 30), (12.0, 20), (8.0, 40)):
         Xr, Ur, info = bt.mpc_track_box(soa(x0), refs, QT, tau_max=tau, T=T, T_pred=H, w=w)
         torch.cuda.synchronize()
         Xr, Ur = aos(Xr), aos(Ur)
+        if (tau, H) == (12.0, 20):
+            Ur_12 = Ur
         assert int(info["status"].max()) == 0
         na = info["n_active"].cpu().numpy()
         assert np.abs(Ur).max() <= tau * (1 + 1e-12)
-        for b in (0, 3):
+        for b in range(5):
             xo, uo, nao = O.solve_mpc_tracking_box(x0[b], xs, us, T, T_pred=H, tau_max=tau, Q_T=g["P_inf"])
             assert rel_err(Ur[b], uo) < 1e-8 and rel_err(Xr[b], xo) < 1e-8
             assert nao.max() > 0 and np.abs(na[:, b] - nao).max() <= 1   # the box really binds, same active sets
@@ -591,7 +593,7 @@ def test_mpc_tracking_with_input_box(bt):
     n = len(x0)
     refp = bt.Ref(soa(np.repeat(xs[None], n, 0)), soa(np.repeat(us[None], n, 0)))
     Xp, Up, _ = bt.mpc_track_box(soa(x0), refp, QT, tau_max=12.0, T=T, T_pred=20, w=w)
-    assert rel_err(aos(Up), Ur) < 1e-10
+    assert rel_err(aos(Up), Ur_12) < 1e-10
 
 
 # ------------------------------------------------------------------------------------- full-size properties
