@@ -831,6 +831,35 @@ def test_newton_short_horizons(bt, fa_ref, kernel, N, monkeypatch):
         assert rel_err(st.hist_cost[:len(h["cost"]), b].cpu().numpy(), h["cost"]) < TOL
 
 
+@pytest.mark.parametrize("kernel", ["duo", "ring", "ldg"])
+def test_newton_non_finite_problems_do_not_disturb_their_neighbours(bt, fa_ref, kernel, monkeypatch):
+    """NaN / inf / absurd initial states in some lanes of a warp: the reference's `cost_new < ...` is False for NaN, so
+    those problems fail the line search at the first iteration (status 3, iterate kept); every other lane gives the
+    same bits as in a batch without them."""
+    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    xr, ur = _short_ref(fa_ref)
+    x0 = np.random.default_rng(41).uniform(-0.2, 0.2, (40, 4))
+    bad = {3: np.nan, 17: np.inf, 33: -np.inf}
+    x0b = x0.copy()
+    for b, v in bad.items():
+        x0b[b, b % 4] = v
+    x0b[20] = [1e12, -3e11, 0.0, 0.0]   # finite, far beyond the range of the polynomial sincos
+    ref = bt.make_ref(xr, ur)
+    a = bt.newton_solve(soa(x0), ref, max_iters=4, tol=1e-6, gamma_0=0.5)
+    c = bt.newton_solve(soa(x0b), ref, max_iters=4, tol=1e-6, gamma_0=0.5)
+    torch.cuda.synchronize()
+    Xa, Xc, Ua, Uc = aos(a.X), aos(c.X), aos(a.U), aos(c.U)
+    good = [b for b in range(40) if b not in bad and b != 20]
+    assert np.array_equal(Xa[good], Xc[good]) and np.array_equal(Ua[good], Uc[good])
+    assert torch.equal(a.iters[good], c.iters[good]) and torch.equal(a.status[good], c.status[good])
+    for b in bad:
+        assert int(c.status[b]) == 3 and int(c.iters[b]) == 1 and int(c.hist_ntry[0, b]) == 20
+        assert not np.isfinite(Xc[b]).all() and float(np.abs(Uc[b]).max()) == 0.0
+    # the huge-angle problem follows the oracle (library sincos): same decisions
+    x, u, Ko, so, h = O.newton_Algorithm(x0b[20], xr, ur, max_iters=4, tol=1e-6, gamma_0=0.5)
+    assert int(c.status[20]) == h["status"] and int(c.iters[20]) == h["iters"]
+
+
 def test_newton_warm_start(bt, fa_ref):
     """init = 2: start from caller-supplied inputs instead of u = 0 (the commented-out alternative at tg:310)."""
     xr, ur = _short_ref(fa_ref)
