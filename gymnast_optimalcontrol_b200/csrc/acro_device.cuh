@@ -150,15 +150,11 @@ __device__ __forceinline__ Eom eom(const Model& m, const Trig& t, double w1, dou
   const double hs2 = m.h * t.s2;
   const double grav2 = m.g2 * t.s12;
   const double grav1 = fma(m.g1, t.s1, grav2);
-  // r1 = tau1 + h s2 w2 w1 + h s2 (w1+w2) w2 - f1 w1 - G1 ; r2 = u1 - h s2 w1^2 - f2 w2 - G2
-  double r1;
-  if (ACT) {
-    const double tau1 = (m.tau1 != 0.0) ? m.tau1 * u0 : 0.0;
-    r1 = tau1 + hs2 * w2 * w1 + hs2 * (w1 + w2) * w2 - m.f1 * w1 - grav1;
-  } else {
-    r1 = hs2 * w2 * w1 + hs2 * (w1 + w2) * w2 - m.f1 * w1 - grav1;
-  }
-  const double r2 = u1 - hs2 * w1 * w1 - m.f2 * w2 - grav2;
+  // r1 = tau1 + h s2 w2 w1 + h s2 (w1+w2) w2 - f1 w1 - G1 = tau1 + h s2 w2 (2 w1 + w2) - (f1 w1 + G1)
+  // r2 = u1 - h s2 w1^2 - f2 w2 - G2                        = (u1 - h s2 w1 w1) - (f2 w2 + G2)
+  double r1 = fma(hs2 * w2, fma(2.0, w1, w2), -fma(m.f1, w1, grav1));
+  if (ACT) r1 += (m.tau1 != 0.0) ? m.tau1 * u0 : 0.0;
+  const double r2 = fma(-(hs2 * w1), w1, u1) - fma(m.f2, w2, grav2);
   // det M = M11 M22 - M12^2 = (a1 a3 - a3^2) - h^2 cos^2(th2): two dependent operations after cos(th2)
   const double det = fma(-m.hsq, t.c2 * t.c2, m.det0);
   e.inv_det = rcp_nr(det);
@@ -196,7 +192,7 @@ __device__ __forceinline__ void f_eval(const Model& m, const double x[4], double
 // Returns the largest high word of |angle| any of the four stages saw.
 template <bool FAST>
 __device__ __forceinline__ int rk4_step_t(const Model& m, const double x[4], double u0, double u1, double xn[4]) {
-  const double h = m.dt, hh = 0.5 * m.dt;
+  const double h = m.dt, hh = 0.5 * m.dt, h6 = m.dt * (1.0 / 6.0);
   double k1[4], k2[4], k3[4], k4[4], y[4];
   int amax = max(abs_hi(x[0]), abs_hi(x[1]));
   f_eval_t<FAST>(m, x, u0, u1, k1);
@@ -214,8 +210,8 @@ __device__ __forceinline__ int rk4_step_t(const Model& m, const double x[4], dou
   f_eval_t<FAST>(m, y, u0, u1, k4);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const double s = k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i];
-    xn[i] = x[i] + (h * s) * (1.0 / 6.0);
+    const double s = fma(2.0, k3[i], fma(2.0, k2[i], k1[i])) + k4[i];
+    xn[i] = fma(h6, s, x[i]);  // x + (dt/6) (k1 + 2 k2 + 2 k3 + k4)   dynamics.py:193
   }
   return amax;
 }
@@ -327,7 +323,7 @@ __device__ __forceinline__ LinD linearize_d(const Model& m, const double x[4], d
 template <bool FAST>
 __device__ __forceinline__ int rk4_step_lin_t(const Model& m, const double x[4], double u0, double u1,
                                                  double xn[4], LinD& L) {
-  const double h = m.dt, hh = 0.5 * m.dt;
+  const double h = m.dt, hh = 0.5 * m.dt, h6 = m.dt * (1.0 / 6.0);
   double k1[4], k2[4], k3[4], k4[4], y[4];
   int amax = max(abs_hi(x[0]), abs_hi(x[1]));
   {
@@ -353,8 +349,8 @@ __device__ __forceinline__ int rk4_step_lin_t(const Model& m, const double x[4],
   f_eval_t<FAST>(m, y, u0, u1, k4);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const double s = k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i];
-    xn[i] = x[i] + (h * s) * (1.0 / 6.0);
+    const double s = fma(2.0, k3[i], fma(2.0, k2[i], k1[i])) + k4[i];
+    xn[i] = fma(h6, s, x[i]);  // x + (dt/6) (k1 + 2 k2 + 2 k3 + k4)   dynamics.py:193
   }
   return amax;
 }
@@ -446,7 +442,7 @@ __device__ __forceinline__ Trig trig_from(double s1, double c1, double s2, doubl
 template <class Mid>
 __device__ __forceinline__ int rk4_step_overlap(const Model& m, const double x[4], double u0, double u1,
                                                 double xn[4], Mid mid) {
-  const double h = m.dt, hh = 0.5 * m.dt;
+  const double h = m.dt, hh = 0.5 * m.dt, h6 = m.dt * (1.0 / 6.0);
   const double th[4] = {x[0], x[1], fma(hh, x[2], x[0]), fma(hh, x[3], x[1])};
   int amax = max(max(abs_hi(th[0]), abs_hi(th[1])), max(abs_hi(th[2]), abs_hi(th[3])));
   double sn[4], cs[4];
@@ -474,8 +470,8 @@ __device__ __forceinline__ int rk4_step_overlap(const Model& m, const double x[4
   const double k3[4] = {w31, w32, e3.dd1, e3.dd2}, k4[4] = {w41, w42, e4.dd1, e4.dd2};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const double s = k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i];
-    xn[i] = x[i] + (h * s) * (1.0 / 6.0);
+    const double s = fma(2.0, k3[i], fma(2.0, k2[i], k1[i])) + k4[i];
+    xn[i] = fma(h6, s, x[i]);  // x + (dt/6) (k1 + 2 k2 + 2 k3 + k4)   dynamics.py:193
   }
   return amax;
 }
@@ -539,7 +535,7 @@ __device__ __forceinline__ double tie(double x, int jz) {
 template <bool ACT, class Mid>
 __device__ __forceinline__ bool rk4_step_rot(const Model& m, const double x[4], double u0, double u1, double xn[4],
                                              TrigCarry& tc, Mid mid) {
-  const double h = m.dt, hh = 0.5 * m.dt;
+  const double h = m.dt, hh = 0.5 * m.dt, h6 = m.dt * (1.0 / 6.0);
   // stage 2: the one full sincos
   const double th2[2] = {fma(hh, x[2], x[0]), fma(hh, x[3], x[1])};
   double s2[2], c2[2];
@@ -576,8 +572,8 @@ __device__ __forceinline__ bool rk4_step_rot(const Model& m, const double x[4], 
   const double k3[4] = {w31, w32, e3.dd1, e3.dd2}, k4[4] = {w41, w42, e4.dd1, e4.dd2};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const double s = k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i];
-    xn[i] = x[i] + (h * s) * (1.0 / 6.0);
+    const double s = fma(2.0, k3[i], fma(2.0, k2[i], k1[i])) + k4[i];
+    xn[i] = fma(h6, s, x[i]);  // x + (dt/6) (k1 + 2 k2 + 2 k3 + k4)   dynamics.py:193
   }
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
