@@ -497,27 +497,45 @@ struct TrigCarry {
   double th[2], s[2], c[2];  // stage-4 angles of the previous step, their sines and cosines
 };
 
+// Taylor coefficients of sin d and cos d - 1.  As literals the compiler rebuilds them from 32-bit immediates in
+// every step of a loop (forty MOV / LDC instructions per time step, 9 % of the chain warp's step); RotC::held()
+// launders them through an empty asm so that they stay in registers across the loop.  The rollout kernels, which
+// are compiled for three blocks per SM, keep the literals (RotC::literals()).
+struct RotC {
+  double s3, s5, s7, s9, c2, c4, c6, c8, c10;
+  __device__ __forceinline__ static RotC literals() {
+    return RotC{-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0,
+                -1.0 / 3628800.0};
+  }
+  __device__ __forceinline__ static RotC held() {
+    RotC r = literals();
+    asm volatile("" : "+d"(r.s3), "+d"(r.s5), "+d"(r.s7), "+d"(r.s9));
+    asm volatile("" : "+d"(r.c2), "+d"(r.c4), "+d"(r.c6), "+d"(r.c8), "+d"(r.c10));
+    return r;
+  }
+};
+
 // (s, c) = (sin, cos)(theta)  ->  (sin, cos)(theta + d)
-__device__ __forceinline__ void rot_small(double d, double s, double c, double& so, double& co) {
+__device__ __forceinline__ void rot_small(const RotC& k, double d, double s, double c, double& so, double& co) {
   const double d2 = d * d;
-  double ps = fma(d2, -1.0 / 5040.0, 1.0 / 120.0);
-  double pc = fma(d2, -1.0 / 720.0, 1.0 / 24.0);
-  ps = fma(d2, ps, -1.0 / 6.0);
-  pc = fma(d2, pc, -0.5);
+  double ps = fma(d2, k.s7, k.s5);
+  double pc = fma(d2, k.c6, k.c4);
+  ps = fma(d2, ps, k.s3);
+  pc = fma(d2, pc, k.c2);
   const double sd = fma(d * d2, ps, d);  // sin d
   const double cm = d2 * pc;             // cos d - 1
   so = s + fma(s, cm, c * sd);
   co = c + fma(c, cm, -(s * sd));
 }
-__device__ __forceinline__ void rot_medium(double d, double s, double c, double& so, double& co) {
+__device__ __forceinline__ void rot_medium(const RotC& k, double d, double s, double c, double& so, double& co) {
   const double d2 = d * d;
-  double ps = fma(d2, 1.0 / 362880.0, -1.0 / 5040.0);
-  double pc = fma(d2, -1.0 / 3628800.0, 1.0 / 40320.0);
-  ps = fma(d2, ps, 1.0 / 120.0);
-  pc = fma(d2, pc, -1.0 / 720.0);
-  ps = fma(d2, ps, -1.0 / 6.0);
-  pc = fma(d2, pc, 1.0 / 24.0);
-  pc = fma(d2, pc, -0.5);
+  double ps = fma(d2, k.s9, k.s7);
+  double pc = fma(d2, k.c10, k.c8);
+  ps = fma(d2, ps, k.s5);
+  pc = fma(d2, pc, k.c6);
+  ps = fma(d2, ps, k.s3);
+  pc = fma(d2, pc, k.c4);
+  pc = fma(d2, pc, k.c2);
   const double sd = fma(d * d2, ps, d);
   const double cm = d2 * pc;
   so = s + fma(s, cm, c * sd);
@@ -533,8 +551,8 @@ __device__ __forceinline__ double tie(double x, int jz) {
 
 // Returns true when the step left the validity range of the incremental formulas (then xn and tc are garbage).
 template <bool ACT, class Mid>
-__device__ __forceinline__ bool rk4_step_rot(const Model& m, const double x[4], double u0, double u1, double xn[4],
-                                             TrigCarry& tc, Mid mid) {
+__device__ __forceinline__ bool rk4_step_rot(const Model& m, const RotC& rc, const double x[4], double u0, double u1,
+                                             double xn[4], TrigCarry& tc, Mid mid) {
   const double h = m.dt, hh = 0.5 * m.dt, h6 = m.dt * (1.0 / 6.0);
   // stage 2: the one full sincos
   const double th2[2] = {fma(hh, x[2], x[0]), fma(hh, x[3], x[1])};
@@ -543,16 +561,16 @@ __device__ __forceinline__ bool rk4_step_rot(const Model& m, const double x[4], 
   // stage 1 from the previous step's stage 4
   const double d1[2] = {x[0] - tc.th[0], x[1] - tc.th[1]};
   double s1[2], c1[2];
-  rot_small(d1[0], tc.s[0], tc.c[0], s1[0], c1[0]);
-  rot_small(d1[1], tc.s[1], tc.c[1], s1[1], c1[1]);
+  rot_small(rc, d1[0], tc.s[0], tc.c[0], s1[0], c1[0]);
+  rot_small(rc, d1[1], tc.s[1], tc.c[1], s1[1], c1[1]);
   const Trig t1 = trig_from(s1[0], c1[0], s1[1], c1[1]);
   const Eom e1 = eom<ACT>(m, t1, x[2], x[3], u0, u1);
   const double w21 = fma(hh, e1.dd1, x[2]), w22 = fma(hh, e1.dd2, x[3]);
   // stage 3 from stage 2
   const double d3[2] = {fma(hh, w21, x[0]) - th2[0], fma(hh, w22, x[1]) - th2[1]};
   double s3[2], c3[2];
-  rot_small(d3[0], s2[0], c2[0], s3[0], c3[0]);
-  rot_small(d3[1], s2[1], c2[1], s3[1], c3[1]);
+  rot_small(rc, d3[0], s2[0], c2[0], s3[0], c3[0]);
+  rot_small(rc, d3[1], s2[1], c2[1], s3[1], c3[1]);
   const Trig t3 = trig_from(s3[0], c3[0], s3[1], c3[1]);
   const int jz = mid();
   const Trig t2 = trig_from(s2[0], c2[0], s2[1], c2[1]);
@@ -562,8 +580,8 @@ __device__ __forceinline__ bool rk4_step_rot(const Model& m, const double x[4], 
   const double th4[2] = {fma(h, w31, x[0]), fma(h, w32, x[1])};
   const double d4[2] = {tie(th4[0] - th2[0], jz), th4[1] - th2[1]};
   double s4[2], c4[2];
-  rot_medium(d4[0], s2[0], c2[0], s4[0], c4[0]);
-  rot_medium(d4[1], s2[1], c2[1], s4[1], c4[1]);
+  rot_medium(rc, d4[0], s2[0], c2[0], s4[0], c4[0]);
+  rot_medium(rc, d4[1], s2[1], c2[1], s4[1], c4[1]);
   const Trig t4 = trig_from(s4[0], c4[0], s4[1], c4[1]);
   const Eom e3 = eom<ACT>(m, t3, w31, w32, u0, u1);
   const double w41 = fma(h, e3.dd1, x[2]), w42 = fma(h, e3.dd2, x[3]);
@@ -615,7 +633,7 @@ __device__ __noinline__ Vec4 rk4_step_redo(const Model& m, double x0, double x1,
 // (initialise with trig_carry_at(m, x[0], x[1])).  One thread per problem: the redo is an ordinary divergent branch.
 __device__ __forceinline__ void rk4_step_inc(const Model& m, const double x[4], double u0, double u1, double xn[4],
                                              TrigCarry& tc) {
-  const bool bad = rk4_step_rot<true>(m, x, u0, u1, xn, tc, []() { return 0; });
+  const bool bad = rk4_step_rot<true>(m, RotC::literals(), x, u0, u1, xn, tc, []() { return 0; });
   if (bad) {
     const Vec4 o = rk4_step_redo(m, x[0], x[1], x[2], x[3], u0, u1);
 #pragma unroll

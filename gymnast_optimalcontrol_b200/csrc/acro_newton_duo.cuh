@@ -115,6 +115,7 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
   uint32_t hready = 1u;
   bool bad = false;
   TrigCarry tc = trig_carry_at(m, xp[0], xp[1]);
+  const RotC rotc = RotC::held();
   for (int k = 0; k < n_stages; ++k) {
     const int cnt = min(SG, steps - k * SG);
     const uint32_t g = r.base + k;
@@ -164,7 +165,7 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
       ++hd.h;
       double xn[4];
       const uint32_t nebar = hd.empty_bar(), nepar = hd.phase() ^ 1u;
-      bad = rk4_step_rot<false>(m, xp, up[0], up[1], xn, tc, [&]() {
+      bad = rk4_step_rot<false>(m, rotc, xp, up[0], up[1], xn, tc, [&]() {
         // operands of the next step and the state of the next hand-off slot, while the FP64 pipe is busy
         // (no branch in here: a branch would cut the step's straight-line code into two scheduling regions)
         in.load(nsrc, ns, lane);
