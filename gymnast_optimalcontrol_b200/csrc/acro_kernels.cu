@@ -1,11 +1,13 @@
 // acro_kernels.cu - sm_100a kernels and the C ABI of libacro_b200.so (see include/acro_abi.h).
 //
-// Thread mapping: one thread = one independent problem (lane-per-problem), so every global
-// access of a warp is 32 consecutive doubles of one SoA row (256 B, coalesced), and no
-// thread ever waits on another: there is no shared memory hazard, no barrier and no
-// collective anywhere on this path.  The time recurrences (RK4 rollout, Riccati sweep) are
-// sequential per problem; the next step's operands are prefetched into registers while the
-// current step computes.
+// Thread mapping of the kernels in this file: one thread = one independent problem (lane-per-problem), so every
+// global access of a warp is 32 consecutive doubles of one SoA row (256 B, coalesced) and no thread ever waits on
+// another.  The time recurrences (RK4 rollout, Riccati sweep) are sequential per problem; the next step's operands
+// are prefetched into registers while the current step computes.
+// The Newton / Armijo loop has two more implementations, chosen by batch size in acro_newton_solve:
+//   acro_newton_ring.cuh  one warp per tile of 32 problems, warp-synchronous, operands through a TMA-fed ring
+//   acro_newton_duo.cuh   two warps per tile (recurrence warp + trailer warp) for batches that leave SMs idle
+// and acro_mpc_box.cuh holds the box-constrained MPC tracker.  There is no collective anywhere on this path.
 #include <cuda_runtime.h>
 
 #include <atomic>
