@@ -147,6 +147,42 @@ def main():
     line("C5 step-size sweep, %d iterates x 200 step sizes" % Pn, "sweep_rollouts_per_sec", Pn * 200 / t, "rollouts/s",
          940.0 * (N - 1), t, nl, peak)
 
+    # ---- config 2 to convergence: B = 4096, tol 1e-4, gamma_0 = 0.1 as task_2 (main.py:55-71), and the
+    # back-tracking regime gamma_0 = 1 over a fixed 30 iterations (Armijo tries differ from problem to problem)
+    B = 4096
+    x0h = np.random.default_rng(1).uniform(-0.2, 0.2, (B, 4))
+    x0h[0] = 0.0
+    x0 = bt.upload(np.ascontiguousarray(x0h.T))
+    state = bt.newton_alloc(B, N, 5000, history=True)
+
+    def run_conv():
+        state.initialised = False
+        bt.newton_solve(x0, ref, max_iters=5000, tol=1e-4, gamma_0=0.1, state=state)
+    t, nl = timeit(run_conv, 1)
+    its = state.iters.double()
+    done = float(its.sum().item())
+    print(json.dumps({"config": "C2 Newton to convergence, B=4096, tol=1e-4, gamma_0=0.1", "metric": "newton_iterations_per_sec",
+                      "value": done / t, "unit": "Newton iterations/s (iterations actually executed)", "seconds": t,
+                      "gpu_launches": nl, "solves_per_sec": B / t, "iterations_min_mean_max": [float(its.min().item()), done / B, float(its.max().item())],
+                      "converged": int((state.status == 1).sum().item()),
+                      "roofline": {"bound": "fp64", "achieved": done / t * 2054.0 * (N - 1) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                   "frac": done / t * 2054.0 * (N - 1) / 1e12 / peak, "flops_per_unit": 2054.0 * (N - 1)}}), flush=True)
+    state = bt.newton_alloc(B, N, 30, history=True)
+
+    def run_bt():
+        state.initialised = False
+        bt.newton_solve(x0, ref, max_iters=30, tol=0.0, gamma_0=1.0, state=state)
+    t, nl = timeit(run_bt, 2)
+    tries = float(state.hist_ntry[:30].double().mean().item())
+    print(json.dumps({"config": "C2 Newton with back-tracking, B=4096, gamma_0=1, 30 iterations", "metric": "newton_iterations_per_sec",
+                      "value": B * 30 / t, "unit": "Newton iterations/s", "seconds": t, "gpu_launches": nl, "armijo_tries_mean": tries,
+                      "forward_passes_per_sec": B * 30 * tries / t,
+                      "roofline": {"bound": "fp64", "achieved": B * 30 / t * (1114.0 + 940.0 * tries) * (N - 1) / 1e12, "peak": peak,
+                                   "unit": "TFLOP/s", "frac": B * 30 / t * (1114.0 + 940.0 * tries) * (N - 1) / 1e12 / peak,
+                                   "flops_per_unit": (1114.0 + 940.0 * tries) * (N - 1),
+                                   "note": "a warp runs a forward pass while ANY of its 32 problems still needs a candidate: "
+                                           "the pass count of a tile is the maximum over its problems"}}), flush=True)
+
     # ---- config 2 in the throughput regime
     hbm = 6551.4
     try:
