@@ -637,6 +637,25 @@ def test_full_size_mpc_with_input_box_properties(bt):
     assert ns.min() >= 500 and ns.mean() < 500 * 6
 
 
+def test_full_size_c2_to_convergence(bt, fa_ref):
+    """Config 2 to convergence (B = 4096, tol 1e-4, gamma_0 = 0.1): every problem converges; problem 0 is task_2 (393
+    iterations, the shipped cost); rows 1-7 need the iteration counts measured with the UNMODIFIED reference during
+    the survey (391, 395, 395, 391, 395, 395, 387 - logged in order of completion of the seven
+    worker processes, hence compared as a multiset; the oracle gives 395 for rows 1 and 2), always one Armijo try."""
+    x_ref, u_ref, _ = fa_ref
+    x0s = np.random.default_rng(1).uniform(-0.2, 0.2, (4096, 4))
+    x0s[0] = 0.0
+    st = _solve(bt, x0s, x_ref, u_ref, max_iters=5000, tol=1e-4, gamma_0=0.1)
+    iters, status = st.iters.cpu().numpy(), st.status.cpu().numpy()
+    assert (status == 1).all()
+    assert iters[0] == 393 and iters[1] == 395 and iters[2] == 395
+    assert sorted(iters[1:8]) == sorted([391, 395, 395, 391, 395, 395, 387])
+    assert abs(st.cost[0].item() - 28063.21834988143) < TOL * 28063.21834988143
+    assert int(st.hist_ntry[:int(iters.max())].max()) == 1
+    d = golden("acrobot_optimal_trajectory")
+    assert rel_err(aos(st.X)[0], d["x"]) < TOL and rel_err(aos(st.U)[0], d["u"]) < TOL
+
+
 def test_full_size_c3_properties(bt):
     """B = 65536 LQR rollouts (config 3): problems 0,1 are the +0.2/+0.3 cases of main.py:104-110; the
     unperturbed problem reproduces the optimal trajectory; every tame rollout ends near the upright."""
