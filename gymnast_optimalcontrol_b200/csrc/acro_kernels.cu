@@ -1631,9 +1631,13 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
     if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                         \
     k_newton_duo<WPB, RPB, SG><<<(unsigned)tiles, 64, smem, (cudaStream_t)stream>>>(a);                            \
   } while (0)
+    // Per-problem references always run the variant that keeps the weights in registers (it takes shared weights too:
+    // WV<true> falls back to them): ptxas puts YIELDs at the loop heads of k_newton_duo<false, true, *> and of no
+    // other variant, which costs 12 % (8.7 against 9.9 M it/s at B = 4096).
+    const bool wreg = per_problem_weights(*w) || ref->per_problem != 0;
     if (tiles > 148) {  // two blocks per SM: 4-step stages (70-90 KB per block)
 #define EXPR(WPB, RPB) LAUNCH_DUO(WPB, RPB, 4)
-      DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+      DISPATCH2(wreg, ref->per_problem != 0, EXPR);
 #undef EXPR
     } else if (!ref->per_problem && getenv("ACRO_DUO_SG") && atoi(getenv("ACRO_DUO_SG")) == 8) {
 #define EXPR(WPB, RPB) LAUNCH_DUO(WPB, false, 8)
@@ -1644,8 +1648,8 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
       DISPATCH2(per_problem_weights(*w), false, EXPR);
 #undef EXPR
     } else {
-#define EXPR(WPB, RPB) LAUNCH_DUO(WPB, true, 8)
-      DISPATCH2(per_problem_weights(*w), true, EXPR);
+#define EXPR(WPB, RPB) LAUNCH_DUO(true, true, 8)
+      DISPATCH2(true, true, EXPR);
 #undef EXPR
     }
 #undef LAUNCH_DUO
