@@ -112,3 +112,31 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), "%s mentions the oracle" % f
+
+
+def test_headline_kernels_carry_no_yield():
+    """ptxas decides by heuristics of its own whether to put a YIELD at the head of the step loops of the
+    warp-specialised Newton kernel; when it does, every time step of the recurrence warp pays about 50 cycles (-10 %,
+    measured: DESIGN.md 4.1 and 7).  The variants the dispatch uses for config 2 (shared / per-problem references,
+    <= 148 and <= 296 tiles) must stay free of it: a harmless-looking source change can flip the decision."""
+    import shutil
+    import subprocess
+    from gymnast_optimalcontrol_b200 import _abi
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    counts, name = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            counts[name] = 0
+        elif name and " YIELD " in line:
+            counts[name] += 1
+    used = ["k_newton_duoILb0ELb0ELi16E", "k_newton_duoILb0ELb0ELi4E", "k_newton_duoILb1ELb1ELi8E", "k_newton_duoILb1ELb1ELi4E",
+            "k_newton_duoILb1ELb0ELi16E"]
+    for tag in used:
+        hits = [n for n in counts if tag in n]
+        assert hits, "kernel variant %s not found in the library" % tag
+        for n in hits:
+            assert counts[n] == 0, "%s: %d YIELD instructions" % (n, counts[n])
