@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(PKG, "libacro_b200.so")
 
 OK, E_INVALID, E_CUDA = 0, -1, -2
 RUNNING, CONVERGED, MAX_ITERS, LINE_SEARCH_FAILED = 0, 1, 2, 3
+NEWTON_KERNELS = {"auto": 0, "duo": 1, "ring": 2, "thread": 3, "ldg": 3, "spec": 4}
 
 
 class AcroParams(C.Structure):
@@ -30,7 +31,8 @@ class AcroRef(C.Structure):
 class AcroNewtonOpts(C.Structure):
     _fields_ = [("max_iters", C.c_int32), ("chunk_iters", C.c_int32), ("max_line_search", C.c_int32),
                 ("init", C.c_int32), ("tol", C.c_double), ("beta", C.c_double), ("c", C.c_double),
-                ("gamma_0", C.c_double)]
+                ("gamma_0", C.c_double), ("kernel", C.c_int32), ("stage_steps", C.c_int32),
+                ("recompute_lin", C.c_int32), ("speculate", C.c_int32)]
 
 
 P = C.c_void_p  # device pointer / stream
@@ -59,6 +61,7 @@ SIGNATURES = {
     "acro_armijo_select": [I64, I32, P, P, P, I32, P, F64, P, P],
     "acro_newton_solve": [PP, PW, PO, I64, I32, P, PR] + [P] * 17 + [P],
     "acro_newton_solve_pp": [PP, P, PW, PO, I64, I32, P, PR] + [P] * 17 + [P],
+    "acro_newton_describe": [PO, I64, I32, I32, I32, C.c_char_p, I32],
     "acro_stepsize_sweep": [PP, PW, I64, I32, P, P, P, P, PR, I32, P, P, P],
     "acro_lqr_gains": [PP, PW, I64, I32, PR, P, P],
     "acro_lqr_track": [PP, I64, I32, PR, P, P, P, P, P],

@@ -1,4 +1,5 @@
 """Build libacro_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+import glob
 import os
 import shutil
 import subprocess
@@ -7,7 +8,6 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libacro_b200.so")
 SOURCES = ["acro_kernels.cu"]
-HEADERS = ["acro_device.cuh", "acro_views.cuh", "acro_newton_ring.cuh", "acro_newton_duo.cuh", os.path.join("..", "..", "include", "acro_abi.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -23,7 +23,9 @@ def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    deps = glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(PKG, "..", "include", "*.h"))
+    return any(os.path.getmtime(f) > t for f in deps)
 
 
 def build(force=False, verbose=False):

@@ -24,17 +24,20 @@ class Kind:
             self.torch = self.cuda = self.pinned = False
 
 
-_pinned_pool = {}
+def pinned_empty(shape, dtype=torch.float64):
+    """A FRESH pinned host tensor for a result.  torch's caching host allocator recycles the blocks of results the
+    caller has dropped, so a loop that overwrites its previous result does not page-lock new memory every call, and
+    two results never alias (a drop-in must not hand the same buffer out twice)."""
+    return torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
 
 
-def _pinned(shape, key):
-    """Reusable pinned staging buffer (one per (key, shape)); the caller owns the result until the next call."""
-    k = (key, tuple(shape))
-    buf = _pinned_pool.get(k)
-    if buf is None:
-        buf = torch.empty(shape, dtype=torch.float64).pin_memory()
-        _pinned_pool[k] = buf
-    return buf
+def to_host(t, stream_sync=True):
+    """Device tensor -> fresh pinned host tensor (asynchronous copy on the current stream, then one synchronise)."""
+    h = pinned_empty(t.shape, t.dtype)
+    h.copy_(t, non_blocking=True)
+    if stream_sync:
+        torch.cuda.current_stream().synchronize()
+    return h
 
 
 def as_device(a):
@@ -80,7 +83,8 @@ def traj_in(a, C):
 
 
 def out(t_soa, kind, tail=None, key="out"):
-    """Device point batch (C,B) or Traj -> caller's kind; tail reshapes the component axis (e.g. (2,4))."""
+    """Device point batch (C,B) or Traj -> caller's kind; tail reshapes the component axis (e.g. (2,4)).
+    Host results are always fresh buffers (`key` is kept for call-site readability only)."""
     t = bt.unpack_soa(t_soa)  # (B,C) / (B,T,C)
     if tail is not None:
         t = t.reshape(*t.shape[:-1], *tail)
@@ -88,13 +92,8 @@ def out(t_soa, kind, tail=None, key="out"):
         t = t[0]
     if kind.torch and kind.cuda:
         return t
-    if kind.torch:
-        if kind.pinned:
-            h = _pinned(t.shape, key)
-            h.copy_(t, non_blocking=False)
-            return h
-        return t.cpu()
-    return t.cpu().numpy()
+    h = to_host(t)
+    return h if kind.torch else h.numpy()
 
 
 def vec_out(t, kind):
@@ -103,4 +102,5 @@ def vec_out(t, kind):
         return t[0].item()
     if kind.torch and kind.cuda:
         return t
-    return t.cpu() if kind.torch else t.cpu().numpy()
+    h = to_host(t)
+    return h if kind.torch else h.numpy()

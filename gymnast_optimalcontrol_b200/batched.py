@@ -338,6 +338,14 @@ class NewtonState:
     hist_ntry: Optional[torch.Tensor] = None
     initialised: bool = False
 
+    def reset(self):
+        """Make the state reusable for a new solve from x0 (same shapes): history back to NaN / 0, init on next call."""
+        self.initialised = False
+        if self.hist_cost is not None:
+            for t in (self.hist_cost, self.hist_sigma_norm, self.hist_gamma):
+                t.fill_(float("nan"))
+            self.hist_ntry.zero_()
+
 
 def newton_alloc(Bn, N, max_iters, history=True):
     st = NewtonState(
@@ -357,13 +365,60 @@ def newton_alloc(Bn, N, max_iters, history=True):
     return st
 
 
+# Named kernel variants of acro_newton_solve (AcroNewtonOpts.kernel / stage_steps / recompute_lin): what the automatic
+# dispatch picks from, by batch size.  `kernel=` of newton_solve takes one of these names (or "auto").
+KERNEL_VARIANTS = {
+    "auto": dict(kernel="auto"),
+    "duo": dict(kernel="duo"),                       # <= 148 tiles: two warps per tile, 16-step stages (8 with per-problem references)
+    "duo4": dict(kernel="duo", stage_steps=4),       # 149-296 tiles: two blocks per SM
+    "duo8": dict(kernel="duo", stage_steps=8),
+    "ring": dict(kernel="ring"),                     # one warp per tile
+    "ring16": dict(kernel="ring", stage_steps=16),
+    "ring4": dict(kernel="ring", stage_steps=4),     # 297-592 tiles
+    "ring2": dict(kernel="ring", stage_steps=2, recompute_lin=2),
+    "ring-rl": dict(kernel="ring", stage_steps=2, recompute_lin=1),  # > 592 tiles: linearisation recomputed (304 B/step-iteration)
+    "thread": dict(kernel="thread"),
+    "ldg": dict(kernel="thread"),
+    "spec": dict(kernel="spec"),                     # <= 148 tiles: duo + speculative parallel Armijo candidates
+}
+# Process-wide default of newton_solve's kernel selection (a Python-side setting: the library reads no environment).
+NEWTON_DEFAULTS = {"kernel": "auto"}
+
+
+def newton_opts(max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, chunk_iters=0, max_line_search=20, init=1,
+                kernel=None, stage_steps=0, recompute_lin=0, speculate=0):
+    if kernel is None:
+        kernel = NEWTON_DEFAULTS["kernel"]
+    if isinstance(kernel, str):
+        v = KERNEL_VARIANTS[kernel]
+        stage_steps = stage_steps or v.get("stage_steps", 0)
+        recompute_lin = recompute_lin or v.get("recompute_lin", 0)
+        kernel = _abi.NEWTON_KERNELS[v["kernel"]]
+    return AcroNewtonOpts(max_iters=int(max_iters), chunk_iters=int(chunk_iters), max_line_search=int(max_line_search),
+                          init=int(init), tol=float(tol), beta=float(beta), c=float(c), gamma_0=float(gamma_0),
+                          kernel=int(kernel), stage_steps=int(stage_steps), recompute_lin=int(recompute_lin),
+                          speculate=int(speculate))
+
+
+def newton_kernel_name(Bn, ref_per_problem=False, weights_per_problem=False, params_per_problem=False, **kw):
+    """Name of the kernel newton_solve launches for a batch of Bn problems with these options (acro_newton_describe)."""
+    o = newton_opts(kw.pop("max_iters", 1), **kw)
+    buf = C.create_string_buffer(128)
+    call("acro_newton_describe", C.byref(o), int(Bn), int(ref_per_problem), int(weights_per_problem),
+         int(params_per_problem), buf, 128)
+    return buf.value.decode()
+
+
 def newton_solve(x0, ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, w=None, params=DEFAULT_PARAMS,
-                 state=None, chunk_iters=0, max_line_search=20, history=True, warm_start_U=None, params_b=None):
+                 state=None, chunk_iters=0, max_line_search=20, history=True, warm_start_U=None, params_b=None,
+                 kernel=None, stage_steps=0, recompute_lin=0, speculate=0):
     """newton_Algorithm (trajectory_generation.py:298-398) for a batch, x0 (4,B).
 
     One kernel launch runs the whole loop for every problem.  Pass the returned state back
     (with chunk_iters) to continue a solve in pieces.  warm_start_U (Traj, C=2) replaces the reference's
-    u = 0 initial guess (tg:311).  params_b (11,B): physical parameters per problem (phys_params)."""
+    u = 0 initial guess (tg:311).  params_b (11,B): physical parameters per problem (phys_params).
+    kernel / stage_steps / recompute_lin / speculate: AcroNewtonOpts kernel selection ("auto", "duo", "ring",
+    "thread", "spec"); the default picks by batch size."""
     w = newton_weights() if w is None else w
     Bn = x0.shape[1]
     N = ref.N
@@ -373,8 +428,8 @@ def newton_solve(x0, ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, w=N
     if init and warm_start_U is not None:
         state.U.data.copy_(warm_start_U.data)
         init = 2
-    o = AcroNewtonOpts(max_iters=int(max_iters), chunk_iters=int(chunk_iters), max_line_search=int(max_line_search),
-                       init=init, tol=float(tol), beta=float(beta), c=float(c), gamma_0=float(gamma_0))
+    o = newton_opts(max_iters, tol, beta, c, gamma_0, chunk_iters, max_line_search, init, kernel, stage_steps,
+                    recompute_lin, speculate)
     s = state
     call("acro_newton_solve_pp", C.byref(params), _p(params_b), w.ref(), C.byref(o), Bn, N, _p(x0), ref.ref(), _p(s.X), _p(s.U), _p(s.Xw),
          _p(s.Uw), _p(s.lin), _p(s.K), _p(s.S), _p(s.cost), _p(s.delta_J), _p(s.sigma_norm), _p(s.gamma_acc),

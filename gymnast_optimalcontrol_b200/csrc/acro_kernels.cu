@@ -1390,6 +1390,61 @@ __global__ void k_fp64_peak(double* __restrict__ out, int iters, double b, doubl
 
 }  // namespace acro
 
+namespace acro {
+// Which Newton kernel a call runs: the one place that decides (acro_newton_solve and acro_newton_describe share it).
+struct NewtonPlan {
+  int kernel, stage_steps, recompute_lin;
+};
+static int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    n = 148;  // B200 (no device: acro_newton_describe on a CPU-only box)
+  return n;
+}
+static int newton_plan(const AcroNewtonOpts& o, int64_t B, bool rpb, bool wpb, bool ppb, bool tma_ok, NewtonPlan& plan) {
+  (void)wpb;
+  const int64_t tiles = (B + 31) / 32;
+  const int n_sm = sm_count();
+  int k = o.kernel, sg = o.stage_steps, rl = o.recompute_lin;
+  ACRO_REQUIRE(k >= ACRO_NEWTON_AUTO && k <= ACRO_NEWTON_SPEC, "acro_newton_solve: unknown kernel");
+  ACRO_REQUIRE(sg == 0 || sg == 2 || sg == 4 || sg == 8 || sg == 16, "acro_newton_solve: stage_steps must be 0, 2, 4, 8 or 16");
+  ACRO_REQUIRE(rl >= 0 && rl <= 2, "acro_newton_solve: recompute_lin must be 0, 1 or 2");
+  if (k == ACRO_NEWTON_AUTO) {
+    // per-problem physical parameters: the one-thread-per-problem kernel derives its model per thread.
+    // Buffers that are not 128-byte aligned cannot be the source of bulk copies: same kernel.
+    if (ppb || !tma_ok) k = ACRO_NEWTON_THREAD;
+    // at most two tiles per SM (config 2: 128 tiles): split every tile between two warps on two SM sub-partitions
+    else k = (tiles <= 2 * int64_t(n_sm)) ? ACRO_NEWTON_DUO : ACRO_NEWTON_RING;
+  }
+  if (k != ACRO_NEWTON_THREAD) {
+    ACRO_REQUIRE(tma_ok, "acro_newton_solve: the duo / ring kernels need 128-byte aligned X, U, Xw, Uw, lin_ws, K, S and reference buffers");
+    ACRO_REQUIRE(!ppb, "acro_newton_solve: per-problem physical parameters run on ACRO_NEWTON_THREAD");
+  }
+  if (k == ACRO_NEWTON_SPEC) k = ACRO_NEWTON_DUO;  // (speculative kernel: see acro_newton_spec.cuh)
+  if (k == ACRO_NEWTON_DUO) {
+    // one block per SM: deep stages (16 time steps per bulk copy, 220 KB of shared memory); two blocks per SM: 4-step
+    // stages (70-90 KB).  Per-problem references need 50 % more shared memory per stage: 8 instead of 16.
+    if (sg == 0) sg = (tiles > n_sm) ? 4 : (rpb ? 8 : 16);
+    ACRO_REQUIRE(sg == 4 || sg == 8 || (sg == 16 && !rpb), "acro_newton_solve: duo kernel: stage_steps 4, 8 (or 16 with a shared reference)");
+    rl = 0;
+  } else if (k == ACRO_NEWTON_RING) {
+    // at most one block per SM: 16 steps per stage; up to four: 4 steps; beyond: 2 steps (25 KB per block, eight blocks
+    // = two warps per sub-partition)
+    if (sg == 0) sg = (tiles <= n_sm && !rpb) ? 16 : (tiles > 4 * int64_t(n_sm) ? 2 : 4);
+    ACRO_REQUIRE(sg == 2 || sg == 4 || (sg == 16 && !rpb), "acro_newton_solve: ring kernel: stage_steps 2, 4 (or 16 with a shared reference)");
+    rl = (rl == 0) ? (sg == 2) : (rl == 1);
+    ACRO_REQUIRE(!rl || sg == 2, "acro_newton_solve: recompute_lin needs stage_steps = 2");
+  } else {
+    sg = 0;
+    rl = 0;
+  }
+  plan.kernel = k;
+  plan.stage_steps = sg;
+  plan.recompute_lin = rl;
+  return ACRO_OK;
+}
+}  // namespace acro
+
 // =========================================================================================
 // C ABI
 // =========================================================================================
@@ -1397,7 +1452,7 @@ using namespace acro;
 
 extern "C" {
 
-const char* acro_version(void) { return "acro_b200 0.1.0 (sm_100a, abi 1)"; }
+const char* acro_version(void) { return "acro_b200 0.2.0 (sm_100a, abi 2)"; }
 const char* acro_last_error_string(void) { return g_err; }
 int64_t acro_launch_count(void) { return g_launches.load(); }
 
@@ -1590,123 +1645,105 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
   a.h_sn = hist_sigma_norm;
   a.h_gamma = hist_gamma;
   a.h_ntry = hist_ntry;
-  // Default: the warp-synchronous kernel with TMA-fed shared-memory rings (one warp per block); it is the faster
-  // one at every batch size measured on B200 (profiles/newton_batch_sweep.py).  The one-thread-per-problem
-  // kernel with register prefetch remains for buffers that are not 128-byte aligned and for A/B runs.
-  const int64_t tiles = (B + 31) / 32;
-  const char* force = getenv("ACRO_NEWTON_KERNEL");
   auto aligned = [](const void* q, uintptr_t al) { return (reinterpret_cast<uintptr_t>(q) % al) == 0; };
-  bool ring = aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) &&
-              aligned(lin_ws, 128) && aligned(K, 128) && aligned(S, 128) &&
-              aligned(ref->x, ref->per_problem ? 128 : 32) && aligned(ref->u, ref->per_problem ? 128 : 16);
-  if (force && !strcmp(force, "ldg")) ring = false;
-  if (params_b) {
-    // per-problem physical parameters: the one-thread-per-problem kernel derives its model per thread
+  const bool tma_ok = aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) &&
+                      aligned(lin_ws, 128) && aligned(K, 128) && aligned(S, 128) &&
+                      aligned(ref->x, ref->per_problem ? 128 : 32) && aligned(ref->u, ref->per_problem ? 128 : 16);
+  NewtonPlan plan;
+  const int rc = newton_plan(*opts, B, ref->per_problem != 0, per_problem_weights(*w), params_b != nullptr, tma_ok, plan);
+  if (rc != ACRO_OK) return rc;
+  const int64_t tiles = (B + 31) / 32;
+  const bool wpb = per_problem_weights(*w), rpb = ref->per_problem != 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (plan.kernel == ACRO_NEWTON_THREAD) {
     const Cfg c = cfg_for(B);
-#define EXPR(WPB, RPB) k_newton<WPB, RPB, true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(a)
-    DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+    if (params_b) {
+#define EXPR(WPB, RPB) k_newton<WPB, RPB, true><<<c.grid, c.block, 0, s>>>(a)
+      DISPATCH2(wpb, rpb, EXPR);
 #undef EXPR
-    ACRO_LAUNCH_CHECK("acro_newton_solve");
-    return ACRO_OK;
-  }
-  if (force && !strcmp(force, "ring")) {
-    ACRO_REQUIRE(aligned(X, 128) && aligned(U, 128) && aligned(Xw, 128) && aligned(Uw, 128) && aligned(lin_ws, 128) &&
-                     aligned(K, 128) && aligned(S, 128),
-                 "acro_newton_solve: ring kernel needs 128-byte aligned buffers");
-    ring = true;
-  }
-  // At most two tiles per SM (config 2: 128 tiles): split every tile between two warps on two SM sub-partitions.
-  bool duo = ring && tiles <= 296;
-  if (force && !strcmp(force, "ring")) duo = false;
-  if (force && !strcmp(force, "duo")) {
-    ACRO_REQUIRE(ring, "acro_newton_solve: duo kernel needs 128-byte aligned buffers");
-    duo = true;
-  }
-  if (duo) {
+    } else {
+#define EXPR(WPB, RPB) k_newton<WPB, RPB><<<c.grid, c.block, 0, s>>>(a)
+      DISPATCH2(wpb, rpb, EXPR);
+#undef EXPR
+    }
+  } else if (plan.kernel == ACRO_NEWTON_DUO) {
 #define LAUNCH_DUO(WPB, RPB, SG)                                                                                   \
   do {                                                                                                             \
     constexpr int smem = DuoSmem<RPB, SG>::total;                                                                  \
     cudaError_t e_ = cudaFuncSetAttribute(k_newton_duo<WPB, RPB, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           smem);                                                                   \
     if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                         \
-    k_newton_duo<WPB, RPB, SG><<<(unsigned)tiles, 64, smem, (cudaStream_t)stream>>>(a);                            \
+    k_newton_duo<WPB, RPB, SG><<<(unsigned)tiles, 64, smem, s>>>(a);                                               \
   } while (0)
     // Per-problem references always run the variant that keeps the weights in registers (it takes shared weights too:
     // WV<true> falls back to them): ptxas puts YIELDs at the loop heads of k_newton_duo<false, true, *> and of no
     // other variant, which costs 12 % (8.7 against 9.9 M it/s at B = 4096).
-    const bool wreg = per_problem_weights(*w) || ref->per_problem != 0;
-    if (tiles > 148) {  // two blocks per SM: 4-step stages (70-90 KB per block)
+    const bool wreg = wpb || rpb;
+    if (plan.stage_steps == 4) {
 #define EXPR(WPB, RPB) LAUNCH_DUO(WPB, RPB, 4)
-      DISPATCH2(wreg, ref->per_problem != 0, EXPR);
+      DISPATCH2(wreg, rpb, EXPR);
 #undef EXPR
-    } else if (!ref->per_problem && getenv("ACRO_DUO_SG") && atoi(getenv("ACRO_DUO_SG")) == 8) {
+    } else if (plan.stage_steps == 8 && !rpb) {
 #define EXPR(WPB, RPB) LAUNCH_DUO(WPB, false, 8)
-      DISPATCH2(per_problem_weights(*w), false, EXPR);
+      DISPATCH2(wpb, false, EXPR);
 #undef EXPR
-    } else if (!ref->per_problem) {
-#define EXPR(WPB, RPB) LAUNCH_DUO(WPB, false, 16)
-      DISPATCH2(per_problem_weights(*w), false, EXPR);
-#undef EXPR
+    } else if (plan.stage_steps == 8) {
+      LAUNCH_DUO(true, true, 8);
     } else {
-#define EXPR(WPB, RPB) LAUNCH_DUO(true, true, 8)
-      DISPATCH2(true, true, EXPR);
+#define EXPR(WPB, RPB) LAUNCH_DUO(WPB, false, 16)
+      DISPATCH2(wpb, false, EXPR);
 #undef EXPR
     }
 #undef LAUNCH_DUO
-  } else if (ring) {
-#define LAUNCH_RING(WPB, RPB, SG)                                                                                   \
+  } else {
+#define LAUNCH_RING(WPB, RPB, SG, RL)                                                                               \
   do {                                                                                                              \
     constexpr int smem = ACRO_RING_D * stage_bytes<RPB, SG>() + ACRO_RING_D * 8;                                    \
-    cudaError_t e_ = cudaFuncSetAttribute(k_newton_ring<WPB, RPB, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          smem);                                                                    \
-    if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                          \
-    k_newton_ring<WPB, RPB, SG><<<(unsigned)tiles, 32, smem, (cudaStream_t)stream>>>(a);                            \
-  } while (0)
-#define LAUNCH_RING_RL(WPB, RPB, SG)                                                                                \
-  do {                                                                                                              \
-    constexpr int smem = ACRO_RING_D * stage_bytes<RPB, SG>() + ACRO_RING_D * 8;                                    \
-    cudaError_t e_ = cudaFuncSetAttribute(k_newton_ring<WPB, RPB, SG, true>,                                        \
+    cudaError_t e_ = cudaFuncSetAttribute(k_newton_ring<WPB, RPB, SG, RL>,                                          \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
     if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                          \
-    k_newton_ring<WPB, RPB, SG, true><<<(unsigned)tiles, 32, smem, (cudaStream_t)stream>>>(a);                      \
+    k_newton_ring<WPB, RPB, SG, RL><<<(unsigned)tiles, 32, smem, s>>>(a);                                           \
   } while (0)
-    // at most one block per SM: deep stages (16 steps per bulk copy); otherwise 4 steps per stage, 4 blocks per SM.
-    // Per-problem references need 50 % more shared memory per stage: they always use the 4-step stages.
-    const char* sg_env = getenv("ACRO_RING_SG");
-    const int sg_force = sg_env ? atoi(sg_env) : 0;
-    if ((tiles <= 148 && !ref->per_problem && !sg_force) || sg_force == 16) {
-#define EXPR(WPB, RPB) LAUNCH_RING(WPB, false, 16)
-      DISPATCH2(per_problem_weights(*w), false, EXPR);
+    if (plan.stage_steps == 16) {
+#define EXPR(WPB, RPB) LAUNCH_RING(WPB, false, 16, false)
+      DISPATCH2(wpb, false, EXPR);
 #undef EXPR
-    } else if ((tiles > 592 && !sg_force) || sg_force == 2) {
-      // more tiles than SM sub-partitions: 2-step stages (25 KB per block), eight blocks = two warps per sub-partition.
-      // This regime is HBM bound: the backward pass recomputes the linearisation about (x_t, u_t) instead of
-      // streaming the 80 B the forward pass would have stored for it (304 instead of 464 B per problem-step-iteration;
-      // ACRO_RING_RL=0 keeps the stored linearisation for A/B runs).
-      const char* rl_env = getenv("ACRO_RING_RL");
-      if (rl_env && atoi(rl_env) == 0) {
-#define EXPR(WPB, RPB) LAUNCH_RING(WPB, RPB, 2)
-        DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+    } else if (plan.stage_steps == 2 && plan.recompute_lin) {
+      // more tiles than SM sub-partitions: this regime is HBM bound, and the backward pass recomputes the linearisation
+      // about (x_t, u_t) instead of streaming the 80 B the forward pass would have stored for it (304 instead of 464 B
+      // per problem-step-iteration)
+#define EXPR(WPB, RPB) LAUNCH_RING(WPB, RPB, 2, true)
+      DISPATCH2(wpb, rpb, EXPR);
 #undef EXPR
-      } else {
-#define EXPR(WPB, RPB) LAUNCH_RING_RL(WPB, RPB, 2)
-        DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+    } else if (plan.stage_steps == 2) {
+#define EXPR(WPB, RPB) LAUNCH_RING(WPB, RPB, 2, false)
+      DISPATCH2(wpb, rpb, EXPR);
 #undef EXPR
-      }
     } else {
-#define EXPR(WPB, RPB) LAUNCH_RING(WPB, RPB, 4)
-      DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#define EXPR(WPB, RPB) LAUNCH_RING(WPB, RPB, 4, false)
+      DISPATCH2(wpb, rpb, EXPR);
 #undef EXPR
     }
 #undef LAUNCH_RING
-#undef LAUNCH_RING_RL
-  } else {
-    const Cfg c = cfg_for(B);
-#define EXPR(WPB, RPB) k_newton<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(a)
-    DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
-#undef EXPR
   }
   ACRO_LAUNCH_CHECK("acro_newton_solve");
+  return ACRO_OK;
+}
+
+int acro_newton_describe(const AcroNewtonOpts* opts, int64_t B, int ref_per_problem, int weights_per_problem,
+                         int params_per_problem, char* buf, int buf_len) {
+  ACRO_REQUIRE(opts && buf && buf_len > 0 && B > 0, "acro_newton_describe: bad argument");
+  NewtonPlan plan;
+  const int rc = newton_plan(*opts, B, ref_per_problem != 0, weights_per_problem != 0, params_per_problem != 0, true, plan);
+  if (rc != ACRO_OK) return rc;
+  const bool wpb = weights_per_problem != 0, rpb = ref_per_problem != 0;
+  const char* tf[2] = {"false", "true"};
+  if (plan.kernel == ACRO_NEWTON_THREAD)
+    snprintf(buf, buf_len, "acro::k_newton<%s,%s,%s>", tf[wpb], tf[rpb], tf[params_per_problem != 0]);
+  else if (plan.kernel == ACRO_NEWTON_DUO)
+    snprintf(buf, buf_len, "acro::k_newton_duo<%s,%s,%d>", tf[wpb || rpb], tf[rpb], plan.stage_steps);
+  else
+    snprintf(buf, buf_len, "acro::k_newton_ring<%s,%s,%d,%s>", tf[wpb], tf[rpb], plan.stage_steps, tf[plan.recompute_lin]);
   return ACRO_OK;
 }
 

@@ -202,9 +202,65 @@ def plot_armijo_line_search(*args, **kwargs):
     return None
 
 
+class _NewtonSlot:
+    """Device state + batch-major staging of one in-flight batched solve (see _NewtonPipeline)."""
+
+    def __init__(self, Bn, N, max_iters):
+        self.key = (Bn, N, max_iters)
+        self.state = bt.newton_alloc(Bn, N, max_iters, history=True)
+        self.copied = None  # event: the D2H copies out of this slot have completed
+
+
+class _NewtonPipeline:
+    """Double-buffered solver state and a copy stream, so that the device-to-host copies of one solve overlap the
+    kernel of the next one (trajectory_generation.newton_Algorithm(..., block=False)).
+
+    Solve i runs on the caller's stream into slot i mod 2; its results are un-tiled and copied to fresh pinned host
+    tensors on the copy stream, which waits for the solve's event; solve i+1 (other slot) starts at once.  A slot is
+    reused only after its copies have completed (stream-side wait, no host synchronisation)."""
+
+    def __init__(self, depth=2):
+        self.depth, self.slots, self.n, self.copy_stream = depth, {}, 0, None
+
+    def slot(self, Bn, N, max_iters):
+        dev_i = torch.cuda.current_device()
+        if self.copy_stream is None or self.copy_stream.device.index != dev_i:
+            self.copy_stream = torch.cuda.Stream()
+            self.slots = {}
+        i = self.n % self.depth
+        self.n += 1
+        sl = self.slots.get(i)
+        if sl is None or sl.key != (Bn, N, max_iters):
+            sl = self.slots[i] = _NewtonSlot(Bn, N, max_iters)
+        if sl.copied is not None:
+            torch.cuda.current_stream().wait_event(sl.copied)
+        return sl
+
+
+_pipeline = _NewtonPipeline()
+
+
+class PendingNewton:
+    """Handle of a batched solve whose results are on their way to the host; ``result()`` waits for the copies and
+    returns what ``newton_Algorithm`` returns."""
+
+    def __init__(self, done, build):
+        self._done, self._build, self._value = done, build, None
+
+    def ready(self):
+        return self._value is not None or self._done.query()
+
+    def result(self):
+        if self._value is None:
+            self._done.synchronize()
+            self._value = self._build()
+            self._build = None
+        return self._value
+
+
 def newton_Algorithm(x0, x_ref, u_ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1, plot_armijo_iters=10, *,
                      Q=None, R=None, Q_T=None, return_history=False, history_stride=1, verbose=True,
-                     return_state=False, params_b=None):
+                     return_state=False, params_b=None, return_gains=True, block=True, kernel=None):
     """Regularised Newton method with Armijo line search (trajectory_generation.py:298-398).
 
     One problem: returns ``(x_traj, u_traj, K, sigma, history)`` with the reference's types (K and sigma
@@ -213,6 +269,11 @@ def newton_Algorithm(x0, x_ref, u_ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gam
     Batch (x0 of shape (B,4)): arrays with a leading batch axis; history['cost'] is (B, iters+1) padded with
     NaN past each problem's last iteration, plus 'iters', 'status', 'n_try', 'gamma'.
     params_b (B, 11): every problem its own physical parameters (domain randomisation).
+    return_gains=False: K and sigma (half of the bytes a batched solve returns) stay on the device and come back as
+    ``batched.Traj`` handles instead of host arrays.
+    block=False (batched, without return_history): returns a ``PendingNewton`` at once; its ``result()`` gives the
+    tuple.  The device-to-host copies of this solve then overlap the kernel of the next call.
+    kernel: a name of ``batched.KERNEL_VARIANTS`` (default: chosen by batch size).
     """
     u_ref_n = u_ref.shape[0] if u_ref.ndim == 2 else u_ref.shape[1]
     x_ref_n = x_ref.shape[0] if x_ref.ndim == 2 else x_ref.shape[1]
@@ -227,54 +288,116 @@ def newton_Algorithm(x0, x_ref, u_ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gam
     x0d, kind = _io.state_in(x0, nx)
     ref = _ref(x_ref, u_ref)
     w = _weights(Q, R, Q_T)
-    kw = dict(max_iters=max_iters, tol=tol, beta=beta, c=c, gamma_0=gamma_0, w=w, params=active_params())
+    kw = dict(max_iters=max_iters, tol=tol, beta=beta, c=c, gamma_0=gamma_0, w=w, params=active_params(), kernel=kernel)
     if params_b is not None:  # physical parameters per problem (B, 11): see batched.phys_params
         kw["params_b"] = bt.phys_params(params_b, x0d.shape[1])
     x_trajs, sigmas = [], []
 
-    def snap(t, key):
-        o = _io.out(t, kind, key=key)
-        return o.clone() if isinstance(o, torch.Tensor) else o.copy()
-
     if return_history:
         # history['x_trajs'][0] is the initial open-loop rollout (tg:322-327); one launch per stored iterate after that
-        x_trajs.append(snap(bt.rollout_open_loop(x0d, None, N=ref.N, params=active_params(),
-                                                 params_b=kw.get("params_b")), "hx"))
+        x_trajs.append(_io.out(bt.rollout_open_loop(x0d, None, N=ref.N, params=active_params(),
+                                                    params_b=kw.get("params_b")), kind))
         st, done = None, 0
         while True:
             st = bt.newton_solve(x0d, ref, state=st, chunk_iters=history_stride, **kw)
             done += history_stride
-            x_trajs.append(snap(st.X, "hx"))
-            sigmas.append(snap(st.S, "hs"))
+            # the reference logs sigma in every iteration (tg:341-342) and the iterate only after an ACCEPTED step
+            # (tg:387-388): a line-search failure breaks out before that (tg:367-369)
+            sigmas.append(_io.out(st.S, kind))
+            if not bool((st.status == 3).all()):
+                x_trajs.append(_io.out(st.X, kind))
             if bool((st.status != 0).all()) or done >= max_iters:
                 break
-    else:
-        st = bt.newton_solve(x0d, ref, **kw)
-    iters = st.iters.cpu().numpy()
-    status = st.status.cpu().numpy()
-    n_it = int(iters.max()) if iters.size else 0
-    hc = st.hist_cost[:n_it + 1].cpu().numpy().T  # (B, n_it+1)
-    hs = st.hist_sigma_norm[:n_it].cpu().numpy().T
-    if verbose:
-        for b in np.where(status == 3)[0][:8]:
-            print(f"Iteration {iters[b] - 1}: Line search failed to find sufficient decrease.")
-        for b in np.where(status == 1)[0][:8]:
-            print(f"Converged at iteration {iters[b] - 1}!")
-    x_traj = _io.out(st.X, kind, key="x")
-    u_traj = _io.out(st.U, kind, key="u")
-    K = _io.out(st.K, kind, tail=(2, 4), key="K")
-    sigma = _io.out(st.S, kind, key="S")
-    if kind.batched:
-        history = {"cost": hc, "sigma_norm": hs, "iters": iters, "status": status,
-                   "n_try": st.hist_ntry[:n_it].cpu().numpy().T, "gamma": st.hist_gamma[:n_it].cpu().numpy().T,
-                   "x_trajs": x_trajs, "sigmas": sigmas}
-    else:
-        n_acc = int(np.isfinite(hc[0]).sum()) - 1
-        history = {"cost": list(hc[0][:n_acc + 1]), "sigma_norm": list(hs[0][:int(iters[0])]), "x_trajs": x_trajs,
-                   "sigmas": sigmas, "iters": int(iters[0]), "status": int(status[0]),
-                   "n_try": list(st.hist_ntry[:int(iters[0]), 0].cpu().numpy()),
-                   "gamma": list(st.hist_gamma[:int(iters[0]), 0].cpu().numpy())}
-        K, sigma = list(K), list(sigma)
-    if return_state:
-        return x_traj, u_traj, K, sigma, history, st
-    return x_traj, u_traj, K, sigma, history
+        pend = _finish_newton(st, kind, verbose, return_gains, x_trajs, sigmas, return_state, None)
+        return pend.result() if block else pend
+    sl = _pipeline.slot(x0d.shape[1], ref.N, int(max_iters)) if kind.batched else None
+    if sl is not None:
+        sl.state.reset()
+    st = bt.newton_solve(x0d, ref, state=None if sl is None else sl.state, **kw)
+    pend = _finish_newton(st, kind, verbose, return_gains, x_trajs, sigmas, return_state, sl)
+    return pend if (not block and kind.batched) else pend.result()
+
+
+
+def _finish_newton(st, kind, verbose, return_gains, x_trajs, sigmas, return_state, slot):
+    """Queue the un-tiling and the device-to-host copies of a finished (queued) solve on the copy stream; the returned
+    handle builds the reference-shaped tuple once they are done."""
+    host = not (kind.torch and kind.cuda)
+    solved = torch.cuda.Event()
+    solved.record()
+    cs = _pipeline.copy_stream if slot is not None else None
+    outs = {}
+    ctx = torch.cuda.stream(cs) if cs is not None else _Null()
+    with ctx:
+        if cs is not None:
+            cs.wait_event(solved)
+
+        def fetch(name, dev_t):
+            if host:
+                h = _io.pinned_empty(dev_t.shape, dev_t.dtype)
+                h.copy_(dev_t, non_blocking=True)
+                outs[name] = (h, dev_t)  # keep the device staging alive until the copy has run
+            else:
+                outs[name] = (dev_t, None)
+
+        def traj(name, t, tail=None):
+            a = t.batch_major()
+            if tail is not None:
+                a = a.reshape(*a.shape[:-1], *tail)
+            fetch(name, a if kind.batched else a[0])
+
+        traj("x", st.X)
+        traj("u", st.U)
+        if return_gains:
+            traj("K", st.K, (2, 4))
+            traj("S", st.S)
+        for name in ("iters", "status", "hist_cost", "hist_sigma_norm", "hist_ntry", "hist_gamma"):
+            fetch(name, getattr(st, name))
+        done = torch.cuda.Event()
+        done.record()
+    if slot is not None:
+        slot.copied = done
+
+    def build():
+        g = {k: (v[0] if kind.torch else v[0].numpy()) if host else v[0] for k, v in outs.items()}
+        np_of = (lambda v: v.numpy()) if host else (lambda v: v.cpu().numpy())
+        iters, status = np_of(outs["iters"][0]), np_of(outs["status"][0])
+        n_it = int(iters.max()) if iters.size else 0
+        hc = np_of(outs["hist_cost"][0])[:n_it + 1].T  # (B, n_it+1)
+        hs = np_of(outs["hist_sigma_norm"][0])[:n_it].T
+        hn = np_of(outs["hist_ntry"][0])[:n_it].T
+        hg = np_of(outs["hist_gamma"][0])[:n_it].T
+        if verbose:
+            if not kind.batched:  # the reference's progress line, every 10th iteration (tg:391-392)
+                for k in range(0, len(hc[0]) - 1, 10):
+                    if np.isfinite(hc[0][k + 1]):
+                        print(f"Iter {k}: Cost={hc[0][k + 1]:.2f}, diff_cost={hc[0][k] - hc[0][k + 1]:.2e}, ")
+            for b in np.where(status == 3)[0][:8]:
+                print(f"Iteration {iters[b] - 1}: Line search failed to find sufficient decrease.")
+            for b in np.where(status == 1)[0][:8]:
+                print(f"Converged at iteration {iters[b] - 1}!")
+        K, sigma = (g["K"], g["S"]) if return_gains else (st.K, st.S)
+        if kind.batched:
+            history = {"cost": hc, "sigma_norm": hs, "iters": iters, "status": status, "n_try": hn, "gamma": hg,
+                       "x_trajs": x_trajs, "sigmas": sigmas}
+        else:
+            # accepted steps: every iteration but a final one whose line search failed (tg:367-369)
+            n_acc = int(iters[0]) - (1 if int(status[0]) == 3 else 0)
+            history = {"cost": list(hc[0][:n_acc + 1]), "sigma_norm": list(hs[0][:int(iters[0])]), "x_trajs": x_trajs,
+                       "sigmas": sigmas, "iters": int(iters[0]), "status": int(status[0]),
+                       "n_try": list(hn[0][:int(iters[0])]), "gamma": list(hg[0][:int(iters[0])])}
+            if return_gains:
+                K, sigma = list(K), list(sigma)
+        if return_state:
+            return g["x"], g["u"], K, sigma, history, st
+        return g["x"], g["u"], K, sigma, history
+
+    return PendingNewton(done, build)
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

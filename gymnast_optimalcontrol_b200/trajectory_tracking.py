@@ -81,6 +81,20 @@ def solver_mpc(x0, A_list, B_list, Q, R, Q_T, T_pred, u_ref=None):
     return U0.cpu().numpy()[:, 0], Xo.batch_major()[0].cpu().numpy(), Uo.batch_major()[0].cpu().numpy()
 
 
+def _pad_time(a, n):
+    """Zero-pad the time axis (second to last) to n rows: the reference allocates x_real / u_real with the shapes of
+    x_ref / u_ref (tt:27-28) and fills the first T / T-1 rows."""
+    t = a.shape[-2]
+    if t >= n:
+        return a
+    if isinstance(a, torch.Tensor):
+        out = a.new_zeros(*a.shape[:-2], n, a.shape[-1])
+    else:
+        out = np.zeros(a.shape[:-2] + (n, a.shape[-1]))
+    out[..., :t, :] = a
+    return out
+
+
 def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return_info=False, tau_max=None):
     """trajectory_tracking.py:8-69.  x0 (4,) or (B,4); reference shared (N,4) or per problem (B,N,4).
 
@@ -102,7 +116,7 @@ def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return
                                         T_pred=int(T_pred), w=w, x_f=x_f, u_f=u_f, params=p)
         if int(info["status"].max()) != 0:
             print("Attention! mpc solver: active-set iteration limit reached for %d problem(s)" % int((info["status"] != 0).sum()))
-        xr, ur = _io.out(Xr, kind, key="xr"), _io.out(Ur, kind, key="ur")
+        xr, ur = _pad_time(_io.out(Xr, kind, key="xr"), ref.N), _pad_time(_io.out(Ur, kind, key="ur"), ref.N - 1)
         if return_info:
             return xr, ur, dict(n_solves=(int(T) - 1) * x0d.shape[1], n_sweeps=info["n_sweeps"].cpu().numpy(),
                                 n_active=info["n_active"].cpu().numpy().T, status=info["status"].cpu().numpy(),
@@ -110,7 +124,7 @@ def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return
         return xr, ur
     Xr, Ur, K0, n_solves = bt.mpc_track(x0d, ref, P[:, :, 0].contiguous(), T=int(T), T_pred=int(T_pred), w=w,
                                         x_f=x_f, u_f=u_f, params=p)
-    xr, ur = _io.out(Xr, kind, key="xr"), _io.out(Ur, kind, key="ur")
+    xr, ur = _pad_time(_io.out(Xr, kind, key="xr"), ref.N), _pad_time(_io.out(Ur, kind, key="ur"), ref.N - 1)
     if return_info:
         return xr, ur, dict(n_solves=n_solves, K0=None if K0 is None else K0.cpu().numpy().reshape(-1, 2, 4),
                             P_inf=P.cpu().numpy()[:, :, 0])

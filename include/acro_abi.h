@@ -11,7 +11,7 @@
  *  - Every function returns 0 on success, a negative ACRO_E_* code otherwise, never throws,
  *    and is asynchronous on the given stream (a cudaStream_t passed as void*; NULL = the
  *    legacy default stream).  There is no global mutable state apart from a thread-local
- *    error string (acro_last_error_string).
+ *    error string (acro_last_error_string) and the launch counter; no environment variable is read.
  *  - All array pointers are caller-owned DEVICE pointers to FP64 (or int32 where stated)
  *    unless a parameter is documented as HOST.  The library allocates nothing.
  *  - Point batches are structure-of-arrays with the problem index fastest:
@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define ACRO_ABI_VERSION 1
+#define ACRO_ABI_VERSION 2
 
 /* error codes */
 #define ACRO_OK 0
@@ -106,7 +106,22 @@ typedef struct AcroNewtonOpts {
   double beta;          /* tg:365 */
   double c;             /* tg:361 */
   double gamma_0;       /* tg:344 */
+  /* Kernel selection (all 0 = automatic, by batch size and SM count of the current device).  Every variant
+   * computes the same iteration; they differ in how a tile of 32 problems is mapped to warps, and agree to
+   * rounding (1e-12) but not bit for bit (different sin/cos evaluation order), so pin `kernel`/`stage_steps`
+   * when results must not depend on the batch size of the call (sharding across GPUs). */
+  int32_t kernel;       /* ACRO_NEWTON_AUTO / _DUO / _RING / _THREAD / _SPEC */
+  int32_t stage_steps;  /* time steps per TMA stage of the ring kernels: 0 auto, or 2, 4, 8, 16 */
+  int32_t recompute_lin; /* large-batch ring kernel: 0 auto, 1 backward pass recomputes the linearisation
+                            (304 B per problem-step-iteration), 2 it streams the one the forward pass stored (464 B) */
+  int32_t speculate;    /* Armijo candidates evaluated in parallel per round by ACRO_NEWTON_SPEC: 0 auto
+                            (from the previous iteration's number of tries), 1..8 fixed */
 } AcroNewtonOpts;
+#define ACRO_NEWTON_AUTO 0
+#define ACRO_NEWTON_DUO 1    /* two warps per tile (recurrence + trailer), at most two tiles per SM */
+#define ACRO_NEWTON_RING 2   /* one warp per tile, TMA-fed ring */
+#define ACRO_NEWTON_THREAD 3 /* one thread per problem, register prefetch (no alignment requirement) */
+#define ACRO_NEWTON_SPEC 4   /* eight warps per tile: like DUO, plus speculative parallel Armijo candidates */
 
 const char* acro_version(void);
 const char* acro_last_error_string(void);
@@ -195,6 +210,10 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
                       double* sigma_norm, double* gamma_acc, int32_t* iters, int32_t* status,
                       double* hist_cost, double* hist_sigma_norm, double* hist_gamma,
                       int32_t* hist_ntry, void* stream);
+/* Name of the kernel acro_newton_solve would launch for these options and this batch on the current device
+ * (e.g. "acro::k_newton_duo<false,false,16>"), for logs and bench.py; launches nothing. */
+int acro_newton_describe(const AcroNewtonOpts* opts, int64_t B, int ref_per_problem, int weights_per_problem,
+                         int params_per_problem, char* buf, int buf_len);
 /* The step-size sweep of plot_armijo_line_search  tg:257-264: P base iterates (X,U,K,S with
  * batch size P) x S_n shared step sizes steps[S_n] -> cost [S_n][P]. */
 int acro_stepsize_sweep(const AcroParams* p, const AcroWeights* w, int64_t P, int N, const double* X,

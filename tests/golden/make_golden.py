@@ -223,13 +223,171 @@ def g_sweep():
     save("sweep_iter0", steps=steps, costs=costs, delta_J=float(dJ))
 
 
+# ------------------------------------------------------------------------------------------------------------
+# Round 2: SURVEY 8(d) sample sizes.  The reference is a per-problem Python loop (3-5 Newton iterations/s/core), so
+# these run in a fork()ed pool (the SymPy model is built once in the parent).  --workers sets the pool size.
+# ------------------------------------------------------------------------------------------------------------
+WORKERS = 6
+
+
+def _pool_map(fn, items):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(WORKERS) as pool:
+        return pool.map(fn, items, chunksize=1)
+
+
+def c2_x0():
+    """The config-2 batch of SURVEY 8(d): seed 1, problem 0 = task_2."""
+    x0 = np.random.default_rng(1).uniform(-0.2, 0.2, (4096, 4))
+    x0[0] = 0.0
+    return x0
+
+
+# first / last lane of the first / last tile, tile boundaries, and a spread over the batch
+C2_CONV_ROWS = [1, 31, 32, 63, 777, 1024, 2047, 2048, 2500, 3000, 3333, 3840, 4000, 4064, 4094, 4095]
+
+
+def _c2_conv_one(i):
+    x_ref, u_ref, _ = fully_actuated_ref()
+    t = time.time()
+    o = run_newton(c2_x0()[i], x_ref, u_ref, 5000, 1e-4, 0.1, keep=0)
+    print("  c2 row %d: %d iterations, %.0f s" % (i, len(o["sigma_norm"]), time.time() - t), flush=True)
+    return o
+
+
+def g_c2conv():
+    """16 problems of the config-2 batch to convergence (gamma_0 = 0.1, tol = 1e-4) with the unmodified reference."""
+    outs = _pool_map(_c2_conv_one, C2_CONV_ROWS)
+    n = max(len(o["cost"]) for o in outs)
+
+    def pad(v, m):
+        return np.concatenate([np.asarray(v, dtype=float), np.full(m - len(v), np.nan)])
+
+    save("newton_c2_converged", rows=np.array(C2_CONV_ROWS), x0=c2_x0()[C2_CONV_ROWS],
+         iters=np.array([len(o["sigma_norm"]) for o in outs]),
+         cost=np.array([pad(o["cost"], n) for o in outs]), sigma_norm=np.array([pad(o["sigma_norm"], n - 1) for o in outs]),
+         n_try=np.array([pad(o["n_try"], n - 1) for o in outs]), gamma_acc=np.array([pad(o["gamma_acc"], n - 1) for o in outs]),
+         x=np.array([o["x"] for o in outs]), u=np.array([o["u"] for o in outs]), sigma=np.array([o["sigma"] for o in outs]),
+         K=np.array([o["K"] for o in outs]), x_prev=np.array([o["x_prev"] for o in outs]),
+         u_prev=np.array([o["u_prev"] for o in outs]))
+
+
+def c2_3it_rows():
+    r = np.random.default_rng(11).choice(np.arange(64, 4032), 56, replace=False)
+    return np.sort(np.concatenate([[0, 31, 32, 63, 4032, 4063, 4064, 4095], r]))
+
+
+def _c2_3it_one(args):
+    i, gamma_0 = args
+    x_ref, u_ref, _ = fully_actuated_ref()
+    o = run_newton(c2_x0()[i], x_ref, u_ref, 3, 1e-4, gamma_0, keep=0)
+    return o
+
+
+def g_c2three():
+    """64 problems of the config-2 batch x 3 iterations, at gamma_0 = 0.1 and gamma_0 = 1 (back-tracking)."""
+    rows = c2_3it_rows()
+    arrs = dict(rows=rows, x0=c2_x0()[rows])
+    for tag, g0 in (("g01", 0.1), ("g1", 1.0)):
+        outs = _pool_map(_c2_3it_one, [(int(i), g0) for i in rows])
+        arrs.update({tag + "_x": np.array([o["x"] for o in outs]), tag + "_u": np.array([o["u"] for o in outs]),
+                     tag + "_sigma": np.array([o["sigma"] for o in outs]), tag + "_cost": np.array([o["cost"] for o in outs]),
+                     tag + "_sigma_norm": np.array([o["sigma_norm"] for o in outs]),
+                     tag + "_n_try": np.array([o["n_try"] for o in outs]),
+                     tag + "_gamma_acc": np.array([o["gamma_acc"] for o in outs]),
+                     # K of 8 of them (the gains do not compress: 32 KB per problem)
+                     tag + "_K8": np.array([o["K"] for o in outs[:8]])})
+    save("newton_c2_three_iters", **arrs)
+
+
+def c3_x0():
+    """The config-3 batch of SURVEY 8(d): seed 2, problems 0, 1 = the perturbations of main.py:104-110."""
+    with ref_import.in_ref_dir():
+        d = np.load("trajectories_npz/acrobot_optimal_trajectory.npz")
+    x0 = d["x"][0] + np.random.default_rng(2).uniform(-0.3, 0.3, (65536, 4))
+    x0[0] = d["x"][0] + 0.2
+    x0[1] = d["x"][0] + 0.3
+    return x0, d["x"], d["u"]
+
+
+def c3_rows():
+    r = np.random.default_rng(12).choice(np.arange(32, 65504), 248, replace=False)
+    return np.sort(np.concatenate([[0, 1, 30, 31, 65504, 65505, 65534, 65535], r]))
+
+
+_C3 = {}
+
+
+def _c3_one(i):
+    x0, x_opt, u_opt = _C3["x0"], _C3["x_opt"], _C3["u_opt"]
+    with np.errstate(all="ignore"):
+        xt, ut = rtt.simulate_tracking(x_opt, u_opt, _C3["K"], x0[i])
+    return xt[::10], ut[::10], xt.sum(axis=0), ut.sum(axis=0)
+
+
+def g_lqr256():
+    """256 problems of the config-3 batch: tracked rollouts sampled every 10th step + column sums over time."""
+    x0, x_opt, u_opt = c3_x0()
+    _C3.update(x0=x0, x_opt=x_opt, u_opt=u_opt, K=rtt.solve_LQR_tracking(x_opt, u_opt))
+    rows = c3_rows()
+    res = _pool_map(_c3_one, [int(i) for i in rows])
+    save("lqr_tracking_c3", rows=rows, x0=x0[rows], x_track_10=np.array([r[0] for r in res]),
+         u_track_10=np.array([r[1] for r in res]), x_sum=np.array([r[2] for r in res]), u_sum=np.array([r[3] for r in res]))
+
+
+SWEEP_GAMMA_IDX = np.array([0, 7, 16, 40, 80, 120, 159, 199])  # of linspace(0, 1.25, 200)  (tg:257-258)
+
+
+def c5_rows():
+    return np.sort(np.random.default_rng(13).choice(4096, 256, replace=False))
+
+
+def _c5_one(args):
+    p, k = args
+    x_ref, u_ref, _ = fully_actuated_ref()
+    u_ref = trim(x_ref, u_ref)
+    x0 = c2_x0()[p]
+    if k == 0:
+        u = np.zeros_like(u_ref)
+        x = rtg.simulate_open_loop(x0, u)
+    else:
+        with CallLog() as log:
+            x, u, _, _, h = rtg.newton_Algorithm(x0, x_ref, u_ref, max_iters=k, tol=1e-4, gamma_0=0.1, plot_armijo_iters=0)
+        assert len(h["sigma_norm"]) == k
+    lists = rtg.build_stage_lists(x, u, x_ref, u_ref, [None] * len(x))
+    K, sig, dJ = rtg.calculate_K_and_sigma(*lists)
+    steps = np.linspace(0, 1.25, 200)[SWEEP_GAMMA_IDX]
+    costs = np.zeros(len(steps))
+    for i, s in enumerate(steps):
+        xn, un = rtg.forward_closed_loop_update(x, u, K, sig, gamma=s)
+        costs[i] = rtg.total_cost(xn, un, x_ref, u_ref, rtg.Q, rtg.R, rtg.Q_T)
+    return costs, float(dJ), x[-1].copy(), float(np.max(np.abs(np.array(sig))))
+
+
+def g_sweep256():
+    """Config 5: 256 base iterates = Newton iterate k_p (k_p = p mod 50, gamma_0 = 0.1) of config-2 problem p, each
+    with the cost along the search direction at 8 of the 200 step sizes of tg:257-258."""
+    rows = c5_rows()
+    ks = rows % 50
+    res = _pool_map(_c5_one, [(int(p), int(k)) for p, k in zip(rows, ks)])
+    save("sweep_c5", rows=rows, k=ks, gamma_idx=SWEEP_GAMMA_IDX, steps=np.linspace(0, 1.25, 200)[SWEEP_GAMMA_IDX],
+         costs=np.array([r[0] for r in res]), delta_J=np.array([r[1] for r in res]), x_T=np.array([r[2] for r in res]),
+         sigma_norm=np.array([r[3] for r in res]))
+
+
+ALL_R2 = dict(c2conv=g_c2conv, c2three=g_c2three, lqr256=g_lqr256, sweep256=g_sweep256)
+
+
 ALL = dict(shipped=g_shipped, dyn=g_dyn, blocks=g_blocks, pinf=g_pinf, lqr=g_lqr, gamma1=g_gamma1, c2=g_c2, sweep=g_sweep,
            task1=g_task1, task2=g_task2)
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*", default=None)
+    ap.add_argument("--workers", type=int, default=WORKERS)
     a = ap.parse_args()
+    WORKERS = a.workers
+    ALL.update(ALL_R2)
     for k in (a.only or list(ALL)):
         t = time.time()
         ALL[k]()

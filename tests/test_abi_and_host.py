@@ -30,17 +30,31 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "libacro_b200.so does not export %s" % n
     bound = set(_abi.SIGNATURES) | set(_abi.QUERIES) | set(_abi.SIZES)
     assert set(names) == bound, (set(names) ^ bound)
-    assert b"sm_100a" in lib.acro_version.__call__.__self__.acro_version() if False else True
     assert "sm_100a" in _abi.version()
     assert _abi.launch_count() == 0
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every struct of include/acro_abi.h, as gcc lays them out, against the ctypes mirror."""
+    import subprocess
     from gymnast_optimalcontrol_b200 import _abi
-    assert ctypes.sizeof(_abi.AcroParams) == 12 * 8 + 8
-    assert ctypes.sizeof(_abi.AcroWeights) == 36 * 8 + 3 * 8
-    assert ctypes.sizeof(_abi.AcroRef) == 24
-    assert ctypes.sizeof(_abi.AcroNewtonOpts) == 16 + 32
+    structs = {"AcroParams": _abi.AcroParams, "AcroWeights": _abi.AcroWeights, "AcroRef": _abi.AcroRef,
+               "AcroNewtonOpts": _abi.AcroNewtonOpts}
+    lines = []
+    for name, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(void){%s return 0;}\n' % (HEADER, "".join(lines))
+    c, exe = tmp_path / "layout.c", tmp_path / "layout"
+    c.write_text(src)
+    subprocess.run(["gcc", "-o", str(exe), str(c)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls), name
+        for f, _ in cls._fields_:
+            assert int(got["%s.%s" % (name, f)]) == getattr(cls, f).offset, (name, f)
+    assert ctypes.sizeof(_abi.AcroNewtonOpts) == 16 + 32 + 16
 
 
 def test_invalid_arguments_return_error_codes_without_a_gpu():
@@ -140,3 +154,41 @@ def test_headline_kernels_carry_no_yield():
         assert hits, "kernel variant %s not found in the library" % tag
         for n in hits:
             assert counts[n] == 0, "%s: %d YIELD instructions" % (n, counts[n])
+
+
+def test_staged_reference_is_the_unmodified_reference():
+    """oracle/build_ref.py stages the reference for the GPU box's CPU arm: byte-for-byte copies (sha256 of source and
+    copy recorded), git-ignored, and ref_import finds the tree."""
+    from oracle import build_ref, ref_import
+    if os.path.isfile("/root/reference/dynamics.py"):
+        man = build_ref.build()
+        assert sorted(man) == sorted(build_ref.FILES)
+        for rel, h in man.items():
+            assert build_ref.sha256(os.path.join("/root/reference", rel)) == h
+    if os.path.isdir(build_ref.DST):
+        assert build_ref.check()
+    ign = open(os.path.join(ROOT, ".gitignore")).read()
+    assert "oracle/_ref/" in ign
+    assert "oracle/_ref" not in open(os.path.join(ROOT, ".gpurunignore")).read()
+    assert ref_import.REF_ROOT in ("/root/reference", build_ref.DST) or "ACRO_REFERENCE_ROOT" in os.environ
+
+
+def test_kernel_variants_and_plan():
+    """Kernel selection is an AcroNewtonOpts field (no environment variable): acro_newton_describe names what
+    acro_newton_solve would launch; bad combinations are refused."""
+    from gymnast_optimalcontrol_b200 import _abi
+    from gymnast_optimalcontrol_b200 import batched as bt
+    assert bt.newton_kernel_name(4096) == "acro::k_newton_duo<false,false,16>"
+    assert bt.newton_kernel_name(4096, ref_per_problem=True) == "acro::k_newton_duo<true,true,8>"
+    assert bt.newton_kernel_name(8192) == "acro::k_newton_duo<false,false,4>"
+    assert bt.newton_kernel_name(16384) == "acro::k_newton_ring<false,false,4,false>"
+    assert bt.newton_kernel_name(65536) == "acro::k_newton_ring<false,false,2,true>"
+    assert bt.newton_kernel_name(65536, kernel="ring2") == "acro::k_newton_ring<false,false,2,false>"
+    assert bt.newton_kernel_name(64, kernel="ldg") == "acro::k_newton<false,false,false>"
+    assert bt.newton_kernel_name(64, params_per_problem=True) == "acro::k_newton<false,false,true>"
+    with pytest.raises(_abi.AcroError):
+        bt.newton_kernel_name(64, kernel="ring", stage_steps=8)
+    with pytest.raises(_abi.AcroError):
+        bt.newton_kernel_name(64, kernel="duo", ref_per_problem=True, stage_steps=16)
+    src = open(os.path.join(ROOT, "gymnast_optimalcontrol_b200", "csrc", "acro_kernels.cu")).read()
+    assert "getenv" not in src

@@ -179,3 +179,94 @@ def test_per_problem_parameters_through_the_dropins(mods):
         assert rel_err(Xo[b], O.simulate_open_loop(x[b], Ut[b], m)) < TOL
     with pytest.raises(ValueError):
         dyn.dynamics(x, u, params_b=rows[:3])
+
+
+# ------------------------------------------------------------------------------------- round 2: ownership, pipelining, shapes
+def test_results_of_consecutive_calls_do_not_alias(mods):
+    """Pinned-host torch inputs get pinned-host results: every call returns a FRESH buffer (the staging
+    buffer used to be cached per shape, so x1 = dynamics(xp, u1); x2 = dynamics(xp, u2) made x1 IS x2)."""
+    dyn, tg, tt = mods
+    rng = np.random.default_rng(5)
+    xp = torch.from_numpy(rng.uniform(-1, 1, (64, 4))).pin_memory()
+    u1 = torch.from_numpy(rng.uniform(-2, 2, (64, 2))).pin_memory()
+    u2 = torch.from_numpy(rng.uniform(-2, 2, (64, 2))).pin_memory()
+    x1 = dyn.dynamics(xp, u1)
+    keep = x1.clone()
+    x2 = dyn.dynamics(xp, u2)
+    assert x1.is_pinned() and x2.is_pinned() and x1.data_ptr() != x2.data_ptr()
+    assert torch.equal(x1, keep) and not torch.equal(x1, x2)
+    for b in (0, 63):
+        assert rel_err(x1[b].numpy(), O.dynamics(xp[b].numpy(), u1[b].numpy())) < TOL
+        assert rel_err(x2[b].numpy(), O.dynamics(xp[b].numpy(), u2[b].numpy())) < TOL
+
+
+def test_pipelined_newton_equals_blocking_newton(mods, fa_ref):
+    """newton_Algorithm(block=False): three solves in flight over two solver-state slots; every result equals the
+    blocking call bit for bit, results own their buffers, the history of a short solve is not polluted by the longer
+    solve that used the slot before it."""
+    dyn, tg, tt = mods
+    x_ref, u_ref, _ = fa_ref
+    rng = np.random.default_rng(9)
+    x0s = [torch.from_numpy(rng.uniform(-0.2, 0.2, (96, 4))).pin_memory() for _ in range(3)]
+    xr, ur = torch.from_numpy(x_ref).pin_memory(), torch.from_numpy(u_ref).pin_memory()
+    kws = [dict(max_iters=5, tol=1e-4, gamma_0=1.0), dict(max_iters=5, tol=1e-4, gamma_0=0.1), dict(max_iters=5, tol=50.0, gamma_0=0.5)]
+    blocking = [tg.newton_Algorithm(x0, xr, ur, verbose=False, **kw) for x0, kw in zip(x0s, kws)]
+    pend = [tg.newton_Algorithm(x0, xr, ur, verbose=False, block=False, **kw) for x0, kw in zip(x0s, kws)]
+    res = [p.result() for p in pend]
+    for a, b in zip(blocking, res):
+        for i in range(4):
+            assert torch.equal(a[i], b[i]) and a[i].data_ptr() != b[i].data_ptr() and b[i].is_pinned()
+        for k in ("cost", "sigma_norm", "n_try", "gamma", "iters", "status"):
+            assert np.array_equal(a[4][k], b[4][k], equal_nan=True), k
+    # the third solve stops early (tol = 50): rows of the history beyond each problem's last iteration are NaN, not
+    # left-overs of the first solve that ran in the same slot
+    h = res[2][4]
+    assert h["iters"].min() < 5
+    for b in range(96):
+        assert np.isnan(h["cost"][b, h["iters"][b] + 1:]).all()
+    # return_gains=False: K and sigma stay on the device
+    x, u, K, s, hh = tg.newton_Algorithm(x0s[1], xr, ur, verbose=False, return_gains=False, **kws[1])
+    from gymnast_optimalcontrol_b200.batched import Traj
+    assert isinstance(K, Traj) and isinstance(s, Traj) and torch.equal(x, blocking[1][0])
+    assert torch.equal(K.batch_major().reshape(96, 500, 2, 4).cpu(), blocking[1][2])
+
+
+def test_history_lists_follow_the_reference(mods, fa_ref):
+    """history['x_trajs'] / ['sigmas'] / ['cost'] / ['sigma_norm'] lengths as the reference builds them (tg:322-327,
+    341-342, 387-388): a line-search failure appends sigma but no iterate and no cost; progress line every 10th
+    iteration (tg:391-392)."""
+    dyn, tg, tt = mods
+    x_ref, u_ref, _ = fa_ref
+    x, u, K, s, h = tg.newton_Algorithm(np.zeros(4), x_ref, u_ref, max_iters=3, tol=1e-4, gamma_0=0.1, return_history=True, verbose=False)
+    assert len(h["x_trajs"]) == 4 and len(h["sigmas"]) == 3 and len(h["cost"]) == 4 and len(h["sigma_norm"]) == 3
+    g = golden("newton_task2")
+    assert rel_err(np.array(h["x_trajs"]), g["x_trajs"][:4]) < TOL and rel_err(np.array(h["sigmas"]), g["sigmas"][:3]) < TOL
+    # c = 1e6 can never be satisfied: the first line search fails (tg:367-369)
+    x, u, K, s, h = tg.newton_Algorithm(np.zeros(4), x_ref, u_ref, max_iters=3, tol=1e-4, gamma_0=0.1, c=1e6, return_history=True, verbose=False)
+    assert h["status"] == 3 and h["iters"] == 1
+    assert len(h["x_trajs"]) == 1 and len(h["sigmas"]) == 1 and len(h["cost"]) == 1 and len(h["sigma_norm"]) == 1
+    # non-finite initial cost: same lengths (the count comes from iters / status, not from isfinite)
+    x, u, K, s, h = tg.newton_Algorithm(np.array([np.nan, 0, 0, 0]), x_ref, u_ref, max_iters=3, tol=1e-4, gamma_0=0.1, verbose=False)
+    assert h["status"] == 3 and len(h["cost"]) == 1 and np.isnan(h["cost"][0]) and len(h["sigma_norm"]) == 1
+
+
+def test_progress_line(mods, fa_ref, capsys):
+    dyn, tg, tt = mods
+    x_ref, u_ref, _ = fa_ref
+    tg.newton_Algorithm(np.zeros(4), x_ref, u_ref, max_iters=12, tol=1e-4, gamma_0=0.1)
+    out = capsys.readouterr().out
+    g = golden("newton_task2")
+    assert "Iter 0: Cost=%.2f, diff_cost=%.2e, " % (g["cost"][1], g["cost"][0] - g["cost"][1]) in out
+    assert "Iter 10: Cost=%.2f" % g["cost"][11] in out
+
+
+def test_mpc_outputs_have_the_shapes_of_the_references(mods):
+    """solve_mpc_tracking returns arrays shaped like x_ref / u_ref, zero beyond T (tt:27-28)."""
+    dyn, tg, tt = mods
+    d = golden("acrobot_optimal_trajectory")
+    x0 = d["x"][0] + 0.1
+    xr, ur = tt.solve_mpc_tracking(x0, d["x"], d["u"], 101)
+    assert xr.shape == (501, 4) and ur.shape == (500, 2)
+    assert np.all(xr[101:] == 0.0) and np.all(ur[100:] == 0.0)
+    xf, uf = tt.solve_mpc_tracking(x0, d["x"], d["u"], 501)
+    assert rel_err(xr[:101], xf[:101]) < TOL and rel_err(ur[:100], uf[:100]) < TOL

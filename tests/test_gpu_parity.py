@@ -552,8 +552,10 @@ def test_mpc_tracking_shared_and_per_problem(bt):
         Xp, Up, _, nsp = bt.mpc_track(soa(x0), refp, QT, T=501, T_pred=H, w=w)
         assert nsp == 500 * 6
         assert rel_err(aos(Xp), xo) < TOL and rel_err(aos(Up), uo) < TOL
-    # figures/mpc/tracking_dx_0.1_err.png: initial control error ~0.81
-    assert abs(abs(aos(Ur)[0, 0, 1] - d["u"][0, 1]) - 0.81) < 0.05 or True
+        if H == 75:
+            # the only artefact the reference ships for its MPC (figures/mpc/tracking_dx_0.1_err.png, main.py:127-143:
+            # x0 = x_ref[0] + 0.1, horizon 75): initial control error ~0.81; the Riccati restatement gives 0.80644713
+            assert abs(abs(aos(Ur)[0, 0, 1] - d["u"][0, 1]) - 0.80644713) < 1e-6
 
 
 def test_mpc_tracking_with_input_box(bt):
@@ -678,18 +680,23 @@ def test_full_size_c3_properties(bt):
     assert np.median(np.abs(xe[ok] - d["x"][-1]).max(axis=1)) < 1e-2
 
 
-# ------------------------------------------------------------------------------------- ragged batches (ring kernel)
+# ------------------------------------------------------------------------------------- ragged batches, every kernel variant
+# every kernel acro_newton_solve can dispatch to (AcroNewtonOpts.kernel / stage_steps / recompute_lin), forced on small
+# batches here and run at their own batch sizes in test_dispatch_variants_at_their_batch_sizes
+VARIANTS = ["duo", "duo4", "duo8", "ring", "ring4", "ring2", "ring-rl", "ldg"]
+
+
 def _short_ref(fa_ref, N=61):
     x_ref, u_ref, _ = fa_ref
     return x_ref[:N].copy(), u_ref[:N - 1].copy()
 
 
-@pytest.mark.parametrize("kernel", ["duo", "ring", "ldg"])
+@pytest.mark.parametrize("kernel", VARIANTS)
 def test_newton_ragged_line_search_failures(bt, fa_ref, kernel, monkeypatch):
     """gamma_0 = 1 on a short horizon: problems back-track up to 20 times and fail the line search at different
     iterations (status 3 after 3-7 iterations).  A warp therefore holds finished and running problems side by
     side; 40 problems = one full tile + a partial one.  Same tries, same accepted steps, same final iterates."""
-    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    monkeypatch.setitem(bt.NEWTON_DEFAULTS, "kernel", kernel)
     xr, ur = _short_ref(fa_ref)
     x0 = np.random.default_rng(11).uniform(-0.3, 0.3, (40, 4))
     st = bt.newton_solve(soa(x0), bt.make_ref(xr, ur), max_iters=25, tol=2e-3, gamma_0=1.0)
@@ -710,11 +717,11 @@ def test_newton_ragged_line_search_failures(bt, fa_ref, kernel, monkeypatch):
     assert len(seen) >= 3  # genuinely ragged
 
 
-@pytest.mark.parametrize("kernel", ["duo", "ring", "ldg"])
+@pytest.mark.parametrize("kernel", VARIANTS)
 def test_newton_ragged_convergence_per_problem_refs_and_weights(bt, fa_ref, kernel, monkeypatch):
     """Per-problem reference trajectories (scaled copies) and per-problem weights: problems converge after different
     numbers of iterations inside the same warp."""
-    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    monkeypatch.setitem(bt.NEWTON_DEFAULTS, "kernel", kernel)
     xr0, ur0 = _short_ref(fa_ref)
     n = 40
     a = np.linspace(0.2, 1.5, n)
@@ -756,20 +763,15 @@ def test_newton_kernels_agree(bt, fa_ref, monkeypatch):
     x0s = np.random.default_rng(8).uniform(-0.2, 0.2, (45, 4))
     ref = bt.make_ref(x_ref, u_ref)
     out = {}
-    for kernel in ("duo", "ring", "ldg", "ring-rl"):
-        # "ring-rl": the large-batch variant (2-step stages, linearisation recomputed in the backward pass)
-        monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel.split("-")[0])
-        if kernel == "ring-rl":
-            monkeypatch.setenv("ACRO_RING_SG", "2")
-        else:
-            monkeypatch.delenv("ACRO_RING_SG", raising=False)
+    for kernel in VARIANTS:
+        monkeypatch.setitem(bt.NEWTON_DEFAULTS, "kernel", kernel)
         st = bt.newton_solve(soa(x0s), ref, max_iters=6, tol=1e-4, gamma_0=1.0, chunk_iters=3)
         st = bt.newton_solve(soa(x0s), ref, max_iters=6, tol=1e-4, gamma_0=1.0, state=st)
         torch.cuda.synchronize()
         out[kernel] = (aos(st.X), aos(st.U), kmat(st.K), aos(st.S), st.hist_cost[:7].cpu().numpy(),
                        st.hist_ntry[:6].cpu().numpy(), st.hist_gamma[:6].cpu().numpy(), st.iters.cpu().numpy(),
                        st.status.cpu().numpy(), st.sigma_norm.cpu().numpy(), st.delta_J.cpu().numpy())
-    for kernel in ("duo", "ldg", "ring-rl"):
+    for kernel in VARIANTS:
         a, b = out[kernel], out["ring"]
         for i in (5, 6, 7, 8):
             assert np.array_equal(a[i], b[i]), (kernel, i)
@@ -778,13 +780,13 @@ def test_newton_kernels_agree(bt, fa_ref, monkeypatch):
         assert rel_err(a[2], b[2]) < 1e-8
 
 
-@pytest.mark.parametrize("kernel", ["duo", "ring", "ldg"])
+@pytest.mark.parametrize("kernel", VARIANTS)
 def test_newton_pivot_swap_and_fast_spins(bt, fa_ref, kernel, monkeypatch):
     """(i) A control weight whose off-diagonal exceeds R[0,0]: the 2x2 factorisation pivots on the second row
     (the duo kernel compiles that choice in for shared weights).  (ii) Initial velocities of 15-25 rad/s: the stage
     angles of a step differ by more than the incremental sincos of the duo kernel accepts (2^-3 rad), so its
     redo-with-full-sincos path runs in some lanes of a warp and not in others."""
-    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    monkeypatch.setitem(bt.NEWTON_DEFAULTS, "kernel", kernel)
     xr, ur = _short_ref(fa_ref, N=81)
     rng = np.random.default_rng(17)
     x0 = rng.uniform(-0.2, 0.2, (36, 4))
@@ -806,12 +808,12 @@ def test_newton_pivot_swap_and_fast_spins(bt, fa_ref, kernel, monkeypatch):
             assert rel_err(S[b], so) < TOL and rel_err(K[b], Ko) < 1e-7
 
 
-@pytest.mark.parametrize("kernel", ["duo", "ring"])
+@pytest.mark.parametrize("kernel", [v for v in VARIANTS if v != "ldg"])
 def test_newton_repeated_launches_are_bitwise_identical(bt, fa_ref, kernel, monkeypatch):
     """The warp-specialised kernels synchronise through mbarriers, a hand-off ring and proxy fences: a missing
     ordering would show up as run-to-run differences.  12 launches of a back-tracking batch (two tiles + a partial
     one, shared and per-problem references) must give the same bits."""
-    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    monkeypatch.setitem(bt.NEWTON_DEFAULTS, "kernel", kernel)
     xr, ur = _short_ref(fa_ref, N=101)
     n = 70
     x0 = np.random.default_rng(23).uniform(-0.3, 0.3, (n, 4))
@@ -830,12 +832,12 @@ def test_newton_repeated_launches_are_bitwise_identical(bt, fa_ref, kernel, monk
                     assert np.array_equal(a, b, equal_nan=True), (rep, i)
 
 
-@pytest.mark.parametrize("kernel", ["duo", "ring", "ldg"])
+@pytest.mark.parametrize("kernel", VARIANTS)
 @pytest.mark.parametrize("N", [2, 3, 16, 17, 18, 33, 49])
 def test_newton_short_horizons(bt, fa_ref, kernel, N, monkeypatch):
     """Horizons around the stage sizes of the TMA rings (16 steps per stage; fewer steps than one stage, exactly
     one stage, one step more) and the degenerate N = 2 (a single time step)."""
-    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    monkeypatch.setitem(bt.NEWTON_DEFAULTS, "kernel", kernel)
     x_ref, u_ref, _ = fa_ref
     t0 = 150  # a stretch of the reference where the inputs are large
     xr, ur = x_ref[t0:t0 + N].copy(), u_ref[t0:t0 + N - 1].copy()
@@ -850,12 +852,12 @@ def test_newton_short_horizons(bt, fa_ref, kernel, N, monkeypatch):
         assert rel_err(st.hist_cost[:len(h["cost"]), b].cpu().numpy(), h["cost"]) < TOL
 
 
-@pytest.mark.parametrize("kernel", ["duo", "ring", "ldg"])
+@pytest.mark.parametrize("kernel", VARIANTS)
 def test_newton_non_finite_problems_do_not_disturb_their_neighbours(bt, fa_ref, kernel, monkeypatch):
     """NaN / inf / absurd initial states in some lanes of a warp: the reference's `cost_new < ...` is False for NaN, so
     those problems fail the line search at the first iteration (status 3, iterate kept); every other lane gives the
     same bits as in a batch without them."""
-    monkeypatch.setenv("ACRO_NEWTON_KERNEL", kernel)
+    monkeypatch.setitem(bt.NEWTON_DEFAULTS, "kernel", kernel)
     xr, ur = _short_ref(fa_ref)
     x0 = np.random.default_rng(41).uniform(-0.2, 0.2, (40, 4))
     bad = {3: np.nan, 17: np.inf, 33: -np.inf}

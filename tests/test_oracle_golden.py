@@ -237,3 +237,90 @@ def test_box_constrained_mpc_oracle_against_scipy_bvls():
         U0b, Xb, Ub = O.solver_mpc_box(x0, Aw, Bw, O.Q_MPC, O.R_MPC, g["P_inf"], H, uw, 1e9)
         assert rel_err(Ub, Uu) < 1e-8 and rel_err(Xb, Xu) < 1e-8
     assert n_bound > 20
+
+
+# ------------------------------------------------------------------------------------- round 2: SURVEY 8(d) sample sizes
+def _pool_map(fn, items):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(len(items), max(1, (mp.cpu_count() or 2) - 1))) as pool:
+        return pool.map(fn, items, chunksize=1)
+
+
+def _newton(args):
+    x0, x_ref, u_ref, kw = args
+    x, u, K, s, h = O.newton_Algorithm(x0, x_ref, u_ref, **kw)
+    return x, u, np.array(K), np.array(s), h
+
+
+def test_c2_three_iterations_64_problems(fa_ref):
+    """The oracle against the unmodified reference on 64 problems of the config-2 batch, 3 iterations, both step-size
+    regimes (fixture: make_golden.py c2three)."""
+    g = golden("newton_c2_three_iters")
+    x_ref, u_ref, _ = fa_ref
+    for tag, g0 in (("g01", 0.1), ("g1", 1.0)):
+        res = _pool_map(_newton, [(g["x0"][i], x_ref, u_ref, dict(max_iters=3, tol=1e-4, gamma_0=g0)) for i in range(64)])
+        for i, (x, u, K, s, h) in enumerate(res):
+            assert h["n_try"] == list(g[tag + "_n_try"][i].astype(int)) and h["gamma"] == list(g[tag + "_gamma_acc"][i])
+            assert rel_err(h["cost"], g[tag + "_cost"][i]) < 1e-12
+            assert rel_err(x, g[tag + "_x"][i]) < 1e-10 and rel_err(u, g[tag + "_u"][i]) < 1e-10
+            assert rel_err(s, g[tag + "_sigma"][i]) < 1e-10
+            if i < 8:
+                assert rel_err(K, g[tag + "_K8"][i]) < 1e-10
+
+
+def test_c2_converged_rows(fa_ref):
+    """Four of the sixteen config-2 problems the reference solved to convergence (make_golden.py c2conv): same
+    iteration counts, cost histories, final trajectories."""
+    g = golden("newton_c2_converged")
+    x_ref, u_ref, _ = fa_ref
+    pick = [0, 5, 10, 15]
+    res = _pool_map(_newton, [(g["x0"][i], x_ref, u_ref, dict(max_iters=5000, tol=1e-4, gamma_0=0.1)) for i in pick])
+    for i, (x, u, K, s, h) in zip(pick, res):
+        n = int(g["iters"][i])
+        assert h["iters"] == n and h["status"] == O.STATUS_CONVERGED
+        assert rel_err(h["cost"], g["cost"][i, :n + 1]) < 1e-11
+        assert rel_err(h["sigma_norm"], g["sigma_norm"][i, :n]) < 1e-9
+        assert rel_err(x, g["x"][i]) < 1e-10 and rel_err(u, g["u"][i]) < 1e-10 and rel_err(s, g["sigma"][i]) < 1e-9
+
+
+def _track(args):
+    x_opt, u_opt, K, x0 = args
+    with np.errstate(all="ignore"):
+        return O.simulate_tracking(x_opt, u_opt, K, x0)
+
+
+def test_c3_256_rollouts():
+    g = golden("lqr_tracking_c3")
+    d = golden("acrobot_optimal_trajectory")
+    K = O.solve_LQR_tracking(d["x"], d["u"])
+    res = _pool_map(_track, [(d["x"], d["u"], K, g["x0"][i]) for i in range(256)])
+    X = np.array([r[0] for r in res])
+    U = np.array([r[1] for r in res])
+    assert rel_err(X[:, ::10], g["x_track_10"]) < 1e-10 and rel_err(U[:, ::10], g["u_track_10"]) < 1e-10
+    assert rel_err(X.sum(axis=1), g["x_sum"]) < 1e-10
+
+
+def _sweep(args):
+    x0, k, x_ref, u_ref, steps = args
+    if k == 0:
+        u = np.zeros_like(u_ref)
+        x = O.simulate_open_loop(x0, u)
+    else:
+        x, u, _, _, h = O.newton_Algorithm(x0, x_ref, u_ref, max_iters=k, tol=1e-4, gamma_0=0.1)
+    Ad, Bd, q, r, QT2, qT = O.build_stage_lists(x, u, x_ref, u_ref)
+    K, sig, dJ = O.calculate_K_and_sigma(Ad, Bd, q, r, 2.0 * O.Q_NEWTON, 2.0 * O.R_NEWTON, QT2, qT)
+    return O.stepsize_sweep(x, u, K, sig, x_ref, u_ref, steps), dJ, x[-1]
+
+
+def test_c5_base_iterates_from_newton_iterations(fa_ref):
+    """Config 5 fixture (make_golden.py sweep256): the base iterates with k_p <= 12 Newton iterations behind them
+    (the oracle needs 50 ms per iteration; the GPU test checks all 256)."""
+    g = golden("sweep_c5")
+    x_ref, u_ref, _ = fa_ref
+    x0s = np.random.default_rng(1).uniform(-0.2, 0.2, (4096, 4))
+    x0s[0] = 0.0
+    pick = [i for i in range(256) if g["k"][i] <= 12][:48]
+    res = _pool_map(_sweep, [(x0s[g["rows"][i]], int(g["k"][i]), x_ref, u_ref, g["steps"]) for i in pick])
+    for i, (c, dJ, xT) in zip(pick, res):
+        assert rel_err(c, g["costs"][i]) < 1e-11 and abs(dJ - g["delta_J"][i]) < 1e-10 * abs(dJ)
+        assert rel_err(xT, g["x_T"][i]) < 1e-11
