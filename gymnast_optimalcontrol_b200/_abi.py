@@ -32,7 +32,7 @@ class AcroNewtonOpts(C.Structure):
     _fields_ = [("max_iters", C.c_int32), ("chunk_iters", C.c_int32), ("max_line_search", C.c_int32),
                 ("init", C.c_int32), ("tol", C.c_double), ("beta", C.c_double), ("c", C.c_double),
                 ("gamma_0", C.c_double), ("kernel", C.c_int32), ("stage_steps", C.c_int32),
-                ("recompute_lin", C.c_int32), ("speculate", C.c_int32)]
+                ("recompute_lin", C.c_int32), ("speculate", C.c_int32), ("spec_ws", C.c_void_p)]
 
 
 P = C.c_void_p  # device pointer / stream
@@ -45,6 +45,7 @@ SIGNATURES = {
     "acro_rk4_step": [PP, I64, P, P, P, P],
     "acro_linearize": [PP, I64, P, P, P, P, I32, P],
     "acro_rollout_open_loop": [PP, I64, I32, P, P, P, P],
+    "acro_equilibrium": [PP, P, I64, P, P, F64, I32, P, P, P],
     "acro_continuous_dynamics_pp": [PP, P, I64, P, P, P, P],
     "acro_rk4_step_pp": [PP, P, I64, P, P, P, P],
     "acro_linearize_pp": [PP, P, I64, P, P, P, P, I32, P],
@@ -78,7 +79,7 @@ SIGNATURES = {
     "acro_unpack_soa": [I64, I32, I32, P, P, P],
 }
 QUERIES = {"acro_version": C.c_char_p, "acro_last_error_string": C.c_char_p, "acro_launch_count": C.c_int64}
-SIZES = {"acro_mpc_box_ws_doubles": ([I64, I32], C.c_int64)}
+SIZES = {"acro_mpc_box_ws_doubles": ([I64, I32], C.c_int64), "acro_newton_spec_ws_doubles": ([I64, I32], C.c_int64)}
 
 
 class AcroError(RuntimeError):

@@ -24,11 +24,44 @@ class Kind:
             self.torch = self.cuda = self.pinned = False
 
 
+class PinnedPool:
+    """Pinned host memory for results.  A block is handed out again only when nothing made from it is alive any more
+    (tensor views, NumPy arrays: the reference count of its storage is back to that of the pool's own handle), so two
+    results never alias - and a loop that drops its previous results never page-locks new memory, which costs
+    milliseconds and synchronises the device (torch's own caching host allocator did allocate in the steady state of the
+    pipelined solves: profiles/r2_e2e_probe.txt)."""
+    LIMIT = 8 << 30  # bytes kept; idle blocks beyond that are released
+
+    def __init__(self):
+        self.blocks = []
+        probe = torch.empty(8, dtype=torch.uint8)
+        self._count = getattr(torch._C, "_storage_Use_Count", None)
+        self._base = self._uses(probe) if self._count else 0
+
+    def _uses(self, b):
+        return self._count(b.untyped_storage()._cdata)
+
+    def empty(self, shape, dtype=torch.float64):
+        shape = tuple(int(v) for v in shape)
+        n = int(np.prod(shape, dtype=np.int64)) * torch.empty(0, dtype=dtype).element_size()
+        if self._count is None or n == 0:
+            return torch.empty(shape, dtype=dtype, pin_memory=True)
+        for b in self.blocks:
+            if n <= b.numel() <= 2 * n + 4096 and self._uses(b) <= self._base:
+                return b[:n].view(dtype).view(shape)
+        if sum(b.numel() for b in self.blocks) + n > self.LIMIT:
+            self.blocks = [b for b in self.blocks if self._uses(b) > self._base]
+        b = torch.empty((n + 4095) // 4096 * 4096, dtype=torch.uint8, pin_memory=True)
+        self.blocks.append(b)
+        return b[:n].view(dtype).view(shape)
+
+
+_pool = PinnedPool()
+
+
 def pinned_empty(shape, dtype=torch.float64):
-    """A FRESH pinned host tensor for a result.  torch's caching host allocator recycles the blocks of results the
-    caller has dropped, so a loop that overwrites its previous result does not page-lock new memory every call, and
-    two results never alias (a drop-in must not hand the same buffer out twice)."""
-    return torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+    """A pinned host tensor for a result that no live result shares memory with (PinnedPool)."""
+    return _pool.empty(shape, dtype)
 
 
 def to_host(t, stream_sync=True):

@@ -261,6 +261,16 @@ def linearize(x, u, discrete=False, params=DEFAULT_PARAMS, params_b=None):
     return A, Bm
 
 
+def equilibrium(u_target, theta_guess, params=DEFAULT_PARAMS, params_b=None, tol=1e-13, max_iter=50):
+    """compute_equilibrium (tg:22-39) for a batch: u_target (2,B), theta_guess (2,B) -> theta (2,B), n_iter (B,) int32
+    (negative: no convergence)."""
+    Bn = u_target.shape[1]
+    theta, n = _empty(2, Bn), _empty(Bn, dtype=torch.int32)
+    call("acro_equilibrium", C.byref(params), _p(params_b), Bn, _p(u_target), _p(theta_guess), float(tol), int(max_iter),
+         _p(theta), _p(n, torch.int32), _stream())
+    return theta, n
+
+
 # ------------------------------------------------------------------------------------------
 # G1-G11
 # ------------------------------------------------------------------------------------------
@@ -337,6 +347,7 @@ class NewtonState:
     hist_gamma: Optional[torch.Tensor] = None
     hist_ntry: Optional[torch.Tensor] = None
     initialised: bool = False
+    spec_ws: Optional[torch.Tensor] = None  # candidate trajectories of the speculative kernel (allocated on first use)
 
     def reset(self):
         """Make the state reusable for a new solve from x0 (same shapes): history back to NaN / 0, init on next call."""
@@ -380,6 +391,9 @@ KERNEL_VARIANTS = {
     "thread": dict(kernel="thread"),
     "ldg": dict(kernel="thread"),
     "spec": dict(kernel="spec"),                     # <= 148 tiles: duo + speculative parallel Armijo candidates
+    "spec1": dict(kernel="spec", speculate=1),       # one candidate per round: the duo path inside the speculative kernel
+    "spec3": dict(kernel="spec", speculate=3),       # fixed number of candidates per round
+    "spec8": dict(kernel="spec", speculate=8),
 }
 # Process-wide default of newton_solve's kernel selection (a Python-side setting: the library reads no environment).
 NEWTON_DEFAULTS = {"kernel": "auto"}
@@ -393,6 +407,7 @@ def newton_opts(max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, chunk_iters=0
         v = KERNEL_VARIANTS[kernel]
         stage_steps = stage_steps or v.get("stage_steps", 0)
         recompute_lin = recompute_lin or v.get("recompute_lin", 0)
+        speculate = speculate or v.get("speculate", 0)
         kernel = _abi.NEWTON_KERNELS[v["kernel"]]
     return AcroNewtonOpts(max_iters=int(max_iters), chunk_iters=int(chunk_iters), max_line_search=int(max_line_search),
                           init=int(init), tol=float(tol), beta=float(beta), c=float(c), gamma_0=float(gamma_0),
@@ -431,6 +446,10 @@ def newton_solve(x0, ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, w=N
     o = newton_opts(max_iters, tol, beta, c, gamma_0, chunk_iters, max_line_search, init, kernel, stage_steps,
                     recompute_lin, speculate)
     s = state
+    if o.kernel == _abi.NEWTON_KERNELS["spec"]:
+        if s.spec_ws is None:
+            s.spec_ws = torch.zeros(int(_abi.lib.acro_newton_spec_ws_doubles(Bn, N)), dtype=F64, device=device())
+        o.spec_ws = s.spec_ws.data_ptr()
     call("acro_newton_solve_pp", C.byref(params), _p(params_b), w.ref(), C.byref(o), Bn, N, _p(x0), ref.ref(), _p(s.X), _p(s.U), _p(s.Xw),
          _p(s.Uw), _p(s.lin), _p(s.K), _p(s.S), _p(s.cost), _p(s.delta_J), _p(s.sigma_norm), _p(s.gamma_acc),
          _p(s.iters, torch.int32), _p(s.status, torch.int32), _p(s.hist_cost), _p(s.hist_sigma_norm), _p(s.hist_gamma),

@@ -189,6 +189,43 @@ __global__ void k_linearize(const __grid_constant__ Model m0, const double* __re
 }
 
 // ---------------------------------------------------------------------------------------
+// compute_equilibrium (tg:22-39): G(theta1, theta2) = u_target, one Newton iteration per thread.
+//   g1 sin(th1) + g2 sin(th1 + th2) = u[0],   g2 sin(th1 + th2) = u[1]
+// (the reference hands the same two equations to MINPACK's hybr; the root is the same to rounding)
+// ---------------------------------------------------------------------------------------
+template <bool PPB>
+__global__ void k_equilibrium(const __grid_constant__ Model m0, const double* __restrict__ pb, int64_t B,
+                              const double* __restrict__ ut, const double* __restrict__ th0, double tol, int max_iter,
+                              double* __restrict__ theta, int32_t* __restrict__ n_iter) {
+  const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  ACRO_MODEL(PPB, m0, pb, B, b);
+  double t1 = th0[b], t2 = th0[B + b];
+  const double u0 = ut[b], u1 = ut[B + b];
+  int n = -max_iter;
+  for (int i = 0; i <= max_iter; ++i) {
+    double s1, c1, s12, c12;
+    sincos(t1, &s1, &c1);
+    sincos(t1 + t2, &s12, &c12);
+    const double r0 = fma(m.g1, s1, m.g2 * s12) - u0, r1 = m.g2 * s12 - u1;
+    if (fmax(fabs(r0), fabs(r1)) < tol) {
+      n = i;
+      break;
+    }
+    if (i == max_iter) break;
+    const double j11 = m.g2 * c12, j00 = fma(m.g1, c1, j11);
+    const Lu2 lu = lu2(j00, j11, j11, j11);
+    double d0, d1;
+    lu2_solve(lu, r0, r1, d0, d1);
+    t1 -= d0;
+    t2 -= d1;
+  }
+  theta[b] = t1;
+  theta[B + b] = t2;
+  n_iter[b] = n;
+}
+
+// ---------------------------------------------------------------------------------------
 // G1 open-loop rollout, G8 cost, G3 costate
 // ---------------------------------------------------------------------------------------
 template <bool PPB>
@@ -350,7 +387,10 @@ __device__ __forceinline__ void store_lin(double* __restrict__ lin, int t, int64
 // ---------------------------------------------------------------------------------------
 // HAVE_LIN: the discrete linearisation about (X, U) was already written by the forward pass that produced
 // the iterate (rk4_step_lin), so this pass is pure Riccati algebra on loaded operands.
-template <bool WPB, bool RPB, bool HAVE_LIN>
+// ACT0: the fully-actuated plant (tau_1 = u[0] acts on the first joint, fully_actuated_ref_gen.py:20-73): B_d has two
+// columns, G = R + B'PB is a full 2x2; the compact linearisation streamed between passes holds one column only, so
+// this variant always linearises itself (HAVE_LIN = false).
+template <bool WPB, bool RPB, bool HAVE_LIN, bool ACT0 = false>
 __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, const RefV<RPB>& ref, int N,
                                               const double* __restrict__ X, const double* __restrict__ U,
                                               const double* __restrict__ lin, double* __restrict__ K,
@@ -425,7 +465,7 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
       }
     }
     double Kt[8], st[2];
-    riccati_step<true, false>(P, p, L, m.dt, Qh, col, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, r, Kt, st, dJ);
+    riccati_step<true, ACT0>(P, p, L, m.dt, Qh, col, w.R2(0, 0), w.R2(0, 1), w.R2(1, 1), q, r, Kt, st, dJ);
     if (HAVE_LIN && t > 0) Lc = load_lin(lin, t - 1, N - 1, b);
 #pragma unroll
     for (int e = 0; e < 8; ++e) K[soa(t, 8, e, N - 1, b)] = Kt[e];
@@ -440,7 +480,7 @@ __device__ __forceinline__ void backward_pass(const Model& m, const WV<WPB>& w, 
   sn_out = sn;
 }
 
-template <bool WPB, bool RPB>
+template <bool WPB, bool RPB, bool ACT0 = false>
 __global__ void k_riccati_affine(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B,
                                  int N, const double* __restrict__ X, const double* __restrict__ U,
                                  const double* rx, const double* ru, double* __restrict__ K,
@@ -450,7 +490,7 @@ __global__ void k_riccati_affine(const __grid_constant__ Model m, const __grid_c
   const WV<WPB> w(kw, B, b);
   const RefV<RPB> ref{rx, ru, N, b};
   double d, s;
-  backward_pass<WPB, RPB, false>(m, w, ref, N, X, U, nullptr, K, S, B, b, d, s);
+  backward_pass<WPB, RPB, false, ACT0>(m, w, ref, N, X, U, nullptr, K, S, B, b, d, s);
   dJ[b] = d;
   sn[b] = s;
 }
@@ -622,13 +662,14 @@ struct NewtonArgs {
   const double* pb;  // per-problem physical parameters [11][B] or nullptr (k_newton<.., PPB = true> only)
   const double *rx, *ru;
   double *X, *U, *Xw, *Uw, *lin, *K, *S;
+  double* spec_ws;  // candidate trajectories of k_newton_spec (AcroNewtonOpts.spec_ws) or nullptr
   double *cost, *dJ, *sn, *gacc;
   int32_t *iters, *status;
   double *h_cost, *h_sn, *h_gamma;
   int32_t* h_ntry;
 };
 
-template <bool WPB, bool RPB, bool PPB = false>
+template <bool WPB, bool RPB, bool PPB = false, bool ACT0 = false>
 __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
   const int64_t B = a.B, b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
@@ -657,9 +698,13 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
         a.U[soa(t, 2, 1, N - 1, b)] = 0.0;
       }
       double xn[4];
-      LinD L;
-      rk4_step_lin(m, x, u0, u1, xn, L);
-      store_lin(a.lin, t, N - 1, b, L);
+      if (ACT0) {
+        rk4_step(m, x, u0, u1, xn);
+      } else {
+        LinD L;
+        rk4_step_lin(m, x, u0, u1, xn, L);
+        store_lin(a.lin, t, N - 1, b, L);
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         x[c] = xn[c];
@@ -682,13 +727,13 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
     const double* Uc = cur ? a.Uw : a.U;
     double* Xo = cur ? a.X : a.Xw;
     double* Uo = cur ? a.U : a.Uw;
-    backward_pass<WPB, RPB, true>(m, w, ref, N, Xc, Uc, a.lin, a.K, a.S, B, b, dJ, sn);
+    backward_pass<WPB, RPB, !ACT0, ACT0>(m, w, ref, N, Xc, Uc, a.lin, a.K, a.S, B, b, dJ, sn);
     if (a.h_sn) a.h_sn[int64_t(it) * B + b] = sn;
     double gamma = a.o.gamma_0, cn = 0.0;
     int tries = 0;
     bool ok = false;
     for (int i = 0; i < a.o.max_line_search; ++i) {
-      cn = forward_pass<WPB, RPB, true, true>(m, w, ref, N, Xc, Uc, a.K, a.S, B, b, gamma, Xo, Uo, B, b, a.lin);
+      cn = forward_pass<WPB, RPB, true, !ACT0>(m, w, ref, N, Xc, Uc, a.K, a.S, B, b, gamma, Xo, Uo, B, b, a.lin);
       ++tries;
       // accept iff cost_new < cost_k + c*gamma*delta_J  (strict, NaN rejects)   tg:361
       const double thr = __dadd_rn(cost_k, __dmul_rn(__dmul_rn(a.o.c, gamma), dJ));
@@ -735,6 +780,7 @@ __global__ void k_newton(const __grid_constant__ NewtonArgs a) {
 }  // namespace acro
 #include "acro_newton_ring.cuh"
 #include "acro_newton_duo.cuh"
+#include "acro_newton_spec.cuh"
 namespace acro {
 
 // ---------------------------------------------------------------------------------------
@@ -891,7 +937,7 @@ __global__ void k_riccati_lists(int64_t B, int T, const double* __restrict__ A, 
 // ---------------------------------------------------------------------------------------
 // T1 LQR gains, T2 LQR tracking
 // ---------------------------------------------------------------------------------------
-template <bool WPB, bool RPB>
+template <bool WPB, bool RPB, bool ACT0 = false>
 __global__ void k_lqr_gains(const __grid_constant__ Model m, const __grid_constant__ KWeights kw, int64_t B, int N,
                             const double* rx, const double* ru, double* __restrict__ K) {
   const int64_t b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -912,7 +958,7 @@ __global__ void k_lqr_gains(const __grid_constant__ Model m, const __grid_consta
     for (int c = 0; c < 4; ++c) x[c] = ref.X(t, c);
     const LinD L = linearize_d(m, x, ref.U(t, 0), ref.U(t, 1));
     double Kt[8], st[2];
-    riccati_step<false, false>(P, p, L, m.dt, Qh, col, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, Kt, st, dummy);
+    riccati_step<false, ACT0>(P, p, L, m.dt, Qh, col, w.R(0, 0), w.R(0, 1), w.R(1, 1), p, p, Kt, st, dummy);
     if (RPB) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) K[soa(t, 8, e, N - 1, b)] = Kt[e];
@@ -1418,10 +1464,17 @@ static int newton_plan(const AcroNewtonOpts& o, int64_t B, bool rpb, bool wpb, b
   }
   if (k != ACRO_NEWTON_THREAD) {
     ACRO_REQUIRE(tma_ok, "acro_newton_solve: the duo / ring kernels need 128-byte aligned X, U, Xw, Uw, lin_ws, K, S and reference buffers");
-    ACRO_REQUIRE(!ppb, "acro_newton_solve: per-problem physical parameters run on ACRO_NEWTON_THREAD");
+    ACRO_REQUIRE(!ppb, "acro_newton_solve: per-problem physical parameters and the fully-actuated plant run on ACRO_NEWTON_THREAD");
   }
-  if (k == ACRO_NEWTON_SPEC) k = ACRO_NEWTON_DUO;  // (speculative kernel: see acro_newton_spec.cuh)
-  if (k == ACRO_NEWTON_DUO) {
+  if (k == ACRO_NEWTON_SPEC) {
+    // eight warps per tile, one block per SM (acro_newton_spec.cuh); needs the candidate workspace
+    ACRO_REQUIRE(tiles <= n_sm, "acro_newton_solve: the speculative kernel runs one tile per SM (B <= 32 x SM count)");
+    ACRO_REQUIRE(o.spec_ws != nullptr, "acro_newton_solve: the speculative kernel needs AcroNewtonOpts.spec_ws (acro_newton_spec_ws_doubles)");
+    ACRO_REQUIRE(o.speculate >= 0 && o.speculate <= 8, "acro_newton_solve: speculate must be 0 (adaptive) or 1..8");
+    ACRO_REQUIRE(sg == 0 || (sg == 16 && !rpb) || (sg == 8 && rpb), "acro_newton_solve: speculative kernel: stage_steps 16 (8 with per-problem references)");
+    sg = rpb ? 8 : 16;
+    rl = 0;
+  } else if (k == ACRO_NEWTON_DUO) {
     // one block per SM: deep stages (16 time steps per bulk copy, 220 KB of shared memory); two blocks per SM: 4-step
     // stages (70-90 KB).  Per-problem references need 50 % more shared memory per stage: 8 instead of 16.
     if (sg == 0) sg = (tiles > n_sm) ? 4 : (rpb ? 8 : 16);
@@ -1504,6 +1557,18 @@ int acro_linearize(const AcroParams* p, int64_t B, const double* x, const double
   return acro_linearize_pp(p, nullptr, B, x, u, A, Bm, discrete, stream);
 }
 
+int acro_equilibrium(const AcroParams* p, const double* params_b, int64_t B, const double* u_target, const double* theta_guess,
+                     double tol, int max_iter, double* theta, int32_t* n_iter, void* stream) {
+  ACRO_REQUIRE(p && u_target && theta_guess && theta && n_iter && B > 0 && max_iter > 0 && tol > 0.0, "acro_equilibrium: bad argument");
+  const Cfg c = cfg_for(B);
+  if (params_b)
+    k_equilibrium<true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), params_b, B, u_target, theta_guess, tol, max_iter, theta, n_iter);
+  else
+    k_equilibrium<false><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(make_model(*p), nullptr, B, u_target, theta_guess, tol, max_iter, theta, n_iter);
+  ACRO_LAUNCH_CHECK("acro_equilibrium");
+  return ACRO_OK;
+}
+
 int acro_rollout_open_loop_pp(const AcroParams* p, const double* params_b, int64_t B, int N, const double* x0,
                               const double* U, double* X, void* stream) {
   ACRO_REQUIRE(p && x0 && X && B > 0 && N >= 1, "acro_rollout_open_loop: bad argument");
@@ -1536,7 +1601,6 @@ int acro_total_cost(const AcroWeights* w, int64_t B, int N, const double* X, con
 int acro_costate(const AcroParams* p, const AcroWeights* w, int64_t B, int N, const double* X, const double* U,
                  const AcroRef* ref, double* lam, void* stream) {
   ACRO_REQUIRE(p && w && X && U && ref && ref->x && ref->u && lam && B > 0 && N >= 2, "acro_costate: bad argument");
-  ACRO_REQUIRE(!p->actuated_tau1, "acro_costate: fully-actuated plant not supported here");
   const Cfg c = cfg_for(B);
   const KWeights kw = make_weights(*w);
   const Model m = make_model(*p);
@@ -1553,15 +1617,22 @@ int acro_riccati_affine(const AcroParams* p, const AcroWeights* w, int64_t B, in
                         double* sigma_norm, void* stream) {
   ACRO_REQUIRE(p && w && X && U && ref && ref->x && ref->u && K && S && delta_J && sigma_norm && B > 0 && N >= 2,
                "acro_riccati_affine: bad argument");
-  ACRO_REQUIRE(!p->actuated_tau1, "acro_riccati_affine: fully-actuated plant not supported here");
   const Cfg c = cfg_for(B);
   const KWeights kw = make_weights(*w);
   const Model m = make_model(*p);
+  if (p->actuated_tau1) {
+#define EXPR(WPB, RPB)                                                                                   \
+  k_riccati_affine<WPB, RPB, true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, kw, B, N, X, U, ref->x, ref->u, K, S, \
+                                                                                 delta_J, sigma_norm)
+    DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+#undef EXPR
+  } else {
 #define EXPR(WPB, RPB)                                                                                   \
   k_riccati_affine<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, kw, B, N, X, U, ref->x, ref->u, K, S, \
                                                                            delta_J, sigma_norm)
-  DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
+    DISPATCH2(per_problem_weights(*w), ref->per_problem != 0, EXPR);
 #undef EXPR
+  }
   ACRO_LAUNCH_CHECK("acro_riccati_affine");
   return ACRO_OK;
 }
@@ -1617,7 +1688,7 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
                "acro_newton_solve: bad argument");
   ACRO_REQUIRE(!opts->init || x0, "acro_newton_solve: x0 required when init");
   ACRO_REQUIRE(opts->max_iters >= 0 && opts->max_line_search >= 1, "acro_newton_solve: bad options");
-  ACRO_REQUIRE(!p->actuated_tau1, "acro_newton_solve: fully-actuated plant not supported here");
+  ACRO_REQUIRE(!(p->actuated_tau1 && params_b), "acro_newton_solve: the fully-actuated plant takes shared physical parameters");
   NewtonArgs a;
   a.m = make_model(*p);
   a.kw = make_weights(*w);
@@ -1633,6 +1704,7 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
   a.Xw = Xw;
   a.Uw = Uw;
   a.lin = lin_ws;
+  a.spec_ws = opts->spec_ws;
   a.K = K;
   a.S = S;
   a.cost = cost;
@@ -1650,14 +1722,20 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
                       aligned(lin_ws, 128) && aligned(K, 128) && aligned(S, 128) &&
                       aligned(ref->x, ref->per_problem ? 128 : 32) && aligned(ref->u, ref->per_problem ? 128 : 16);
   NewtonPlan plan;
-  const int rc = newton_plan(*opts, B, ref->per_problem != 0, per_problem_weights(*w), params_b != nullptr, tma_ok, plan);
+  // the fully-actuated plant runs on the one-thread-per-problem kernel (planned like per-problem physical parameters)
+  const int rc = newton_plan(*opts, B, ref->per_problem != 0, per_problem_weights(*w), params_b != nullptr || p->actuated_tau1,
+                             tma_ok, plan);
   if (rc != ACRO_OK) return rc;
   const int64_t tiles = (B + 31) / 32;
   const bool wpb = per_problem_weights(*w), rpb = ref->per_problem != 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (plan.kernel == ACRO_NEWTON_THREAD) {
     const Cfg c = cfg_for(B);
-    if (params_b) {
+    if (p->actuated_tau1) {
+#define EXPR(WPB, RPB) k_newton<WPB, RPB, false, true><<<c.grid, c.block, 0, s>>>(a)
+      DISPATCH2(wpb, rpb, EXPR);
+#undef EXPR
+    } else if (params_b) {
 #define EXPR(WPB, RPB) k_newton<WPB, RPB, true><<<c.grid, c.block, 0, s>>>(a)
       DISPATCH2(wpb, rpb, EXPR);
 #undef EXPR
@@ -1666,6 +1744,23 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
       DISPATCH2(wpb, rpb, EXPR);
 #undef EXPR
     }
+  } else if (plan.kernel == ACRO_NEWTON_SPEC) {
+#define LAUNCH_SPEC(WPB, RPB, SG)                                                                                   \
+  do {                                                                                                              \
+    constexpr int smem = SpecSmem<RPB, SG>::total;                                                                  \
+    cudaError_t e_ = cudaFuncSetAttribute(k_newton_spec<WPB, RPB, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          smem);                                                                    \
+    if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                          \
+    k_newton_spec<WPB, RPB, SG><<<(unsigned)tiles, ACRO_SPEC_W * 32, smem, s>>>(a);                                 \
+  } while (0)
+    if (rpb) {
+      LAUNCH_SPEC(true, true, 8);
+    } else {
+#define EXPR(WPB, RPB) LAUNCH_SPEC(WPB, false, 16)
+      DISPATCH2(wpb, false, EXPR);
+#undef EXPR
+    }
+#undef LAUNCH_SPEC
   } else if (plan.kernel == ACRO_NEWTON_DUO) {
 #define LAUNCH_DUO(WPB, RPB, SG)                                                                                   \
   do {                                                                                                             \
@@ -1730,11 +1825,18 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
   return ACRO_OK;
 }
 
+int64_t acro_newton_spec_ws_doubles(int64_t B, int N) {
+  if (B <= 0 || N < 2) return 0;
+  return int64_t(ACRO_SPEC_W) * ((B + 31) / 32) * 32 * (int64_t(N) * 4 + int64_t(N - 1) * 2);
+}
+
 int acro_newton_describe(const AcroNewtonOpts* opts, int64_t B, int ref_per_problem, int weights_per_problem,
                          int params_per_problem, char* buf, int buf_len) {
   ACRO_REQUIRE(opts && buf && buf_len > 0 && B > 0, "acro_newton_describe: bad argument");
   NewtonPlan plan;
-  const int rc = newton_plan(*opts, B, ref_per_problem != 0, weights_per_problem != 0, params_per_problem != 0, true, plan);
+  AcroNewtonOpts o = *opts;
+  if (!o.spec_ws) o.spec_ws = reinterpret_cast<double*>(uintptr_t(128));  // (planning only: nothing is dereferenced)
+  const int rc = newton_plan(o, B, ref_per_problem != 0, weights_per_problem != 0, params_per_problem != 0, true, plan);
   if (rc != ACRO_OK) return rc;
   const bool wpb = weights_per_problem != 0, rpb = ref_per_problem != 0;
   const char* tf[2] = {"false", "true"};
@@ -1742,6 +1844,8 @@ int acro_newton_describe(const AcroNewtonOpts* opts, int64_t B, int ref_per_prob
     snprintf(buf, buf_len, "acro::k_newton<%s,%s,%s>", tf[wpb], tf[rpb], tf[params_per_problem != 0]);
   else if (plan.kernel == ACRO_NEWTON_DUO)
     snprintf(buf, buf_len, "acro::k_newton_duo<%s,%s,%d>", tf[wpb || rpb], tf[rpb], plan.stage_steps);
+  else if (plan.kernel == ACRO_NEWTON_SPEC)
+    snprintf(buf, buf_len, "acro::k_newton_spec<%s,%s,%d>", tf[wpb || rpb], tf[rpb], plan.stage_steps);
   else
     snprintf(buf, buf_len, "acro::k_newton_ring<%s,%s,%d,%s>", tf[wpb], tf[rpb], plan.stage_steps, tf[plan.recompute_lin]);
   return ACRO_OK;
@@ -1818,14 +1922,20 @@ int acro_lqr_gains(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
                    void* stream) {
   ACRO_REQUIRE(p && w && traj && traj->x && traj->u && K && B > 0 && N >= 2, "acro_lqr_gains: bad argument");
   ACRO_REQUIRE(traj->per_problem || B == 1, "acro_lqr_gains: a shared trajectory is one problem (B = 1)");
-  ACRO_REQUIRE(!p->actuated_tau1, "acro_lqr_gains: fully-actuated plant not supported here");
   const Cfg c = cfg_for(B);
   const KWeights kw = make_weights(*w);
   const Model m = make_model(*p);
+  if (p->actuated_tau1) {
+#define EXPR(WPB, RPB) \
+  k_lqr_gains<WPB, RPB, true><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, kw, B, N, traj->x, traj->u, K)
+    DISPATCH2(per_problem_weights(*w), traj->per_problem != 0, EXPR);
+#undef EXPR
+  } else {
 #define EXPR(WPB, RPB) \
   k_lqr_gains<WPB, RPB><<<c.grid, c.block, 0, (cudaStream_t)stream>>>(m, kw, B, N, traj->x, traj->u, K)
-  DISPATCH2(per_problem_weights(*w), traj->per_problem != 0, EXPR);
+    DISPATCH2(per_problem_weights(*w), traj->per_problem != 0, EXPR);
 #undef EXPR
+  }
   ACRO_LAUNCH_CHECK("acro_lqr_gains");
   return ACRO_OK;
 }

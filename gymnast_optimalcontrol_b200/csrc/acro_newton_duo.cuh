@@ -53,7 +53,14 @@ struct Hand {
   __device__ __forceinline__ uint32_t full_bar() const { return full + (h & (ACRO_DUO_R - 1)) * 8; }
   __device__ __forceinline__ uint32_t empty_bar() const { return empty + (h & (ACRO_DUO_R - 1)) * 8; }
   __device__ __forceinline__ uint32_t phase() const { return (h / ACRO_DUO_R) & 1u; }
+  // hand-off number h + d: its empty barrier and the parity whose completion means "slot free"
+  __device__ __forceinline__ uint32_t empty_bar_at(uint32_t d) const { return empty + ((h + d) & (ACRO_DUO_R - 1)) * 8; }
+  __device__ __forceinline__ uint32_t free_parity_at(uint32_t d) const { return (((h + d) / ACRO_DUO_R) & 1u) ^ 1u; }
 };
+// NI variants of the chain loops (k_newton_spec) contain no mbarrier phase check: instead of testing the next hand-off
+// slot in every step, every ACRO_DUO_LOOK-th step makes sure (blocking, behind a call) that the next ACRO_DUO_LOOK slots
+// are free - the trailer frees them in order, so the one furthest ahead suffices.
+#define ACRO_DUO_LOOK 4
 
 enum { DUO_EXIT = 0, DUO_BACKWARD = 1, DUO_FORWARD = 2 };
 
@@ -99,17 +106,17 @@ struct FwdIn {
   }
 };
 
-template <bool RPB, int SG>
+template <bool RPB, int SG, bool NI = false>
 __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r, Hand& hd, int lane, double gamma) {
   constexpr unsigned FULL = 0xffffffffu;
   const int steps = N - 1, n_stages = (steps + SG - 1) / SG;
   double xp[4];
   FwdIn<SG> in;
-  mbar_wait(r.bars + ring_slot(r.base) * 8, ring_parity(r.base));
+  mbar_wait_t<NI>(r.bars + ring_slot(r.base) * 8, ring_parity(r.base));
   in.load(r.data + ring_slot(r.base) * stage_bytes<RPB, SG>(), 0, lane);
 #pragma unroll
   for (int c = 0; c < 4; ++c) xp[c] = in.x[c];  // x+_0 = x_0
-  mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);  // the hand-off slot of the first step is free (all are, between passes)
+  mbar_wait_t<NI>(hd.empty_bar(), hd.phase() ^ 1u);  // the hand-off slot of the first step is free (all are, between passes)
   // State carried into the next step's single "anything unusual?" branch, so that the step itself is straight-line
   // code: is the next hand-off slot free, and did the step just taken leave the range of the polynomial sincos.
   uint32_t hready = 1u;
@@ -126,7 +133,8 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
       // where the operands of the next step live: this stage, the next stage (whose bulk copies were issued at
       // least a stage ago: the wait is a formality), or nowhere (last step of the pass: reload this step's)
       const bool cross = (s + 1 == cnt) && (k + 1 < n_stages);
-      if (__any_sync(FULL, cross || bad || !hready)) {
+      const bool look = NI && (hd.h % ACRO_DUO_LOOK) == 0;
+      if (__any_sync(FULL, cross || bad || (NI ? look : !hready))) {
         if (bad) {  // the last step left the range of the incremental sincos: redo it with a full sincos per stage
           double xo[4], uo[2];  // its inputs are still in the hand-off slot they were written to
           const uint32_t pslot = hd.data + ((hd.h - 1) & (ACRO_DUO_R - 1)) * ACRO_DUO_SLOT_BYTES + lane * 8;
@@ -140,8 +148,12 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
           tc = trig_carry_at(m, xp[0], xp[1]);
         }
         __syncwarp();
-        if (cross) mbar_wait(nbar, npar);
-        if (!hready) mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);  // the trailer is ACRO_DUO_R steps behind
+        if (cross) mbar_wait_t<NI>(nbar, npar);
+        if (NI) {
+          if (look) mbar_wait_call(hd.empty_bar_at(ACRO_DUO_LOOK - 1), hd.free_parity_at(ACRO_DUO_LOOK - 1));
+        } else if (!hready) {
+          mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);  // the trailer is ACRO_DUO_R steps behind
+        }
       }
       const uint32_t nsrc = cross ? nstage : stage;
       const int ns = (s + 1 < cnt) ? s + 1 : (cross ? 0 : s);
@@ -169,7 +181,7 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
         // operands of the next step and the state of the next hand-off slot, while the FP64 pipe is busy
         // (no branch in here: a branch would cut the step's straight-line code into two scheduling regions)
         in.load(nsrc, ns, lane);
-        hready = mbar_test(nebar, nepar);
+        if (!NI) hready = mbar_test(nebar, nepar);
         int acc = __double2loint(in.x[0]) | __double2loint(in.x[1]) | __double2loint(in.x[2]) | __double2loint(in.x[3]) |
                   __double2loint(in.u[0]) | __double2loint(in.u[1]) | __double2loint(in.s[0]) | __double2loint(in.s[1]);
 #pragma unroll
@@ -196,6 +208,7 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
     __syncwarp();
     if (!hready) mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);
   }
+  if (NI) mbar_wait_call(hd.empty_bar(), hd.phase() ^ 1u);
   {  // terminal state
     const uint32_t slot = hd.slot(), fbar = hd.full_bar();
 #pragma unroll
@@ -209,7 +222,7 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
 // ---------------------------------------------------------------------------------------------------------
 // forward pass, trailer warp: cost of the candidate, its linearisation, all stores, ring refills
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB, int SG>
+template <bool WPB, bool RPB, int SG, bool NI = false>
 __device__ __forceinline__ double duo_forward_trailer(const Model& m, const WV<WPB>& w, int N, const TilePtrs& p, Ring& r,
                                                       Hand& hd, int lane, bool store, double* __restrict__ Xo,
                                                       double* __restrict__ Uo, double* __restrict__ Lo,
@@ -224,12 +237,12 @@ __device__ __forceinline__ double duo_forward_trailer(const Model& m, const WV<W
     const int cnt = min(SG, steps - k * SG);
     const uint32_t g = r.base + k;
     const uint32_t stage = r.data + ring_slot(g) * stage_bytes<RPB, SG>();
-    mbar_wait(r.bars + ring_slot(g) * 8, ring_parity(g));
+    mbar_wait_t<NI>(r.bars + ring_slot(g) * 8, ring_parity(g));
     for (int s = 0; s < cnt; ++s) {
       double xr[4], ur[2], xp[4], up[2];
       lds_ref<RPB, SG>(stage, s, lane, xr, ur);
       const uint32_t slot = hd.slot();
-      mbar_wait(hd.full_bar(), hd.phase());
+      mbar_wait_t<NI>(hd.full_bar(), hd.phase());
 #pragma unroll
       for (int c = 0; c < 4; ++c) xp[c] = lds(slot + c * 256 + lane * 8);
 #pragma unroll
@@ -276,7 +289,7 @@ __device__ __forceinline__ double duo_forward_trailer(const Model& m, const WV<W
   double xp[4], ex[4];
   {
     const uint32_t slot = hd.slot();
-    mbar_wait(hd.full_bar(), hd.phase());
+    mbar_wait_t<NI>(hd.full_bar(), hd.phase());
 #pragma unroll
     for (int c = 0; c < 4; ++c) xp[c] = lds(slot + c * 256 + lane * 8);
     __syncwarp();
@@ -307,7 +320,7 @@ __device__ __forceinline__ void lds_lin(uint32_t stage, int s, int lane, LinD& L
   L.b[1] = lds(b + 9 * 256);
 }
 
-template <bool WPB, bool RPB, int SG, int SW>
+template <bool WPB, bool RPB, int SG, int SW, bool NI = false>
 __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>& w, int N, Ring& r, Hand& hd, int lane) {
   constexpr unsigned FULL = 0xffffffffu;
   const int steps = N - 1, n_stages = (steps + SG - 1) / SG;
@@ -320,11 +333,11 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
     for (int j = i; j < 4; ++j) P[sym(i, j)] = w.QT2(i, j);
   LinD L;
   L.b0[0] = L.b0[1] = 0.0;
-  mbar_wait(r.bars + ring_slot(r.base) * 8, ring_parity(r.base));
+  mbar_wait_t<NI>(r.bars + ring_slot(r.base) * 8, ring_parity(r.base));
   lds_lin<SG>(r.data + ring_slot(r.base) * stage_bytes<RPB, SG>(), cnt_of(0) - 1, lane, L);
   const QhQ2<WV<WPB>> Qh{w};
   const Lu2Col col = lu2_col(w.R2(0, 0), w.R2(0, 1));
-  mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);  // the hand-off slot of the first step is free (all are, between passes)
+  mbar_wait_t<NI>(hd.empty_bar(), hd.phase() ^ 1u);  // the hand-off slot of the first step is free (all are, between passes)
   uint32_t hready = 1u;
   for (int k = 0; k < n_stages; ++k) {
     const int cnt = cnt_of(k);
@@ -339,9 +352,14 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
       const bool cross = (s == 0) && (k + 1 < n_stages);
       // (no vote here: with __any_sync in this loop ptxas puts a YIELD at the head of both chain loops, 50 cycles
       // per step; the condition is the same in every lane)
-      if (cross || !hready) {
-        if (cross) mbar_wait(nbar, npar);
-        if (!hready) mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);
+      const bool look = NI && (hd.h % ACRO_DUO_LOOK) == 0;
+      if (cross || (NI ? look : !hready)) {
+        if (cross) mbar_wait_t<NI>(nbar, npar);
+        if (NI) {
+          if (look) mbar_wait_call(hd.empty_bar_at(ACRO_DUO_LOOK - 1), hd.free_parity_at(ACRO_DUO_LOOK - 1));
+        } else if (!hready) {
+          mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);
+        }
       }
       const uint32_t nsrc = cross ? nstage : stage;
       const int ns = (s > 0) ? s - 1 : (cross ? ncnt - 1 : s);
@@ -363,7 +381,7 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
       __syncwarp();
       mbar_arrive_lane0(fbar, lane);
       ++hd.h;
-      hready = mbar_test(hd.empty_bar(), hd.phase() ^ 1u);
+      if (!NI) hready = mbar_test(hd.empty_bar(), hd.phase() ^ 1u);
       L = Ln;
     }
   }
@@ -373,7 +391,7 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
 // ---------------------------------------------------------------------------------------------------------
 // backward pass, trailer warp: cost gradients, sigma, delta_J, costate, stores, ring refills
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB, int SG, int SW>
+template <bool WPB, bool RPB, int SG, int SW, bool NI = false>
 __device__ __forceinline__ void duo_backward_trailer(const Model& m, const WV<WPB>& w, int N, const TilePtrs& p, Ring& r,
                                                      Hand& hd, int lane, bool store, double* __restrict__ K,
                                                      double* __restrict__ S, const double xT[4], const double xrT[4],
@@ -403,7 +421,7 @@ __device__ __forceinline__ void duo_backward_trailer(const Model& m, const WV<WP
     const int cnt = cnt_of(k);
     const uint32_t g = r.base + k;
     const uint32_t stage = r.data + ring_slot(g) * stage_bytes<RPB, SG>();
-    mbar_wait(r.bars + ring_slot(g) * 8, ring_parity(g));
+    mbar_wait_t<NI>(r.bars + ring_slot(g) * 8, ring_parity(g));
     for (int s = cnt - 1; s >= 0; --s) {
       double x[4], u[2], xr[4], ur[2];
       LinD L;
@@ -434,7 +452,7 @@ __device__ __forceinline__ void duo_backward_trailer(const Model& m, const WV<WP
       double Kt[8], inv_u11, qsel, st[2];
       {
         const uint32_t slot = hd.slot();
-        mbar_wait(hd.full_bar(), hd.phase());
+        mbar_wait_t<NI>(hd.full_bar(), hd.phase());
 #pragma unroll
         for (int e = 0; e < 8; ++e) Kt[e] = lds(slot + e * 256 + lane * 8);
         inv_u11 = lds(slot + 8 * 256 + lane * 8);

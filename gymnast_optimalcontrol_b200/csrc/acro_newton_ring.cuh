@@ -44,6 +44,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// The same wait as a real function call.  In a kernel whose blocks may hold more than two warps ptxas puts a YIELD at
+// the head of every loop that contains an mbarrier phase check (try_wait or test_wait), which costs the warp-specialised
+// loops of k_newton_spec a quarter of their speed; with the spin loop behind a call the loops stay YIELD-free
+// (profiles/README.md, "YIELD").  NI = "no inlined phase checks".
+__device__ __noinline__ void mbar_wait_call(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+template <bool NI>
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity) {
+  if (NI)
+    mbar_wait_call(bar, parity);
+  else
+    mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)

@@ -50,6 +50,9 @@ def compute_equilibrium(u_target, theta_guess, version=1, tol=1e-14, max_iter=50
         g1 sin(th1) + g2 sin(th1 + th2) = u1,      g2 sin(th1 + th2) = u2,
     so a Newton iteration from the same initial guess is used here (host side: this builds an input of the hot
     path once per problem family).  Raises RuntimeError like the reference if it does not converge."""
+    if (isinstance(u_target, torch.Tensor) and u_target.dim() == 2) or (not isinstance(u_target, torch.Tensor)
+                                                                         and np.ndim(u_target) == 2):
+        return compute_equilibrium_batch(u_target, theta_guess, version=version, tol=max(tol, 1e-13), max_iter=max_iter)
     p = bt.PARAM_SETS[version]
     g1 = p["g"] * (p["lc1"] * p["m1"] + p["m2"] * p["l1"])
     g2 = p["g"] * p["m2"] * p["lc2"]
@@ -65,14 +68,33 @@ def compute_equilibrium(u_target, theta_guess, version=1, tol=1e-14, max_iter=50
     raise RuntimeError("Root finder failed: Newton iteration on G(theta) = u did not converge")
 
 
+def compute_equilibrium_batch(u_target, theta_guess, version=1, tol=1e-13, max_iter=50, params_b=None):
+    """compute_equilibrium for B targets at once on the device (acro_equilibrium): u_target (B,2), theta_guess (B,2) or
+    (2,) -> x_e (B,4), u_e (B,2), same kind of array as u_target.  Raises RuntimeError like the reference (tg:33-34) if
+    any problem does not converge.  params_b (B,11): every problem its own physical parameters."""
+    ut, kind = _io.state_in(u_target, nu)
+    Bn = ut.shape[1]
+    tg_ = theta_guess.detach().cpu().numpy() if isinstance(theta_guess, torch.Tensor) else np.asarray(theta_guess, dtype=np.float64)
+    th0 = bt.upload(np.ascontiguousarray(np.broadcast_to(tg_, (Bn, 2)).T))
+    pb = None if params_b is None else bt.phys_params(params_b, Bn)
+    theta, n = bt.equilibrium(ut, th0, params=bt.make_params(version, dt), params_b=pb, tol=tol, max_iter=max_iter)
+    if bool((n < 0).any()):
+        raise RuntimeError("Root finder failed: Newton iteration on G(theta) = u did not converge for %d of %d targets"
+                           % (int((n < 0).sum()), Bn))
+    x_e = torch.cat([theta, torch.zeros_like(theta)], dim=0)  # [theta1, theta2, 0, 0]
+    return _io.out(x_e, kind), _io.out(ut, kind)
+
+
 def define_reference_piecewise(T, x_e1, x_e2, u_e1, u_e2):
     """Two constant segments, x_e1 for t < T/2 and x_e2 after (trajectory_generation.py:41-58).  Host-side
-    construction of an input; not a compute kernel."""
+    construction of an input; not a compute kernel.  Batched: x_e1, x_e2 (B,4) and u_e1, u_e2 (B,2) give x_ref (B,N,4),
+    u_ref (B,N,2)."""
     n = int(T / dt) + 1
     t_ref = np.linspace(0.0, T, n)
     first = (t_ref < T / 2.0)[:, None]
-    x_ref = np.where(first, np.asarray(x_e1, dtype=float)[None], np.asarray(x_e2, dtype=float)[None])
-    u_ref = np.where(first, np.asarray(u_e1, dtype=float)[None], np.asarray(u_e2, dtype=float)[None])
+    a = [np.asarray(v.detach().cpu() if isinstance(v, torch.Tensor) else v, dtype=float) for v in (x_e1, x_e2, u_e1, u_e2)]
+    x_ref = np.where(first, a[0][..., None, :], a[1][..., None, :])
+    u_ref = np.where(first, a[2][..., None, :], a[3][..., None, :])
     return t_ref, x_ref, u_ref
 
 

@@ -116,6 +116,8 @@ typedef struct AcroNewtonOpts {
                             (304 B per problem-step-iteration), 2 it streams the one the forward pass stored (464 B) */
   int32_t speculate;    /* Armijo candidates evaluated in parallel per round by ACRO_NEWTON_SPEC: 0 auto
                             (from the previous iteration's number of tries), 1..8 fixed */
+  double* spec_ws;      /* DEVICE workspace of ACRO_NEWTON_SPEC (candidate trajectories), 128-byte aligned,
+                            acro_newton_spec_ws_doubles(B, N) doubles; NULL otherwise */
 } AcroNewtonOpts;
 #define ACRO_NEWTON_AUTO 0
 #define ACRO_NEWTON_DUO 1    /* two warps per tile (recurrence + trailer), at most two tiles per SM */
@@ -140,6 +142,15 @@ int acro_rk4_step(const AcroParams* p, int64_t B, const double* x, const double*
  * A [16][B] (4x4 row-major), Bm [8][B] (4x2 row-major). */
 int acro_linearize(const AcroParams* p, int64_t B, const double* x, const double* u, double* A,
                    double* Bm, int discrete, void* stream);
+
+/* ---- reference builders ------------------------------------------------ */
+/* compute_equilibrium(u_target, theta_guess)  trajectory_generation.py:22-39 for a batch: solves the gravity balance
+ * G(theta1, theta2) = u_target by Newton's method from theta_guess (the reference uses SciPy's hybr on the same two
+ * equations).  u_target [2][B], theta_guess [2][B] -> theta [2][B] (x_e = [theta1, theta2, 0, 0], u_e = u_target),
+ * n_iter [B] int32: iterations used, or -max_iter if max|residual| >= tol after max_iter iterations (the reference
+ * raises RuntimeError there).  params_b: per-problem physical parameters [11][B] or NULL. */
+int acro_equilibrium(const AcroParams* p, const double* params_b, int64_t B, const double* u_target,
+                     const double* theta_guess, double tol, int max_iter, double* theta, int32_t* n_iter, void* stream);
 
 /* ---- G1-G11: trajectory_generation.py ---------------------------------------------- */
 /* simulate_open_loop(x0, u_traj)  tg:74-87.  x0 [4][B], U {N-1 x 2} (NULL = zeros)
@@ -210,6 +221,8 @@ int acro_newton_solve(const AcroParams* p, const AcroWeights* w, const AcroNewto
                       double* sigma_norm, double* gamma_acc, int32_t* iters, int32_t* status,
                       double* hist_cost, double* hist_sigma_norm, double* hist_gamma,
                       int32_t* hist_ntry, void* stream);
+/* Size of AcroNewtonOpts.spec_ws in doubles (8 candidate copies of X and U). */
+int64_t acro_newton_spec_ws_doubles(int64_t B, int N);
 /* Name of the kernel acro_newton_solve would launch for these options and this batch on the current device
  * (e.g. "acro::k_newton_duo<false,false,16>"), for logs and bench.py; launches nothing. */
 int acro_newton_describe(const AcroNewtonOpts* opts, int64_t B, int ref_per_problem, int weights_per_problem,

@@ -54,7 +54,7 @@ def test_struct_layouts_match_header(tmp_path):
         assert int(got[name]) == ctypes.sizeof(cls), name
         for f, _ in cls._fields_:
             assert int(got["%s.%s" % (name, f)]) == getattr(cls, f).offset, (name, f)
-    assert ctypes.sizeof(_abi.AcroNewtonOpts) == 16 + 32 + 16
+    assert ctypes.sizeof(_abi.AcroNewtonOpts) == 16 + 32 + 16 + 8
 
 
 def test_invalid_arguments_return_error_codes_without_a_gpu():
@@ -192,3 +192,28 @@ def test_kernel_variants_and_plan():
         bt.newton_kernel_name(64, kernel="duo", ref_per_problem=True, stage_steps=16)
     src = open(os.path.join(ROOT, "gymnast_optimalcontrol_b200", "csrc", "acro_kernels.cu")).read()
     assert "getenv" not in src
+
+
+def test_pinned_pool_never_hands_out_memory_that_is_still_referenced(monkeypatch):
+    """Results live in pinned host blocks that are recycled only when every tensor / NumPy view of them is gone
+    (successive results must not alias; round 2: no page-locking in the steady state)."""
+    import torch
+    from gymnast_optimalcontrol_b200 import _io
+    orig = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: orig(*a, **{kk: v for kk, v in k.items() if kk != "pin_memory"}))
+    pool = _io.PinnedPool()
+    a = pool.empty((4, 5))
+    pa = a.data_ptr()
+    b = pool.empty((4, 5))
+    assert b.data_ptr() != pa
+    del a
+    c = pool.empty((4, 5))
+    assert c.data_ptr() == pa  # recycled once dropped
+    row, arr = c[1], c.numpy()
+    del c
+    assert pool.empty((4, 5)).data_ptr() != pa  # a view and a NumPy array still point into the block
+    del row
+    assert pool.empty((4, 5)).data_ptr() != pa
+    del arr
+    assert pool.empty((4, 5)).data_ptr() == pa
+    assert pool.empty((3,), torch.int32).dtype == torch.int32

@@ -683,7 +683,7 @@ def test_full_size_c3_properties(bt):
 # ------------------------------------------------------------------------------------- ragged batches, every kernel variant
 # every kernel acro_newton_solve can dispatch to (AcroNewtonOpts.kernel / stage_steps / recompute_lin), forced on small
 # batches here and run at their own batch sizes in test_dispatch_variants_at_their_batch_sizes
-VARIANTS = ["duo", "duo4", "duo8", "ring", "ring4", "ring2", "ring-rl", "ldg"]
+VARIANTS = ["duo", "duo4", "duo8", "ring", "ring4", "ring2", "ring-rl", "ldg", "spec", "spec1", "spec3", "spec8"]
 
 
 def _short_ref(fa_ref, N=61):

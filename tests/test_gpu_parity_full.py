@@ -112,7 +112,8 @@ def c2_x0():
     return x0
 
 
-def test_c2_sixteen_problems_to_convergence_vs_reference(bt, fa_ref):
+@pytest.mark.parametrize("kernel", ["auto", "spec"])
+def test_c2_sixteen_problems_to_convergence_vs_reference(bt, fa_ref, kernel):
     """Config 2 (B = 4096, gamma_0 = 0.1, tol = 1e-4) to convergence: 16 problems spread over the batch against runs
     of the unmodified reference (387-399 iterations each): iteration counts, every cost and max|sigma| of the
     history, Armijo tries and accepted steps, final x, u, sigma at 1e-9; gains by assert_gain_parity."""
@@ -121,7 +122,7 @@ def test_c2_sixteen_problems_to_convergence_vs_reference(bt, fa_ref):
     x0s = c2_x0()
     rows = g["rows"]
     assert len(rows) >= 16 and np.array_equal(x0s[rows], g["x0"])
-    st = bt.newton_solve(soa(x0s), bt.make_ref(x_ref, u_ref), max_iters=5000, tol=1e-4, gamma_0=0.1)
+    st = bt.newton_solve(soa(x0s), bt.make_ref(x_ref, u_ref), max_iters=5000, tol=1e-4, gamma_0=0.1, kernel=kernel)
     torch.cuda.synchronize()
     assert bool((st.status == 1).all())
     its = st.iters.cpu().numpy()
@@ -138,8 +139,9 @@ def test_c2_sixteen_problems_to_convergence_vs_reference(bt, fa_ref):
         assert_gain_parity(K[i].reshape(-1, 2, 4), g["K"][i], g["x_prev"][i], g["u_prev"][i], x_ref, u_ref)
 
 
+@pytest.mark.parametrize("kernel", ["auto", "spec", "spec8"])
 @pytest.mark.parametrize("tag,gamma_0", [("g01", 0.1), ("g1", 1.0)])
-def test_c2_sixty_four_problems_three_iterations_vs_reference(bt, fa_ref, tag, gamma_0):
+def test_c2_sixty_four_problems_three_iterations_vs_reference(bt, fa_ref, tag, gamma_0, kernel):
     """Config 2, 64 problems x 3 iterations (8 of them the corner lanes of the first and last tile) against the
     unmodified reference, at the shipped step size and in the back-tracking regime."""
     g = golden("newton_c2_three_iters")
@@ -147,7 +149,7 @@ def test_c2_sixty_four_problems_three_iterations_vs_reference(bt, fa_ref, tag, g
     x0s = c2_x0()
     rows = g["rows"]
     assert len(rows) == 64 and np.array_equal(x0s[rows], g["x0"])
-    st = bt.newton_solve(soa(x0s), bt.make_ref(x_ref, u_ref), max_iters=3, tol=1e-4, gamma_0=gamma_0)
+    st = bt.newton_solve(soa(x0s), bt.make_ref(x_ref, u_ref), max_iters=3, tol=1e-4, gamma_0=gamma_0, kernel=kernel)
     torch.cuda.synchronize()
     X, U, K, S = (t.batch_major()[rows].cpu().numpy() for t in (st.X, st.U, st.K, st.S))
     assert np.array_equal(st.hist_ntry[:3, rows].cpu().numpy().T, g[tag + "_n_try"].astype(np.int32))
@@ -190,7 +192,7 @@ def test_c3_256_rollouts_vs_reference(bt):
 def test_c4_sixteen_problems_500_steps(bt, H):
     """Config 4 (B = 16 384 acrobots, 500 receding-horizon steps): 16 sampled problems against the oracle's Riccati
     restatement of solve_mpc_tracking (tt:8-69), with the shared reference (gains computed once per time step) and with
-    per-problem references (every problem a differently scaled copy of the optimal trajectory, every problem its own
+    per-problem references (16 different converged swing-up trajectories spread over the batch, every problem its own
     500 sweeps).  Parity against CasADi/IPOPT itself is unpinned."""
     d = golden("acrobot_optimal_trajectory")
     gp = golden("p_inf")
@@ -210,18 +212,24 @@ def test_c4_sixteen_problems_500_steps(bt, H):
     assert rel_err(K0.cpu().numpy().reshape(500, 2, 4), K0o) < TOL
     assert rel_err(Xr.batch_major()[rows].cpu().numpy(), xo) < TOL
     assert rel_err(Ur.batch_major()[rows].cpu().numpy(), uo) < TOL
-    # per-problem references: scaled copies of the optimal trajectory (linearisation points differ per problem)
-    a = rng.uniform(0.9, 1.1, Bn)
-    xs = torch.from_numpy(d["x"]).cuda()[None] * torch.from_numpy(a).cuda()[:, None, None]
-    us = torch.from_numpy(d["u"]).cuda()[None] * torch.from_numpy(a).cuda()[:, None, None]
+    # per-problem references: problem b tracks the converged swing-up of config-2 problem rows[b % 16] (the 16 trajectories
+    # the unmodified reference solved to convergence, make_golden.py c2conv): dynamically consistent and all different,
+    # so every problem linearises about its own points and runs its own 500 sweeps
+    gc = golden("newton_c2_converged")
+    which = np.arange(Bn) % 16
+    which[rows] = np.arange(16)  # the sampled problems cover all 16 references
+    xs = torch.from_numpy(gc["x"]).cuda()[torch.from_numpy(which).cuda()]
+    us = torch.from_numpy(gc["u"]).cuda()[torch.from_numpy(which).cuda()]
     refp = bt.Ref(bt.Traj.from_batch_major(xs), bt.Traj.from_batch_major(us))
-    x0p = xs[:, 0].cpu().numpy() + (x0 - d["x"][0])
+    x0p = gc["x"][which, 0] + (x0 - d["x"][0])
     Xp, Up, _, nsp = bt.mpc_track(soa(x0p), refp, QT, T=501, T_pred=H, w=w)
     assert nsp == 500 * Bn
-    res = pool_map(_oracle_mpc, [(x0p[b], d["x"] * a[b], d["u"] * a[b], H) for b in rows])
+    res = pool_map(_oracle_mpc, [(x0p[b], gc["x"][which[b]], gc["u"][which[b]], H) for b in rows])
     Xp_s, Up_s = Xp.batch_major()[rows].cpu().numpy(), Up.batch_major()[rows].cpu().numpy()
     for i, (xo, uo) in enumerate(res):
+        assert np.isfinite(xo).all()
         assert rel_err(Xp_s[i], xo) < TOL and rel_err(Up_s[i], uo) < TOL, rows[i]
+    assert bool(torch.isfinite(Xp.data).all())
 
 
 # ------------------------------------------------------------------------------------- config 5
