@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libacro_b200.so")
+# (ACRO_B200_LIB: development hook for A/B runs of two builds of the library; the default is the in-tree build)
+LIB_PATH = os.environ.get("ACRO_B200_LIB") or os.path.join(PKG, "libacro_b200.so")
 
 OK, E_INVALID, E_CUDA = 0, -1, -2
 RUNNING, CONVERGED, MAX_ITERS, LINE_SEARCH_FAILED = 0, 1, 2, 3

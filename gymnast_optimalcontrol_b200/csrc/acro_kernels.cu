@@ -1447,7 +1447,7 @@ static int sm_count() {
     n = 148;  // B200 (no device: acro_newton_describe on a CPU-only box)
   return n;
 }
-static int newton_plan(const AcroNewtonOpts& o, int64_t B, bool rpb, bool wpb, bool ppb, bool tma_ok, NewtonPlan& plan) {
+static int newton_plan(const AcroNewtonOpts& o, int64_t B, bool rpb, bool wpb, bool ppb, bool act, bool tma_ok, NewtonPlan& plan) {
   (void)wpb;
   const int64_t tiles = (B + 31) / 32;
   const int n_sm = sm_count();
@@ -1456,19 +1456,20 @@ static int newton_plan(const AcroNewtonOpts& o, int64_t B, bool rpb, bool wpb, b
   ACRO_REQUIRE(sg == 0 || sg == 2 || sg == 4 || sg == 8 || sg == 16, "acro_newton_solve: stage_steps must be 0, 2, 4, 8 or 16");
   ACRO_REQUIRE(rl >= 0 && rl <= 2, "acro_newton_solve: recompute_lin must be 0, 1 or 2");
   if (k == ACRO_NEWTON_AUTO) {
-    // per-problem physical parameters: the one-thread-per-problem kernel derives its model per thread.
-    // Buffers that are not 128-byte aligned cannot be the source of bulk copies: same kernel.
-    if (ppb || !tma_ok) k = ACRO_NEWTON_THREAD;
+    // the fully-actuated plant runs on the one-thread-per-problem kernel; buffers that are not 128-byte aligned cannot
+    // be the source of bulk copies: same kernel.
+    if (act || !tma_ok) k = ACRO_NEWTON_THREAD;
     // at most two tiles per SM (config 2: 128 tiles): split every tile between two warps on two SM sub-partitions
     else k = (tiles <= 2 * int64_t(n_sm)) ? ACRO_NEWTON_DUO : ACRO_NEWTON_RING;
   }
   if (k != ACRO_NEWTON_THREAD) {
     ACRO_REQUIRE(tma_ok, "acro_newton_solve: the duo / ring kernels need 128-byte aligned X, U, Xw, Uw, lin_ws, K, S and reference buffers");
-    ACRO_REQUIRE(!ppb, "acro_newton_solve: per-problem physical parameters and the fully-actuated plant run on ACRO_NEWTON_THREAD");
+    ACRO_REQUIRE(!act, "acro_newton_solve: the fully-actuated plant runs on ACRO_NEWTON_THREAD");
   }
   if (k == ACRO_NEWTON_SPEC) {
     // eight warps per tile, one block per SM (acro_newton_spec.cuh); needs the candidate workspace
     ACRO_REQUIRE(tiles <= n_sm, "acro_newton_solve: the speculative kernel runs one tile per SM (B <= 32 x SM count)");
+    ACRO_REQUIRE(!ppb, "acro_newton_solve: the speculative kernel takes shared physical parameters");
     ACRO_REQUIRE(o.spec_ws != nullptr, "acro_newton_solve: the speculative kernel needs AcroNewtonOpts.spec_ws (acro_newton_spec_ws_doubles)");
     ACRO_REQUIRE(o.speculate >= 0 && o.speculate <= 8, "acro_newton_solve: speculate must be 0 (adaptive) or 1..8");
     ACRO_REQUIRE(sg == 0 || (sg == 16 && !rpb) || (sg == 8 && rpb), "acro_newton_solve: speculative kernel: stage_steps 16 (8 with per-problem references)");
@@ -1485,8 +1486,10 @@ static int newton_plan(const AcroNewtonOpts& o, int64_t B, bool rpb, bool wpb, b
     // = two warps per sub-partition)
     if (sg == 0) sg = (tiles <= n_sm && !rpb) ? 16 : (tiles > 4 * int64_t(n_sm) ? 2 : 4);
     ACRO_REQUIRE(sg == 2 || sg == 4 || (sg == 16 && !rpb), "acro_newton_solve: ring kernel: stage_steps 2, 4 (or 16 with a shared reference)");
+    if (ppb && sg == 16) sg = 4;  // (per-problem physical parameters: 4- and 2-step stages are instantiated)
     rl = (rl == 0) ? (sg == 2) : (rl == 1);
     ACRO_REQUIRE(!rl || sg == 2, "acro_newton_solve: recompute_lin needs stage_steps = 2");
+    ACRO_REQUIRE(!ppb || rl || sg == 4, "acro_newton_solve: ring kernel with per-problem physical parameters: stage_steps 4, or 2 with recompute_lin");
   } else {
     sg = 0;
     rl = 0;
@@ -1723,8 +1726,8 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
                       aligned(ref->x, ref->per_problem ? 128 : 32) && aligned(ref->u, ref->per_problem ? 128 : 16);
   NewtonPlan plan;
   // the fully-actuated plant runs on the one-thread-per-problem kernel (planned like per-problem physical parameters)
-  const int rc = newton_plan(*opts, B, ref->per_problem != 0, per_problem_weights(*w), params_b != nullptr || p->actuated_tau1,
-                             tma_ok, plan);
+  const int rc = newton_plan(*opts, B, ref->per_problem != 0, per_problem_weights(*w), params_b != nullptr,
+                             p->actuated_tau1 != 0, tma_ok, plan);
   if (rc != ACRO_OK) return rc;
   const int64_t tiles = (B + 31) / 32;
   const bool wpb = per_problem_weights(*w), rpb = ref->per_problem != 0;
@@ -1774,7 +1777,27 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
     // WV<true> falls back to them): ptxas puts YIELDs at the loop heads of k_newton_duo<false, true, *> and of no
     // other variant, which costs 12 % (8.7 against 9.9 M it/s at B = 4096).
     const bool wreg = wpb || rpb;
-    if (plan.stage_steps == 4) {
+    if (params_b) {
+      // per-problem physical parameters: the variants with the weights in registers (they take shared weights too)
+#define LAUNCH_DUO_PPB(RPB, SG)                                                                                          \
+  do {                                                                                                                   \
+    constexpr int smem = DuoSmem<RPB, SG>::total;                                                                        \
+    cudaError_t e_ = cudaFuncSetAttribute(k_newton_duo<true, RPB, SG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          smem);                                                                         \
+    if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                               \
+    k_newton_duo<true, RPB, SG, true><<<(unsigned)tiles, 64, smem, s>>>(a);                                              \
+  } while (0)
+      if (plan.stage_steps == 4) {
+        if (rpb) LAUNCH_DUO_PPB(true, 4); else LAUNCH_DUO_PPB(false, 4);
+      } else if (rpb) {
+        LAUNCH_DUO_PPB(true, 8);
+      } else if (plan.stage_steps == 8) {
+        LAUNCH_DUO_PPB(false, 8);
+      } else {
+        LAUNCH_DUO_PPB(false, 16);
+      }
+#undef LAUNCH_DUO_PPB
+    } else if (plan.stage_steps == 4) {
 #define EXPR(WPB, RPB) LAUNCH_DUO(WPB, RPB, 4)
       DISPATCH2(wreg, rpb, EXPR);
 #undef EXPR
@@ -1799,7 +1822,22 @@ int acro_newton_solve_pp(const AcroParams* p, const double* params_b, const Acro
     if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                          \
     k_newton_ring<WPB, RPB, SG, RL><<<(unsigned)tiles, 32, smem, s>>>(a);                                           \
   } while (0)
-    if (plan.stage_steps == 16) {
+    if (params_b) {
+#define LAUNCH_RING_PPB(RPB, SG, RL)                                                                                  \
+  do {                                                                                                                  \
+    constexpr int smem = ACRO_RING_D * stage_bytes<RPB, SG>() + ACRO_RING_D * 8;                                        \
+    cudaError_t e_ = cudaFuncSetAttribute(k_newton_ring<true, RPB, SG, RL, true>,                                       \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                           \
+    if (e_ != cudaSuccess) return cuda_fail(e_, "acro_newton_solve/smem");                                              \
+    k_newton_ring<true, RPB, SG, RL, true><<<(unsigned)tiles, 32, smem, s>>>(a);                                        \
+  } while (0)
+      if (plan.stage_steps == 2) {
+        if (rpb) LAUNCH_RING_PPB(true, 2, true); else LAUNCH_RING_PPB(false, 2, true);
+      } else {
+        if (rpb) LAUNCH_RING_PPB(true, 4, false); else LAUNCH_RING_PPB(false, 4, false);
+      }
+#undef LAUNCH_RING_PPB
+    } else if (plan.stage_steps == 16) {
 #define EXPR(WPB, RPB) LAUNCH_RING(WPB, false, 16, false)
       DISPATCH2(wpb, false, EXPR);
 #undef EXPR
@@ -1836,12 +1874,16 @@ int acro_newton_describe(const AcroNewtonOpts* opts, int64_t B, int ref_per_prob
   NewtonPlan plan;
   AcroNewtonOpts o = *opts;
   if (!o.spec_ws) o.spec_ws = reinterpret_cast<double*>(uintptr_t(128));  // (planning only: nothing is dereferenced)
-  const int rc = newton_plan(o, B, ref_per_problem != 0, weights_per_problem != 0, params_per_problem != 0, true, plan);
+  const int rc = newton_plan(o, B, ref_per_problem != 0, weights_per_problem != 0, params_per_problem != 0, false, true, plan);
   if (rc != ACRO_OK) return rc;
   const bool wpb = weights_per_problem != 0, rpb = ref_per_problem != 0;
   const char* tf[2] = {"false", "true"};
   if (plan.kernel == ACRO_NEWTON_THREAD)
     snprintf(buf, buf_len, "acro::k_newton<%s,%s,%s>", tf[wpb], tf[rpb], tf[params_per_problem != 0]);
+  else if (plan.kernel == ACRO_NEWTON_DUO && params_per_problem)
+    snprintf(buf, buf_len, "acro::k_newton_duo<true,%s,%d,true>", tf[rpb], plan.stage_steps);
+  else if (plan.kernel == ACRO_NEWTON_RING && params_per_problem)
+    snprintf(buf, buf_len, "acro::k_newton_ring<true,%s,%d,%s,true>", tf[rpb], plan.stage_steps, tf[plan.recompute_lin]);
   else if (plan.kernel == ACRO_NEWTON_DUO)
     snprintf(buf, buf_len, "acro::k_newton_duo<%s,%s,%d>", tf[wpb || rpb], tf[rpb], plan.stage_steps);
   else if (plan.kernel == ACRO_NEWTON_SPEC)

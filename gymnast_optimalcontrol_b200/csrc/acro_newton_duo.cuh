@@ -44,6 +44,10 @@ __device__ __forceinline__ void duo_bar() {
   asm volatile("bar.sync 1, 64;" ::: "memory");
 }
 
+// NI variants of the chain loops (k_newton_spec) contain no mbarrier phase check: instead of testing the next hand-off
+// slot in every step, every ACRO_DUO_LOOK-th step makes sure (blocking, behind a call) that the next ACRO_DUO_LOOK slots
+// are free - the trailer frees them in order, so the one furthest ahead suffices.
+#define ACRO_DUO_LOOK 4
 struct Hand {
   uint32_t data, full, empty;  // shared addresses: slot 0, full barrier 0, empty barrier 0
   uint32_t h;                  // hand-offs so far (identical in both warps)
@@ -56,11 +60,28 @@ struct Hand {
   // hand-off number h + d: its empty barrier and the parity whose completion means "slot free"
   __device__ __forceinline__ uint32_t empty_bar_at(uint32_t d) const { return empty + ((h + d) & (ACRO_DUO_R - 1)) * 8; }
   __device__ __forceinline__ uint32_t free_parity_at(uint32_t d) const { return (((h + d) / ACRO_DUO_R) & 1u) ^ 1u; }
+  // hand-off number hh (absolute): its full barrier and the parity whose completion means "produced"
+  __device__ __forceinline__ uint32_t full_bar_of(uint32_t hh) const { return full + (hh & (ACRO_DUO_R - 1)) * 8; }
+  __device__ __forceinline__ uint32_t full_parity_of(uint32_t hh) const { return (hh / ACRO_DUO_R) & 1u; }
 };
-// NI variants of the chain loops (k_newton_spec) contain no mbarrier phase check: instead of testing the next hand-off
-// slot in every step, every ACRO_DUO_LOOK-th step makes sure (blocking, behind a call) that the next ACRO_DUO_LOOK slots
-// are free - the trailer frees them in order, so the one furthest ahead suffices.
-#define ACRO_DUO_LOOK 4
+// The trailer's side of the same idea (NI): every ACRO_DUO_LOOK-th hand-off it waits (behind a call) until the chain has
+// produced the next ACRO_DUO_LOOK hand-offs - or the last one of the pass - and then reads them without waiting.
+#ifndef ACRO_SPEC_TRAILER_NI
+#define ACRO_SPEC_TRAILER_NI 1  // 0: the NI trailers keep the inlined per-step wait (ptxas then puts a YIELD in their loops)
+#endif
+// h_ok: hand-offs below this number are known to have been produced (starts at hd.h when a pass begins)
+template <bool NI>
+__device__ __forceinline__ void hand_wait_full(const Hand& hd, uint32_t h_last, uint32_t& h_ok) {
+  if (NI && ACRO_SPEC_TRAILER_NI) {
+    if (hd.h >= h_ok) {
+      const uint32_t hh = min(hd.h + (ACRO_DUO_LOOK - 1), h_last);
+      mbar_wait_call(hd.full_bar_of(hh), hd.full_parity_of(hh));
+      h_ok = hh + 1u;
+    }
+  } else {
+    mbar_wait(hd.full_bar(), hd.phase());
+  }
+}
 
 enum { DUO_EXIT = 0, DUO_BACKWARD = 1, DUO_FORWARD = 2 };
 
@@ -150,7 +171,9 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
         __syncwarp();
         if (cross) mbar_wait_t<NI>(nbar, npar);
         if (NI) {
+#ifndef ACRO_SPEC_NO_LOOK
           if (look) mbar_wait_call(hd.empty_bar_at(ACRO_DUO_LOOK - 1), hd.free_parity_at(ACRO_DUO_LOOK - 1));
+#endif
         } else if (!hready) {
           mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);  // the trailer is ACRO_DUO_R steps behind
         }
@@ -230,6 +253,8 @@ __device__ __forceinline__ double duo_forward_trailer(const Model& m, const WV<W
   const int steps = N - 1, n_stages = (steps + SG - 1) / SG;
   for (int k = 0; k < ACRO_RING_D && k < n_stages; ++k) ring_fill<RPB, true, SG>(r, p, k, k * SG, min(SG, steps - k * SG));
   double cost = 0.0;
+  const uint32_t h_last = hd.h + uint32_t(steps);  // the terminal state is hand-off number steps of this pass
+  uint32_t h_ok = hd.h;
   double* po_x = Xo + lane;
   double* po_u = Uo + lane;
   double* po_l = Lo + lane;
@@ -242,7 +267,7 @@ __device__ __forceinline__ double duo_forward_trailer(const Model& m, const WV<W
       double xr[4], ur[2], xp[4], up[2];
       lds_ref<RPB, SG>(stage, s, lane, xr, ur);
       const uint32_t slot = hd.slot();
-      mbar_wait_t<NI>(hd.full_bar(), hd.phase());
+      hand_wait_full<NI>(hd, h_last, h_ok);
 #pragma unroll
       for (int c = 0; c < 4; ++c) xp[c] = lds(slot + c * 256 + lane * 8);
 #pragma unroll
@@ -289,7 +314,10 @@ __device__ __forceinline__ double duo_forward_trailer(const Model& m, const WV<W
   double xp[4], ex[4];
   {
     const uint32_t slot = hd.slot();
-    mbar_wait_t<NI>(hd.full_bar(), hd.phase());
+    if (NI && ACRO_SPEC_TRAILER_NI)
+      mbar_wait_call(hd.full_bar(), hd.phase());
+    else
+      mbar_wait(hd.full_bar(), hd.phase());
 #pragma unroll
     for (int c = 0; c < 4; ++c) xp[c] = lds(slot + c * 256 + lane * 8);
     __syncwarp();
@@ -356,7 +384,9 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
       if (cross || (NI ? look : !hready)) {
         if (cross) mbar_wait_t<NI>(nbar, npar);
         if (NI) {
+#ifndef ACRO_SPEC_NO_LOOK
           if (look) mbar_wait_call(hd.empty_bar_at(ACRO_DUO_LOOK - 1), hd.free_parity_at(ACRO_DUO_LOOK - 1));
+#endif
         } else if (!hready) {
           mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);
         }
@@ -414,6 +444,8 @@ __device__ __forceinline__ void duo_backward_trailer(const Model& m, const WV<WP
     }
   }
   double dJ = 0.0, sn = 0.0;
+  const uint32_t h_last = hd.h + uint32_t(steps) - 1u;  // last hand-off of this pass
+  uint32_t h_ok = hd.h;
   const Lu2Col col = lu2_col(w.R2(0, 0), w.R2(0, 1));
   double* pk = K + (steps - 1) * kSK + lane;
   double* ps = S + (steps - 1) * kSS + lane;
@@ -452,7 +484,7 @@ __device__ __forceinline__ void duo_backward_trailer(const Model& m, const WV<WP
       double Kt[8], inv_u11, qsel, st[2];
       {
         const uint32_t slot = hd.slot();
-        mbar_wait_t<NI>(hd.full_bar(), hd.phase());
+        hand_wait_full<NI>(hd, h_last, h_ok);
 #pragma unroll
         for (int e = 0; e < 8; ++e) Kt[e] = lds(slot + e * 256 + lane * 8);
         inv_u11 = lds(slot + 8 * 256 + lane * 8);
@@ -503,7 +535,9 @@ struct DuoSmem {
 // ---------------------------------------------------------------------------------------------------------
 // kernel: two warps per block, block = tile of 32 problems
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB, int SG>
+// PPB: every problem its own physical parameters (a.pb, see model_per_problem): the lumped model constants live in
+// registers of both warps instead of the constant bank.
+template <bool WPB, bool RPB, int SG, bool PPB = false>
 __global__ void __launch_bounds__(64) k_newton_duo(const __grid_constant__ NewtonArgs a) {
   extern __shared__ __align__(128) unsigned char ring_smem[];
   constexpr unsigned FULL = 0xffffffffu;
@@ -514,6 +548,7 @@ __global__ void __launch_bounds__(64) k_newton_duo(const __grid_constant__ Newto
   const bool valid = b < B;
   const int64_t bs = valid ? b : B - 1;  // padding lanes shadow the last problem and never write
   const int N = a.N;
+  ACRO_MODEL(PPB, a.m, a.pb, B, bs);
   const WV<WPB> w(a.kw, B, bs);
   const uint32_t sbase = smem_u32(ring_smem);
   Ring r;
@@ -572,15 +607,15 @@ __global__ void __launch_bounds__(64) k_newton_duo(const __grid_constant__ Newto
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) xT[cc] = p.x[(N - 1) * sx + cc * 32 + lane];
         if (WPB)
-          duo_backward_trailer<WPB, RPB, SG, 2>(a.m, w, N, p, r, hd, lane, store, tK, tS, xT, xrT, dJ, sn);
+          duo_backward_trailer<WPB, RPB, SG, 2>(m, w, N, p, r, hd, lane, store, tK, tS, xT, xrT, dJ, sn);
         else if (swap_shared)
-          duo_backward_trailer<WPB, RPB, SG, 1>(a.m, w, N, p, r, hd, lane, store, tK, tS, xT, xrT, dJ, sn);
+          duo_backward_trailer<WPB, RPB, SG, 1>(m, w, N, p, r, hd, lane, store, tK, tS, xT, xrT, dJ, sn);
         else
-          duo_backward_trailer<WPB, RPB, SG, 0>(a.m, w, N, p, r, hd, lane, store, tK, tS, xT, xrT, dJ, sn);
+          duo_backward_trailer<WPB, RPB, SG, 0>(m, w, N, p, r, hd, lane, store, tK, tS, xT, xrT, dJ, sn);
         res[lane] = dJ;
         res[32 + lane] = sn;
       } else {
-        const double cst = duo_forward_trailer<WPB, RPB, SG>(a.m, w, N, p, r, hd, lane, store, tX[cur ^ 1], tU[cur ^ 1], tL, xrT);
+        const double cst = duo_forward_trailer<WPB, RPB, SG>(m, w, N, p, r, hd, lane, store, tX[cur ^ 1], tU[cur ^ 1], tL, xrT);
         res[64 + lane] = cst;
       }
       // what this warp stored with ordinary stores is the source of the next pass's bulk copies
@@ -623,7 +658,7 @@ __global__ void __launch_bounds__(64) k_newton_duo(const __grid_constant__ Newto
       c_acc += quad2(eu, [&](int i, int j) { return w.R(i, j); });
       double xn[4];
       LinD L;
-      rk4_step_lin(a.m, x, u0, u1, xn, L);
+      rk4_step_lin(m, x, u0, u1, xn, L);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         pl[j * 32] = L.a[0][j];
@@ -669,11 +704,11 @@ __global__ void __launch_bounds__(64) k_newton_duo(const __grid_constant__ Newto
     }
     duo_bar();  // A
     if (WPB)
-      duo_backward_chain<WPB, RPB, SG, 2>(a.m, w, N, r, hd, lane);
+      duo_backward_chain<WPB, RPB, SG, 2>(m, w, N, r, hd, lane);
     else if (swap_shared)
-      duo_backward_chain<WPB, RPB, SG, 1>(a.m, w, N, r, hd, lane);
+      duo_backward_chain<WPB, RPB, SG, 1>(m, w, N, r, hd, lane);
     else
-      duo_backward_chain<WPB, RPB, SG, 0>(a.m, w, N, r, hd, lane);
+      duo_backward_chain<WPB, RPB, SG, 0>(m, w, N, r, hd, lane);
     duo_bar();  // B
     if (run) {
       dJ = res[lane];
@@ -691,7 +726,7 @@ __global__ void __launch_bounds__(64) k_newton_duo(const __grid_constant__ Newto
         cmd[1] = cur;
       }
       duo_bar();  // A
-      duo_forward_chain<RPB, SG>(a.m, N, r, hd, lane, gamma);
+      duo_forward_chain<RPB, SG>(m, N, r, hd, lane, gamma);
       duo_bar();  // B
       const double c = res[64 + lane];
       if (need) {

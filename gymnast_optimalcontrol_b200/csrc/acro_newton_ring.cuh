@@ -19,6 +19,14 @@
 
 namespace acro {
 
+#ifndef ACRO_MODEL
+// PPB: physical parameters per problem (`pb`, see model_per_problem); otherwise the shared model in the constant bank
+#define ACRO_MODEL(PPB, m0, pb, B, b) \
+  Model m_loc_;                        \
+  if (PPB) m_loc_ = model_per_problem(m0, pb, B, b); \
+  const Model& m = PPB ? m_loc_ : m0
+#endif
+
 #define ACRO_RING_D 3  // stages per ring
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -391,7 +399,8 @@ __device__ __forceinline__ void backward_ring(const Model& m, const WV<WPB>& w, 
 // ---------------------------------------------------------------------------------------------------------
 // kernel: one warp per block, block = tile of 32 problems
 // ---------------------------------------------------------------------------------------------------------
-template <bool WPB, bool RPB, int SG, bool RL = false>
+// PPB: every problem its own physical parameters (a.pb, see model_per_problem)
+template <bool WPB, bool RPB, int SG, bool RL = false, bool PPB = false>
 __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ NewtonArgs a) {
   extern __shared__ __align__(128) unsigned char ring_smem[];
   constexpr unsigned FULL = 0xffffffffu;
@@ -400,6 +409,7 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
   const bool valid = b < B;
   const int64_t bs = valid ? b : B - 1;  // padding lanes shadow the last problem and never write per-problem scalars
   const int N = a.N;
+  ACRO_MODEL(PPB, a.m, a.pb, B, bs);
   const WV<WPB> w(a.kw, B, bs);
   Ring r;
   r.data = smem_u32(ring_smem);
@@ -461,10 +471,10 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
       c_acc += quad2(eu, [&](int i, int j) { return w.R(i, j); });
       double xn[4];
       if (RL) {
-        rk4_step(a.m, x, u0, u1, xn);
+        rk4_step(m, x, u0, u1, xn);
       } else {
         LinD L;
-        rk4_step_lin(a.m, x, u0, u1, xn, L);
+        rk4_step_lin(m, x, u0, u1, xn, L);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           pl[j * 32] = L.a[0][j];
@@ -511,7 +521,7 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
 #pragma unroll
     for (int c = 0; c < 4; ++c) xT[c] = p.x[(N - 1) * sx + c * 32 + lane];
     double dJn, snn;
-    backward_ring<WPB, RPB, SG, RL>(a.m, w, N, p, r, lane, run, tK, tS, xT, xrT, dJn, snn);
+    backward_ring<WPB, RPB, SG, RL>(m, w, N, p, r, lane, run, tK, tS, xT, xrT, dJn, snn);
     if (run) {
       dJ = dJn;
       sn = snn;
@@ -525,7 +535,7 @@ __global__ void __launch_bounds__(32) k_newton_ring(const __grid_constant__ Newt
     double gamma = a.o.gamma_0, cn = 0.0;
     int tries = 0;
     for (int i = 0; i < a.o.max_line_search && __any_sync(FULL, need); ++i) {
-      const double c = forward_ring<WPB, RPB, SG, RL>(a.m, w, N, p, r, lane, gamma, need, Xo, Uo, tL, xrT);
+      const double c = forward_ring<WPB, RPB, SG, RL>(m, w, N, p, r, lane, gamma, need, Xo, Uo, tL, xrT);
       if (need) {
         ++tries;
         // accept iff cost_new < cost_k + c*gamma*delta_J  (strict, NaN rejects)   tg:361

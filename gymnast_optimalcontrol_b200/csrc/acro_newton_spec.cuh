@@ -30,7 +30,11 @@ enum { SPEC_EXIT = 0, SPEC_BACKWARD = 1, SPEC_FORWARD_DUO = 2, SPEC_FORWARD_SPEC
 
 __device__ __forceinline__ void spec_bar() {
   __syncwarp();
+#ifdef ACRO_SPEC_IDLE_EXIT  // experiment: only warps 0 and 1 exist (speculate = 1 only)
+  asm volatile("bar.sync 1, 64;" ::: "memory");
+#else
   asm volatile("bar.sync 1, 256;" ::: "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_inval(uint32_t bar) {
   asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -202,45 +206,48 @@ __device__ __forceinline__ void spec_commit(const Model& m, int N, int warp, int
                                             const double* __restrict__ xsrc, const double* __restrict__ usrc,
                                             double* __restrict__ Xo, double* __restrict__ Uo, double* __restrict__ Lo) {
   // xsrc / usrc: per lane, time step 0 of the trajectory to commit (its accepted candidate buffer; lanes with nothing to
-  // commit point at valid data and never store)
+  // commit point at valid data and never store).  The gathers come from DRAM (the candidate buffers were just written
+  // and are several times the L2): every warp keeps the operands of its next ACRO_COMMIT_AHEAD steps in flight.
+  constexpr int AH = 3;
   const int steps = N - 1;
-  double x[4], u[2], xn[4], un[2];
-  int t = warp;
-  if (t < steps) {
+  double x[AH][4], u[AH][2];
+  auto fetch = [&](int slot, int t) {
+    if (t < steps) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) x[c] = ldcg(xsrc + int64_t(t) * kSX + c * 32);
+      for (int c = 0; c < 4; ++c) x[slot][c] = ldcg(xsrc + int64_t(t) * kSX + c * 32);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) u[c] = ldcg(usrc + int64_t(t) * kSU + c * 32);
-  }
-  for (; t < steps; t += ACRO_SPEC_W) {
-    const int tn = t + ACRO_SPEC_W;
-    if (tn < steps) {  // next step's operands before this step's arithmetic
-#pragma unroll
-      for (int c = 0; c < 4; ++c) xn[c] = ldcg(xsrc + int64_t(tn) * kSX + c * 32);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) un[c] = ldcg(usrc + int64_t(tn) * kSU + c * 32);
+      for (int c = 0; c < 2; ++c) u[slot][c] = ldcg(usrc + int64_t(t) * kSU + c * 32);
     }
-    const LinD L = linearize_d(m, x, u[0], u[1]);
-    if (commit) {
-      double* px = Xo + int64_t(t) * kSX + lane;
-      double* pu = Uo + int64_t(t) * kSU + lane;
-      double* pl = Lo + int64_t(t) * kSL + lane;
+  };
 #pragma unroll
-      for (int c = 0; c < 4; ++c) px[c * 32] = x[c];
+  for (int a = 0; a < AH; ++a) fetch(a, warp + a * ACRO_SPEC_W);
+  for (int t0 = warp; t0 < steps; t0 += AH * ACRO_SPEC_W) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) pu[c * 32] = u[c];
+    for (int a = 0; a < AH; ++a) {
+      const int t = t0 + a * ACRO_SPEC_W;
+      if (t < steps) {
+        const double xs[4] = {x[a][0], x[a][1], x[a][2], x[a][3]};
+        const double u0 = u[a][0], u1 = u[a][1];
+        fetch(a, t + AH * ACRO_SPEC_W);  // the slot is free again: its next occupant
+        const LinD L = linearize_d(m, xs, u0, u1);
+        if (commit) {
+          double* px = Xo + int64_t(t) * kSX + lane;
+          double* pu = Uo + int64_t(t) * kSU + lane;
+          double* pl = Lo + int64_t(t) * kSL + lane;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        pl[j * 32] = L.a[0][j];
-        pl[(4 + j) * 32] = L.a[1][j];
+          for (int c = 0; c < 4; ++c) px[c * 32] = xs[c];
+          pu[0] = u0;
+          pu[32] = u1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            pl[j * 32] = L.a[0][j];
+            pl[(4 + j) * 32] = L.a[1][j];
+          }
+          pl[8 * 32] = L.b[0];
+          pl[9 * 32] = L.b[1];
+        }
       }
-      pl[8 * 32] = L.b[0];
-      pl[9 * 32] = L.b[1];
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) x[c] = xn[c];
-    u[0] = un[0];
-    u[1] = un[1];
   }
   if (warp == steps % ACRO_SPEC_W && commit) {  // terminal state
 #pragma unroll
@@ -313,6 +320,9 @@ __global__ void __launch_bounds__(ACRO_SPEC_W * 32, 1) k_newton_spec(const __gri
   p.rx = RPB ? a.rx + oN * sx : a.rx;
   p.ru = RPB ? a.ru + oM * su : a.ru;
 
+#ifdef ACRO_SPEC_IDLE_EXIT
+  if (warp >= 2) return;
+#endif
   if (warp != 0) {
     // ------------------------------------------------------------------------------ workers (warp 1 = the duo trailer)
     for (;;) {

@@ -270,3 +270,23 @@ def test_mpc_outputs_have_the_shapes_of_the_references(mods):
     assert np.all(xr[101:] == 0.0) and np.all(ur[100:] == 0.0)
     xf, uf = tt.solve_mpc_tracking(x0, d["x"], d["u"], 501)
     assert rel_err(xr[:101], xf[:101]) < TOL and rel_err(ur[:100], uf[:100]) < TOL
+
+
+def test_batched_reference_builders(mods):
+    """task_1's recipe (main.py:33-41) for a batch of target torques: equilibria on the device, piecewise references,
+    then the solver on per-problem references."""
+    dyn, tg, tt = mods
+    g = golden("newton_task1")
+    u2 = np.array([[0.5, 0.5], [0.4, 0.4], [0.3, 0.6]])
+    x_e1, u_e1 = tg.compute_equilibrium(np.zeros((3, 2)), (0.1, -0.1))
+    x_e2, u_e2 = tg.compute_equilibrium(u2, (0.35, -0.35))
+    assert x_e1.shape == (3, 4) and np.abs(x_e2[0] - g["x_e2"]).max() < 1e-9 and np.abs(x_e1[0] - g["x_e1"]).max() < 1e-9
+    xs, us = tg.compute_equilibrium(u2[0], (0.35, -0.35))  # the single-problem call of the reference
+    assert np.abs(xs - g["x_e2"]).max() < 1e-10
+    t_ref, x_ref, u_ref = tg.define_reference_piecewise(10.0, x_e1, x_e2, u_e1, u_e2)
+    assert x_ref.shape == (3, 501, 4) and u_ref.shape == (3, 501, 2)
+    assert rel_err(x_ref[0], g["x_ref"]) < 1e-9 and rel_err(u_ref[0], g["u_ref"]) < 1e-12
+    x, u, K, s, h = tg.newton_Algorithm(x_e1, x_ref, u_ref, max_iters=3, tol=1e-4, gamma_0=0.05, verbose=False)
+    assert rel_err(h["cost"][0], g["cost"][:4]) < 1e-8
+    with pytest.raises(RuntimeError, match="Root finder failed"):
+        tg.compute_equilibrium(np.array([[0.0, 50.0]]), (0.1, 0.1))

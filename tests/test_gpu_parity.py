@@ -167,13 +167,20 @@ def test_per_problem_physical_parameters(bt):
     assert np.array_equal(s1[0], aos(bt.rk4_step(soa(x[:1]), soa(u[:1])))[0])
 
 
-def test_newton_per_problem_physical_parameters(bt, fa_ref):
-    """The Newton / Armijo loop with every problem its own plant (domain randomisation) against the oracle."""
+@pytest.mark.parametrize("kernel,per_problem_ref", [("auto", False), ("auto", True), ("duo4", False), ("duo8", False), ("ring4", False),
+                                                    ("ring4", True), ("ring-rl", False), ("ldg", False)])
+def test_newton_per_problem_physical_parameters(bt, fa_ref, kernel, per_problem_ref):
+    """The Newton / Armijo loop with every problem its own plant (domain randomisation) against the oracle, on the
+    warp-specialised kernels (model constants in registers, template flag PPB) and the one-thread-per-problem kernel."""
     xr, ur = _short_ref(fa_ref, N=81)
     n = 35
     sets, rows = _random_phys(n, 9)
     x0 = np.random.default_rng(10).uniform(-0.2, 0.2, (n, 4))
-    st = bt.newton_solve(soa(x0), bt.make_ref(xr, ur), max_iters=4, tol=1e-6, gamma_0=0.5, params_b=bt.phys_params(rows))
+    name = bt.newton_kernel_name(n, kernel=kernel, params_per_problem=True, ref_per_problem=per_problem_ref)
+    print(kernel, "->", name)
+    assert ("k_newton<" in name) == (kernel == "ldg") and name.endswith("true>")
+    ref = bt.Ref(soa(np.repeat(xr[None], n, 0)), soa(np.repeat(ur[None], n, 0))) if per_problem_ref else bt.make_ref(xr, ur)
+    st = bt.newton_solve(soa(x0), ref, max_iters=4, tol=1e-6, gamma_0=0.5, params_b=bt.phys_params(rows), kernel=kernel)
     torch.cuda.synchronize()
     X, U, K, S = aos(st.X), aos(st.U), kmat(st.K), aos(st.S)
     for b in (0, 1, 2, 3, 17, 31, 32, 34):
@@ -952,3 +959,69 @@ def test_huge_angles_take_the_library_path(bt):
     assert rel_err(s[2], so[2]) < TOL
     assert np.isfinite(s[:2]).all() and not np.isfinite(s[3:]).all()
     assert not np.isfinite(f[3]).all() and not np.isfinite(f[4]).all()
+
+
+# ------------------------------------------------------------------------------------- round 2: SURVEY 8f
+def test_newton_fully_actuated_plant(bt):
+    """The fully-actuated plant (tau_1 live: dynamics.py:113 carries it, fully_actuated_ref_gen.py:20-73 uses it) inside
+    the solvers: B_d has two columns, G = R + B'PB is a full 2x2.  Newton / Armijo iterations, the stand-alone Riccati
+    pass and the LQR gains against the oracle with the same plant; the reference trajectory is the fully-actuated
+    swing-up itself with BOTH of its torques."""
+    f = golden("fully_actuated_trajectory")
+    x_ref, u_ref = f["x"], f["u"]
+    assert np.abs(u_ref[:, 0]).max() > 1.0  # tau_1 is really used
+    pa = bt.make_params(1, actuated_tau1=True)
+    m = O.Model(actuated_tau1=True)
+    n = 40
+    x0 = np.random.default_rng(31).uniform(-0.2, 0.2, (n, 4))
+    ref = bt.make_ref(x_ref, u_ref)
+    w = bt.Weights(np.diag([130.0, 30.0, 1e-4, 1e-4]), np.diag([0.5, 1.5]), np.diag([130.0, 130.0, 1.0, 1.0]))
+    st = bt.newton_solve(soa(x0), ref, max_iters=4, tol=1e-6, gamma_0=0.5, w=w, params=pa)
+    torch.cuda.synchronize()
+    X, U, K, S = aos(st.X), aos(st.U), kmat(st.K), aos(st.S)
+    for b in (0, 1, 31, 32, 39):
+        x, u, Ko, so, h = O.newton_Algorithm(x0[b], x_ref, u_ref, max_iters=4, tol=1e-6, gamma_0=0.5, Q=w.Q, R=w.R, Q_T=w.QT, m=m)
+        assert int(st.status[b]) == h["status"] and int(st.iters[b]) == h["iters"]
+        assert list(st.hist_ntry[:len(h["n_try"]), b].cpu().numpy()) == h["n_try"]
+        assert rel_err(st.hist_cost[:len(h["cost"]), b].cpu().numpy(), h["cost"]) < TOL
+        assert rel_err(X[b], x) < TOL and rel_err(U[b], u) < TOL
+        assert rel_err(S[b], so) < TOL and rel_err(K[b], Ko) < 1e-7
+        assert np.abs(Ko[:, 0]).max() > 1e-3 and np.abs(u[:, 0]).max() > 1e-3  # the first input is in play
+    # the warp-specialised kernels refuse the plant instead of silently ignoring tau_1
+    with pytest.raises(Exception):
+        bt.newton_solve(soa(x0), ref, max_iters=1, w=w, params=pa, kernel="duo")
+    # stand-alone backward pass and LQR gains
+    _, Ui, Xi = _random_iterates(8)
+    Kd, Sd, dJ, sn = bt.riccati_affine(soa(Xi), soa(Ui), ref, w, params=pa)
+    for b in (0, 7):
+        Ad, Bd, q, r, QT2, qT = O.build_stage_lists(Xi[b], Ui[b], x_ref, u_ref, w.Q, w.R, w.QT, m)
+        Ko, so, dJo = O.calculate_K_and_sigma(Ad, Bd, q, r, 2 * w.Q, 2 * w.R, QT2, qT)
+        assert rel_err(kmat(Kd)[b], Ko) < TOL and rel_err(aos(Sd)[b], so) < TOL and abs(dJ[b].item() - dJo) < TOL * abs(dJo)
+    Kl = bt.lqr_gains(bt.make_ref(x_ref, u_ref), params=pa).cpu().numpy().reshape(500, 2, 4)
+    assert rel_err(Kl, np.array(O.solve_LQR_tracking(x_ref, u_ref, m=m))) < 1e-8
+
+
+def test_equilibrium_batch(bt):
+    """compute_equilibrium (tg:22-39) for a batch: G(theta) = u_target by Newton's method on the device; the two
+    equilibria of task_1 (main.py:33-37) against the roots SciPy's hybr found in the reference run (fixture)."""
+    g = golden("newton_task1")
+    ut = np.array([[0.0, 0.0], [0.5, 0.5]])
+    th0 = np.array([[0.1, -0.1], [0.35, -0.35]])
+    theta, n = bt.equilibrium(soa(ut), soa(th0))
+    th = aos(theta)
+    assert (n.cpu().numpy() >= 0).all()
+    assert np.abs(th[0] - g["x_e1"][:2]).max() < 1e-9 and np.abs(th[1] - g["x_e2"][:2]).max() < 1e-9
+    # random targets: u = G(theta*) for known theta*, start nearby; per-problem physical parameters
+    rng = np.random.default_rng(3)
+    nB = 1000
+    sets, rows = _random_phys(nB, 8)
+    ts = np.stack([rng.uniform(-0.6, 0.6, nB), rng.uniform(-0.6, 0.6, nB)], axis=1)
+    G = np.zeros((nB, 2))
+    for b in range(nB):
+        m = O.Model(sets[b])
+        G[b] = [m.g1 * np.sin(ts[b, 0]) + m.g2 * np.sin(ts[b].sum()), m.g2 * np.sin(ts[b].sum())]
+    theta, n = bt.equilibrium(soa(G), soa(ts + rng.uniform(-0.1, 0.1, (nB, 2))), params_b=bt.phys_params(rows))
+    assert (n.cpu().numpy() >= 0).all() and np.abs(aos(theta) - ts).max() < 1e-10
+    # an unreachable target (|u_2| > g2) reports failure instead of returning garbage
+    theta, n = bt.equilibrium(soa(np.array([[0.0, 50.0]])), soa(np.array([[0.1, 0.1]])))
+    assert int(n[0]) < 0
