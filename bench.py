@@ -328,6 +328,8 @@ class Ctx:
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local)
+        from gymnast_optimalcontrol_b200 import sharding as _sh
+        self.cpus = _sh.bind_to_gpu_numa(self.local) if self.world > 1 else None  # before any pinned allocation
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
@@ -587,9 +589,9 @@ def long_horizon_block(cx, a):
     u_ref = np.vstack([u_fa, np.zeros((N - 1 - u_fa.shape[0], 2))])
     out = {"horizon_steps": N - 1, "reference": "fully-actuated swing-up (500 steps) then the upright equilibrium, dt = 0.02",
            "gamma_0": 0.1, "unit": "Newton iterations/s at N = 10 001 (not rescaled)"}
-    for B in (4096, 32768):
-        rate, t_step, done, ntry, st = newton_block(cx, B, 3, 0.1, 2, 1, N=N, ref_xy=(x_ref, u_ref), gather=False)
-        out["batch_%d" % B] = {"value": rate, "ms_per_step": 1e3 * t_step, "newton_iters_per_step": 3, "armijo_tries_mean": ntry,
+    for B in (4096, 16384, 32768):
+        rate, t_step, done, ntry, st = newton_block(cx, B, 10, 0.1, 2, 1, N=N, ref_xy=(x_ref, u_ref), gather=False)
+        out["batch_%d" % B] = {"value": rate, "ms_per_step": 1e3 * t_step, "newton_iters_per_step": 10, "armijo_tries_mean": ntry,
                                "kernel": cx.bt.newton_kernel_name(B), "batch_per_gpu": B}
         del st
         cx.torch.cuda.empty_cache()
@@ -612,8 +614,15 @@ def run_native(a):
     back = None
     if not a.quick:
         rate, t_step, done, ntry, st = newton_block(cx, B, iters, 1.0, max(2, a.steps // 2), 1)
+        tile_max = float(st.hist_ntry[:iters].reshape(iters, -1, 32).max(dim=2).values.double().mean().item()) if B % 32 == 0 else None
         back = {"metric": "newton_iterations_per_sec", "value": rate, "ms_per_step": 1e3 * t_step, "gamma_0": 1.0,
-                "armijo_tries_mean": ntry, "kernel": bt.newton_kernel_name(B),
+                "armijo_tries_mean": ntry, "armijo_tries_tile_max_mean": tile_max, "iterations_done_per_step": done,
+                "iterations_nominal_per_step": B * iters * world,
+                "kernel": bt.newton_kernel_name(B, gamma_0=1.0),
+                "note": "a tile of 32 problems needs a forward pass for every candidate ANY of its problems still has to try (tile-max, "
+                        "not the mean); k_newton_spec evaluates up to 8 candidates per round in parallel and takes the decisions of the "
+                        "sequential loop; problems whose line search fails (status 3, tg:367-369) stop, so fewer than the nominal "
+                        "iterations are done and counted",
                 "config": "config 2 with the reference's default gamma_0 = 1 (trajectory_generation.py:298): the back-tracking regime"}
         frac_flops = (FLOPS_FIXED + FLOPS_PER_TRY * ntry) * (N_STEPS - 1) * rate / world / 1e12
         back["achieved_tflops_per_gpu"] = frac_flops
@@ -675,6 +684,7 @@ def run_native(a):
                       "rescaled_10k_equivalent_at_this_batch": value / world * (N_STEPS - 1) / 1e4,
                       "real_10k_horizon": {k: v["value"] / world for k, v in longh.items() if k.startswith("batch_")},
                       "met_at_batch_4096": bool(longh["batch_4096"]["value"] / world >= 1e6),
+                      "met_at_batch_16384": bool(longh["batch_16384"]["value"] / world >= 1e6),
                       "met_at_batch_32768": bool(longh["batch_32768"]["value"] / world >= 1e6)}
         line = {
             "metric": "newton_iterations_per_sec", "value": value, "unit": "Newton iterations/s (N=501 time steps each)",
@@ -689,6 +699,9 @@ def run_native(a):
                            "step i overlap the kernel of step i+1 (double-buffered solver state)",
                     "sync": {"value": e2e_sync, "ms_per_step": 1e3 * e["t_sync"] / a.steps,
                              "api": "the same with blocking calls (block=True): solve, then copy"}},
+            "host_binding": {"cpus_of_rank0": len(cx.cpus) if cx.cpus else None,
+                             "note": "ranks of a multi-GPU run are pinned to the CPU cores NVML reports next to their GPU before pinned "
+                                     "host memory is allocated (sharding.bind_to_gpu_numa)"},
             "gpu_launches": int(h["launches"]), "roofline": roof, "cpu_baseline": cpu, "clocks": h["clocks"],
             "backtracking": back, "mpc": mpc, "strong": strong, "long_horizon": longh, "target": target,
             "check": {"iterations_done_per_step_all_ranks": h["done_per_step"], "iterations_nominal_per_step": B * iters * world,

@@ -168,20 +168,68 @@ def main():
                       "roofline": {"bound": "fp64", "achieved": done / t * 2054.0 * (N - 1) / 1e12, "peak": peak, "unit": "TFLOP/s",
                                    "frac": done / t * 2054.0 * (N - 1) / 1e12 / peak, "flops_per_unit": 2054.0 * (N - 1)}}), flush=True)
     state = bt.newton_alloc(B, N, 30, history=True)
+    for kern in ("auto", "duo"):
+        def run_bt():
+            state.reset()
+            bt.newton_solve(x0, ref, max_iters=30, tol=0.0, gamma_0=1.0, state=state, kernel=kern)
+        t, nl = timeit(run_bt, 2)
+        tries = float(state.hist_ntry[:30].double().mean().item())
+        done = float(state.iters.double().sum().item())
+        print(json.dumps({"config": "C2 Newton with back-tracking, B=4096, gamma_0=1, 30 iterations, kernel=%s" % kern,
+                          "kernel": bt.newton_kernel_name(B, gamma_0=1.0, kernel=kern), "metric": "newton_iterations_per_sec",
+                          "value": done / t, "unit": "Newton iterations/s (iterations actually executed)", "seconds": t, "gpu_launches": nl,
+                          "armijo_tries_mean": tries, "tile_max_tries_mean": float(state.hist_ntry[:30].reshape(30, -1, 32).max(dim=2).values.double().mean().item()),
+                          "roofline": {"bound": "fp64", "achieved": done / t * (1114.0 + 940.0 * tries) * (N - 1) / 1e12, "peak": peak,
+                                       "unit": "TFLOP/s", "frac": done / t * (1114.0 + 940.0 * tries) * (N - 1) / 1e12 / peak,
+                                       "flops_per_unit": (1114.0 + 940.0 * tries) * (N - 1),
+                                       "note": "a tile runs a forward pass for every candidate ANY of its 32 problems still needs (tile-max); "
+                                               "k_newton_spec evaluates up to 8 of them in parallel"}}), flush=True)
 
-    def run_bt():
-        state.initialised = False
-        bt.newton_solve(x0, ref, max_iters=30, tol=0.0, gamma_0=1.0, state=state)
-    t, nl = timeit(run_bt, 2)
-    tries = float(state.hist_ntry[:30].double().mean().item())
-    print(json.dumps({"config": "C2 Newton with back-tracking, B=4096, gamma_0=1, 30 iterations", "metric": "newton_iterations_per_sec",
-                      "value": B * 30 / t, "unit": "Newton iterations/s", "seconds": t, "gpu_launches": nl, "armijo_tries_mean": tries,
-                      "forward_passes_per_sec": B * 30 * tries / t,
-                      "roofline": {"bound": "fp64", "achieved": B * 30 / t * (1114.0 + 940.0 * tries) * (N - 1) / 1e12, "peak": peak,
-                                   "unit": "TFLOP/s", "frac": B * 30 / t * (1114.0 + 940.0 * tries) * (N - 1) / 1e12 / peak,
-                                   "flops_per_unit": (1114.0 + 940.0 * tries) * (N - 1),
-                                   "note": "a warp runs a forward pass while ANY of its 32 problems still needs a candidate: "
-                                           "the pass count of a tile is the maximum over its problems"}}), flush=True)
+    # ---- SURVEY 8f rank 1 inside the fast kernels: every problem its own physical parameters / its own reference
+    rng = np.random.default_rng(7)
+    for Bp in ((4096,) if a.quick else (4096, 65536)):
+        rows = np.array([[getattr(bt.DEFAULT_PARAMS, f) for f in bt.PHYS_FIELDS]] * Bp)
+        rows[:, :8] *= rng.uniform(0.97, 1.03, (Bp, 8))
+        pb = bt.phys_params(rows)
+        x0p = bt.upload(np.ascontiguousarray(np.random.default_rng(1).uniform(-0.2, 0.2, (Bp, 4)).T))
+        stp = bt.newton_alloc(Bp, N, 20, history=False)
+
+        def run_pp():
+            stp.reset()
+            bt.newton_solve(x0p, ref, max_iters=20, tol=0.0, gamma_0=0.1, state=stp, params_b=pb)
+        t, nl = timeit(run_pp, 2)
+        line("C2 Newton with per-problem physical parameters (+-3 %%), B=%d, 20 iterations" % Bp, "newton_iterations_per_sec",
+             float(stp.iters.double().sum().item()) / t, "Newton iterations/s", 2054.0 * (N - 1), t, nl, peak,
+             {"kernel": bt.newton_kernel_name(Bp, params_per_problem=True)})
+        del stp
+    refp = bt.Ref(bt.Traj.from_batch_major(bt.upload(np.repeat(fa["x"][None], 4096, 0))),
+                  bt.Traj.from_batch_major(bt.upload(np.repeat(u_ref[None], 4096, 0))))
+    stp = bt.newton_alloc(4096, N, 20, history=False)
+
+    def run_rp():
+        stp.reset()
+        bt.newton_solve(x0, refp, max_iters=20, tol=0.0, gamma_0=0.1, state=stp)
+    t, nl = timeit(run_rp, 2)
+    line("C2 Newton with per-problem references, B=4096, 20 iterations", "newton_iterations_per_sec",
+         float(stp.iters.double().sum().item()) / t, "Newton iterations/s", 2054.0 * (N - 1), t, nl, peak,
+         {"kernel": bt.newton_kernel_name(4096, ref_per_problem=True)})
+    del stp, refp
+    # the fully-actuated plant (tau_1 live) on the one-thread-per-problem kernel
+    pa = bt.make_params(1, actuated_tau1=True)
+    refa = bt.make_ref(fa["x"], fa["u"])
+    wa = bt.Weights(np.diag([130.0, 30.0, 1e-4, 1e-4]), np.diag([0.5, 1.5]), np.diag([130.0, 130.0, 1.0, 1.0]))
+    for Ba in ((4096,) if a.quick else (4096, 65536)):
+        x0a = bt.upload(np.ascontiguousarray(np.random.default_rng(1).uniform(-0.2, 0.2, (Ba, 4)).T))
+        sta = bt.newton_alloc(Ba, N, 10, history=False)
+
+        def run_act():
+            sta.reset()
+            bt.newton_solve(x0a, refa, max_iters=10, tol=0.0, gamma_0=0.5, state=sta, params=pa, w=wa)
+        t, nl = timeit(run_act, 2)
+        line("C2-like Newton on the fully-actuated plant, B=%d, 10 iterations" % Ba, "newton_iterations_per_sec",
+             float(sta.iters.double().sum().item()) / t, "Newton iterations/s", 2054.0 * (N - 1), t, nl, peak,
+             {"kernel": "acro::k_newton<false,false,false,true>"})
+        del sta
 
     # ---- config 2 in the throughput regime
     hbm = 6551.4

@@ -397,6 +397,11 @@ KERNEL_VARIANTS = {
 }
 # Process-wide default of newton_solve's kernel selection (a Python-side setting: the library reads no environment).
 NEWTON_DEFAULTS = {"kernel": "auto"}
+SPEC_AUTO_GAMMA = 0.5  # acro_kernels.cu: ACRO_SPEC_AUTO_GAMMA
+
+
+def sm_count():
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count if torch.cuda.is_available() else 148
 
 
 def newton_opts(max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, chunk_iters=0, max_line_search=20, init=1,
@@ -417,7 +422,10 @@ def newton_opts(max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, chunk_iters=0
 
 def newton_kernel_name(Bn, ref_per_problem=False, weights_per_problem=False, params_per_problem=False, **kw):
     """Name of the kernel newton_solve launches for a batch of Bn problems with these options (acro_newton_describe)."""
+    kw.setdefault("gamma_0", 0.1)
     o = newton_opts(kw.pop("max_iters", 1), **kw)
+    if o.kernel == 0 and o.gamma_0 >= SPEC_AUTO_GAMMA:
+        o.spec_ws = 128  # (what newton_solve does: it provides the workspace when the automatic choice may need it)
     buf = C.create_string_buffer(128)
     call("acro_newton_describe", C.byref(o), int(Bn), int(ref_per_problem), int(weights_per_problem),
          int(params_per_problem), buf, 128)
@@ -446,7 +454,10 @@ def newton_solve(x0, ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1.0, w=N
     o = newton_opts(max_iters, tol, beta, c, gamma_0, chunk_iters, max_line_search, init, kernel, stage_steps,
                     recompute_lin, speculate)
     s = state
-    if o.kernel == _abi.NEWTON_KERNELS["spec"]:
+    # the speculative kernel needs room for 8 candidate trajectories per problem: allocate it when that kernel is asked
+    # for, or when the automatic choice may fall on it (one tile per SM, large initial step: see acro_abi.h)
+    if o.kernel == _abi.NEWTON_KERNELS["spec"] or (o.kernel == 0 and float(gamma_0) >= SPEC_AUTO_GAMMA and params_b is None
+                                                   and ntiles(Bn) <= sm_count() and not params.actuated_tau1):
         if s.spec_ws is None:
             s.spec_ws = torch.zeros(int(_abi.lib.acro_newton_spec_ws_doubles(Bn, N)), dtype=F64, device=device())
         o.spec_ws = s.spec_ws.data_ptr()

@@ -171,9 +171,7 @@ __device__ __forceinline__ void duo_forward_chain(const Model& m, int N, Ring& r
         __syncwarp();
         if (cross) mbar_wait_t<NI>(nbar, npar);
         if (NI) {
-#ifndef ACRO_SPEC_NO_LOOK
           if (look) mbar_wait_call(hd.empty_bar_at(ACRO_DUO_LOOK - 1), hd.free_parity_at(ACRO_DUO_LOOK - 1));
-#endif
         } else if (!hready) {
           mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);  // the trailer is ACRO_DUO_R steps behind
         }
@@ -384,9 +382,7 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
       if (cross || (NI ? look : !hready)) {
         if (cross) mbar_wait_t<NI>(nbar, npar);
         if (NI) {
-#ifndef ACRO_SPEC_NO_LOOK
           if (look) mbar_wait_call(hd.empty_bar_at(ACRO_DUO_LOOK - 1), hd.free_parity_at(ACRO_DUO_LOOK - 1));
-#endif
         } else if (!hready) {
           mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);
         }

@@ -30,11 +30,7 @@ enum { SPEC_EXIT = 0, SPEC_BACKWARD = 1, SPEC_FORWARD_DUO = 2, SPEC_FORWARD_SPEC
 
 __device__ __forceinline__ void spec_bar() {
   __syncwarp();
-#ifdef ACRO_SPEC_IDLE_EXIT  // experiment: only warps 0 and 1 exist (speculate = 1 only)
-  asm volatile("bar.sync 1, 64;" ::: "memory");
-#else
   asm volatile("bar.sync 1, 256;" ::: "memory");
-#endif
 }
 __device__ __forceinline__ void mbar_inval(uint32_t bar) {
   asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -320,9 +316,6 @@ __global__ void __launch_bounds__(ACRO_SPEC_W * 32, 1) k_newton_spec(const __gri
   p.rx = RPB ? a.rx + oN * sx : a.rx;
   p.ru = RPB ? a.ru + oM * su : a.ru;
 
-#ifdef ACRO_SPEC_IDLE_EXIT
-  if (warp >= 2) return;
-#endif
   if (warp != 0) {
     // ------------------------------------------------------------------------------ workers (warp 1 = the duo trailer)
     for (;;) {

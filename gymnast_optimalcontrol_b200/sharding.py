@@ -52,3 +52,25 @@ def gather_summary(local, n_problems, group=None):
     recv = torch.empty(world, F, width, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(recv.view(world * F, width), send.contiguous(), group=group)
     return torch.cat([recv[r, :, :sizes[r]] for r in range(world)], dim=1)
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPU cores next to GPU `device_index` (NVML's CPU affinity of the device), BEFORE any pinned
+    host memory is allocated: page-locked result buffers then live on the GPU's own NUMA node, and the device-to-host
+    copies of the ranks of an 8-GPU box do not all cross to one socket.  Returns the CPU list, or None if NVML or the
+    affinity call is not available (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1 and 64 * i + b < n_cpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001  (no NVML, no permission, not Linux: run unbound)
+        return None

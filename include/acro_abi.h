@@ -117,7 +117,9 @@ typedef struct AcroNewtonOpts {
   int32_t speculate;    /* Armijo candidates evaluated in parallel per round by ACRO_NEWTON_SPEC: 0 auto
                             (from the previous iteration's number of tries), 1..8 fixed */
   double* spec_ws;      /* DEVICE workspace of ACRO_NEWTON_SPEC (candidate trajectories), 128-byte aligned,
-                            acro_newton_spec_ws_doubles(B, N) doubles; NULL otherwise */
+                            acro_newton_spec_ws_doubles(B, N) doubles, or NULL.  With kernel = ACRO_NEWTON_AUTO the
+                            speculative kernel is chosen when this workspace is given, the batch is at most one tile per
+                            SM and gamma_0 >= 0.5 (a line search that starts with a large step back-tracks) */
 } AcroNewtonOpts;
 #define ACRO_NEWTON_AUTO 0
 #define ACRO_NEWTON_DUO 1    /* two warps per tile (recurrence + trailer), at most two tiles per SM */

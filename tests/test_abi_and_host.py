@@ -154,6 +154,34 @@ def test_headline_kernels_carry_no_yield():
         assert hits, "kernel variant %s not found in the library" % tag
         for n in hits:
             assert counts[n] == 0, "%s: %d YIELD instructions" % (n, counts[n])
+    # k_newton_spec (blocks of eight warps): ptxas puts a YIELD at the head of every loop that contains an inlined
+    # mbarrier phase check, so its step loops wait behind a call (mbar_wait_call, NI variants of the duo loops).  Every
+    # loop that does real FP64 work per trip (the chain / trailer / candidate steps) must be free of YIELD; the spin loop
+    # inside mbar_wait_call and the cold paths may keep theirs.
+    import re
+    spec = [n for n in counts if "k_newton_specILb0ELb0ELi16E" in n]
+    assert spec
+    body, cur = [], None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+        elif cur == spec[0] and re.search(r"/\*[0-9a-f]{4,6}\*/", line):
+            body.append(line)
+    addr = lambda l: int(re.search(r"/\*([0-9a-f]{4,6})\*/", l).group(1), 16)
+    loops = []
+    for l in body:
+        m = re.search(r"\bBRA\b.*?(0x[0-9a-f]+)", l)
+        if m and int(m.group(1), 16) < addr(l):
+            loops.append((int(m.group(1), 16), addr(l)))
+    hot = 0
+    for lo, hi in loops:
+        ins = [l for l in body if lo <= addr(l) <= hi]
+        fp64 = sum(1 for l in ins if re.search(r"\bD(FMA|MUL|ADD)\b", l))
+        reads_ring = any(re.search(r"\bLDS\b", l) for l in ins)  # (the commit loop gathers from global memory: not a ring consumer)
+        if 150 <= fp64 and len(ins) < 800 and reads_ring:  # a step loop (forward chain / candidate / trailer), not an enclosing pass loop
+            hot += 1
+            assert not any(" YIELD " in l for l in ins), "k_newton_spec: YIELD in the step loop at 0x%x" % lo
+    assert hot >= 4
 
 
 def test_staged_reference_is_the_unmodified_reference():
@@ -185,7 +213,12 @@ def test_kernel_variants_and_plan():
     assert bt.newton_kernel_name(65536) == "acro::k_newton_ring<false,false,2,true>"
     assert bt.newton_kernel_name(65536, kernel="ring2") == "acro::k_newton_ring<false,false,2,false>"
     assert bt.newton_kernel_name(64, kernel="ldg") == "acro::k_newton<false,false,false>"
-    assert bt.newton_kernel_name(64, params_per_problem=True) == "acro::k_newton<false,false,true>"
+    assert bt.newton_kernel_name(64, params_per_problem=True) == "acro::k_newton_duo<true,false,16,true>"
+    assert bt.newton_kernel_name(64, params_per_problem=True, kernel="ldg") == "acro::k_newton<false,false,true>"
+    # a large initial step size back-tracks: the automatic choice is the speculative kernel (one tile per SM only)
+    assert bt.newton_kernel_name(4096, gamma_0=1.0) == "acro::k_newton_spec<false,false,16>"
+    assert bt.newton_kernel_name(4096, gamma_0=0.49) == "acro::k_newton_duo<false,false,16>"
+    assert bt.newton_kernel_name(8192, gamma_0=1.0) == "acro::k_newton_duo<false,false,4>"
     with pytest.raises(_abi.AcroError):
         bt.newton_kernel_name(64, kernel="ring", stage_steps=8)
     with pytest.raises(_abi.AcroError):
