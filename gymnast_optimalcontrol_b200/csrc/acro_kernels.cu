@@ -1475,7 +1475,9 @@ static int newton_plan(const AcroNewtonOpts& o, int64_t B, bool rpb, bool wpb, b
   if (k == ACRO_NEWTON_SPEC) {
     // eight warps per tile, one block per SM (acro_newton_spec.cuh); needs the candidate workspace
     ACRO_REQUIRE(tiles <= n_sm, "acro_newton_solve: the speculative kernel runs one tile per SM (B <= 32 x SM count)");
+#ifndef ACRO_SPEC_TIMING
     ACRO_REQUIRE(!ppb, "acro_newton_solve: the speculative kernel takes shared physical parameters");
+#endif
     ACRO_REQUIRE(o.spec_ws != nullptr, "acro_newton_solve: the speculative kernel needs AcroNewtonOpts.spec_ws (acro_newton_spec_ws_doubles)");
     ACRO_REQUIRE(o.speculate >= 0 && o.speculate <= 8, "acro_newton_solve: speculate must be 0 (adaptive) or 1..8");
     ACRO_REQUIRE(sg == 0 || (sg == 16 && !rpb) || (sg == 8 && rpb), "acro_newton_solve: speculative kernel: stage_steps 16 (8 with per-problem references)");

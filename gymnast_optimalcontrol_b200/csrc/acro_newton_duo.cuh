@@ -48,6 +48,12 @@ __device__ __forceinline__ void duo_bar() {
 // slot in every step, every ACRO_DUO_LOOK-th step makes sure (blocking, behind a call) that the next ACRO_DUO_LOOK slots
 // are free - the trailer frees them in order, so the one furthest ahead suffices.
 #define ACRO_DUO_LOOK 4
+// ... and the trailer waits for batches of ACRO_DUO_LOOK_T hand-offs.  With ACRO_DUO_R = 8 slots the chain never waits for
+// the trailer as long as LOOK_T * (trailer step) + (wake-up latency) < (R - LOOK + 1) * (chain step): batches of 4 made the
+// trailer the bottleneck of the backward pass (637 instead of 420 cycles per step, profiles/r2_spec_timing_*.txt), 3 do not.
+#ifndef ACRO_DUO_LOOK_T
+#define ACRO_DUO_LOOK_T 3
+#endif
 struct Hand {
   uint32_t data, full, empty;  // shared addresses: slot 0, full barrier 0, empty barrier 0
   uint32_t h;                  // hand-offs so far (identical in both warps)
@@ -74,7 +80,7 @@ template <bool NI>
 __device__ __forceinline__ void hand_wait_full(const Hand& hd, uint32_t h_last, uint32_t& h_ok) {
   if (NI && ACRO_SPEC_TRAILER_NI) {
     if (hd.h >= h_ok) {
-      const uint32_t hh = min(hd.h + (ACRO_DUO_LOOK - 1), h_last);
+      const uint32_t hh = min(hd.h + (ACRO_DUO_LOOK_T - 1), h_last);
       mbar_wait_call(hd.full_bar_of(hh), hd.full_parity_of(hh));
       h_ok = hh + 1u;
     }

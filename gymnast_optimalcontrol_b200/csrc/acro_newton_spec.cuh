@@ -28,6 +28,26 @@ namespace acro {
 
 enum { SPEC_EXIT = 0, SPEC_BACKWARD = 1, SPEC_FORWARD_DUO = 2, SPEC_FORWARD_SPEC = 3, SPEC_COMMIT = 4 };
 
+// ACRO_SPEC_TIMING (profiles/spec_timing.py): block 0 logs clock64 at the pass boundaries of warps 0 and 1 into the buffer
+// passed as params_b: records of 4 x int64 {warp * 16 + command, after barrier A, pass function returned, after barrier B}
+#ifdef ACRO_SPEC_TIMING
+#define SPEC_T_DECL long long spec_t_[3]; int spec_t_n_ = 0; (void)spec_t_n_;
+#define SPEC_T(i) spec_t_[i] = clock64()
+#define SPEC_T_FLUSH(warp_, cmd_)                                                                             \
+  if (blockIdx.x == 0 && lane == 0 && a.pb && spec_t_n_ < 2000) {                                             \
+    long long* tb_ = reinterpret_cast<long long*>(const_cast<double*>(a.pb)) + ((warp_) * 2000 + spec_t_n_) * 4; \
+    tb_[0] = (warp_) * 16 + (cmd_);                                                                           \
+    tb_[1] = spec_t_[0];                                                                                      \
+    tb_[2] = spec_t_[1];                                                                                      \
+    tb_[3] = spec_t_[2];                                                                                      \
+    ++spec_t_n_;                                                                                              \
+  }
+#else
+#define SPEC_T_DECL
+#define SPEC_T(i)
+#define SPEC_T_FLUSH(warp_, cmd_)
+#endif
+
 __device__ __forceinline__ void spec_bar() {
   __syncwarp();
   asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -318,8 +338,10 @@ __global__ void __launch_bounds__(ACRO_SPEC_W * 32, 1) k_newton_spec(const __gri
 
   if (warp != 0) {
     // ------------------------------------------------------------------------------ workers (warp 1 = the duo trailer)
+    SPEC_T_DECL
     for (;;) {
       spec_bar();  // A: command published
+      SPEC_T(0);
       asm volatile("fence.proxy.async;" ::: "memory");
       const int c = cmd[0], cur = cmd[1], J = cmd[2];
       if (c == SPEC_EXIT) break;
@@ -369,10 +391,13 @@ __global__ void __launch_bounds__(ACRO_SPEC_W * 32, 1) k_newton_spec(const __gri
         spec_commit(a.m, N, warp, lane, commit, xs, us, tX[cur ^ 1], tU[cur ^ 1], tL);
       }
       // what this warp stored with ordinary stores is read by other warps and by the next pass's bulk copies
+      SPEC_T(1);
       __threadfence();
       asm volatile("fence.proxy.async;" ::: "memory");
       __syncwarp();
       spec_bar();  // B: pass complete, results published
+      SPEC_T(2);
+      if (warp == 1) { SPEC_T_FLUSH(1, c) }
     }
     return;
   }
@@ -453,11 +478,15 @@ __global__ void __launch_bounds__(ACRO_SPEC_W * 32, 1) k_newton_spec(const __gri
       cmd[2] = J;
     }
   };
+  SPEC_T_DECL
   auto after_pass = [&]() {
+    SPEC_T(1);
     __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp();
     spec_bar();  // B
+    SPEC_T(2);
+    SPEC_T_FLUSH(0, cmd[0])
   };
 
   while (__any_sync(FULL, run) && (a.o.chunk_iters <= 0 || done < a.o.chunk_iters)) {
@@ -467,6 +496,7 @@ __global__ void __launch_bounds__(ACRO_SPEC_W * 32, 1) k_newton_spec(const __gri
     flags[lane] = run ? 1 : 0;
     publish(SPEC_BACKWARD, 0);
     spec_bar();  // A
+    SPEC_T(0);
     if (WPB)
       duo_backward_chain<WPB, RPB, SG, 2, true>(a.m, w, N, r, hd, lane);
     else if (swap_shared)
@@ -491,6 +521,7 @@ __global__ void __launch_bounds__(ACRO_SPEC_W * 32, 1) k_newton_spec(const __gri
         // a lone candidate: the chain / trailer pair writes it (and its linearisation) straight to the other buffer
         publish(SPEC_FORWARD_DUO, 1);
         spec_bar();  // A
+        SPEC_T(0);
         duo_forward_chain<RPB, SG, true>(a.m, N, r, hd, lane, gamma);
         after_pass();
         const double c = res[64 + lane];
@@ -519,6 +550,7 @@ __global__ void __launch_bounds__(ACRO_SPEC_W * 32, 1) k_newton_spec(const __gri
         }
         publish(SPEC_FORWARD_SPEC, J);
         spec_bar();  // A
+        SPEC_T(0);
         const double c0 = spec_forward<WPB, RPB, SG>(a.m, w, N, p, r, empty_bars, true, lane, gamma, need, cX0, cU0, xrT, hd.zmask);
         cand[lane] = c0;
         after_pass();
@@ -546,6 +578,7 @@ __global__ void __launch_bounds__(ACRO_SPEC_W * 32, 1) k_newton_spec(const __gri
       sel[lane] = commit ? acc_buf : -1;
       publish(SPEC_COMMIT, 0);
       spec_bar();  // A
+      SPEC_T(0);
       const double* xs = commit ? cX0 + acc_buf * cXs + lane : tX[cur] + lane;
       const double* us = commit ? cU0 + acc_buf * cUs + lane : tU[cur] + lane;
       spec_commit(a.m, N, 0, lane, commit, xs, us, tX[cur ^ 1], tU[cur ^ 1], tL);

@@ -1,6 +1,5 @@
 #!/bin/bash
-# round 2 evidence pass (one GPU): tests, bench (both arms), secondary configs, ncu launch list, ncu --set full of the
-# headline kernel and of the speculative kernel
+# round 2 evidence pass (one GPU), part 1: tests, bench (both arms), secondary configs, probes, ncu launch list
 set -x
 O=gpurun_out
 mkdir -p $O
@@ -13,6 +12,7 @@ tail -2 $O/r2_bench_configs.err
 timeout 300 python profiles/spec_probe.py 4096 50 > $O/r2_spec_probe.txt 2>&1
 timeout 300 python profiles/e2e_probe.py > $O/r2_e2e_probe.txt 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches.csv python bench.py --steps 2 --warmup 1 --iters 4 --no-cpu > $O/r2_ncu_list.log 2>&1
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:k_newton_duo -c 1 -f -o $O/r2_newton_duo python bench.py --steps 1 --warmup 0 --iters 4 --no-cpu --no-mpc --quick > $O/r2_ncu_duo.log 2>&1
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:k_newton_spec -c 1 -f -o $O/r2_newton_spec python profiles/spec_probe.py --one 1.0 spec 4096 30 > $O/r2_ncu_spec.log 2>&1
-ls -la $O | tail -15
+ACRO_B200_LIB=$PWD/gymnast_optimalcontrol_b200/libacro_b200_T.so timeout 120 python profiles/spec_timing.py 0.1 1 > $O/r2_spec_timing_g01.txt 2>&1
+ACRO_B200_LIB=$PWD/gymnast_optimalcontrol_b200/libacro_b200_T.so timeout 120 python profiles/spec_timing.py 1.0 0 > $O/r2_spec_timing_g1.txt 2>&1
+head -30 $O/r2_spec_timing_g01.txt
+du -sh $O
