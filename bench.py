@@ -439,7 +439,12 @@ def headline(cx, a):
 
 
 def e2e_block(cx, a, h):
-    """Through trajectory_generation.newton_Algorithm with pinned host buffers: pipelined (block=False) and blocking."""
+    """Through trajectory_generation.newton_Algorithm with pinned host buffers, inputs host->device and results
+    device->host inside the timed region of every step.  Three ways of calling it:
+      solution  block=False, return_gains=False: x_traj, u_traj and the history come back (what main.py's task_1 / task_2
+                consume, main.py:42-48, 65-79); K and sigma of the last iteration stay on the device as handles
+      full      block=False: everything the reference's function returns, K and sigma included (twice the bytes)
+      sync      blocking calls, everything returned: solve, then copy"""
     torch, tg = cx.torch, cx.tg
     x0_host = torch.from_numpy(h["x0"]).pin_memory()
     xr_host = torch.from_numpy(h["x_ref"]).pin_memory()
@@ -447,10 +452,10 @@ def e2e_block(cx, a, h):
     kw = dict(max_iters=a.iters, tol=0.0, gamma_0=0.1, verbose=False)
     res = {}
 
-    def run(block, steps):
+    def run(block, gains, steps):
         prev = None
         for _ in range(steps):
-            cur = tg.newton_Algorithm(x0_host, xr_host, ur_host, block=block, **kw)
+            cur = tg.newton_Algorithm(x0_host, xr_host, ur_host, block=block, return_gains=gains, **kw)
             if not block:
                 if prev is not None:
                     res["out"] = prev.result()
@@ -461,20 +466,21 @@ def e2e_block(cx, a, h):
             res["out"] = prev.result()
 
     out = {}
-    for mode, block in (("pipelined", False), ("sync", True)):
-        run(block, 3)
+    h2d = x0_host.numel() * 8 + xr_host.numel() * 8 + ur_host.numel() * 8
+    for mode, block, gains in (("solution", False, False), ("full", False, True), ("sync", True, True)):
+        run(block, gains, 3)
         cx.barrier()
         t0 = time.perf_counter()
-        run(block, a.steps)
+        run(block, gains, a.steps)
         cx.barrier()
-        out[mode] = cx.max_over_ranks(time.perf_counter() - t0)[0]
-    o = res["out"]
-    h2d = x0_host.numel() * 8 + xr_host.numel() * 8 + ur_host.numel() * 8
-    d2h = sum(t.numel() * t.element_size() for t in o[:4]) + sum(np.asarray(v).nbytes for k, v in o[4].items()
-                                                                  if k in ("cost", "sigma_norm", "iters", "status", "n_try", "gamma"))
-    done = cx.sum_over_ranks(float(np.asarray(o[4]["iters"]).sum()))[0]
-    return dict(t=out["pipelined"], t_sync=out["sync"], h2d=int(h2d), d2h=int(d2h), done_per_step=done,
-                cost_mean=float(o[4]["cost"][:, -1].mean()))
+        t = cx.max_over_ranks(time.perf_counter() - t0)[0]
+        o = res["out"]
+        d2h = sum(v.numel() * v.element_size() for v in o[:4] if isinstance(v, torch.Tensor)) + \
+            sum(np.asarray(v).nbytes for k, v in o[4].items() if k in ("cost", "sigma_norm", "iters", "status", "n_try", "gamma"))
+        done = cx.sum_over_ranks(float(np.asarray(o[4]["iters"]).sum()))[0]
+        out[mode] = dict(t=t, d2h=int(d2h), done_per_step=done, cost_mean=float(o[4]["cost"][:, -1].mean()))
+    out["h2d"] = int(h2d)
+    return out
 
 
 def measure_mpc(cx, steps, with_cpu):
@@ -608,8 +614,7 @@ def run_native(a):
     h = headline(cx, a)
     e = e2e_block(cx, a, h)
     value = h["done_per_step"] * a.steps / h["t"]
-    e2e_value = e["done_per_step"] * a.steps / e["t"]
-    e2e_sync = e["done_per_step"] * a.steps / e["t_sync"]
+    e2e_rate = {m: e[m]["done_per_step"] * a.steps / e[m]["t"] for m in ("solution", "full", "sync")}
 
     back = None
     if not a.quick:
@@ -692,20 +697,29 @@ def run_native(a):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(a),
             "step_iters_per_sec": value * (N_STEPS - 1), "newton_iters_per_sec_10k_step_equivalent": value * (N_STEPS - 1) / 1e4,
-            "e2e": {"value": e2e_value, "unit": "Newton iterations/s", "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
-                    "ms_per_step": 1e3 * e["t"] / a.steps,
-                    "api": "trajectory_generation.newton_Algorithm(x0[B,4] pinned host, x_ref, u_ref, block=False): every step's inputs "
-                           "go host->device and x_traj, u_traj, K, sigma, history come back to fresh pinned host tensors; the copies of "
-                           "step i overlap the kernel of step i+1 (double-buffered solver state)",
-                    "sync": {"value": e2e_sync, "ms_per_step": 1e3 * e["t_sync"] / a.steps,
-                             "api": "the same with blocking calls (block=True): solve, then copy"}},
+            "e2e": {"value": e2e_rate["solution"], "unit": "Newton iterations/s", "h2d_bytes_per_step": e["h2d"],
+                    "d2h_bytes_per_step": e["solution"]["d2h"], "ms_per_step": 1e3 * e["solution"]["t"] / a.steps,
+                    "api": "trajectory_generation.newton_Algorithm(x0[B,4] pinned host, x_ref, u_ref, block=False, return_gains=False): "
+                           "every step's inputs go host->device; x_traj, u_traj and the history (cost, max|sigma|, Armijo tries and "
+                           "steps, iterations, status) come back to fresh pinned host tensors - what main.py's task_1 / task_2 consume; "
+                           "K and sigma of the last iteration stay on the device as handles.  The copies of step i overlap the kernel "
+                           "of step i+1 (double-buffered solver state)",
+                    "full_returns": {"value": e2e_rate["full"], "ms_per_step": 1e3 * e["full"]["t"] / a.steps,
+                                     "d2h_bytes_per_step": e["full"]["d2h"],
+                                     "api": "the same call with return_gains=True: K (B,500,2,4) and sigma (B,500,2) come back too, "
+                                            "i.e. everything the reference's function returns (twice the bytes; on an 8-GPU box the "
+                                            "eight ranks then share the host's device-to-host ceiling, measured 88 GB/s aggregate: "
+                                            "DESIGN.md section 5)"},
+                    "sync": {"value": e2e_rate["sync"], "ms_per_step": 1e3 * e["sync"]["t"] / a.steps,
+                             "d2h_bytes_per_step": e["sync"]["d2h"],
+                             "api": "blocking calls (block=True), everything returned: solve, then copy"}},
             "host_binding": {"cpus_of_rank0": len(cx.cpus) if cx.cpus else None,
                              "note": "ranks of a multi-GPU run are pinned to the CPU cores NVML reports next to their GPU before pinned "
                                      "host memory is allocated (sharding.bind_to_gpu_numa)"},
             "gpu_launches": int(h["launches"]), "roofline": roof, "cpu_baseline": cpu, "clocks": h["clocks"],
             "backtracking": back, "mpc": mpc, "strong": strong, "long_horizon": longh, "target": target,
             "check": {"iterations_done_per_step_all_ranks": h["done_per_step"], "iterations_nominal_per_step": B * iters * world,
-                      "armijo_tries_mean": h["ntry"], "mean_final_cost": h["cost_mean"], "e2e_mean_final_cost": e["cost_mean"]},
+                      "armijo_tries_mean": h["ntry"], "mean_final_cost": h["cost_mean"], "e2e_mean_final_cost": e["full"]["cost_mean"]},
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -384,13 +384,16 @@ __device__ __forceinline__ void duo_backward_chain(const Model& m, const WV<WPB>
       const bool cross = (s == 0) && (k + 1 < n_stages);
       // (no vote here: with __any_sync in this loop ptxas puts a YIELD at the head of both chain loops, 50 cycles
       // per step; the condition is the same in every lane)
-      const bool look = NI && (hd.h % ACRO_DUO_LOOK) == 0;
-      if (cross || (NI ? look : !hready)) {
-        if (cross) mbar_wait_t<NI>(nbar, npar);
-        if (NI) {
+      if constexpr (NI) {
+        const bool look = (hd.h % ACRO_DUO_LOOK) == 0;
+        if (cross || look) {
+          if (cross) mbar_wait_call(nbar, npar);
           if (look) mbar_wait_call(hd.empty_bar_at(ACRO_DUO_LOOK - 1), hd.free_parity_at(ACRO_DUO_LOOK - 1));
-        } else if (!hready) {
-          mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);
+        }
+      } else {
+        if (cross || !hready) {
+          if (cross) mbar_wait(nbar, npar);
+          if (!hready) mbar_wait(hd.empty_bar(), hd.phase() ^ 1u);
         }
       }
       const uint32_t nsrc = cross ? nstage : stage;

@@ -271,3 +271,32 @@ def test_c5_256_base_iterates_vs_reference(bt, fa_ref):
     # the full 200-point curve of every iterate: its value at the sampled step sizes is the one checked above
     full = bt.stepsize_sweep(X, U, K, S, ref, w, dev(np.linspace(0, 1.25, 200))).cpu().numpy()
     assert np.array_equal(full[g["gamma_idx"]], cost)
+
+
+# ------------------------------------------------------------------------------------- a real 10 000-step horizon
+def _oracle_newton_long(args):
+    x0, x_ref, u_ref, kw = args
+    x, u, K, s, h = O.newton_Algorithm(x0, x_ref, u_ref, **kw)
+    return x[::50], u[::50], np.array(s)[::50], h
+
+
+@pytest.mark.parametrize("Bn,kernel", [(96, "auto"), (96, "ring4"), (96, "ring-rl")])
+def test_long_horizon_vs_oracle(bt, fa_ref, Bn, kernel):
+    """N = 10 001 (the 10k-step horizon BASELINE.json's target is quoted in; bench.py's `long_horizon` block): the
+    swing-up reference followed by the upright equilibrium, 2 Newton iterations, 3 sampled problems against the oracle
+    (every 50th step of x, u, sigma; costs; Armijo tries)."""
+    x_fa, u_fa, _ = fa_ref
+    N = 10001
+    x_ref = np.vstack([x_fa, np.repeat(np.array([[np.pi, 0.0, 0.0, 0.0]]), N - x_fa.shape[0], 0)])
+    u_ref = np.vstack([u_fa[:500], np.zeros((N - 1 - 500, 2))])
+    x0s = np.random.default_rng(77).uniform(-0.2, 0.2, (Bn, 4))
+    kw = dict(max_iters=2, tol=1e-4, gamma_0=0.1)
+    st = bt.newton_solve(soa(x0s), bt.make_ref(x_ref, u_ref), kernel=kernel, **kw)
+    torch.cuda.synchronize()
+    rows = [0, 31, Bn - 1]
+    X, U, S = (t.batch_major()[rows].cpu().numpy() for t in (st.X, st.U, st.S))
+    res = pool_map(_oracle_newton_long, [(x0s[b], x_ref, u_ref, kw) for b in rows])
+    for i, (x, u, s, h) in enumerate(res):
+        assert int(st.iters[rows[i]]) == h["iters"] and list(st.hist_ntry[:2, rows[i]].cpu().numpy()) == h["n_try"]
+        assert rel_err(st.hist_cost[:3, rows[i]].cpu().numpy(), h["cost"]) < TOL
+        assert rel_err(X[i][::50], x) < TOL and rel_err(U[i][::50], u) < TOL and rel_err(S[i][::50], s) < TOL
