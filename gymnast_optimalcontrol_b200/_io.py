@@ -73,6 +73,148 @@ def to_host(t, stream_sync=True):
     return h
 
 
+_side = {}
+
+
+def side_streams():
+    """(upload stream, copy stream) of the current device: host->device staging of the next call and device->host
+    copies of the previous one run there, next to the kernels on the caller's stream."""
+    i = torch.cuda.current_device()
+    if i not in _side:
+        _side[i] = (torch.cuda.Stream(), torch.cuda.Stream())
+    return _side[i]
+
+
+def _tensors(objs):
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            yield o
+        elif isinstance(o, bt.Traj):
+            yield o.data
+        elif isinstance(o, bt.Ref):
+            yield from _tensors((o.x, o.u))
+
+
+class upload_scope:
+    """`with upload_scope(enabled) as up:` - uploads and layout kernels inside run on the upload stream, so that
+    they overlap whatever the caller's stream is still computing; on exit the caller's stream waits for them.
+    `up.keep(...)` tells the allocator that the staged tensors are used on the caller's stream."""
+
+    def __init__(self, enabled, *inputs):
+        # inputs already on the device were produced on the caller's stream: they stay there
+        self.enabled = bool(enabled) and not any(isinstance(a, torch.Tensor) and a.is_cuda for a in inputs)
+
+    def __enter__(self):
+        if self.enabled:
+            self.main = torch.cuda.current_stream()
+            self.up = side_streams()[0]
+            self.ctx = torch.cuda.stream(self.up)
+            self.ctx.__enter__()
+        return self
+
+    def keep(self, *objs):
+        if self.enabled:
+            for t in _tensors(objs):
+                t.record_stream(self.main)
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            ev = torch.cuda.Event()
+            ev.record(self.up)
+            self.ctx.__exit__(*exc)
+            self.main.wait_event(ev)
+        return False
+
+
+_deferred = []  # copy-back stages recorded but not yet queued (see out_async)
+
+
+def flush_deferred():
+    """Queue the copy-back stages that out_async(..., defer=True) held back."""
+    while _deferred:
+        _deferred.pop(0)()
+
+
+class Pending:
+    """Handle of a batched call whose results are on their way to the host; ``result()`` waits for the copies and
+    returns what the blocking call returns."""
+
+    def __init__(self, done, build):
+        self._done, self._build, self._value = done, build, None
+
+    def _event(self):
+        if callable(self._done):  # a deferred copy-back: queue it now
+            flush_deferred()
+            self._done = self._done()
+        return self._done
+
+    def ready(self):
+        return self._value is not None or self._event().query()
+
+    def result(self):
+        if self._value is None:
+            self._event().synchronize()
+            self._value = self._build()
+            self._build = None
+        return self._value
+
+
+def out_async(items, kind, defer=False):
+    """items: [(Traj or device tensor, pad_rows or None)] produced on the current stream -> Pending of the list of
+    host (or device, for CUDA callers) results.  Un-tiling and the device-to-host copies run on the copy stream.
+
+    defer=True: the copy-back is only RECORDED here and queued by the next `flush_deferred()` - the next non-blocking
+    call does that right after queueing its own uploads - or by `result()` / `ready()`.  Work queued on the copy stream
+    waits for the solver kernel; with the driver's default of 8 hardware queues the upload stream may share a queue with
+    the copy stream, and uploads queued behind that wait would start only after the kernel (measured:
+    profiles/r2_mpc_e2e_probe.txt)."""
+    main, cs = torch.cuda.current_stream(), side_streams()[1]
+    ready = torch.cuda.Event()
+    ready.record(main)
+    host = not (kind.torch and kind.cuda)
+    outs, box = [], {}
+    for t_soa, _ in items:
+        for t in _tensors((t_soa,)):
+            t.record_stream(cs)
+
+    def start():
+        if "done" in box:
+            return
+        with torch.cuda.stream(cs):
+            cs.wait_event(ready)
+            for t_soa, pad in items:
+                t = bt.unpack_soa(t_soa)
+                if not kind.batched:
+                    t = t[0]
+                if host:
+                    rows = t.shape[-2] if pad is None else max(pad, t.shape[-2])
+                    h = pinned_empty(t.shape[:-2] + (rows, t.shape[-1]), t.dtype)
+                    if rows > t.shape[-2]:
+                        h[..., t.shape[-2]:, :] = 0.0
+                    h[..., :t.shape[-2], :].copy_(t, non_blocking=True)
+                    outs.append((h, t))
+                else:
+                    if pad is not None and pad > t.shape[-2]:
+                        tp = t.new_zeros(*t.shape[:-2], pad, t.shape[-1])
+                        tp[..., :t.shape[-2], :] = t
+                        t = tp
+                    t.record_stream(main)
+                    outs.append((t, None))
+            box["done"] = torch.cuda.Event()
+            box["done"].record(cs)
+        if not host:
+            main.wait_event(box["done"])
+
+    def build():
+        return [(h if kind.torch else h.numpy()) if host else h for h, _ in outs]
+
+    if defer and host:
+        _deferred.append(start)
+        return Pending(lambda: box["done"], build)
+    start()
+    return Pending(box["done"], build)
+
+
 def as_device(a):
     return bt.upload(a)
 

@@ -262,22 +262,7 @@ class _NewtonPipeline:
 _pipeline = _NewtonPipeline()
 
 
-class PendingNewton:
-    """Handle of a batched solve whose results are on their way to the host; ``result()`` waits for the copies and
-    returns what ``newton_Algorithm`` returns."""
-
-    def __init__(self, done, build):
-        self._done, self._build, self._value = done, build, None
-
-    def ready(self):
-        return self._value is not None or self._done.query()
-
-    def result(self):
-        if self._value is None:
-            self._done.synchronize()
-            self._value = self._build()
-            self._build = None
-        return self._value
+PendingNewton = _io.Pending  # handle of a non-blocking batched solve (result(), ready())
 
 
 def newton_Algorithm(x0, x_ref, u_ref, max_iters, tol=1e-6, beta=0.7, c=0.5, gamma_0=1, plot_armijo_iters=10, *,

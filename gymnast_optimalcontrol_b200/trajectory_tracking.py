@@ -47,15 +47,23 @@ def simulate_tracking(x_opt, u_opt, K_reg, x0_perturbed, *, params_b=None):
     return _io.out(Xt, kind, key="xt"), _io.out(Ut, kind, key="ut")
 
 
-def LQR_tracking(x_ref, u_ref, t_ref, x0_perturbed=None, *, params_b=None):
-    """trajectory_tracking.py:219-249.  params_b: the gains are those of the active (nominal) model, the plants differ."""
+def LQR_tracking(x_ref, u_ref, t_ref, x0_perturbed=None, *, params_b=None, block=True):
+    """trajectory_tracking.py:219-249.  params_b: the gains are those of the active (nominal) model, the plants differ.
+    block=False: returns a handle (`.result()` -> the tuple); uploads and copies back run on side streams."""
     if x0_perturbed is None:
         x0_perturbed = x_ref[0].copy() if not isinstance(x_ref, torch.Tensor) else x_ref[0].clone()
-    traj = _ref(x_ref, u_ref)
+    with _io.upload_scope(not block, x_ref, u_ref, x0_perturbed, params_b) as up:
+        traj = _ref(x_ref, u_ref)
+        x0, kind = _io.state_in(x0_perturbed, nx)
+        pb = None if params_b is None else bt.phys_params(params_b, x0.shape[1])
+        up.keep(traj, x0, pb)
+    if not block:
+        _io.flush_deferred()
     K = bt.lqr_gains(traj, bt.Weights(Q_reg, R_Reg), active_params())
-    x0, kind = _io.state_in(x0_perturbed, nx)
-    pb = None if params_b is None else bt.phys_params(params_b, x0.shape[1])
     Xt, Ut = bt.lqr_track(traj, K, x0, active_params(), pb)
+    if not block:
+        pend = _io.out_async([(Xt, None), (Ut, None)], kind, defer=True)
+        return _io.Pending(pend._event, lambda: tuple(pend.result()))
     return _io.out(Xt, kind, key="xt"), _io.out(Ut, kind, key="ut")
 
 
@@ -95,37 +103,88 @@ def _pad_time(a, n):
     return out
 
 
-def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return_info=False, tau_max=None):
-    """trajectory_tracking.py:8-69.  x0 (4,) or (B,4); reference shared (N,4) or per problem (B,N,4).
+_p_inf_cache = {}
 
-    tau_max: switches on the input box the reference keeps behind `test_constraints` (tt:87-91, 112-114; 18 there):
-    -tau_max <= u + u_ref <= tau_max at every step of every horizon, each QP solved exactly."""
-    w = bt.Weights(Q_mpc if Q is None else Q, R_mpc if R is None else R)
-    p = active_params()
-    x0d, kind = _io.state_in(x0, nx)
-    ref = _ref(x_ref, u_ref)
-    # terminal weight: P_inf of the linearisation about the final equilibrium (tt:33-40), all on the device
+
+def _terminal_weight(p, w):
+    """P_inf of the linearisation about the final equilibrium (tt:33-40), computed on the device once per
+    (parameters, weights) and kept there: the convergence check reads a flag back, which must not sit in the way of
+    back-to-back non-blocking calls."""
+    key = (bytes(p), torch.cuda.current_device(),
+           None if w.per_problem else (w.Q.tobytes(), w.R.tobytes(), np.asarray(x_f, dtype=np.float64).tobytes(),
+                                       np.asarray(u_f, dtype=np.float64).tobytes()))
+    hit = _p_inf_cache.get(key) if key[2] is not None else None
+    if hit is not None:
+        return hit
     xf = bt.upload(np.asarray(x_f, dtype=np.float64).reshape(4, 1))
     uf = bt.upload(np.asarray(u_f, dtype=np.float64).reshape(2, 1))
     A_f, B_f = bt.linearize(xf, uf, True, p)
     P, n = bt.p_inf(A_f, B_f, w)
     if int(n[0]) < 0:
         print("P_inf did not converge!!!")
+    P = P[:, :, 0].contiguous()
+    if key[2] is not None:
+        if len(_p_inf_cache) > 64:
+            _p_inf_cache.clear()
+        _p_inf_cache[key] = P
+    return P
+
+
+def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return_info=False, tau_max=None, block=True):
+    """trajectory_tracking.py:8-69.  x0 (4,) or (B,4); reference shared (N,4) or per problem (B,N,4).
+
+    tau_max: switches on the input box the reference keeps behind `test_constraints` (tt:87-91, 112-114; 18 there):
+    -tau_max <= u + u_ref <= tau_max at every step of every horizon, each QP solved exactly.
+    block=False (without return_info): returns a handle at once; `.result()` gives `(x_real, u_real)`.  The uploads of
+    this call run on an upload stream and the copies back on a copy stream, so with several calls in flight the
+    transfers of one batch overlap the kernel of another (pinned host inputs must stay untouched until then)."""
+    w = bt.Weights(Q_mpc if Q is None else Q, R_mpc if R is None else R)
+    p = active_params()
+    P = _terminal_weight(p, w)
+    piped = (not block) and not return_info
+    with _io.upload_scope(piped, x0, x_ref, u_ref) as up:
+        x0d, kind = _io.state_in(x0, nx)
+        ref = _ref(x_ref, u_ref)
+        up.keep(x0d, ref)
+    if piped:
+        _io.flush_deferred()  # copy-back of the previous call: queued after this call's uploads, before its kernel
     if tau_max is not None:
-        Xr, Ur, info = bt.mpc_track_box(x0d, ref, P[:, :, 0].contiguous(), tau_max=float(tau_max), T=int(T),
+        Xr, Ur, info = bt.mpc_track_box(x0d, ref, P, tau_max=float(tau_max), T=int(T),
                                         T_pred=int(T_pred), w=w, x_f=x_f, u_f=u_f, params=p)
+        if piped:
+            return _MpcPending(_io.out_async([(Xr, ref.N), (Ur, ref.N - 1)], kind, defer=True), info["status"])
         if int(info["status"].max()) != 0:
             print("Attention! mpc solver: active-set iteration limit reached for %d problem(s)" % int((info["status"] != 0).sum()))
         xr, ur = _pad_time(_io.out(Xr, kind, key="xr"), ref.N), _pad_time(_io.out(Ur, kind, key="ur"), ref.N - 1)
         if return_info:
             return xr, ur, dict(n_solves=(int(T) - 1) * x0d.shape[1], n_sweeps=info["n_sweeps"].cpu().numpy(),
                                 n_active=info["n_active"].cpu().numpy().T, status=info["status"].cpu().numpy(),
-                                P_inf=P.cpu().numpy()[:, :, 0])
+                                P_inf=P.cpu().numpy())
         return xr, ur
-    Xr, Ur, K0, n_solves = bt.mpc_track(x0d, ref, P[:, :, 0].contiguous(), T=int(T), T_pred=int(T_pred), w=w,
-                                        x_f=x_f, u_f=u_f, params=p)
+    Xr, Ur, K0, n_solves = bt.mpc_track(x0d, ref, P, T=int(T), T_pred=int(T_pred), w=w, x_f=x_f, u_f=u_f, params=p)
+    if piped:
+        return _MpcPending(_io.out_async([(Xr, ref.N), (Ur, ref.N - 1)], kind, defer=True), None)
     xr, ur = _pad_time(_io.out(Xr, kind, key="xr"), ref.N), _pad_time(_io.out(Ur, kind, key="ur"), ref.N - 1)
     if return_info:
         return xr, ur, dict(n_solves=n_solves, K0=None if K0 is None else K0.cpu().numpy().reshape(-1, 2, 4),
-                            P_inf=P.cpu().numpy()[:, :, 0])
+                            P_inf=P.cpu().numpy())
     return xr, ur
+
+
+class _MpcPending:
+    """Handle of a non-blocking solve_mpc_tracking: result() -> (x_real, u_real)."""
+
+    def __init__(self, pend, status):
+        self._pend, self._status = pend, status
+
+    def ready(self):
+        return self._pend.ready()
+
+    def result(self):
+        xr, ur = self._pend.result()
+        if self._status is not None:
+            bad = int((self._status != 0).sum())
+            self._status = None
+            if bad:
+                print("Attention! mpc solver: active-set iteration limit reached for %d problem(s)" % bad)
+        return xr, ur

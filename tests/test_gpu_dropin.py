@@ -290,3 +290,71 @@ def test_batched_reference_builders(mods):
     assert rel_err(h["cost"][0], g["cost"][:4]) < 1e-8
     with pytest.raises(RuntimeError, match="Root finder failed"):
         tg.compute_equilibrium(np.array([[0.0, 50.0]]), (0.1, 0.1))
+
+
+@pytest.mark.parametrize("tau_max", [None, 18.0])
+def test_pipelined_mpc_tracking_equals_blocking(mods, tau_max):
+    """solve_mpc_tracking(block=False): uploads on the upload stream, copies back on the copy stream, several calls in
+    flight - the same numbers as the blocking calls, for shared and per-problem references, host and device inputs,
+    with and without the input box, and with T < N (zero padding)."""
+    dyn, tg, tt = mods
+    d = golden("acrobot_optimal_trajectory")
+    rng = np.random.default_rng(17)
+    Bn = 96
+    calls = []
+    for i in range(4):
+        x0 = d["x"][0] + rng.uniform(-0.1, 0.1, (Bn, 4))
+        if i % 2:
+            xr = np.repeat(d["x"][None], Bn, 0) + rng.uniform(-1e-3, 1e-3, (Bn, 501, 4))
+            ur = np.repeat(d["u"][None], Bn, 0)
+        else:
+            xr, ur = d["x"], d["u"]
+        calls.append((x0, xr, ur, 61 if i == 3 else 81))
+    want = [tt.solve_mpc_tracking(x0, xr, ur, T, tau_max=tau_max) for x0, xr, ur, T in calls]
+    # host (pinned) inputs: everything in flight before the first result is read
+    pin = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in c[:3]) + (c[3],) for c in calls]
+    pend = [tt.solve_mpc_tracking(x0, xr, ur, T, tau_max=tau_max, block=False) for x0, xr, ur, T in pin]
+    for p, (wx, wu) in zip(pend, want):
+        gx, gu = p.result()
+        assert isinstance(gx, torch.Tensor) and gx.is_pinned() and tuple(gx.shape) == wx.shape
+        assert np.array_equal(gx.numpy(), wx) and np.array_equal(gu.numpy(), wu)
+        assert p.ready()
+    # device inputs stay on the caller's stream; results come back as device tensors
+    dev = [tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in c[:3]) + (c[3],) for c in calls]
+    pend = [tt.solve_mpc_tracking(x0, xr, ur, T, tau_max=tau_max, block=False) for x0, xr, ur, T in dev]
+    for p, (wx, wu) in zip(pend, want):
+        gx, gu = p.result()
+        assert gx.is_cuda and np.array_equal(gx.cpu().numpy(), wx) and np.array_equal(gu.cpu().numpy(), wu)
+    # NumPy in, NumPy out
+    gx, gu = tt.solve_mpc_tracking(*calls[1][:3], calls[1][3], tau_max=tau_max, block=False).result()
+    assert isinstance(gx, np.ndarray) and np.array_equal(gx, want[1][0]) and np.array_equal(gu, want[1][1])
+
+
+def test_pipelined_lqr_tracking_equals_blocking(mods):
+    dyn, tg, tt = mods
+    d = golden("acrobot_optimal_trajectory")
+    rng = np.random.default_rng(18)
+    x0s = [d["x"][0] + rng.uniform(-0.1, 0.1, (200, 4)) for _ in range(3)]
+    want = [tt.LQR_tracking(d["x"], d["u"], d["t"], x0_perturbed=x0) for x0 in x0s]
+    pend = [tt.LQR_tracking(d["x"], d["u"], d["t"], x0_perturbed=torch.from_numpy(x0).pin_memory(), block=False) for x0 in x0s]
+    for p, (wx, wu) in zip(pend, want):
+        gx, gu = p.result()
+        assert np.array_equal(gx.numpy(), wx) and np.array_equal(gu.numpy(), wu)
+
+
+def test_terminal_weight_is_cached_per_weights(mods):
+    """P_inf is computed once per (parameters, Q, R) and the cache distinguishes weights."""
+    dyn, tg, tt = mods
+    d = golden("acrobot_optimal_trajectory")
+    x0 = d["x"][0] + 0.05
+    a = tt.solve_mpc_tracking(x0, d["x"], d["u"], 41, return_info=True)
+    b = tt.solve_mpc_tracking(x0, d["x"], d["u"], 41, Q=np.diag([10.0, 10.0, 1.0, 1.0]), return_info=True)
+    c = tt.solve_mpc_tracking(x0, d["x"], d["u"], 41, return_info=True)
+    assert np.array_equal(a[2]["P_inf"], c[2]["P_inf"]) and np.array_equal(a[0], c[0])
+    assert not np.allclose(a[2]["P_inf"], b[2]["P_inf"])
+    assert rel_err(b[2]["P_inf"], tt.compute_P_inf(*[np.asarray(m) for m in _lin_f(dyn)], np.diag([10.0, 10.0, 1.0, 1.0]), tt.R_mpc)) < 1e-9
+
+
+def _lin_f(dyn):
+    A, B = dyn.Calculate_A_B_matrixes(np.array([np.pi, 0, 0, 0]), np.array([0.0, 0.0]))
+    return np.eye(4) + 2e-2 * A, 2e-2 * B
