@@ -80,7 +80,7 @@ SIGNATURES = {
     "acro_unpack_soa": [I64, I32, I32, P, P, P],
 }
 QUERIES = {"acro_version": C.c_char_p, "acro_last_error_string": C.c_char_p, "acro_launch_count": C.c_int64}
-SIZES = {"acro_mpc_box_ws_doubles": ([I64, I32], C.c_int64), "acro_newton_spec_ws_doubles": ([I64, I32], C.c_int64)}
+SIZES = {"acro_mpc_box_ws_doubles": ([I64, I32, I32], C.c_int64), "acro_newton_spec_ws_doubles": ([I64, I32], C.c_int64)}
 
 
 class AcroError(RuntimeError):

@@ -555,7 +555,7 @@ def mpc_track_box(x0, ref, QT_inf, tau_max=18.0, T=None, T_pred=75, w=None, x_f=
     qt_pp = QT_inf.dim() == 3
     Xr, Ur = Traj.empty(T, 4, Bn), Traj.empty(T - 1, 2, Bn)
     lin = Traj.empty(N - 1, 10, Bn) if ref.per_problem else _empty(N - 1, 10)
-    ws = _empty(int(lib.acro_mpc_box_ws_doubles(Bn, int(T_pred))))
+    ws = _empty(int(lib.acro_mpc_box_ws_doubles(Bn, int(T), int(T_pred))))
     ns, st = _empty(Bn, dtype=torch.int32), _empty(Bn, dtype=torch.int32)
     na = _empty(T - 1, Bn, dtype=torch.int32)
     xf = (C.c_double * 4)(*[float(v) for v in x_f])

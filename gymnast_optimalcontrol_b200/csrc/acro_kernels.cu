@@ -2092,7 +2092,9 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
   return ACRO_OK;
 }
 
-int64_t acro_mpc_box_ws_doubles(int64_t B, int T_pred) { return mpc_box_ws_per_problem(T_pred) * B; }
+int64_t acro_mpc_box_ws_doubles(int64_t B, int T, int T_pred) {
+  return mpc_box_ws_per_problem(T_pred) * B + mpc_box_table_doubles(T, T_pred);
+}
 
 int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
                        const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
@@ -2120,6 +2122,8 @@ int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int
   a.x0 = x0;
   a.lin = lin_ws;
   a.ws = ws;
+  a.ktab = nullptr;
+  a.wtab = nullptr;
   a.tau = tau_max;
   a.max_iter = max_iter > 0 ? max_iter : 6 * (T_pred - 1) + 20;
   a.Xr = Xr;
@@ -2137,6 +2141,12 @@ int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int
   } else {
     k_lin_compact<false><<<(N - 1 + 63) / 64, 64, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
     ACRO_LAUNCH_CHECK("acro_mpc_track_box/linearize");
+    if (!qt_per_problem) {  // gains of the empty working set, shared by the batch: one sweep per MPC step
+      a.ktab = ws + mpc_box_ws_per_problem(T_pred) * B;
+      a.wtab = a.ktab + mpc_box_ktab_doubles(T, T_pred);
+      k_mpc_box_gains<<<(T - 1 + 31) / 32, 32, 0, s>>>(a);
+      ACRO_LAUNCH_CHECK("acro_mpc_track_box/gains");
+    }
     k_mpc_track_box<false><<<c.grid, c.block, 0, s>>>(a);
   }
   ACRO_LAUNCH_CHECK("acro_mpc_track_box");

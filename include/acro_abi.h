@@ -304,10 +304,11 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
  *     -tau_max <= u_j + u_ref[t+j] <= tau_max
  * exactly (primal active-set method on Riccati sweeps, csrc/acro_mpc_box.cuh) and applies u_ref[t] + u_0 to the plant.
  * R must be diagonal, weights shared.  Reference shared or per problem; lin_ws as in acro_mpc_track;
- * ws: acro_mpc_box_ws_doubles(B, T_pred) doubles of scratch.  max_iter <= 0: 6 (T_pred-1) + 20 iterations per step.
+ * ws: acro_mpc_box_ws_doubles(B, T, T_pred) doubles of scratch (per-problem part, then the tables a shared reference
+ * uses: gains of the empty working set, (T-1)(T_pred-1) x 4, and the padded window rows, (T+T_pred-3) x 11).  max_iter <= 0: 6 (T_pred-1) + 20 iterations per step.
  * Out: Xr {T x 4}, Ur {T-1 x 2}; optional n_sweeps [B] (active-set iterations of the problem), n_active [T-1][B]
  * (inputs at a bound in the solution of step t), status [B] (1 if a step hit max_iter, else 0). */
-int64_t acro_mpc_box_ws_doubles(int64_t B, int T_pred);
+int64_t acro_mpc_box_ws_doubles(int64_t B, int T, int T_pred);
 int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
                        const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
                        int qt_per_problem, const double* x0, double tau_max, int max_iter, double* lin_ws, double* ws,
