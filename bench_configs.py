@@ -55,7 +55,10 @@ def line(name, metric, value, unit, flops_per_unit, t, launches, peak, extra=Non
     ach = value * flops_per_unit / 1e12
     d = {"config": name, "metric": metric, "value": value, "unit": unit, "seconds": t, "gpu_launches": launches,
          "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                      "flops_per_unit": flops_per_unit}}
+                      "flops_per_unit": flops_per_unit,
+                      "convention": "SURVEY 8(d): dense 4x4 algebra without credit for structure, 40 flops per sin or cos; "
+                                    "the kernels execute fewer FP64 instructions than that, so frac can exceed 1 (pipe "
+                                    "utilisation measured by ncu: DESIGN.md section 4.3)"}}
     if extra:
         d.update(extra)
     print(json.dumps(d), flush=True)
@@ -152,7 +155,10 @@ def main():
         ns = res["s"][3]
         line("C4 MPC tracking, per-problem references, B=16384, H=%d" % H, "mpc_solves_per_sec", ns / t,
              "MPC solves/s (one (H-1)-step Riccati sweep + plant step each)", 550.0 * (H - 1) + 16 + 856, t, nl, peak,
-             {"riccati_sweeps_executed": ns})
+             {"riccati_sweeps_executed": ns,
+              "executed_frac": ns / t * (180.0 * (H - 1) + 16 + 856) / 1e12 / peak,
+              "executed_flops": "a sweep step executes 108 FP64 instructions = 180 flops (A_d has two trivial rows, "
+                                "inner steps need no gain)"})
 
     # ---- config 5: 5000 base iterates x 200 step sizes = 1M closed-loop rollouts
     Pn = 5000 if not a.quick else 1000

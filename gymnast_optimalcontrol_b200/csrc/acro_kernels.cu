@@ -1195,16 +1195,15 @@ __device__ __forceinline__ void mpc_sweep_sw(const WV<WPB>& w, double dt, const 
   LinD L0 = load_lin(lin, t + j, ld, b);
   LinD L1 = load_lin(lin, t + max(j - 1, 0), ld, b);
   LinD L2 = load_lin(lin, t + max(j - 2, 0), ld, b);
+  // (each buffer is refilled right AFTER the step that consumed it: a load into a temporary issued before the step
+  // and copied afterwards makes the copy wait for the load - ncu: 30 % of all stall samples on that one MOV)
   for (; j >= 3; j -= 3) {
-    LinD Ln = load_lin(lin, t + j - 3, ld, b);
     riccati_chain_step<SW, false>(P, L0, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
-    L0 = Ln;
-    Ln = load_lin(lin, t + max(j - 4, 0), ld, b);
+    L0 = load_lin(lin, t + j - 3, ld, b);
     riccati_chain_step<SW, false>(P, L1, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
-    L1 = Ln;
-    Ln = load_lin(lin, t + max(j - 5, 0), ld, b);
+    L1 = load_lin(lin, t + max(j - 4, 0), ld, b);
     riccati_chain_step<SW, false>(P, L2, dt, Qh, col, w.R(0, 1), w.R(1, 1), K, inv_u11, qsel);
-    L2 = Ln;
+    L2 = load_lin(lin, t + max(j - 5, 0), ld, b);
   }
   // j in {0, 1, 2} steps left: L0 = step t+j, L1 = t+j-1, L2 = t+j-2
   if (j == 2) {
@@ -1230,6 +1229,102 @@ __device__ __forceinline__ void mpc_sweep(const WV<WPB>& w, double dt, const dou
     mpc_sweep_sw<WPB, 1>(w, dt, lin, ld, b, n_lin, Lf, QT, t, H, K);
   else
     mpc_sweep_sw<WPB, 0>(w, dt, lin, ld, b, n_lin, Lf, QT, t, H, K);
+}
+
+// Several consecutive receding-horizon solves in one pass: the windows of steps t, t+1, .. overlap in all but a few
+// rows, the first-move gains do not depend on the state, and a single sweep is a dependent chain that leaves the FP64
+// pipe idle two thirds of the time (ncu: 36 % of the issue slots wait for loads, 29 % for the previous DFMA).  Row k
+// of the window of step t (absolute time t + k) is step k - c of the sweep that starts at t + c: each row is loaded
+// once and advances ACRO_MPC_NS independent chains.  Same expressions per chain as mpc_sweep_sw.  H >= NS + 1.
+//
+// The rows come through a ring of ACRO_MPC_RING rows per warp in shared memory, filled with cp.async (every thread
+// copies the ten values of its own problem, so no synchronisation between lanes) and awaited with
+// cp.async.wait_group, which counts GROUPS: the wait for row k leaves the copies of the rows after it in flight.  A
+// register prefetch cannot do that here: ptxas put the loads of all three rotating register buffers on one scoreboard
+// and the first use after the loop's back edge waited for every load in flight, the youngest included (ncu: 23 % of
+// all stall samples on that one DFMA; profiles/r2_mpc_pp_ncu_summary.txt).
+#define ACRO_MPC_RING 6
+#ifndef ACRO_MPC_NS
+#define ACRO_MPC_NS 3  // solves per pass (2: 7.56 ms, 3: 7.14 ms, 4: 6.98 ms with spills, at B = 16 384, H = 75)
+#endif
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// ring: this thread's column of its warp's ring, element (slot, c) at ring[(slot * 10 + c) * 32].
+// NS solves per pass (steps t .. t+NS-1; K[c] = first-move gain of step t + c): row k is step k - c of sweep c.
+template <bool WPB, int SW, int NS>
+__device__ __forceinline__ void mpc_sweepn_sw(const WV<WPB>& w, double dt, const double* __restrict__ lin, int64_t ld,
+                                              int64_t b, int n_lin, const LinD& Lf, const double QT[10], int t, int H,
+                                              double* ring, double (&K)[NS][8]) {
+  double P[NS][10], iu, qs;
+#pragma unroll
+  for (int c = 0; c < NS; ++c)
+#pragma unroll
+    for (int e = 0; e < 10; ++e) P[c][e] = QT[e];
+  const QhQ<WV<WPB>> Qh{w};
+  const Lu2Col col = lu2_col(w.R(0, 0), w.R(0, 1));
+  const double R01 = w.R(0, 1), R11 = w.R(1, 1);
+  auto step = [&](const LinD& L, int k) {
+    if (k >= NS && k <= H - 2) {  // an inner step of every sweep: one basic block, the chains interleave
+#pragma unroll
+      for (int c = 0; c < NS; ++c) riccati_chain_step<SW, false>(P[c], L, dt, Qh, col, R01, R11, K[c], iu, qs);
+    } else {  // the NS-1 rows at either end of the pass: some sweeps only; the last step of a sweep gives its complete gain
+#pragma unroll
+      for (int c = 0; c < NS; ++c) {
+        if (k == c)
+          riccati_chain_step<SW, true>(P[c], L, dt, Qh, col, R01, R11, K[c], iu, qs);
+        else if (k > c && k <= H - 2 + c)
+          riccati_chain_step<SW, false>(P[c], L, dt, Qh, col, R01, R11, K[c], iu, qs);
+      }
+    }
+  };
+  auto fetch = [&](int k, int slot) {  // row k -> ring slot (an empty group below row 0 keeps the group count uniform)
+    if (k >= 0) {
+#pragma unroll
+      for (int c = 0; c < 10; ++c) cp_async8(ring + (slot * 10 + c) * 32, lin + soa(t + k, 10, c, ld, b));
+    }
+    cp_async_commit();
+  };
+  const int ktop = H - 2 + NS - 1;               // top row of the last sweep
+  const int kl = min(ktop, n_lin - 1 - t);       // highest row with a stored linearisation (>= NS - 1)
+#pragma unroll
+  for (int i = 0; i < ACRO_MPC_RING; ++i) fetch(kl - i, i);
+  // padded tail of the window: linearisation about (x_f, u_f)
+  for (int k = ktop; k > kl; --k) step(Lf, k);
+  int slot = 0;
+  for (int k = kl; k >= 0; --k) {
+    cp_async_wait<ACRO_MPC_RING - 1>();
+    LinD L;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      L.a[0][j] = ring[(slot * 10 + j) * 32];
+      L.a[1][j] = ring[(slot * 10 + 4 + j) * 32];
+    }
+    L.b[0] = ring[(slot * 10 + 8) * 32];
+    L.b[1] = ring[(slot * 10 + 9) * 32];
+    L.b0[0] = L.b0[1] = 0.0;
+    step(L, k);
+    fetch(k - ACRO_MPC_RING, slot);  // after the step: the row has been consumed
+    slot = (slot + 1 == ACRO_MPC_RING) ? 0 : slot + 1;
+  }
+  cp_async_wait<0>();
+}
+template <bool WPB, int NS>
+__device__ __forceinline__ void mpc_sweepn(const WV<WPB>& w, double dt, const double* __restrict__ lin, int64_t ld,
+                                           int64_t b, int n_lin, const LinD& Lf, const double QT[10], int t, int H,
+                                           double* ring, double (&K)[NS][8]) {
+  if (WPB)
+    mpc_sweepn_sw<WPB, 2, NS>(w, dt, lin, ld, b, n_lin, Lf, QT, t, H, ring, K);
+  else if (fabs(w.R(0, 1)) > fabs(w.R(0, 0)))
+    mpc_sweepn_sw<WPB, 1, NS>(w, dt, lin, ld, b, n_lin, Lf, QT, t, H, ring, K);
+  else
+    mpc_sweepn_sw<WPB, 0, NS>(w, dt, lin, ld, b, n_lin, Lf, QT, t, H, ring, K);
 }
 
 // shared reference: one thread per time step computes K0[t]
@@ -1306,9 +1401,8 @@ __global__ void k_mpc_track_pp(const __grid_constant__ MpcArgs a) {
     x[c] = a.x0[c * B + b];
     a.Xr[soa(0, 4, c, a.T, b)] = x[c];
   }
-  for (int t = 0; t < a.T - 1; ++t) {
-    double K[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    mpc_sweep(w, a.m.dt, a.lin, a.N - 1, b, a.N - 1, Lf, QT, t, a.H, K);
+  // closed-loop step of the plant with the first-move gain of the solve at step t (tt:46-56)
+  auto plant = [&](int t, const double K[8]) {
     double u[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -1329,6 +1423,26 @@ __global__ void k_mpc_track_pp(const __grid_constant__ MpcArgs a) {
       x[c] = xn[c];
       a.Xr[soa(t + 1, 4, c, a.T, b)] = x[c];
     }
+  };
+  extern __shared__ double mpc_ring[];  // ACRO_MPC_RING rows of 10 x 32 doubles per warp
+  double* const ring = mpc_ring + (threadIdx.x >> 5) * (ACRO_MPC_RING * 320) + (threadIdx.x & 31);
+  int t = 0;
+  if (a.H >= ACRO_MPC_NS + 1) {  // ACRO_MPC_NS solves per pass over their common window rows
+    for (; t + ACRO_MPC_NS - 1 < a.T - 1; t += ACRO_MPC_NS) {
+      double Kn[ACRO_MPC_NS][8];
+#pragma unroll
+      for (int c = 0; c < ACRO_MPC_NS; ++c)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) Kn[c][e] = 0.0;
+      mpc_sweepn<WPB, ACRO_MPC_NS>(w, a.m.dt, a.lin, a.N - 1, b, a.N - 1, Lf, QT, t, a.H, ring, Kn);
+#pragma unroll
+      for (int c = 0; c < ACRO_MPC_NS; ++c) plant(t + c, Kn[c]);
+    }
+  }
+  for (; t < a.T - 1; ++t) {
+    double K[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    mpc_sweep(w, a.m.dt, a.lin, a.N - 1, b, a.N - 1, Lf, QT, t, a.H, K);
+    plant(t, K);
   }
 }
 
@@ -2082,10 +2196,16 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
     k_lin_compact<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
     ACRO_LAUNCH_CHECK("acro_mpc_track/linearize");
     const Cfg c = cfg_for(B);
+    const size_t ring_bytes = size_t(c.block / 32) * ACRO_MPC_RING * 320 * sizeof(double);
+    {
+      cudaError_t e0 = wpb ? cudaFuncSetAttribute(k_mpc_track_pp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)
+                           : cudaFuncSetAttribute(k_mpc_track_pp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
+      ACRO_REQUIRE(e0 == cudaSuccess, "acro_mpc_track: cudaFuncSetAttribute failed");
+    }
     if (wpb)
-      k_mpc_track_pp<true><<<c.grid, c.block, 0, s>>>(a);
+      k_mpc_track_pp<true><<<c.grid, c.block, ring_bytes, s>>>(a);
     else
-      k_mpc_track_pp<false><<<c.grid, c.block, 0, s>>>(a);
+      k_mpc_track_pp<false><<<c.grid, c.block, ring_bytes, s>>>(a);
     ACRO_LAUNCH_CHECK("acro_mpc_track/track");
     if (n_solves) *n_solves = int64_t(T - 1) * B;
   }

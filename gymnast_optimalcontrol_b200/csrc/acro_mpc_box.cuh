@@ -291,20 +291,15 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         };
         BwRec r0 = load_bw(n - 1), r1 = load_bw(n - 2), r2 = load_bw(n - 3);
         for (int j = n - 1; j >= 0; j -= 3) {
-          {
-            const BwRec nx = load_bw(j - 3);
-            bw_step(r0, j);
-            r0 = nx;
-          }
+          bw_step(r0, j);  // a record is refilled right after the step that consumed it
+          r0 = load_bw(j - 3);
           if (j >= 1) {
-            const BwRec nx = load_bw(j - 4);
             bw_step(r1, j - 1);
-            r1 = nx;
+            r1 = load_bw(j - 4);
           }
           if (j >= 2) {
-            const BwRec nx = load_bw(j - 5);
             bw_step(r2, j - 2);
-            r2 = nx;
+            r2 = load_bw(j - 5);
           }
         }
       }
@@ -363,9 +358,8 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         };
         auto v_at = [&](int j) { return vcur[slot(min(j, n - 1))]; };
         double v0 = v_at(0), v1 = v_at(1), v2 = v_at(2), v3 = v_at(3), v4 = v_at(4), v5 = v_at(5);
-        TabRec qa = load_tab(0), qb;
+        TabRec qa = load_tab(0), qb = load_tab(1);
         for (int j = 0; j < n; j += 2) {
-          qb = load_tab(j + 1);
           const double va = v0, vb = v1;
           v0 = v2;
           v1 = v3;
@@ -374,9 +368,10 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
           v4 = v_at(j + 6);
           v5 = v_at(j + 7);
           tab_step(qa, va, j);
+          qa = load_tab(j + 2);
           if (j + 1 < n) {
-            qa = load_tab(j + 2);
             tab_step(qb, vb, j + 1);
+            qb = load_tab(j + 3);
           }
         }
       } else {
@@ -422,20 +417,15 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         };
         FwRec r0 = load_fw(0), r1 = load_fw(1), r2 = load_fw(2);
         for (int j = 0; j < n; j += 3) {
-          {
-            const FwRec nx = load_fw(j + 3);
-            fw_step(r0, j);
-            r0 = nx;
-          }
+          fw_step(r0, j);  // a record is refilled right after the step that consumed it
+          r0 = load_fw(j + 3);
           if (j + 1 < n) {
-            const FwRec nx = load_fw(j + 4);
             fw_step(r1, j + 1);
-            r1 = nx;
+            r1 = load_fw(j + 4);
           }
           if (j + 2 < n) {
-            const FwRec nx = load_fw(j + 5);
             fw_step(r2, j + 2);
-            r2 = nx;
+            r2 = load_fw(j + 5);
           }
         }
         if (keep_states) {
@@ -525,20 +515,15 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         };
         CoRec r0 = load_co(n - 1), r1 = load_co(n - 2), r2 = load_co(n - 3);
         for (int j = n - 1; j >= 0; j -= 3) {
-          {
-            const CoRec nx = load_co(j - 3);
-            co_step(r0, j);
-            r0 = nx;
-          }
+          co_step(r0, j);  // a record is refilled right after the step that consumed it
+          r0 = load_co(j - 3);
           if (j >= 1) {
-            const CoRec nx = load_co(j - 4);
             co_step(r1, j - 1);
-            r1 = nx;
+            r1 = load_co(j - 4);
           }
           if (j >= 2) {
-            const CoRec nx = load_co(j - 5);
             co_step(r2, j - 2);
-            r2 = nx;
+            r2 = load_co(j - 5);
           }
         }
       }

@@ -565,6 +565,35 @@ def test_mpc_tracking_shared_and_per_problem(bt):
             assert abs(abs(aos(Ur)[0, 0, 1] - d["u"][0, 1]) - 0.80644713) < 1e-6
 
 
+@pytest.mark.parametrize("H", [2, 3, 4, 5, 8, 31])
+def test_mpc_per_problem_passes_and_remainders(bt, H):
+    """k_mpc_track_pp runs several consecutive solves per pass over their common window rows (cp.async ring) and the
+    remaining solves one by one: every horizon from the shortest, every T modulo the pass width, windows that run past
+    the end of the reference (padding about x_f), per-problem references that really differ - against the oracle."""
+    d, g, Ad, Bd = _mpc_setup()
+    rng = np.random.default_rng(40 + H)
+    n = 37  # not a multiple of the warp size
+    x0 = d["x"][0] + rng.uniform(-0.1, 0.1, (n, 4))
+    w = bt.mpc_weights()
+    QT = dev(g["P_inf"])
+    for N_, T in ((60, 60), (61, 59), (62, 58), (40, 40)):
+        t0 = 461 if N_ == 40 else 100     # the last case ends at the end of the shipped trajectory
+        xs = np.repeat(d["x"][None, t0:t0 + N_], n, 0) + rng.uniform(-1e-3, 1e-3, (n, N_, 4))
+        us = np.repeat(d["u"][None, t0:t0 + N_ - 1], n, 0) + rng.uniform(-1e-3, 1e-3, (n, N_ - 1, 2))
+        x0s = xs[:, 0] + rng.uniform(-0.002, 0.002, (n, 4))
+        Xp, Up, _, nsp = bt.mpc_track(soa(x0s), bt.Ref(soa(xs), soa(us)), QT, T=T, T_pred=H, w=w)
+        assert nsp == (T - 1) * n
+        Xp, Up = aos(Xp), aos(Up)
+        for b in (0, 1, n - 1):
+            xo, uo = O.solve_mpc_tracking(x0s[b], xs[b], us[b], T, T_pred=H)
+            # a horizon of a few steps does not stabilise the acrobot: compare while the loop has not run away
+            big = np.where(~(np.abs(xo[:T]).max(axis=1) < 20.0))[0]
+            m = T if len(big) == 0 else int(big[0])
+            assert m >= 8
+            tol = TOL if m == T else 1e-7
+            assert rel_err(Xp[b][:m], xo[:m]) < tol and rel_err(Up[b][:m - 1], uo[:m - 1]) < tol
+
+
 def test_mpc_tracking_with_input_box(bt):
     """The input box the reference keeps behind `test_constraints` (tt:87-91, 112-114): every
     receding-horizon QP solved exactly on the GPU (active set on Riccati sweeps) against the dense active-set oracle
