@@ -662,14 +662,17 @@ def run_native(a):
         if mpc:
             ach = mpc.pop("achieved_tflops_per_gpu")
             exe = mpc["value"] / world * (180.0 * 74 + 16 + 856) / 1e12
-            mpc["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fp64_meas, "unit": "TFLOP/s", "frac": ach / fp64_meas,
-                               "executed": {"achieved": exe, "frac": exe / fp64_meas,
-                                            "flops_per_solve": 180.0 * 74 + 16 + 856},
-                               "note": "`frac` uses SURVEY 8(d)'s convention, 550 (H-1) + 16 + 856 flops per solve (dense 4x4 "
-                                       "algebra, no credit for structure): A_d has two trivial rows and the inner steps of a sweep "
-                                       "need no gain, so a step executes 108 FP64 instructions = 180 flops, and `frac` can exceed "
-                                       "1; `executed` counts those.  Two consecutive solves share one pass over their common "
-                                       "window rows (80 B of compact linearisation per row, read once for both)"}
+            mpc["roofline"] = {"bound": "fp64", "achieved": exe, "peak": fp64_meas, "unit": "TFLOP/s", "frac": exe / fp64_meas,
+                               "flops_per_solve": 180.0 * 74 + 16 + 856,
+                               "survey_convention": {"achieved": ach, "frac": ach / fp64_meas,
+                                                     "flops_per_solve": mpc["flops_per_solve"]},
+                               "note": "`achieved` counts EXECUTED flops: a sweep step is 108 FP64 instructions = 180 flops "
+                                       "(A_d has two trivial rows, the inner steps of a sweep need no gain).  SURVEY 8(d)'s "
+                                       "convention (dense 4x4 algebra without credit for structure: 550 (H-1) + 16 + 856 flops "
+                                       "per solve) is under `survey_convention`; by it the kernel runs above the DFMA peak, "
+                                       "which only says that the dense count is not what has to be computed.  Three "
+                                       "consecutive solves share one pass over their common window rows (80 B of compact "
+                                       "linearisation per row through a cp.async ring, read once for the three)"}
         if back:
             back["roofline_frac"] = back.pop("achieved_tflops_per_gpu") / fp64_meas
         flops_iter = (FLOPS_FIXED + FLOPS_PER_TRY * h["ntry"]) * (N_STEPS - 1)

@@ -154,11 +154,11 @@ def main():
         t, nl = timeit(lambda: res.__setitem__("s", bt.mpc_track(x0, refp, QT, T=N, T_pred=H, w=w)), max(1, reps // 2))
         ns = res["s"][3]
         line("C4 MPC tracking, per-problem references, B=16384, H=%d" % H, "mpc_solves_per_sec", ns / t,
-             "MPC solves/s (one (H-1)-step Riccati sweep + plant step each)", 550.0 * (H - 1) + 16 + 856, t, nl, peak,
+             "MPC solves/s (one (H-1)-step Riccati sweep + plant step each)", 180.0 * (H - 1) + 16 + 856, t, nl, peak,
              {"riccati_sweeps_executed": ns,
-              "executed_frac": ns / t * (180.0 * (H - 1) + 16 + 856) / 1e12 / peak,
-              "executed_flops": "a sweep step executes 108 FP64 instructions = 180 flops (A_d has two trivial rows, "
-                                "inner steps need no gain)"})
+              "survey_convention_frac": ns / t * (550.0 * (H - 1) + 16 + 856) / 1e12 / peak,
+              "flops": "executed: a sweep step is 108 FP64 instructions = 180 flops (A_d has two trivial rows, inner steps "
+                       "need no gain); SURVEY 8(d)'s dense count is 550 per step (survey_convention_frac)"})
 
     # ---- config 5: 5000 base iterates x 200 step sizes = 1M closed-loop rollouts
     Pn = 5000 if not a.quick else 1000
