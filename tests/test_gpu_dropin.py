@@ -358,3 +358,33 @@ def test_terminal_weight_is_cached_per_weights(mods):
 def _lin_f(dyn):
     A, B = dyn.Calculate_A_B_matrixes(np.array([np.pi, 0, 0, 0]), np.array([0.0, 0.0]))
     return np.eye(4) + 2e-2 * A, 2e-2 * B
+
+
+def test_constrained_mpc_against_the_shipped_figure(mods):
+    """The only artefact the reference ships for its constrained MPC is figures/mpc/tracking_constrained.png
+    (`test_constraints = True`, tt:87-91, 112-114; IPOPT is not available here, so this is a FIGURE-LEVEL pin, numbers
+    read off the PNG by eye): with |u| <= 18 the elbow torque sits flat on -18 from t ~ 3.45 s to ~ 3.75 s while the
+    reference dips to -23.9, peaks at ~ 13.7 at t ~ 2.82 s (reference 12.5), comes back only to ~ -9 at t ~ 3.88 s
+    (reference -6.5); theta2 overshoots to ~ 0.58 at t ~ 3.4 s (reference 0.32) and undershoots to ~ -3.27 at ~ 4.22 s
+    (reference -3.20); the upright is reached.  The curves start at ~ 0.05 rad: x0 = x_ref[0] + 0.05 (main.py:127)."""
+    dyn, tg, tt = mods
+    d = golden("acrobot_optimal_trajectory")
+    t = d["t"]
+    xr, ur = tt.solve_mpc_tracking(d["x"][0] + 0.05, d["x"], d["u"], 501, tau_max=18.0)
+    u2 = ur[:, 1]
+    assert np.abs(ur).max() <= 18.0 * (1 + 1e-12) and np.abs(ur[:, 0]).max() == 0.0
+    sat = np.where(u2 <= -18.0 * (1 - 1e-12))[0]
+    assert len(sat) == sat.max() - sat.min() + 1                      # one flat segment
+    assert abs(t[sat.min()] - 3.45) <= 0.05 and abs(t[sat.max()] - 3.75) <= 0.05
+    assert d["u"][sat, 1].min() < -23.8                                 # where the reference asks for -23.9
+    i = int(np.argmax(u2))
+    assert abs(t[i] - 2.82) <= 0.04 and abs(u2[i] - 13.7) <= 0.6 and abs(d["u"][:, 1].max() - 12.5) < 0.05
+    w = np.where((t[:-1] > 3.7) & (t[:-1] < 4.0))[0]
+    j = w[np.argmax(u2[w])]
+    assert abs(t[j] - 3.88) <= 0.04 and abs(u2[j] + 9.0) <= 0.5
+    w2 = np.where((t > 3.2) & (t < 3.6))[0]
+    k = w2[np.argmax(xr[w2, 1])]
+    assert abs(t[k] - 3.40) <= 0.04 and abs(xr[k, 1] - 0.58) <= 0.05
+    m = int(np.argmin(xr[:, 1]))
+    assert abs(t[m] - 4.22) <= 0.06 and abs(xr[m, 1] + 3.27) <= 0.06
+    assert np.abs(xr[-1] - np.array([np.pi, 0, 0, 0])).max() < 1e-2
