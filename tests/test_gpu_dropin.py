@@ -388,3 +388,14 @@ def test_constrained_mpc_against_the_shipped_figure(mods):
     m = int(np.argmin(xr[:, 1]))
     assert abs(t[m] - 4.22) <= 0.06 and abs(xr[m, 1] + 3.27) <= 0.06
     assert np.abs(xr[-1] - np.array([np.pi, 0, 0, 0])).max() < 1e-2
+
+
+@pytest.mark.parametrize("dx", [0.05, 0.1, 0.15, 0.2])
+def test_mpc_dropin_against_the_shipped_figures(mods, dx):
+    """main.py's task_4 on the drop-in for the disturbances the reference ships figures for: every peak of the error
+    curves of figures/mpc/tracking_dx_*_err.png (tests/mpc_figures.py); dx = 0.05 is the run with the input box."""
+    import mpc_figures
+    dyn, tg, tt = mods
+    d = golden("acrobot_optimal_trajectory")
+    xr, ur = tt.solve_mpc_tracking(d["x"][0] + dx, d["x"], d["u"], len(d["t"]), tau_max=mpc_figures.FIGURES[dx][0])
+    mpc_figures.check(dx, d["t"], d["x"], d["u"], xr, ur)

@@ -324,3 +324,18 @@ def test_c5_base_iterates_from_newton_iterations(fa_ref):
     for i, (c, dJ, xT) in zip(pick, res):
         assert rel_err(c, g["costs"][i]) < 1e-11 and abs(dJ - g["delta_J"][i]) < 1e-10 * abs(dJ)
         assert rel_err(xT, g["x_T"][i]) < 1e-11
+
+
+@pytest.mark.parametrize("dx", [0.05, 0.1, 0.15, 0.2])
+def test_mpc_oracle_against_the_shipped_figures(dx):
+    """The reference's MPC is CasADi + IPOPT (absent here); what it ships are figures.  The Riccati restatement
+    (and, for dx = 0.05, the active-set solve of the box-constrained QP) reproduces every peak of their error curves
+    (tests/mpc_figures.py: numbers read off figures/mpc/tracking_dx_*_err.png)."""
+    import mpc_figures
+    d = golden("acrobot_optimal_trajectory")
+    tau = mpc_figures.FIGURES[dx][0]
+    if tau is None:
+        xr, ur = O.solve_mpc_tracking(d["x"][0] + dx, d["x"], d["u"], 501, T_pred=75)
+    else:
+        xr, ur, _ = O.solve_mpc_tracking_box(d["x"][0] + dx, d["x"], d["u"], 501, T_pred=75, tau_max=tau)
+    mpc_figures.check(dx, d["t"], d["x"], d["u"], xr, ur)
