@@ -160,6 +160,19 @@ def main():
               "flops": "executed: a sweep step is 108 FP64 instructions = 180 flops (A_d has two trivial rows, inner steps "
                        "need no gain); SURVEY 8(d)'s dense count is 550 per step (survey_convention_frac)"})
 
+    # per-problem physical parameters (+-3 %) in the MPC tracker: own linearisation, own terminal weight, own plant
+    rows = np.array([[getattr(bt.DEFAULT_PARAMS, f) for f in bt.PHYS_FIELDS]] * B)
+    rows[:, :8] *= np.random.default_rng(8).uniform(0.97, 1.03, (B, 8))
+    pbm = bt.phys_params(rows)
+    A_fb, B_fb = bt.linearize(xf.repeat(1, B), bt.upload(np.zeros((2, B))), discrete=True, params_b=pbm)
+    Pb, _ = bt.p_inf(A_fb, B_fb, w)
+    res = {}
+    t, nl = timeit(lambda: res.__setitem__("s", bt.mpc_track(x0, refp, Pb, T=N, T_pred=75, w=w, params_b=pbm)), max(1, reps // 2))
+    ns = res["s"][3]
+    line("C4 MPC tracking with per-problem physical parameters (+-3 %), per-problem references, B=16384, H=75",
+         "mpc_solves_per_sec", ns / t, "MPC solves/s (one (H-1)-step Riccati sweep + plant step each)",
+         180.0 * 74 + 16 + 856, t, nl, peak, {"riccati_sweeps_executed": ns})
+
     # ---- config 5: 5000 base iterates x 200 step sizes = 1M closed-loop rollouts
     Pn = 5000 if not a.quick else 1000
     ref = bt.make_ref(fa["x"], u_ref)

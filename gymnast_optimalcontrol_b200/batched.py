@@ -525,19 +525,27 @@ def mpc_solve(x0, A_w, B_w, QT, w, T_pred, trajectories=True):
 
 
 def mpc_track(x0, ref, QT_inf, T=None, T_pred=75, w=None, x_f=(np.pi, 0.0, 0.0, 0.0), u_f=(0.0, 0.0),
-              params=DEFAULT_PARAMS):
-    """solve_mpc_tracking for a batch.  QT_inf (4,4) shared or (4,4,B).  -> Xr Traj, Ur Traj, K0 or None, n_solves"""
+              params=DEFAULT_PARAMS, params_b=None):
+    """solve_mpc_tracking for a batch.  QT_inf (4,4) shared or (4,4,B).  -> Xr Traj, Ur Traj, K0 or None, n_solves
+    params_b (11,B): every problem its own physical parameters (phys_params; needs a per-problem reference)."""
     w = mpc_weights() if w is None else w
     N, Bn = ref.N, x0.shape[1]
     T = N if T is None else T
     qt_pp = QT_inf.dim() == 3
     pp = ref.per_problem or w.per_problem or qt_pp
     Xr, Ur = Traj.empty(T, 4, Bn), Traj.empty(T - 1, 2, Bn)
-    K0 = None if pp else _empty(T - 1, 8)
-    lin = Traj.empty(N - 1, 10, Bn) if pp else _empty(N - 1, 10)
     xf = (C.c_double * 4)(*[float(v) for v in x_f])
     uf = (C.c_double * 2)(*[float(v) for v in u_f])
     ns = C.c_int64(0)
+    if params_b is not None:
+        if not ref.per_problem:
+            raise ValueError("mpc_track: per-problem physical parameters need a per-problem reference (B, N, 4)")
+        lin = Traj.empty(N - 1, 10, Bn)
+        call("acro_mpc_track_pp", C.byref(params), _p(params_b), w.ref(), Bn, N, int(T), int(T_pred), ref.ref(), xf, uf,
+             _p(QT_inf), int(qt_pp), _p(x0), _p(lin), _p(Xr), _p(Ur), C.byref(ns), _stream())
+        return Xr, Ur, None, int(ns.value)
+    K0 = None if pp else _empty(T - 1, 8)
+    lin = Traj.empty(N - 1, 10, Bn) if pp else _empty(N - 1, 10)
     call("acro_mpc_track", C.byref(params), w.ref(), Bn, N, int(T), int(T_pred), ref.ref(), xf, uf, _p(QT_inf), int(qt_pp),
          _p(x0), _p(K0), _p(lin), _p(Xr), _p(Ur), C.byref(ns), _stream())
     return Xr, Ur, K0, int(ns.value)

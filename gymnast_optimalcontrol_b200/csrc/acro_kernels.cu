@@ -1129,7 +1129,7 @@ __global__ void k_mpc_solve(const __grid_constant__ KWeights kw, int64_t B, int 
 // compact discrete linearisation about a trajectory: lin[t][10][ld] = a[0][0..3], a[1][0..3], b[0], b[1]
 template <bool RPB>
 __global__ void k_lin_compact(const __grid_constant__ Model m, int64_t B, int N, const double* rx, const double* ru,
-                              double* __restrict__ lin) {
+                              double* __restrict__ lin, const double* __restrict__ pb = nullptr) {
   const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   // RPB: one thread per (t, b) with b fastest; shared: one thread per t
   const int64_t nb = RPB ? B : 1;
@@ -1140,7 +1140,8 @@ __global__ void k_lin_compact(const __grid_constant__ Model m, int64_t B, int N,
   double x[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) x[c] = ref.X(t, c);
-  const LinD L = linearize_d(m, x, ref.U(t, 0), ref.U(t, 1));
+  const LinD L = (RPB && pb) ? linearize_d(model_per_problem(m, pb, B, b), x, ref.U(t, 0), ref.U(t, 1))
+                             : linearize_d(m, x, ref.U(t, 0), ref.U(t, 1));
   if (RPB) {
     store_lin(lin, t, N - 1, b, L);
   } else {
@@ -1167,6 +1168,7 @@ struct MpcArgs {
   const double* lin;  // compact linearisation: shared [N-1][10] or [N-1][10][B]
   double* K0;         // shared mode: [(T-1)][8]
   double *Xr, *Ur;
+  const double* pb;   // physical parameters per problem [11][B] (k_mpc_track_pp<.., true>) or null
 };
 
 // One receding-horizon solve: (H-1)-step Riccati sweep over the window starting at time t
@@ -1382,14 +1384,19 @@ __global__ void k_mpc_track_shared(const __grid_constant__ MpcArgs a) {
   }
 }
 
-// per-problem reference / weights: every problem runs its own T-1 sweeps
-template <bool WPB>
+// per-problem reference / weights: every problem runs its own T-1 sweeps.  PPB: every problem its own physical
+// parameters (model_per_problem): the plant step and the padding linearisation about (x_f, u_f) use them, as did
+// k_lin_compact for the window rows.
+template <bool WPB, bool PPB = false>
 __global__ void k_mpc_track_pp(const __grid_constant__ MpcArgs a) {
   const int64_t B = a.B, b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
   const WV<WPB> w(a.kw, B, b);
   const RefV<true> ref{a.rx, a.ru, a.N, b};
-  const LinD Lf = linearize_d(a.m, a.xf, a.uf[0], a.uf[1]);
+  Model m_loc_;
+  if (PPB) m_loc_ = model_per_problem(a.m, a.pb, B, b);
+  const Model& mm = PPB ? m_loc_ : a.m;
+  const LinD Lf = linearize_d(mm, a.xf, a.uf[0], a.uf[1]);
   double QT[10];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -1417,7 +1424,7 @@ __global__ void k_mpc_track_pp(const __grid_constant__ MpcArgs a) {
       a.Ur[soa(t, 2, i, a.T - 1, b)] = u[i];
     }
     double xn[4];
-    rk4_step(a.m, x, u[0], u[1], xn);
+    rk4_step(mm, x, u[0], u[1], xn);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       x[c] = xn[c];
@@ -2150,14 +2157,16 @@ int acro_mpc_solve(const AcroWeights* w, int64_t B, int T_pred, const double* x0
   return ACRO_OK;
 }
 
-int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
-                   const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
-                   int qt_per_problem, const double* x0, double* K0, double* lin_ws, double* Xr, double* Ur,
-                   int64_t* n_solves, void* stream) {
+}  // extern "C"
+static int mpc_track_impl(const AcroParams* p, const double* params_b, const AcroWeights* w, int64_t B, int N, int T,
+                          int T_pred, const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                          int qt_per_problem, const double* x0, double* K0, double* lin_ws, double* Xr, double* Ur,
+                          int64_t* n_solves, void* stream) {
   ACRO_REQUIRE(p && w && ref && ref->x && ref->u && x_f && u_f && QT_inf && x0 && lin_ws && Xr && Ur && B > 0 &&
                    N >= 2 && T >= 2 && T <= N && T_pred >= 2,
                "acro_mpc_track: bad argument");
   ACRO_REQUIRE(!p->actuated_tau1, "acro_mpc_track: fully-actuated plant not supported here");
+  ACRO_REQUIRE(!params_b || ref->per_problem, "acro_mpc_track_pp: per-problem parameters need a per-problem reference layout");
   const bool wpb = per_problem_weights(*w);
   const bool pp = ref->per_problem || wpb || qt_per_problem;
   ACRO_REQUIRE(pp || K0, "acro_mpc_track: K0 workspace required for a shared reference");
@@ -2180,6 +2189,7 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
   a.K0 = K0;
   a.Xr = Xr;
   a.Ur = Ur;
+  a.pb = params_b;
   cudaStream_t s = (cudaStream_t)stream;
   if (!pp) {
     const int nt = N - 1;
@@ -2193,23 +2203,43 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
     if (n_solves) *n_solves = T - 1;
   } else {
     const int64_t n = int64_t(N - 1) * B;
-    k_lin_compact<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
+    k_lin_compact<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws, params_b);
     ACRO_LAUNCH_CHECK("acro_mpc_track/linearize");
     const Cfg c = cfg_for(B);
     const size_t ring_bytes = size_t(c.block / 32) * ACRO_MPC_RING * 320 * sizeof(double);
-    {
-      cudaError_t e0 = wpb ? cudaFuncSetAttribute(k_mpc_track_pp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)
-                           : cudaFuncSetAttribute(k_mpc_track_pp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
-      ACRO_REQUIRE(e0 == cudaSuccess, "acro_mpc_track: cudaFuncSetAttribute failed");
+#define LAUNCH_MPC_PP(WPB_, PPB_)                                                                                    \
+  do {                                                                                                               \
+    cudaError_t e0 = cudaFuncSetAttribute(k_mpc_track_pp<WPB_, PPB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                          (int)ring_bytes);                                                          \
+    ACRO_REQUIRE(e0 == cudaSuccess, "acro_mpc_track: cudaFuncSetAttribute failed");                                  \
+    k_mpc_track_pp<WPB_, PPB_><<<c.grid, c.block, ring_bytes, s>>>(a);                                               \
+  } while (0)
+    if (params_b) {
+      if (wpb) LAUNCH_MPC_PP(true, true); else LAUNCH_MPC_PP(false, true);
+    } else {
+      if (wpb) LAUNCH_MPC_PP(true, false); else LAUNCH_MPC_PP(false, false);
     }
-    if (wpb)
-      k_mpc_track_pp<true><<<c.grid, c.block, ring_bytes, s>>>(a);
-    else
-      k_mpc_track_pp<false><<<c.grid, c.block, ring_bytes, s>>>(a);
+#undef LAUNCH_MPC_PP
     ACRO_LAUNCH_CHECK("acro_mpc_track/track");
     if (n_solves) *n_solves = int64_t(T - 1) * B;
   }
   return ACRO_OK;
+}
+
+extern "C" {
+int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
+                   const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                   int qt_per_problem, const double* x0, double* K0, double* lin_ws, double* Xr, double* Ur,
+                   int64_t* n_solves, void* stream) {
+  return mpc_track_impl(p, nullptr, w, B, N, T, T_pred, ref, x_f, u_f, QT_inf, qt_per_problem, x0, K0, lin_ws, Xr, Ur,
+                        n_solves, stream);
+}
+int acro_mpc_track_pp(const AcroParams* p, const double* params_b, const AcroWeights* w, int64_t B, int N, int T,
+                      int T_pred, const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                      int qt_per_problem, const double* x0, double* lin_ws, double* Xr, double* Ur, int64_t* n_solves,
+                      void* stream) {
+  return mpc_track_impl(p, params_b, w, B, N, T, T_pred, ref, x_f, u_f, QT_inf, qt_per_problem, x0, nullptr, lin_ws, Xr,
+                        Ur, n_solves, stream);
 }
 
 int64_t acro_mpc_box_ws_doubles(int64_t B, int T, int T_pred) {

@@ -130,17 +130,19 @@ def _terminal_weight(p, w):
     return P
 
 
-def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return_info=False, tau_max=None, block=True):
+def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return_info=False, tau_max=None, block=True,
+                       params_b=None):
     """trajectory_tracking.py:8-69.  x0 (4,) or (B,4); reference shared (N,4) or per problem (B,N,4).
 
     tau_max: switches on the input box the reference keeps behind `test_constraints` (tt:87-91, 112-114; 18 there):
     -tau_max <= u + u_ref <= tau_max at every step of every horizon, each QP solved exactly.
     block=False (without return_info): returns a handle at once; `.result()` gives `(x_real, u_real)`.  The uploads of
     this call run on an upload stream and the copies back on a copy stream, so with several calls in flight the
-    transfers of one batch overlap the kernel of another (pinned host inputs must stay untouched until then)."""
+    transfers of one batch overlap the kernel of another (pinned host inputs must stay untouched until then).
+    params_b (B, 11): every problem its own physical parameters (domain randomisation): each linearises the reference
+    with its own model, has its own terminal weight P_inf and steps its own plant (not with tau_max)."""
     w = bt.Weights(Q_mpc if Q is None else Q, R_mpc if R is None else R)
     p = active_params()
-    P = _terminal_weight(p, w)
     piped = (not block) and not return_info
     with _io.upload_scope(piped, x0, x_ref, u_ref) as up:
         x0d, kind = _io.state_in(x0, nx)
@@ -148,6 +150,29 @@ def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return
         up.keep(x0d, ref)
     if piped:
         _io.flush_deferred()  # copy-back of the previous call: queued after this call's uploads, before its kernel
+    if params_b is not None:
+        if tau_max is not None:
+            raise ValueError("solve_mpc_tracking: params_b is not supported together with tau_max")
+        Bn = x0d.shape[1]
+        pb = bt.phys_params(params_b, Bn)
+        if not ref.per_problem:  # every problem linearises the reference with its own model: per-problem layout
+            ref = bt.Ref(bt.Traj.from_batch_major(ref.x.unsqueeze(0).expand(Bn, -1, -1).contiguous()),
+                         bt.Traj.from_batch_major(ref.u.unsqueeze(0).expand(Bn, -1, -1).contiguous()))
+        xf = bt.upload(np.repeat(np.asarray(x_f, dtype=np.float64).reshape(4, 1), Bn, 1))
+        uf = bt.upload(np.repeat(np.asarray(u_f, dtype=np.float64).reshape(2, 1), Bn, 1))
+        A_f, B_f = bt.linearize(xf, uf, True, p, pb)
+        Pb, n = bt.p_inf(A_f, B_f, w)
+        if not piped and int(n.min()) < 0:
+            print("P_inf did not converge!!!")
+        Xr, Ur, _, n_solves = bt.mpc_track(x0d, ref, Pb, T=int(T), T_pred=int(T_pred), w=w, x_f=x_f, u_f=u_f, params=p,
+                                           params_b=pb)
+        if piped:
+            return _MpcPending(_io.out_async([(Xr, ref.N), (Ur, ref.N - 1)], kind, defer=True), None)
+        xr, ur = _pad_time(_io.out(Xr, kind, key="xr"), ref.N), _pad_time(_io.out(Ur, kind, key="ur"), ref.N - 1)
+        if return_info:
+            return xr, ur, dict(n_solves=n_solves, K0=None, P_inf=Pb.cpu().numpy())
+        return xr, ur
+    P = _terminal_weight(p, w)
     if tau_max is not None:
         Xr, Ur, info = bt.mpc_track_box(x0d, ref, P, tau_max=float(tau_max), T=int(T),
                                         T_pred=int(T_pred), w=w, x_f=x_f, u_f=u_f, params=p)

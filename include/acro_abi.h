@@ -296,6 +296,14 @@ int acro_mpc_track(const AcroParams* p, const AcroWeights* w, int64_t B, int N, 
                    const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
                    int qt_per_problem, const double* x0, double* K0, double* lin_ws, double* Xr,
                    double* Ur, int64_t* n_solves, void* stream);
+/* the same with physical parameters per problem (params_b [11][B] as in acro_rk4_step_pp; dynamics.py:15-61): every
+ * problem linearises its reference, pads its window about (x_f, u_f) and steps its plant with its own model.  The
+ * reference must be in the per-problem layout; QT_inf is normally per problem too (acro_linearize_pp at x_f, then
+ * acro_p_inf).  params_b NULL: acro_mpc_track with a per-problem reference. */
+int acro_mpc_track_pp(const AcroParams* p, const double* params_b, const AcroWeights* w, int64_t B, int N, int T,
+                      int T_pred, const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                      int qt_per_problem, const double* x0, double* lin_ws, double* Xr, double* Ur,
+                      int64_t* n_solves, void* stream);
 
 /* ---- measurement helper ------------------------------------------------------------- */
 /* solve_mpc_tracking with the input box of trajectory_tracking.py:87-91, 102-104, 112-114 switched on

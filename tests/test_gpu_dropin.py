@@ -399,3 +399,25 @@ def test_mpc_dropin_against_the_shipped_figures(mods, dx):
     d = golden("acrobot_optimal_trajectory")
     xr, ur = tt.solve_mpc_tracking(d["x"][0] + dx, d["x"], d["u"], len(d["t"]), tau_max=mpc_figures.FIGURES[dx][0])
     mpc_figures.check(dx, d["t"], d["x"], d["u"], xr, ur)
+
+
+def test_mpc_dropin_with_per_problem_parameters(mods):
+    """solve_mpc_tracking(params_b=...): shared reference, every problem its own plant; blocking == non-blocking."""
+    from gymnast_optimalcontrol_b200.batched import PARAM_SETS, PHYS_FIELDS
+    dyn, tg, tt = mods
+    d = golden("acrobot_optimal_trajectory")
+    n = 20
+    rng = np.random.default_rng(5)
+    rows = np.array([[PARAM_SETS[1][f] * (1.0 if (f == "g" or b == 0) else rng.uniform(0.98, 1.02)) for f in PHYS_FIELDS]
+                     for b in range(n)])
+    x0 = d["x"][0] + rng.uniform(-0.05, 0.05, (n, 4))
+    xr, ur = tt.solve_mpc_tracking(x0, d["x"], d["u"], 101, params_b=rows)
+    assert xr.shape == (n, 501, 4) and ur.shape == (n, 500, 2) and np.all(xr[:, 101:] == 0.0)
+    xn, un = tt.solve_mpc_tracking(x0[0], d["x"], d["u"], 101)
+    assert rel_err(xr[0, :101], xn[:101]) < TOL and rel_err(ur[0, :100], un[:100]) < TOL
+    xo, uo = O.solve_mpc_tracking(x0[3], d["x"], d["u"], 101, m=O.Model(dict(zip(PHYS_FIELDS, rows[3]))))
+    assert rel_err(xr[3, :101], xo[:101]) < TOL and rel_err(ur[3, :100], uo[:100]) < TOL
+    gx, gu = tt.solve_mpc_tracking(x0, d["x"], d["u"], 101, params_b=rows, block=False).result()
+    assert np.array_equal(gx, xr) and np.array_equal(gu, ur)
+    with pytest.raises(ValueError):
+        tt.solve_mpc_tracking(x0, d["x"], d["u"], 101, params_b=rows, tau_max=18.0)

@@ -594,6 +594,38 @@ def test_mpc_per_problem_passes_and_remainders(bt, H):
             assert rel_err(Xp[b][:m], xo[:m]) < tol and rel_err(Up[b][:m - 1], uo[:m - 1]) < tol
 
 
+def test_mpc_tracking_per_problem_physical_parameters(bt):
+    """SURVEY 8f rank 1 in the MPC tracker: every problem its own (m, l, lc, I, f) within +-3 %: it linearises the
+    reference, pads the window about x_f, computes its terminal weight and steps its plant with its own model -
+    against the oracle problem by problem; problem 0 carries params_1 and reproduces the shared-parameter run."""
+    from gymnast_optimalcontrol_b200.batched import PARAM_SETS, PHYS_FIELDS
+    d, g, Ad, Bd = _mpc_setup()
+    n, T, H = 35, 61, 40
+    rng = np.random.default_rng(77)
+    sets = [dict(PARAM_SETS[1])] + [{f: PARAM_SETS[1][f] * (1.0 if f == "g" else rng.uniform(0.97, 1.03)) for f in PHYS_FIELDS}
+                                    for _ in range(n - 1)]
+    rows = np.array([[s_[f] for f in PHYS_FIELDS] for s_ in sets])
+    pb = bt.phys_params(rows)
+    w = bt.mpc_weights()
+    xs, us = d["x"][:T], d["u"][:T - 1]
+    x0 = xs[0] + rng.uniform(-0.05, 0.05, (n, 4))
+    refp = bt.Ref(soa(np.repeat(xs[None], n, 0)), soa(np.repeat(us[None], n, 0)))
+    xf = dev(np.repeat(np.array(O.X_F)[:, None], n, 1))
+    uf = dev(np.zeros((2, n)))
+    A_f, B_f = bt.linearize(xf, uf, discrete=True, params_b=pb)
+    P, nit = bt.p_inf(A_f, B_f, w)
+    assert int(nit.min()) > 0
+    Xr, Ur, _, ns = bt.mpc_track(soa(x0), refp, P, T=T, T_pred=H, w=w, params_b=pb)
+    assert ns == (T - 1) * n
+    Xr, Ur = aos(Xr), aos(Ur)
+    for b in (0, 1, 2, 17, n - 1):
+        xo, uo = O.solve_mpc_tracking(x0[b], xs, us, T, T_pred=H, m=O.Model(sets[b]))
+        assert rel_err(Xr[b], xo[:T]) < TOL and rel_err(Ur[b], uo[:T - 1]) < TOL
+    Xn, Un, _, _ = bt.mpc_track(soa(x0[:1]), bt.Ref(soa(xs[None]), soa(us[None])), dev(g["P_inf"]), T=T, T_pred=H, w=w)
+    assert rel_err(Xr[0], aos(Xn)[0]) < 1e-9 and rel_err(Ur[0], aos(Un)[0]) < 1e-9
+    assert np.abs(Xr[1] - Xr[0]).max() > 1e-4   # the parameters matter
+
+
 def test_mpc_tracking_with_input_box(bt):
     """The input box the reference keeps behind `test_constraints` (tt:87-91, 112-114): every
     receding-horizon QP solved exactly on the GPU (active set on Riccati sweeps) against the dense active-set oracle
