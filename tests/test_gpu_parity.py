@@ -594,6 +594,30 @@ def test_mpc_per_problem_passes_and_remainders(bt, H):
             assert rel_err(Xp[b][:m], xo[:m]) < tol and rel_err(Up[b][:m - 1], uo[:m - 1]) < tol
 
 
+@pytest.mark.parametrize("Bn", [20000, 76000])
+def test_mpc_per_problem_block_shapes(bt, Bn):
+    """k_mpc_track_pp with 64- and 128-thread blocks (B >= 18 944 / 75 776): one cp.async ring per warp of the block.
+    A problem's result does not depend on the batch around it: sampled problems are bitwise those of a 5-problem run."""
+    d, g, Ad, Bd = _mpc_setup()
+    T, H = 41, 20
+    rng = np.random.default_rng(91)
+    xs, us = d["x"][100:100 + T], d["u"][100:100 + T - 1]
+    w = bt.mpc_weights()
+    QT = dev(g["P_inf"])
+    x0 = torch.from_numpy(xs[0] + rng.uniform(-0.02, 0.02, (Bn, 4))).cuda()
+    xr = torch.from_numpy(xs).cuda().unsqueeze(0).repeat(Bn, 1, 1)
+    xr += 1e-3 * torch.sin(torch.arange(Bn, device="cuda", dtype=torch.float64))[:, None, None]
+    ur = torch.from_numpy(us).cuda().unsqueeze(0).repeat(Bn, 1, 1)
+    Xr, Ur, _, ns = bt.mpc_track(bt.pack_soa(x0), bt.Ref(bt.pack_soa(xr), bt.pack_soa(ur)), QT, T=T, T_pred=H, w=w)
+    assert ns == (T - 1) * Bn
+    pick = torch.tensor([0, 31, 32, Bn // 2 + 7, Bn - 1], device="cuda")
+    Xs, Us, _, _ = bt.mpc_track(bt.pack_soa(x0[pick].contiguous()), bt.Ref(bt.pack_soa(xr[pick].contiguous()),
+                                                                          bt.pack_soa(ur[pick].contiguous())), QT, T=T, T_pred=H, w=w)
+    assert torch.equal(bt.unpack_soa(Xr)[pick], bt.unpack_soa(Xs)) and torch.equal(bt.unpack_soa(Ur)[pick], bt.unpack_soa(Us))
+    xo, uo = O.solve_mpc_tracking(x0[Bn - 1].cpu().numpy(), xr[Bn - 1].cpu().numpy(), ur[Bn - 1].cpu().numpy(), T, T_pred=H)
+    assert rel_err(bt.unpack_soa(Xr)[Bn - 1].cpu().numpy(), xo[:T]) < TOL
+
+
 def test_mpc_tracking_per_problem_physical_parameters(bt):
     """SURVEY 8f rank 1 in the MPC tracker: every problem its own (m, l, lc, I, f) within +-3 %: it linearises the
     reference, pads the window about x_f, computes its terminal weight and steps its plant with its own model -
