@@ -1245,7 +1245,9 @@ __device__ __forceinline__ void mpc_sweep(const WV<WPB>& w, double dt, const dou
 // register prefetch cannot do that here: ptxas put the loads of all three rotating register buffers on one scoreboard
 // and the first use after the loop's back edge waited for every load in flight, the youngest included (ncu: 23 % of
 // all stall samples on that one DFMA; profiles/r2_mpc_pp_ncu_summary.txt).
+#ifndef ACRO_MPC_RING
 #define ACRO_MPC_RING 6
+#endif
 #ifndef ACRO_MPC_NS
 #define ACRO_MPC_NS 3  // solves per pass (2: 7.56 ms, 3: 7.14 ms, 4: 6.98 ms with spills, at B = 16 384, H = 75)
 #endif
