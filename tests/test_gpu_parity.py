@@ -1110,3 +1110,63 @@ def test_equilibrium_batch(bt):
     # an unreachable target (|u_2| > g2) reports failure instead of returning garbage
     theta, n = bt.equilibrium(soa(np.array([[0.0, 50.0]])), soa(np.array([[0.1, 0.1]])))
     assert int(n[0]) < 0
+
+
+def test_mpc_kernels_stay_inside_their_buffers(bt):
+    """compute-sanitizer is not available on the GPU pool: the MPC kernels (cp.async ring, circular active-set slots,
+    gain tables) are called through the C ABI on buffers carved out of larger allocations whose guard bands must come
+    back untouched; the sizes are the ones the header documents (acro_mpc_box_ws_doubles, {T x 4}, {T-1 x 2}, ...)."""
+    import ctypes as C
+    from gymnast_optimalcontrol_b200 import _abi
+    from gymnast_optimalcontrol_b200.batched import _p, _stream, ntiles
+    d, g, Ad, Bd = _mpc_setup()
+    GUARD = 4096  # doubles on either side
+    canary = float(np.float64(-1.2345678e300))
+
+    def carve(n_doubles, dtype=torch.float64):
+        buf = torch.full((int(n_doubles) + 2 * GUARD,), canary if dtype == torch.float64 else -77, dtype=dtype, device="cuda")
+        return buf, buf[GUARD:GUARD + int(n_doubles)]
+
+    def intact(buf, n, dtype=torch.float64):
+        ref = canary if dtype == torch.float64 else -77
+        return bool((buf[:GUARD] == ref).all()) and bool((buf[GUARD + int(n):] == ref).all())
+
+    rng = np.random.default_rng(123)
+    w = bt.mpc_weights()
+    QT = dev(g["P_inf"])
+    xf = (C.c_double * 4)(np.pi, 0.0, 0.0, 0.0)
+    uf = (C.c_double * 2)(0.0, 0.0)
+    for Bn, N_, T, H in ((37, 60, 60, 9), (70, 48, 45, 31), (33, 40, 40, 4)):
+        t0 = 150
+        xs = np.repeat(d["x"][None, t0:t0 + N_], Bn, 0) + rng.uniform(-1e-3, 1e-3, (Bn, N_, 4))
+        us = np.repeat(d["u"][None, t0:t0 + N_ - 1], Bn, 0)
+        refp = bt.Ref(soa(xs), soa(us))
+        refs = bt.make_ref(xs[0], us[0])
+        x0 = soa(xs[:, 0] + rng.uniform(-0.02, 0.02, (Bn, 4)))
+        nt = ntiles(Bn) * 32
+        # ---- unconstrained, per-problem references (k_lin_compact<true>, k_mpc_track_pp)
+        sizes = dict(lin=nt * (N_ - 1) * 10, Xr=nt * T * 4, Ur=nt * (T - 1) * 2)
+        bufs = {k: carve(v) for k, v in sizes.items()}
+        ns = C.c_int64(0)
+        _abi.call("acro_mpc_track", C.byref(bt.DEFAULT_PARAMS), w.ref(), Bn, N_, T, H, refp.ref(), xf, uf, _p(QT), 0, _p(x0),
+                  C.c_void_p(0), _p(bufs["lin"][1]), _p(bufs["Xr"][1]), _p(bufs["Ur"][1]), C.byref(ns), _stream())
+        torch.cuda.synchronize()
+        for k, v in sizes.items():
+            assert intact(bufs[k][0], v), ("acro_mpc_track", k, Bn, H)
+        assert bool(torch.isfinite(bufs["Xr"][1].view(ntiles(Bn), T, 4, 32)[0, :, :, 0]).all())
+        # ---- with the input box, shared and per-problem references (k_mpc_box_gains, k_mpc_track_box)
+        for ref, per_problem in ((refs, False), (refp, True)):
+            sizes = dict(lin=(nt if per_problem else 1) * (N_ - 1) * 10, ws=_abi.lib.acro_mpc_box_ws_doubles(Bn, T, H),
+                         Xr=nt * T * 4, Ur=nt * (T - 1) * 2)
+            bufs = {k: carve(v) for k, v in sizes.items()}
+            isz = dict(ns=Bn, na=(T - 1) * Bn, st=Bn)
+            ibufs = {k: carve(v, torch.int32) for k, v in isz.items()}
+            _abi.call("acro_mpc_track_box", C.byref(bt.DEFAULT_PARAMS), w.ref(), Bn, N_, T, H, ref.ref(), xf, uf, _p(QT), 0,
+                      _p(x0), 12.0, 0, _p(bufs["lin"][1]), _p(bufs["ws"][1]), _p(bufs["Xr"][1]), _p(bufs["Ur"][1]),
+                      _p(ibufs["ns"][1], torch.int32), _p(ibufs["na"][1], torch.int32), _p(ibufs["st"][1], torch.int32), _stream())
+            torch.cuda.synchronize()
+            for k, v in sizes.items():
+                assert intact(bufs[k][0], v), ("acro_mpc_track_box", k, Bn, H, per_problem)
+            for k, v in isz.items():
+                assert intact(ibufs[k][0], v, torch.int32), ("acro_mpc_track_box", k, Bn, H, per_problem)
+            assert int(ibufs["st"][1].max()) == 0 and int(ibufs["na"][1].max()) > 0
