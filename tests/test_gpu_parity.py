@@ -1170,3 +1170,48 @@ def test_mpc_kernels_stay_inside_their_buffers(bt):
             for k, v in isz.items():
                 assert intact(ibufs[k][0], v, torch.int32), ("acro_mpc_track_box", k, Bn, H, per_problem)
             assert int(ibufs["st"][1].max()) == 0 and int(ibufs["na"][1].max()) > 0
+
+
+@pytest.mark.parametrize("kernel,Bn,gamma_0", [("duo", 70, 0.1), ("spec", 70, 1.0), ("spec8", 45, 1.0), ("duo4", 70, 1.0),
+                                               ("ring4", 70, 1.0), ("ring-rl", 45, 0.1), ("thread", 45, 1.0)])
+def test_newton_kernels_stay_inside_their_buffers(bt, fa_ref, kernel, Bn, gamma_0):
+    """The Newton kernels (TMA rings, hand-off rings, the candidate workspace of the speculative line search) run on a
+    solver state whose every array is carved out of a larger allocation: the guard bands around X, U, K, S, the work
+    trajectories, the linearisation, the histories and the workspace come back untouched, and the solve equals the one
+    on ordinary allocations bit for bit."""
+    from gymnast_optimalcontrol_b200 import _abi
+    from gymnast_optimalcontrol_b200.batched import Traj
+    xr, ur = _short_ref(fa_ref, N=81)
+    N_, iters = 81, 5
+    x0 = np.random.default_rng(50).uniform(-0.2, 0.2, (Bn, 4))
+    ref = bt.make_ref(xr, ur)
+    want = bt.newton_solve(soa(x0), ref, max_iters=iters, tol=0.0, gamma_0=gamma_0, kernel=kernel)
+    GUARD = 2048
+    canary = float(np.float64(-9.87654321e299))
+    st = bt.newton_alloc(Bn, N_, iters, history=True)
+    guards = []
+
+    def recarve(t):
+        flat = t.reshape(-1)
+        fill = canary if t.dtype == torch.float64 else -77
+        buf = torch.full((flat.numel() + 2 * GUARD,), fill, dtype=t.dtype, device="cuda")
+        view = buf[GUARD:GUARD + flat.numel()]
+        view.copy_(flat)
+        guards.append((buf, flat.numel(), fill))
+        return view.view(t.shape)
+
+    for name in ("X", "U", "K", "S", "Xw", "Uw", "lin"):
+        tr = getattr(st, name)
+        setattr(st, name, Traj(recarve(tr.data), tr.B))
+    for name in ("cost", "delta_J", "sigma_norm", "gamma_acc", "iters", "status", "hist_cost", "hist_sigma_norm", "hist_gamma",
+                 "hist_ntry"):
+        setattr(st, name, recarve(getattr(st, name)))
+    st.spec_ws = recarve(torch.zeros(int(_abi.lib.acro_newton_spec_ws_doubles(Bn, N_)), dtype=torch.float64, device="cuda"))
+    got = bt.newton_solve(soa(x0), ref, max_iters=iters, tol=0.0, gamma_0=gamma_0, kernel=kernel, state=st)
+    torch.cuda.synchronize()
+    for buf, n, fill in guards:
+        assert bool((buf[:GUARD] == fill).all()) and bool((buf[GUARD + n:] == fill).all())
+    for name in ("X", "U", "K", "S"):
+        assert torch.equal(getattr(got, name).data[:, :, :, :], getattr(want, name).data)
+    assert torch.equal(got.hist_ntry, want.hist_ntry) and torch.equal(got.iters, want.iters)
+    assert torch.equal(got.hist_cost.nan_to_num(-1.0), want.hist_cost.nan_to_num(-1.0))
