@@ -2289,7 +2289,10 @@ int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int
     const int64_t n = int64_t(N - 1) * B;
     k_lin_compact<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
     ACRO_LAUNCH_CHECK("acro_mpc_track_box/linearize");
-    k_mpc_track_box<true><<<c.grid, c.block, 0, s>>>(a);
+    const size_t ring_bytes = size_t(c.block / 32) * ACRO_BOX_RING * BoxSlot<true>::N * 32 * sizeof(double);
+    ACRO_REQUIRE(cudaFuncSetAttribute(k_mpc_track_box<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes) ==
+                     cudaSuccess, "acro_mpc_track_box: cudaFuncSetAttribute failed");
+    k_mpc_track_box<true><<<c.grid, c.block, ring_bytes, s>>>(a);
   } else {
     k_lin_compact<false><<<(N - 1 + 63) / 64, 64, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
     ACRO_LAUNCH_CHECK("acro_mpc_track_box/linearize");
@@ -2299,7 +2302,8 @@ int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int
       k_mpc_box_gains<<<(T - 1 + 31) / 32, 32, 0, s>>>(a);
       ACRO_LAUNCH_CHECK("acro_mpc_track_box/gains");
     }
-    k_mpc_track_box<false><<<c.grid, c.block, 0, s>>>(a);
+    const size_t ring_bytes = size_t(c.block / 32) * ACRO_BOX_RING * BoxSlot<false>::N * 32 * sizeof(double);
+    k_mpc_track_box<false><<<c.grid, c.block, ring_bytes, s>>>(a);
   }
   ACRO_LAUNCH_CHECK("acro_mpc_track_box");
   return ACRO_OK;

@@ -24,7 +24,7 @@
 // How a solve spends its time (profiles/r2_box_probe.txt): one thread per problem, a few warps per SM, so every loop
 // over the window that waits for its own loads pays a full memory latency per step (2770 cycles per window step in
 // round 1, of which ~400 are arithmetic).  Hence
-//   * the sweeps read their per-problem operands three window steps ahead into a rotating set of registers;
+//   * the general sweeps get their per-problem operands through a cp.async ring in shared memory (below);
 //   * the window slides by renaming: v and the working-set flags live in circular slots (window index j of step t is
 //     slot (t + j) mod n), the candidate v* is written to a second buffer and a full step swaps the two pointers,
 //     the flags are bytes, the number of held inputs is carried along - no copy loops;
@@ -60,7 +60,7 @@ struct MpcBoxArgs {
   int32_t* status;    // [B] 0, or 1 if some step ran into max_iter (out, may be null)
 };
 
-// doubles of workspace per problem: v, v* (2n), gains (5n), states (4n + 4), flags (n bytes, n doubles reserved)
+// doubles of workspace per problem: v, v* (2n), gains (5n), states (4n + 4), flags (n int32, n doubles reserved)
 __host__ __device__ inline int64_t mpc_box_ws_per_problem(int H) { return 12LL * (H - 1) + 4; }
 __host__ __device__ inline int64_t mpc_box_ktab_doubles(int T, int H) { return 4LL * (T - 1) * (H - 1); }
 __host__ __device__ inline int64_t mpc_box_table_doubles(int T, int H) {
@@ -170,6 +170,30 @@ __global__ void k_mpc_box_gains(const __grid_constant__ MpcBoxArgs a) {
   }
 }
 
+// Per-problem operands of the general sweeps come through a ring of ACRO_BOX_RING window steps per warp in shared memory,
+// filled with cp.async (every thread copies the values of its own problem: no synchronisation between lanes) and awaited
+// with cp.async.wait_group, which counts groups - the wait for step j leaves the copies of the steps after it in flight.
+// (Loads into rotating register records all landed on one scoreboard: every first use waited for the youngest load too,
+// 41 % of the stall samples of the first round-2 version, profiles/r2_mpc_box_ncu_summary.txt.)
+#define ACRO_BOX_RING 4
+template <bool RPB>
+struct BoxSlot {
+  static constexpr int N = RPB ? 18 : 8;  // doubles per lane and step: v, flag, K[4] | xb[4], u_ref, k (+ lin[10])
+};
+__device__ __forceinline__ void box_cp8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void box_cp4(double* smem_dst, const int32_t* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void box_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void box_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <bool RPB>
 __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
   const int64_t B = a.B, b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -191,7 +215,7 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
   double* const ws = a.ws + b;
   double* vcur = ws;                   // the feasible iterate v
   double* voth = ws + int64_t(n) * B;  // the minimiser v* of the current working set
-  int8_t* const wk = reinterpret_cast<int8_t*>(a.ws + (11LL * n + 4) * B) + b;  // +1 / -1: held at the upper / lower bound
+  int32_t* const wk = reinterpret_cast<int32_t*>(a.ws + (11LL * n + 4) * B) + b;  // +1 / -1: held at the upper / lower bound
   auto Kg = [&](int j, int c) -> double& { return ws[int64_t(2 * n + 4 * j + c) * B]; };
   auto kg = [&](int j) -> double& { return ws[int64_t(6 * n + j) * B]; };
   auto Xb = [&](int j, int c) -> double& { return ws[int64_t(7 * n + 4 * j + c) * B]; };
@@ -209,6 +233,48 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
     return int64_t(s >= n ? s - n : s) * B;
   };
 
+  extern __shared__ double box_ring[];
+  constexpr int SL = BoxSlot<RPB>::N;
+  double* const ring = box_ring + (threadIdx.x >> 5) * (ACRO_BOX_RING * SL * 32) + (threadIdx.x & 31);
+  auto rs = [&](int s, int e) -> double& { return ring[(s * SL + e) * 32]; };
+  // window step j of absolute time tj -> ring slot s: what every general sweep needs (v, flag) and, with per-problem
+  // references, the linearisation and the reference input of the step
+  // (the rows of a SHARED reference stay broadcast loads at their use: copying them into the ring per lane - 11 more
+  // cp.async per lane and step, 32 times redundant - made the kernel 45 % slower)
+  constexpr bool rows_in_ring = RPB;
+  auto fetch_common = [&](int j, int tj, int s, const double* vbuf) {
+    box_cp8(&rs(s, 0), vbuf + slot(j));
+    box_cp4(&rs(s, 1), wk + slot(j));
+    if (RPB) {
+      if (tj < n_lin) {
+#pragma unroll
+        for (int c = 0; c < 10; ++c) box_cp8(&rs(s, 8 + c), a.lin + soa(tj, 10, c, ld, b));
+      }
+      if (tj < a.N - 1) box_cp8(&rs(s, 6), a.ru + soa(tj, 2, 1, a.N - 1, b));
+    }
+  };
+  auto ring_lin = [&](int tj, int s) {
+    if (!rows_in_ring) return lin_at(tj);
+    if (RPB && tj >= n_lin) return Lf;
+    LinD L;
+    constexpr int o = RPB ? 8 : 0;  // (never read without RPB)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      L.a[0][c] = rs(s, o + c);
+      L.a[1][c] = rs(s, o + 4 + c);
+    }
+    L.b[0] = rs(s, RPB ? 16 : 0);
+    L.b[1] = rs(s, RPB ? 17 : 0);
+    L.b0[0] = L.b0[1] = 0.0;
+    return L;
+  };
+  auto ring_uref = [&](int tj, int s) {
+    if (!rows_in_ring) return uref1(tj);
+    if (RPB && tj >= a.N - 1) return a.uf[1];
+    return rs(s, 6);
+  };
+  auto ring_flag = [&](int s) { return *reinterpret_cast<const int32_t*>(&rs(s, 1)); };
+
   double x[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -225,7 +291,7 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         const double v = fmin(fmax(0.0, lo), hi);
         const int f = (v >= hi) ? 1 : ((v <= lo) ? -1 : 0);
         vcur[slot(j)] = v;
-        wk[slot(j)] = int8_t(f);
+        wk[slot(j)] = f;
         held += (f != 0);
       }
     } else {
@@ -235,7 +301,7 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
       const double v = fmin(fmax(0.0, lo), hi);
       const int f = (v >= hi) ? 1 : ((v <= lo) ? -1 : 0);
       vcur[slot(n - 1)] = v;
-      wk[slot(n - 1)] = int8_t(f);
+      wk[slot(n - 1)] = f;
       held += (f != 0);
     }
     double x0w[4];
@@ -249,27 +315,14 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         double P[10], p[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int e = 0; e < 10; ++e) P[e] = QT[e];
-        struct BwRec {
-          LinD L;
-          double v;
-          int f;
-        };
-        auto load_bw = [&](int j) {
-          BwRec r;
-          j = max(j, 0);
-          if (RPB) r.L = lin_at(t + j);
-          r.v = vcur[slot(j)];
-          r.f = wk[slot(j)];
-          return r;
-        };
-        auto bw_step = [&](const BwRec& r, int j) {
-          const LinD L = RPB ? r.L : lin_at(t + j);
+        auto bw_step = [&](double rv, int rf, const LinD& Lr, int j) {
+          const LinD& L = Lr;
           double S[10], F[4], Pb[4], pn[4];
           box_products(P, L, dt, S, F, Pb);
-          if (r.f != 0) {  // held at v_j (its gain row is never read)
+          if (rf != 0) {  // held at v_j (its gain row is never read)
             double y[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) y[c] = fma(Pb[c], r.v, p[c]);
+            for (int c = 0; c < 4; ++c) y[c] = fma(Pb[c], rv, p[c]);
             box_At(L, dt, y, pn);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -289,19 +342,23 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) p[c] = pn[c];
         };
-        BwRec r0 = load_bw(n - 1), r1 = load_bw(n - 2), r2 = load_bw(n - 3);
-        for (int j = n - 1; j >= 0; j -= 3) {
-          bw_step(r0, j);  // a record is refilled right after the step that consumed it
-          r0 = load_bw(j - 3);
-          if (j >= 1) {
-            bw_step(r1, j - 1);
-            r1 = load_bw(j - 4);
-          }
-          if (j >= 2) {
-            bw_step(r2, j - 2);
-            r2 = load_bw(j - 5);
-          }
+        auto fetch_bw = [&](int j, int s) {
+          if (j >= 0) fetch_common(j, t + j, s, vcur);
+          box_commit();
+        };
+#pragma unroll
+        for (int i = 0; i < ACRO_BOX_RING; ++i) fetch_bw(n - 1 - i, i);
+        int s = 0;
+        for (int j = n - 1; j >= 0; --j) {
+          box_wait<ACRO_BOX_RING - 1>();
+          const double rv = rs(s, 0);
+          const int rf = ring_flag(s);
+          const LinD Lr = ring_lin(t + j, s);
+          bw_step(rv, rf, Lr, j);
+          fetch_bw(j - ACRO_BOX_RING, s);  // after the step: the slot has been consumed
+          s = (s + 1 == ACRO_BOX_RING) ? 0 : s + 1;
         }
+        box_wait<0>();
       }
       // ---- forward sweep (closed loop): minimiser over the free inputs, blocking input
       double alpha = 1.0, dmax = 0.0, vmax = 0.0;
@@ -376,58 +433,43 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         }
       } else {
         double xs[4] = {x0w[0], x0w[1], x0w[2], x0w[3]};
-        struct FwRec {
-          LinD L;
-          double v, K[4], k, ur;
-          int f;
-        };
-        auto load_fw = [&](int j) {
-          FwRec r;
-          j = min(j, n - 1);
-          if (RPB) {
-            r.L = lin_at(t + j);
-            r.ur = uref1(t + j);
-          }
-          r.v = vcur[slot(j)];
-          r.f = wk[slot(j)];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) r.K[c] = Kg(j, c);
-          r.k = kg(j);
-          return r;
-        };
         const bool keep_states = held > 0;  // the costate sweep below reads them
-        auto fw_step = [&](const FwRec& r, int j) {
-          const double vj = r.v;
+        auto fetch_fw = [&](int j, int s) {
+          if (j < n) {
+            fetch_common(j, t + j, s, vcur);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) box_cp8(&rs(s, 2 + c), &Kg(j, c));
+            box_cp8(&rs(s, 7), &kg(j));
+          }
+          box_commit();
+        };
+#pragma unroll
+        for (int i = 0; i < ACRO_BOX_RING; ++i) fetch_fw(i, i);
+        int s = 0;
+        for (int j = 0; j < n; ++j) {
+          box_wait<ACRO_BOX_RING - 1>();
+          const double vj = rs(s, 0);
+          const int rf = ring_flag(s);
           double vs = vj;
           if (keep_states) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) Xb(j, c) = xs[c];
           }
-          if (r.f == 0) {
-            vs = fma(r.K[3], xs[3], fma(r.K[2], xs[2], fma(r.K[1], xs[1], fma(r.K[0], xs[0], r.k))));
-            consider(j, vj, vs, RPB ? r.ur : uref1(t + j));
+          if (rf == 0) {
+            vs = fma(rs(s, 5), xs[3], fma(rs(s, 4), xs[2], fma(rs(s, 3), xs[1], fma(rs(s, 2), xs[0], rs(s, 7)))));
+            consider(j, vj, vs, ring_uref(t + j, s));
           }
           vmax = fmax(vmax, fabs(vj));
           voth[slot(j)] = vs;
-          const LinD L = RPB ? r.L : lin_at(t + j);
+          const LinD L = ring_lin(t + j, s);
           double xn[4];
           box_plant(L, dt, xs, vs, xn);
 #pragma unroll
           for (int c = 0; c < 4; ++c) xs[c] = xn[c];
-        };
-        FwRec r0 = load_fw(0), r1 = load_fw(1), r2 = load_fw(2);
-        for (int j = 0; j < n; j += 3) {
-          fw_step(r0, j);  // a record is refilled right after the step that consumed it
-          r0 = load_fw(j + 3);
-          if (j + 1 < n) {
-            fw_step(r1, j + 1);
-            r1 = load_fw(j + 4);
-          }
-          if (j + 2 < n) {
-            fw_step(r2, j + 2);
-            r2 = load_fw(j + 5);
-          }
+          fetch_fw(j + ACRO_BOX_RING, s);  // after the step: the slot has been consumed
+          s = (s + 1 == ACRO_BOX_RING) ? 0 : s + 1;
         }
+        box_wait<0>();
         if (keep_states) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) Xb(n, c) = xs[c];
@@ -449,7 +491,7 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         }
         const double ur = uref1(t + jb);
         vcur[slot(jb)] = (sb > 0) ? tau - ur : -tau - ur;
-        wk[slot(jb)] = int8_t(sb);
+        wk[slot(jb)] = sb;
         ++held;
         continue;
       }
@@ -477,27 +519,27 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
             lam[i] = sacc;  // half the gradient of the cost with respect to the state
           }
         }
-        struct CoRec {
-          LinD L;
-          double v, xb[4];
-          int f;
-        };
-        auto load_co = [&](int j) {
-          CoRec r;
-          j = max(j, 0);
-          if (RPB) r.L = lin_at(t + j);
-          r.v = vcur[slot(j)];
-          r.f = wk[slot(j)];
+        auto fetch_co = [&](int j, int s) {
+          if (j >= 0) {
+            fetch_common(j, t + j, s, vcur);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) r.xb[c] = Xb(j, c);
-          return r;
+            for (int c = 0; c < 4; ++c) box_cp8(&rs(s, 2 + c), &Xb(j, c));
+          }
+          box_commit();
         };
-        auto co_step = [&](const CoRec& r, int j) {
-          const LinD L = RPB ? r.L : lin_at(t + j);
-          if (r.f != 0) {
-            const double t1 = R11 * r.v, t2 = L.b[0] * lam[2], t3 = L.b[1] * lam[3];
+#pragma unroll
+        for (int i = 0; i < ACRO_BOX_RING; ++i) fetch_co(n - 1 - i, i);
+        int s = 0;
+        for (int j = n - 1; j >= 0; --j) {
+          box_wait<ACRO_BOX_RING - 1>();
+          const double rv = rs(s, 0);
+          const int rf = ring_flag(s);
+          const double xb0 = rs(s, 2), xb1 = rs(s, 3), xb2 = rs(s, 4), xb3 = rs(s, 5);
+          const LinD L = ring_lin(t + j, s);
+          if (rf != 0) {
+            const double t1 = R11 * rv, t2 = L.b[0] * lam[2], t3 = L.b[1] * lam[3];
             const double g = t1 + t2 + t3, scale = fabs(t1) + fabs(t2) + fabs(t3);
-            const double viol = double(r.f) * g;  // must be <= 0 at the upper bound, >= 0 at the lower one
+            const double viol = double(rf) * g;  // must be <= 0 at the upper bound, >= 0 at the lower one
             if (viol > 1e-10 * scale + 1e-300 && viol / (scale + 1e-300) > worst) {
               worst = viol / (scale + 1e-300);
               jw = j;
@@ -505,27 +547,18 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
           }
           double al[4];
           box_At(L, dt, lam, al);
+          const double xbv[4] = {xb0, xb1, xb2, xb3};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            double sacc = w.Q(i, 0) * r.xb[0];
+            double sacc = w.Q(i, 0) * xbv[0];
 #pragma unroll
-            for (int c = 1; c < 4; ++c) sacc = fma(w.Q(i, c), r.xb[c], sacc);
+            for (int c = 1; c < 4; ++c) sacc = fma(w.Q(i, c), xbv[c], sacc);
             lam[i] = sacc + al[i];
           }
-        };
-        CoRec r0 = load_co(n - 1), r1 = load_co(n - 2), r2 = load_co(n - 3);
-        for (int j = n - 1; j >= 0; j -= 3) {
-          co_step(r0, j);  // a record is refilled right after the step that consumed it
-          r0 = load_co(j - 3);
-          if (j >= 1) {
-            co_step(r1, j - 1);
-            r1 = load_co(j - 4);
-          }
-          if (j >= 2) {
-            co_step(r2, j - 2);
-            r2 = load_co(j - 5);
-          }
+          fetch_co(j - ACRO_BOX_RING, s);  // after the step: the slot has been consumed
+          s = (s + 1 == ACRO_BOX_RING) ? 0 : s + 1;
         }
+        box_wait<0>();
       }
       if (jw < 0) break;  // optimal
       wk[slot(jw)] = 0;   // release the input whose multiplier has the wrong sign (the most violating one)
