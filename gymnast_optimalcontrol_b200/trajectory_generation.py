@@ -389,7 +389,7 @@ def _finish_newton(st, kind, verbose, return_gains, x_trajs, sigmas, return_stat
                        "x_trajs": x_trajs, "sigmas": sigmas}
         else:
             # accepted steps: every iteration but a final one whose line search failed (tg:367-369)
-            n_acc = int(iters[0]) - (1 if int(status[0]) == 3 else 0)
+            n_acc = max(int(iters[0]) - (1 if int(status[0]) == 3 else 0), 0)  # history['cost'] always holds the initial cost (tg:322-327)
             history = {"cost": list(hc[0][:n_acc + 1]), "sigma_norm": list(hs[0][:int(iters[0])]), "x_trajs": x_trajs,
                        "sigmas": sigmas, "iters": int(iters[0]), "status": int(status[0]),
                        "n_try": list(hn[0][:int(iters[0])]), "gamma": list(hg[0][:int(iters[0])])}
