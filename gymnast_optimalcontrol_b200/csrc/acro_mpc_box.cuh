@@ -361,12 +361,11 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         box_wait<0>();
       }
       // ---- forward sweep (closed loop): minimiser over the free inputs, blocking input
-      double alpha = 1.0, dmax = 0.0, vmax = 0.0;
+      double alpha = 1.0;
       int jb = -1, sb = 0;
-      // the candidate vs of input j: distance to v, blocking ratio
+      // the candidate vs of input j: blocking ratio of the step from v towards it
       auto consider = [&](int j, double vj, double vs, double ur) {
         const double lo = -tau - ur, hi = tau - ur, d = vs - vj;
-        dmax = fmax(dmax, fabs(d));
         if (vs > hi && d > 0.0) {
           const double q = (hi - vj) / d;
           if (q < alpha) {
@@ -403,7 +402,6 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         auto tab_step = [&](const TabRec& q, double vj, int j) {
           const double vs = fma(q.K[3], xs[3], fma(q.K[2], xs[2], fma(q.K[1], xs[1], fma(q.K[0], xs[0], 0.0))));
           consider(j, vj, vs, q.r[10]);
-          vmax = fmax(vmax, fabs(vj));
           voth[slot(j)] = vs;
           double xn[4];
           xn[0] = fma(dt, xs[2], xs[0]);
@@ -459,7 +457,6 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
             vs = fma(rs(s, 5), xs[3], fma(rs(s, 4), xs[2], fma(rs(s, 3), xs[1], fma(rs(s, 2), xs[0], rs(s, 7)))));
             consider(j, vj, vs, ring_uref(t + j, s));
           }
-          vmax = fmax(vmax, fabs(vj));
           voth[slot(j)] = vs;
           const LinD L = ring_lin(t + j, s);
           double xn[4];
