@@ -2302,7 +2302,16 @@ int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int
       k_mpc_box_gains<<<(T - 1 + 31) / 32, 32, 0, s>>>(a);
       ACRO_LAUNCH_CHECK("acro_mpc_track_box/gains");
     }
-    const size_t ring_bytes = size_t(c.block / 32) * ACRO_BOX_RING * BoxSlot<false>::N * 32 * sizeof(double);
+    // per warp: the operand ring and, when the tables are used, their staged copies (gains 2 x 4n, window rows 11 (n+1))
+    const int nb = T_pred - 1;
+    size_t ring_bytes = size_t(c.block / 32) * (ACRO_BOX_RING * BoxSlot<false>::N * 32 + (a.ktab ? 8 * nb + 11 * (nb + 1) : 0)) *
+                        sizeof(double);
+    if (ring_bytes > 200 * 1024) {  // a horizon too long to stage: every solve runs its own backward sweep, rows from global memory
+      a.ktab = nullptr;
+      ring_bytes = size_t(c.block / 32) * ACRO_BOX_RING * BoxSlot<false>::N * 32 * sizeof(double);
+    }
+    ACRO_REQUIRE(cudaFuncSetAttribute(k_mpc_track_box<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes) ==
+                     cudaSuccess, "acro_mpc_track_box: cudaFuncSetAttribute failed");
     k_mpc_track_box<false><<<c.grid, c.block, ring_bytes, s>>>(a);
   }
   ACRO_LAUNCH_CHECK("acro_mpc_track_box");

@@ -30,7 +30,8 @@
 //     the flags are bytes, the number of held inputs is carried along - no copy loops;
 //   * with a shared reference and an empty working set the gains of the backward sweep are the same for every
 //     problem: k_mpc_box_gains computes them once per MPC step (table [T-1][n][4]) and a solve whose working set
-//     is empty runs only the forward sweep (the feasibility check of the unconstrained minimiser) against the table.
+//     is empty runs only the forward sweep (the feasibility check of the unconstrained minimiser) against the table;
+//     table and window rows of the step are staged in shared memory per warp, the next step's prefetched.
 #pragma once
 #include "acro_device.cuh"
 #include "acro_views.cuh"
@@ -219,11 +220,43 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
   auto Kg = [&](int j, int c) -> double& { return ws[int64_t(2 * n + 4 * j + c) * B]; };
   auto kg = [&](int j) -> double& { return ws[int64_t(6 * n + j) * B]; };
   auto Xb = [&](int j, int c) -> double& { return ws[int64_t(7 * n + 4 * j + c) * B]; };
+  // Shared reference: the tables of the current MPC step live in shared memory, one copy per warp - the gains of the
+  // empty working set (n x 4, double-buffered: the next step's are fetched while this one is solved) and the window rows
+  // (circular, n + 1 rows of 11: the window slides by one row per step).  Filled by the lanes of the warp together with
+  // cp.async at the top of every step, where the lanes meet (__syncwarp); read-only in between.  (Reading them from
+  // global memory at their use - broadcast loads that hit in L1 - left ~35 % of the stall samples on their first use.)
+  extern __shared__ double box_ring[];
+  constexpr int SL = BoxSlot<RPB>::N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int na = int(min(int64_t(32), B - (b - lane)));  // lanes of this warp that own a problem (the others have left)
+  const unsigned lanes = na == 32 ? 0xffffffffu : ((1u << na) - 1u);
+  double* const ksm = box_ring + nwarps * (ACRO_BOX_RING * SL * 32) + warp * (8 * n + 11 * (n + 1));
+  double* const wsm = ksm + 8 * n;
+  int t_now = 0, w0 = 0;  // the MPC step being solved; slot of its first window row (= t mod (n + 1))
+  auto wrow = [&](int tj) -> const double* {
+    int i = w0 + (tj - t_now);
+    if (i >= n + 1) i -= n + 1;
+    return wsm + i * 11;
+  };
   auto lin_at = [&](int tj) {
+    if (tab) {
+      const double* r = wrow(tj);
+      LinD L;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        L.a[0][c] = r[c];
+        L.a[1][c] = r[4 + c];
+      }
+      L.b[0] = r[8];
+      L.b[1] = r[9];
+      L.b0[0] = L.b0[1] = 0.0;
+      return L;
+    }
     if (!RPB && a.wtab) return box_load_row(a.wtab, tj);
     return tj < n_lin ? load_lin(a.lin, tj, ld, b) : Lf;
   };
   auto uref1 = [&](int tj) {
+    if (tab) return wrow(tj)[10];
     if (!RPB && a.wtab) return __ldg(a.wtab + int64_t(tj) * 11 + 10);
     return tj < a.N - 1 ? ref.U(tj, 1) : a.uf[1];
   };
@@ -233,9 +266,7 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
     return int64_t(s >= n ? s - n : s) * B;
   };
 
-  extern __shared__ double box_ring[];
-  constexpr int SL = BoxSlot<RPB>::N;
-  double* const ring = box_ring + (threadIdx.x >> 5) * (ACRO_BOX_RING * SL * 32) + (threadIdx.x & 31);
+  double* const ring = box_ring + warp * (ACRO_BOX_RING * SL * 32) + lane;
   auto rs = [&](int s, int e) -> double& { return ring[(s * SL + e) * 32]; };
   // window step j of absolute time tj -> ring slot s: what every general sweep needs (v, flag) and, with per-problem
   // references, the linearisation and the reference input of the step
@@ -283,6 +314,28 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
   }
   int sweeps = 0, stat = 0, held = 0;
   for (int t = 0; t < a.T - 1; ++t) {
+    if (tab) {
+      auto stage = [&](double* dst, const double* src, int count) {
+        for (int i = lane; i < count; i += na) box_cp8(dst + i, src + i);
+      };
+      if (t == 0) {
+        stage(ksm, a.ktab, 4 * n);
+        stage(wsm, a.wtab, 11 * n);
+        box_commit();
+      } else {
+        w0 = (w0 + 1 == n + 1) ? 0 : w0 + 1;
+      }
+      t_now = t;
+      box_wait<0>();
+      __syncwarp(lanes);  // every lane has finished step t-1 and the tables of step t have landed
+      if (t + 1 < a.T - 1) {  // tables of step t+1: its gains into the other buffer, the row that enters its window
+        stage(ksm + ((t + 1) & 1) * 4 * n, a.ktab + int64_t(t + 1) * n * 4, 4 * n);
+        int i = w0 + n;
+        if (i >= n + 1) i -= n + 1;
+        stage(wsm + i * 11, a.wtab + int64_t(t + n) * 11, 11);
+      }
+      box_commit();
+    }
     // ---- start: the previous solution shifted by one step (same absolute times, hence still feasible and with the
     // same working set), the new last input at the point of its interval closest to 0
     if (t == 0) {
@@ -383,37 +436,25 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
         }
       };
       if (from_table) {
-        // nothing is held: gains from the table, table rows one step ahead, v three steps ahead
+        // nothing is held: gains and window rows from the staged tables, v six steps ahead
         double xs[4] = {x0w[0], x0w[1], x0w[2], x0w[3]};
-        const double* const krow = a.ktab + int64_t(t) * n * 4;
-        const double* const wrow = a.wtab + int64_t(t) * 11;
-        struct TabRec {
-          double K[4], r[11];
-        };
-        auto load_tab = [&](int j) {
-          TabRec q;
-          j = min(j, n - 1);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) q.K[c] = __ldg(krow + j * 4 + c);
-#pragma unroll
-          for (int c = 0; c < 11; ++c) q.r[c] = __ldg(wrow + j * 11 + c);
-          return q;
-        };
-        auto tab_step = [&](const TabRec& q, double vj, int j) {
-          const double vs = fma(q.K[3], xs[3], fma(q.K[2], xs[2], fma(q.K[1], xs[1], fma(q.K[0], xs[0], 0.0))));
-          consider(j, vj, vs, q.r[10]);
+        const double* const krow = ksm + (t & 1) * 4 * n;
+        auto tab_step = [&](double vj, int j) {
+          const double* const q = wrow(t + j);
+          const double* const K = krow + j * 4;
+          const double vs = fma(K[3], xs[3], fma(K[2], xs[2], fma(K[1], xs[1], fma(K[0], xs[0], 0.0))));
+          consider(j, vj, vs, q[10]);
           voth[slot(j)] = vs;
           double xn[4];
           xn[0] = fma(dt, xs[2], xs[0]);
           xn[1] = fma(dt, xs[3], xs[1]);
-          xn[2] = fma(q.r[8], vs, fma(q.r[3], xs[3], fma(q.r[2], xs[2], fma(q.r[1], xs[1], q.r[0] * xs[0]))));
-          xn[3] = fma(q.r[9], vs, fma(q.r[7], xs[3], fma(q.r[6], xs[2], fma(q.r[5], xs[1], q.r[4] * xs[0]))));
+          xn[2] = fma(q[8], vs, fma(q[3], xs[3], fma(q[2], xs[2], fma(q[1], xs[1], q[0] * xs[0]))));
+          xn[3] = fma(q[9], vs, fma(q[7], xs[3], fma(q[6], xs[2], fma(q[5], xs[1], q[4] * xs[0]))));
 #pragma unroll
           for (int c = 0; c < 4; ++c) xs[c] = xn[c];
         };
         auto v_at = [&](int j) { return vcur[slot(min(j, n - 1))]; };
         double v0 = v_at(0), v1 = v_at(1), v2 = v_at(2), v3 = v_at(3), v4 = v_at(4), v5 = v_at(5);
-        TabRec qa = load_tab(0), qb = load_tab(1);
         for (int j = 0; j < n; j += 2) {
           const double va = v0, vb = v1;
           v0 = v2;
@@ -422,12 +463,8 @@ __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
           v3 = v5;
           v4 = v_at(j + 6);
           v5 = v_at(j + 7);
-          tab_step(qa, va, j);
-          qa = load_tab(j + 2);
-          if (j + 1 < n) {
-            tab_step(qb, vb, j + 1);
-            qb = load_tab(j + 3);
-          }
+          tab_step(va, j);
+          if (j + 1 < n) tab_step(vb, j + 1);
         }
       } else {
         double xs[4] = {x0w[0], x0w[1], x0w[2], x0w[3]};
