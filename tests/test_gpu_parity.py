@@ -1215,3 +1215,28 @@ def test_newton_kernels_stay_inside_their_buffers(bt, fa_ref, kernel, Bn, gamma_
         assert torch.equal(getattr(got, name).data[:, :, :, :], getattr(want, name).data)
     assert torch.equal(got.hist_ntry, want.hist_ntry) and torch.equal(got.iters, want.iters)
     assert torch.equal(got.hist_cost.nan_to_num(-1.0), want.hist_cost.nan_to_num(-1.0))
+
+
+def test_box_mpc_block_shapes_and_long_horizon_fallback(bt):
+    """k_mpc_track_box with 128-thread blocks (B >= 75 776): four warps, each with its own operand ring and staged tables;
+    and a horizon too long for the staged tables at that block size (the library then lets every solve run its own
+    backward sweep with the window rows read from global memory).  Sampled problems equal a 3-problem run."""
+    d, g, Ad, Bd = _mpc_setup()
+    w = bt.mpc_weights()
+    QT = dev(g["P_inf"])
+    Bn = 76000
+    rng = np.random.default_rng(93)
+    for (t0, N_, T, H, tau) in ((150, 45, 40, 20, 12.0), (120, 360, 4, 340, 12.0)):
+        xs, us = d["x"][t0:t0 + N_], d["u"][t0:t0 + N_ - 1]
+        ref = bt.make_ref(xs, us)
+        x0 = torch.from_numpy(xs[0] + rng.uniform(-0.02, 0.02, (Bn, 4))).cuda()
+        Xr, Ur, info = bt.mpc_track_box(bt.pack_soa(x0), ref, QT, tau_max=tau, T=T, T_pred=H, w=w)
+        assert int(info["status"].max()) == 0
+        pick = torch.tensor([0, 33, Bn - 1], device="cuda")
+        Xs, Us, infos = bt.mpc_track_box(bt.pack_soa(x0[pick].contiguous()), ref, QT, tau_max=tau, T=T, T_pred=H, w=w)
+        assert rel_err(bt.unpack_soa(Xr)[pick].cpu().numpy(), bt.unpack_soa(Xs).cpu().numpy()) < 1e-12
+        assert rel_err(bt.unpack_soa(Ur)[pick].cpu().numpy(), bt.unpack_soa(Us).cpu().numpy()) < 1e-12
+        assert torch.equal(info["n_active"][:, pick], infos["n_active"])
+        if H == 20:
+            xo, uo, nao = O.solve_mpc_tracking_box(x0[33].cpu().numpy(), xs, us, T, T_pred=H, tau_max=tau, Q_T=g["P_inf"])
+            assert rel_err(bt.unpack_soa(Xr)[33].cpu().numpy(), xo[:T]) < 1e-8 and nao.max() > 0
