@@ -70,7 +70,7 @@ def test_random_mpc_configurations(bt, seed):
             # the box must admit the trivial part of the QP: the first input stays at the point closest to zero
             xo, uo, nao = O.solve_mpc_tracking_box(x0[b], xr_b(b), ub, T, T_pred=H, tau_max=tau, Q_T=g["P_inf"])
             m = prefix(xo, T)
-            tol = 1e-8 if m == T else 1e-6
+            tol = 1e-9 if m == T else 1e-6
             assert m >= min(T, 4), (H, N_, T, t0, n, tau)
             assert rel_err(Xb[b][:m], xo[:m]) < tol and rel_err(Ub[b][:m - 1], uo[:m - 1]) < tol, (H, N_, T, t0, n, tau)
             assert np.abs(na[:m - 1, b] - nao[:m - 1]).max() <= 1
