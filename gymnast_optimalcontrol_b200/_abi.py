@@ -75,6 +75,8 @@ SIGNATURES = {
                           P, P, C.POINTER(C.c_int64), P],
     "acro_mpc_track_box": [PP, PW, I64, I32, I32, I32, PR, C.POINTER(C.c_double), C.POINTER(C.c_double), P, I32, P, F64, I32,
                            P, P, P, P, P, P, P, P],
+    "acro_mpc_track_box_pp": [PP, P, PW, I64, I32, I32, I32, PR, C.POINTER(C.c_double), C.POINTER(C.c_double), P, I32, P, F64,
+                              I32, P, P, P, P, P, P, P, P],
     "acro_bench_fp64_peak": [I32, I32, I32, P, P],
     "acro_bench_fp64_chain": [I32, I32, I32, I32, I32, P, P, P],
     "acro_transpose": [I64, I64, P, P, P],

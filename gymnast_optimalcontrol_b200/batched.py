@@ -552,10 +552,10 @@ def mpc_track(x0, ref, QT_inf, T=None, T_pred=75, w=None, x_f=(np.pi, 0.0, 0.0, 
 
 
 def mpc_track_box(x0, ref, QT_inf, tau_max=18.0, T=None, T_pred=75, w=None, x_f=(np.pi, 0.0, 0.0, 0.0), u_f=(0.0, 0.0),
-                  params=DEFAULT_PARAMS, max_iter=0):
+                  params=DEFAULT_PARAMS, max_iter=0, params_b=None):
     """solve_mpc_tracking with the input box -tau_max <= u + u_ref <= tau_max of tt:87-91, 112-114 switched on; every
     step is solved exactly (active set on Riccati sweeps).  -> Xr Traj, Ur Traj, info {n_sweeps (B,), n_active (T-1,B),
-    status (B,)}"""
+    status (B,)}.  params_b (11,B): every problem its own physical parameters (needs a per-problem reference)."""
     from ._abi import lib
     w = mpc_weights() if w is None else w
     N, Bn = ref.N, x0.shape[1]
@@ -568,6 +568,13 @@ def mpc_track_box(x0, ref, QT_inf, tau_max=18.0, T=None, T_pred=75, w=None, x_f=
     na = _empty(T - 1, Bn, dtype=torch.int32)
     xf = (C.c_double * 4)(*[float(v) for v in x_f])
     uf = (C.c_double * 2)(*[float(v) for v in u_f])
+    if params_b is not None:
+        if not ref.per_problem:
+            raise ValueError("mpc_track_box: per-problem physical parameters need a per-problem reference (B, N, 4)")
+        call("acro_mpc_track_box_pp", C.byref(params), _p(params_b), w.ref(), Bn, N, int(T), int(T_pred), ref.ref(), xf, uf,
+             _p(QT_inf), int(qt_pp), _p(x0), float(tau_max), int(max_iter), _p(lin), _p(ws), _p(Xr), _p(Ur),
+             _p(ns, torch.int32), _p(na, torch.int32), _p(st, torch.int32), _stream())
+        return Xr, Ur, {"n_sweeps": ns, "n_active": na, "status": st}
     call("acro_mpc_track_box", C.byref(params), w.ref(), Bn, N, int(T), int(T_pred), ref.ref(), xf, uf, _p(QT_inf), int(qt_pp),
          _p(x0), float(tau_max), int(max_iter), _p(lin), _p(ws), _p(Xr), _p(Ur), _p(ns, torch.int32), _p(na, torch.int32),
          _p(st, torch.int32), _stream())

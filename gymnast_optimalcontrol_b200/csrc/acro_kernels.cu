@@ -2248,13 +2248,16 @@ int64_t acro_mpc_box_ws_doubles(int64_t B, int T, int T_pred) {
   return mpc_box_ws_per_problem(T_pred) * B + mpc_box_table_doubles(T, T_pred);
 }
 
-int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
-                       const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
-                       int qt_per_problem, const double* x0, double tau_max, int max_iter, double* lin_ws, double* ws,
-                       double* Xr, double* Ur, int32_t* n_sweeps, int32_t* n_active, int32_t* status, void* stream) {
+}  // extern "C"
+static int mpc_track_box_impl(const AcroParams* p, const double* params_b, const AcroWeights* w, int64_t B, int N, int T,
+                              int T_pred, const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                              int qt_per_problem, const double* x0, double tau_max, int max_iter, double* lin_ws,
+                              double* ws, double* Xr, double* Ur, int32_t* n_sweeps, int32_t* n_active, int32_t* status,
+                              void* stream) {
   ACRO_REQUIRE(p && w && ref && ref->x && ref->u && x_f && u_f && QT_inf && x0 && lin_ws && ws && Xr && Ur && B > 0 &&
                    N >= 2 && T >= 2 && T <= N && T_pred >= 2 && tau_max > 0.0,
                "acro_mpc_track_box: bad argument");
+  ACRO_REQUIRE(!params_b || ref->per_problem, "acro_mpc_track_box_pp: per-problem parameters need a per-problem reference layout");
   ACRO_REQUIRE(!p->actuated_tau1, "acro_mpc_track_box: fully-actuated plant not supported here");
   ACRO_REQUIRE(!per_problem_weights(*w), "acro_mpc_track_box: per-problem weights not supported here");
   ACRO_REQUIRE(w->R[1] == 0.0 && w->R[2] == 0.0, "acro_mpc_track_box: R must be diagonal");
@@ -2276,6 +2279,7 @@ int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int
   a.ws = ws;
   a.ktab = nullptr;
   a.wtab = nullptr;
+  a.pb = params_b;
   a.tau = tau_max;
   a.max_iter = max_iter > 0 ? max_iter : 6 * (T_pred - 1) + 20;
   a.Xr = Xr;
@@ -2287,12 +2291,18 @@ int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int
   const Cfg c = cfg_for(B);
   if (ref->per_problem) {
     const int64_t n = int64_t(N - 1) * B;
-    k_lin_compact<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
+    k_lin_compact<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws, params_b);
     ACRO_LAUNCH_CHECK("acro_mpc_track_box/linearize");
     const size_t ring_bytes = size_t(c.block / 32) * ACRO_BOX_RING * BoxSlot<true>::N * 32 * sizeof(double);
-    ACRO_REQUIRE(cudaFuncSetAttribute(k_mpc_track_box<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes) ==
-                     cudaSuccess, "acro_mpc_track_box: cudaFuncSetAttribute failed");
-    k_mpc_track_box<true><<<c.grid, c.block, ring_bytes, s>>>(a);
+    if (params_b) {
+      ACRO_REQUIRE(cudaFuncSetAttribute(k_mpc_track_box<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)ring_bytes) == cudaSuccess, "acro_mpc_track_box: cudaFuncSetAttribute failed");
+      k_mpc_track_box<true, true><<<c.grid, c.block, ring_bytes, s>>>(a);
+    } else {
+      ACRO_REQUIRE(cudaFuncSetAttribute(k_mpc_track_box<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes) ==
+                       cudaSuccess, "acro_mpc_track_box: cudaFuncSetAttribute failed");
+      k_mpc_track_box<true><<<c.grid, c.block, ring_bytes, s>>>(a);
+    }
   } else {
     k_lin_compact<false><<<(N - 1 + 63) / 64, 64, 0, s>>>(a.m, B, N, ref->x, ref->u, lin_ws);
     ACRO_LAUNCH_CHECK("acro_mpc_track_box/linearize");
@@ -2316,6 +2326,22 @@ int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int
   }
   ACRO_LAUNCH_CHECK("acro_mpc_track_box");
   return ACRO_OK;
+}
+
+extern "C" {
+int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int N, int T, int T_pred,
+                       const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                       int qt_per_problem, const double* x0, double tau_max, int max_iter, double* lin_ws, double* ws,
+                       double* Xr, double* Ur, int32_t* n_sweeps, int32_t* n_active, int32_t* status, void* stream) {
+  return mpc_track_box_impl(p, nullptr, w, B, N, T, T_pred, ref, x_f, u_f, QT_inf, qt_per_problem, x0, tau_max, max_iter,
+                            lin_ws, ws, Xr, Ur, n_sweeps, n_active, status, stream);
+}
+int acro_mpc_track_box_pp(const AcroParams* p, const double* params_b, const AcroWeights* w, int64_t B, int N, int T,
+                          int T_pred, const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
+                          int qt_per_problem, const double* x0, double tau_max, int max_iter, double* lin_ws, double* ws,
+                          double* Xr, double* Ur, int32_t* n_sweeps, int32_t* n_active, int32_t* status, void* stream) {
+  return mpc_track_box_impl(p, params_b, w, B, N, T, T_pred, ref, x_f, u_f, QT_inf, qt_per_problem, x0, tau_max, max_iter,
+                            lin_ws, ws, Xr, Ur, n_sweeps, n_active, status, stream);
 }
 
 int acro_bench_fp64_peak(int blocks, int threads, int iters, double* out, void* stream) {

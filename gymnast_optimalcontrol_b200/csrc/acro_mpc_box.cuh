@@ -59,6 +59,7 @@ struct MpcBoxArgs {
   int32_t* n_sweeps;  // [B] total active-set iterations of the problem (out, may be null)
   int32_t* n_active;  // [T-1][B] inputs at a bound in the solution of step t (out, may be null)
   int32_t* status;    // [B] 0, or 1 if some step ran into max_iter (out, may be null)
+  const double* pb;   // physical parameters per problem [11][B] (k_mpc_track_box<true, true>) or null
 };
 
 // doubles of workspace per problem: v, v* (2n), gains (5n), states (4n + 4), flags (n int32, n doubles reserved)
@@ -195,13 +196,16 @@ __device__ __forceinline__ void box_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <bool RPB>
+// PPB (with RPB): every problem its own physical parameters - plant step and padding linearisation with its own model
+template <bool RPB, bool PPB = false>
 __global__ void k_mpc_track_box(const __grid_constant__ MpcBoxArgs a) {
   const int64_t B = a.B, b = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (b >= B) return;
   const WV<false> w(a.kw, B, b);
   const RefV<RPB> ref{a.rx, a.ru, a.N, b};
-  const Model& m = a.m;
+  Model m_loc_;
+  if (PPB) m_loc_ = model_per_problem(a.m, a.pb, B, b);
+  const Model& m = PPB ? m_loc_ : a.m;
   const double dt = m.dt, R11 = w.R(1, 1), tau = a.tau;
   const int n = a.H - 1, n_lin = a.N - 1;
   const int64_t ld = RPB ? int64_t(a.N - 1) : 0;

@@ -140,7 +140,7 @@ def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return
     this call run on an upload stream and the copies back on a copy stream, so with several calls in flight the
     transfers of one batch overlap the kernel of another (pinned host inputs must stay untouched until then).
     params_b (B, 11): every problem its own physical parameters (domain randomisation): each linearises the reference
-    with its own model, has its own terminal weight P_inf and steps its own plant (not with tau_max)."""
+    with its own model, has its own terminal weight P_inf and steps its own plant (also with tau_max)."""
     w = bt.Weights(Q_mpc if Q is None else Q, R_mpc if R is None else R)
     p = active_params()
     piped = (not block) and not return_info
@@ -151,8 +151,6 @@ def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return
     if piped:
         _io.flush_deferred()  # copy-back of the previous call: queued after this call's uploads, before its kernel
     if params_b is not None:
-        if tau_max is not None:
-            raise ValueError("solve_mpc_tracking: params_b is not supported together with tau_max")
         Bn = x0d.shape[1]
         pb = bt.phys_params(params_b, Bn)
         if not ref.per_problem:  # every problem linearises the reference with its own model: per-problem layout
@@ -164,6 +162,19 @@ def solve_mpc_tracking(x0, x_ref, u_ref, T, *, T_pred=75, Q=None, R=None, return
         Pb, n = bt.p_inf(A_f, B_f, w)
         if not piped and int(n.min()) < 0:
             print("P_inf did not converge!!!")
+        if tau_max is not None:
+            Xr, Ur, info = bt.mpc_track_box(x0d, ref, Pb, tau_max=float(tau_max), T=int(T), T_pred=int(T_pred), w=w, x_f=x_f,
+                                            u_f=u_f, params=p, params_b=pb)
+            if piped:
+                return _MpcPending(_io.out_async([(Xr, ref.N), (Ur, ref.N - 1)], kind, defer=True), info["status"])
+            if int(info["status"].max()) != 0:
+                print("Attention! mpc solver: active-set iteration limit reached for %d problem(s)" % int((info["status"] != 0).sum()))
+            xr, ur = _pad_time(_io.out(Xr, kind, key="xr"), ref.N), _pad_time(_io.out(Ur, kind, key="ur"), ref.N - 1)
+            if return_info:
+                return xr, ur, dict(n_solves=(int(T) - 1) * Bn, n_sweeps=info["n_sweeps"].cpu().numpy(),
+                                    n_active=info["n_active"].cpu().numpy().T, status=info["status"].cpu().numpy(),
+                                    P_inf=Pb.cpu().numpy())
+            return xr, ur
         Xr, Ur, _, n_solves = bt.mpc_track(x0d, ref, Pb, T=int(T), T_pred=int(T_pred), w=w, x_f=x_f, u_f=u_f, params=p,
                                            params_b=pb)
         if piped:

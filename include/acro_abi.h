@@ -321,6 +321,13 @@ int acro_mpc_track_box(const AcroParams* p, const AcroWeights* w, int64_t B, int
                        const AcroRef* ref, const double* x_f, const double* u_f, const double* QT_inf,
                        int qt_per_problem, const double* x0, double tau_max, int max_iter, double* lin_ws, double* ws,
                        double* Xr, double* Ur, int32_t* n_sweeps, int32_t* n_active, int32_t* status, void* stream);
+/* the same with physical parameters per problem (params_b [11][B]; per-problem reference layout, QT_inf normally per
+ * problem): own linearisation, own padding about (x_f, u_f), own plant */
+int acro_mpc_track_box_pp(const AcroParams* p, const double* params_b, const AcroWeights* w, int64_t B, int N, int T,
+                          int T_pred, const AcroRef* ref, const double* x_f, const double* u_f,
+                          const double* QT_inf, int qt_per_problem, const double* x0, double tau_max, int max_iter,
+                          double* lin_ws, double* ws, double* Xr, double* Ur, int32_t* n_sweeps, int32_t* n_active,
+                          int32_t* status, void* stream);
 
 /* Runs blocks x threads threads, each doing iters x 8 independent dependent-chain DFMAs
  * (16 flops per thread per iteration); out [blocks*threads].  Timed by bench.py to get the

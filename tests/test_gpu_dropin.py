@@ -419,5 +419,12 @@ def test_mpc_dropin_with_per_problem_parameters(mods):
     assert rel_err(xr[3, :101], xo[:101]) < TOL and rel_err(ur[3, :100], uo[:100]) < TOL
     gx, gu = tt.solve_mpc_tracking(x0, d["x"], d["u"], 101, params_b=rows, block=False).result()
     assert np.array_equal(gx, xr) and np.array_equal(gu, ur)
-    with pytest.raises(ValueError):
-        tt.solve_mpc_tracking(x0, d["x"], d["u"], 101, params_b=rows, tau_max=18.0)
+    # the same with the input box (a stretch where it binds), against the oracle with that problem's model
+    t0 = 150
+    xs, us = d["x"][t0:t0 + 60], d["u"][t0:t0 + 59]
+    x0b = xs[0] + rng.uniform(-0.02, 0.02, (n, 4))
+    xb, ub, info = tt.solve_mpc_tracking(x0b, xs, us, 46, T_pred=20, params_b=rows, tau_max=12.0, return_info=True)
+    assert info["n_active"].max() > 0 and np.abs(ub).max() <= 12.0 * (1 + 1e-12)
+    for b in (0, 7):
+        xo, uo, nao = O.solve_mpc_tracking_box(x0b[b], xs, us, 46, T_pred=20, tau_max=12.0, m=O.Model(dict(zip(PHYS_FIELDS, rows[b]))))
+        assert rel_err(xb[b, :46], xo) < TOL and rel_err(ub[b, :45], uo) < TOL
